@@ -1,0 +1,235 @@
+/* npm_b200.h — C-ABI of libnpm_b200.so: the B200 (sm_100a) replacement for the
+ * NumPy calls on np-modeling's layer forward/backward hot path.
+ *
+ * The reference (levendlee/np-modeling) has no FFI layer: its "operator API" is
+ * the Python Layer protocol (layers/layer.py:27-45) whose primitives call NumPy
+ * directly.  Each entry point below replaces the NumPy expression(s) at the
+ * cited reference file:line; the Python mirror in np-modeling_b200/layers/ package
+ * keeps the reference's class / attribute names and calls these through ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Contract (all functions):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer to fp32
+ *     (row-major, densely packed unless a stride is passed) unless the name
+ *     says `host`;
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     allocates, never synchronises; workspaces are caller-provided, sized by
+ *     the matching *_workspace() query;
+ *   - returns NPM_OK (0) or a negative code; npm_last_error() returns a
+ *     thread-local human-readable message for the last failure;
+ *   - no CPU fallback: without a usable sm_100 device every compute call fails.
+ */
+#ifndef NPM_B200_H_
+#define NPM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPM_OK               0
+#define NPM_ERR_INVALID     (-1)  /* bad argument / shape / alignment            */
+#define NPM_ERR_CUDA        (-2)  /* CUDA runtime or driver error                */
+#define NPM_ERR_UNSUPPORTED (-3)  /* valid request this build cannot serve       */
+
+/* Contraction precision of the tensor-core paths (GEMM / conv / attention). */
+#define NPM_PREC_TF32   0   /* one tcgen05 kind::tf32 pass                      */
+#define NPM_PREC_3XTF32 1   /* hi/lo split, three passes, ~fp32 accuracy        */
+#define NPM_PREC_FP32   2   /* CUDA-core fp32 FMA (exact-order SIMT kernel)     */
+
+typedef void* npm_stream_t; /* cudaStream_t */
+
+/* ---- library state -------------------------------------------------------- */
+const char* npm_last_error(void);
+int         npm_version(void);
+/* Number of kernels this library launched since the last reset (bench.py's
+ * gpu_launches claim is read from here). */
+uint64_t    npm_launch_count(void);
+void        npm_reset_launch_count(void);
+/* Default contraction precision used when a call passes precision < 0.
+ * Returns the previous value. */
+int         npm_set_precision(int precision);
+int         npm_get_precision(void);
+/* Device properties of the current device as this library sees them. */
+int         npm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- general strided-batched GEMM ---------------------------------------- */
+/* C[z][m,n] (=|+=) alpha * sum_k A[z][m,k] * B[z][k,n] (+ bias[n]) (then ReLU)
+ * A element (m,k) lives at a + z1*a_bs1 + z2*a_bs2 + m*a_rs + k*a_cs, with
+ * exactly one of a_rs/a_cs equal to 1; same for B element (k,n) with b_rs/b_cs.
+ * C is row-major with leading dimension ldc.  z = z2*nb1 + z1.
+ * Replaces np.matmul / np.einsum throughout the reference hot path. */
+#define NPM_GEMM_RELU   1   /* apply max(.,0) after bias                        */
+#define NPM_GEMM_ACCUM  2   /* C += result instead of C = result                */
+typedef struct npm_gemm_desc {
+    const float* a;
+    const float* b;
+    float*       c;
+    const float* bias;        /* length n, or NULL                              */
+    int64_t m, n, k;
+    int64_t a_rs, a_cs;
+    int64_t b_rs, b_cs;
+    int64_t ldc;
+    int32_t nb1, nb2;
+    int64_t a_bs1, a_bs2, b_bs1, b_bs2, c_bs1, c_bs2;
+    float   alpha;
+    int32_t flags;
+    int32_t precision;        /* NPM_PREC_* or <0 for the library default       */
+} npm_gemm_desc;
+int npm_gemm(const npm_gemm_desc* d, npm_stream_t stream);
+
+/* ---- Linear / Dense (layers/mlp.py) --------------------------------------- */
+/* y[m,n] = x[m,k] @ W + b.  w_out_major = 0: W is [k,n] (Linear._w, mlp.py:18);
+ * w_out_major = 1: W is [n,k] (the MultiHeadAttention projection weights viewed
+ * as [H*dk, D], attentions.py:46-57).  relu != 0 fuses Dense's ReLU
+ * (mlp.py:70-72) — the pre-activation is then NOT written.   mlp.py:21-25 */
+int npm_linear_fwd(const float* x, const float* w, const float* b, float* y,
+                   int64_t m, int64_t k, int64_t n, int w_out_major, int relu,
+                   npm_stream_t stream);
+/* dx[m,k] = dy[m,n] @ W^T.                                         mlp.py:36 */
+int npm_linear_bwd_dx(const float* dy, const float* w, float* dx,
+                      int64_t m, int64_t k, int64_t n, int w_out_major,
+                      npm_stream_t stream);
+/* dw = x^T @ dy (layout per w_out_major), db[n] = sum_m dy (db may be NULL).
+ * workspace: npm_colsum_workspace(m, n) bytes (may be NULL when db is NULL).
+ *                                                               mlp.py:34-35 */
+int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db,
+                         int64_t m, int64_t k, int64_t n, int w_out_major,
+                         void* workspace, npm_stream_t stream);
+
+/* ---- column sum: out[c] = sum_r x[r,c]   (bias / beta gradients) ---------- */
+size_t npm_colsum_workspace(int64_t rows, int64_t cols);
+int npm_colsum(const float* x, float* out, int64_t rows, int64_t cols,
+               void* workspace, npm_stream_t stream);
+
+/* ---- activations (layers/activations.py) ---------------------------------- */
+int npm_relu_fwd(const float* x, float* y, int64_t n, npm_stream_t stream);      /* :13-15 */
+/* dx = dy where x >= 0 else 0 (note >=, activations.py:19) */
+int npm_relu_bwd(const float* x, const float* dy, float* dx, int64_t n,
+                 npm_stream_t stream);
+/* row softmax over the last axis, max-shifted (activations.py:23-31). In place ok. */
+int npm_softmax_fwd(const float* x, float* y, int64_t rows, int64_t cols,
+                    npm_stream_t stream);
+/* dx = scale * y * (dy - sum(dy*y)) — closed form of the Jacobian einsum at
+ * activations.py:33-45. In place on dy ok. */
+int npm_softmax_bwd(const float* y, const float* dy, float* dx, int64_t rows,
+                    int64_t cols, float scale, npm_stream_t stream);
+
+/* ---- LayerNormalization (layers/normalizations.py:33-75) ------------------ */
+/* out = gamma*(x-mean)*rstd + beta; mean/rstd [rows] are saved for backward. */
+int npm_layernorm_fwd(const float* x, const float* gamma, const float* beta,
+                      float* out, float* mean, float* rstd, int64_t rows,
+                      int64_t cols, float epsilon, npm_stream_t stream);
+size_t npm_layernorm_bwd_workspace(int64_t rows, int64_t cols);
+/* dx (closed form of the [..,C,C] Jacobian, :60-71), dgamma, dbeta (:55-56). */
+int npm_layernorm_bwd(const float* dz, const float* x, const float* gamma,
+                      const float* mean, const float* rstd, float* dx,
+                      float* dgamma, float* dbeta, int64_t rows, int64_t cols,
+                      void* workspace, npm_stream_t stream);
+
+/* ---- DropOut (layers/normalizations.py:9-30) ------------------------------ */
+/* Element i is kept iff philox4x32_10(counter=(offset+i)/4, key=seed)[(offset+i)%4]
+ * < floor(keep_prob * 2^32); kept values are scaled by 1/keep_prob.  If
+ * ext_mask != NULL it is used instead (1 byte per element, non-zero = keep):
+ * the reference's own test injects the layer's mask into its oracle the same
+ * way (normalizations_test.py:28). */
+int npm_dropout_fwd(const float* x, float* y, int64_t n, float keep_prob,
+                    uint64_t seed, uint64_t offset, const uint8_t* ext_mask,
+                    npm_stream_t stream);
+int npm_dropout_bwd(const float* dy, float* dx, int64_t n, float keep_prob,
+                    uint64_t seed, uint64_t offset, const uint8_t* ext_mask,
+                    npm_stream_t stream);
+int npm_dropout_mask(uint8_t* mask, int64_t n, float keep_prob, uint64_t seed,
+                     uint64_t offset, npm_stream_t stream);
+
+/* ---- residual / elementwise glue (layers/transformer.py `out += skip`) ---- */
+int npm_add_inplace(float* y, const float* x, int64_t n, npm_stream_t stream);
+/* out = a + b + c (c may be NULL): sums MHA's (dquery,dkey,dvalue), :85,:196 */
+int npm_add3(const float* a, const float* b, const float* c, float* out,
+             int64_t n, npm_stream_t stream);
+int npm_scale(float* x, float s, int64_t n, npm_stream_t stream);
+int npm_fill(float* x, float v, int64_t n, npm_stream_t stream);
+
+/* ---- attention core (layers/attentions.py:103-112, :146-162) -------------- */
+/* q [B,Sq,H,dk], k [B,Skv,H,dk], v [B,Skv,H,dv]  → o [B,Sq,H,dv]
+ * o = softmax(q k^T / sqrt(dk)) v per (b,h); unmasked (the reference's mask
+ * path raises, attentions.py:84).  `saved` (npm_mha_core_saved_bytes) must be
+ * kept by the caller from fwd to bwd; its content is private to the library. */
+size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv,
+                                int64_t dk, int64_t dv);
+size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq,
+                                      int64_t Skv, int64_t dk, int64_t dv);
+int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o,
+                     void* saved, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
+                     int64_t dk, int64_t dv, npm_stream_t stream);
+int npm_mha_core_bwd(const float* q, const float* k, const float* v,
+                     const float* o, const float* d_o, const void* saved,
+                     float* dq, float* dk_out, float* dv_out, void* scratch,
+                     int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk,
+                     int64_t dv, npm_stream_t stream);
+/* Copies the attention probabilities [B,H,Sq,Skv] out of `saved` (debug /
+ * parity with MultiHeadAttention._attention_scores). */
+int npm_mha_core_scores(const void* saved, float* p_out, int64_t B, int64_t H,
+                        int64_t Sq, int64_t Skv, npm_stream_t stream);
+
+/* ---- Conv2D (layers/conv.py) ---------------------------------------------- */
+/* NHWC activations, HWIO filters, SAME padding, stride 1, odd ksize.
+ * y = conv(x, f) + b (then ReLU if relu != 0).                 conv.py:44-48 */
+size_t npm_conv2d_workspace(int64_t N, int64_t H, int64_t W, int64_t Cin,
+                            int64_t Cout, int ksize);
+int npm_conv2d_fwd(const float* x, const float* f, const float* b, float* y,
+                   int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                   int ksize, int relu, void* workspace, npm_stream_t stream);
+/* dx = conv(dy, flipHW(f)^T_IO).                             conv.py:110-153 */
+int npm_conv2d_bwd_dx(const float* dy, const float* f, float* dx, int64_t N,
+                      int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                      int ksize, void* workspace, npm_stream_t stream);
+/* dw[i,j] = xpad[:,i:,j:,:]^T @ dy ; db = sum_{n,h,w} dy.  conv.py:55,156-194 */
+int npm_conv2d_bwd_dw_db(const float* x, const float* dy, float* dw, float* db,
+                         int64_t N, int64_t H, int64_t W, int64_t Cin,
+                         int64_t Cout, int ksize, void* workspace,
+                         npm_stream_t stream);
+
+/* ---- losses (loss.py) ------------------------------------------------------ */
+/* loss_out: one device float. MSE: sum((y-t)^2)/n, grad 2(y-t)/n  (:20-29).
+ * CE (on probabilities): -sum(t*log y), grad -t/y                  (:32-39). */
+int npm_mse_fwd(const float* y, const float* t, float* loss_out, int64_t n,
+                npm_stream_t stream);
+int npm_mse_bwd(const float* y, const float* t, float* dy, int64_t n,
+                npm_stream_t stream);
+int npm_ce_fwd(const float* y, const float* t, float* loss_out, int64_t n,
+               npm_stream_t stream);
+int npm_ce_bwd(const float* y, const float* t, float* dy, int64_t n,
+               npm_stream_t stream);
+
+/* ---- optimizers (optimizer.py) — one multi-tensor launch ------------------- */
+/* A device-resident table of tensors; entry i updates param[i][0..numel[i]).
+ * Work is cut into chunks of NPM_OPT_CHUNK elements; chunk_begin[i] is the number
+ * of chunks of entries 0..i-1 (ascending), n_chunks their total. */
+#define NPM_OPT_CHUNK 8192
+typedef struct npm_tensor_entry {
+    float*       param;
+    const float* grad;
+    float*       m;           /* Adam first moment  (NULL for SGD)              */
+    float*       v;           /* Adam second moment (NULL for SGD)              */
+    int64_t      numel;
+    int64_t      chunk_begin;
+} npm_tensor_entry;
+/* param -= lr * grad_scale * grad                              optimizer.py:30-33 */
+int npm_sgd_multi(const npm_tensor_entry* table_dev, int32_t n_tensors,
+                  int64_t n_chunks, float lr, float grad_scale,
+                  npm_stream_t stream);
+/* g = grad_scale*grad; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ * param -= lr * (m/(1-b1^t)) / sqrt(v/(1-b2^t) + eps)   (eps INSIDE the sqrt)
+ *                                                           optimizer.py:50-69 */
+int npm_adam_multi(const npm_tensor_entry* table_dev, int32_t n_tensors,
+                   int64_t n_chunks, float lr, float beta1, float beta2,
+                   float epsilon, int32_t t, float grad_scale,
+                   npm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPM_B200_H_ */

@@ -1,0 +1,297 @@
+// api.cu — library state, error plumbing, GEMM dispatch and the Linear / attention-core
+// entry points of the C-ABI (include/npm_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace npm {
+
+// ------------------------------------------------------------------- state
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_precision{NPM_PREC_3XTF32};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return NPM_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return NPM_ERR_CUDA;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            sms = v;
+        else
+            return 148;   // B200; do not cache a failed query
+    }
+    return sms;
+}
+
+// implemented in gemm_tc.cu / gemm_simt.cu / rowops.cu
+bool gemm_tc_supported(const npm_gemm_desc& d);
+int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream);
+int gemm_simt_launch(const npm_gemm_desc& d, cudaStream_t stream);
+size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
+int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
+
+static int require_sm100() {
+    static int ok = -1;
+    if (ok < 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+            set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+            return NPM_ERR_CUDA;
+        }
+        ok = (major == 10) ? 1 : 0;
+    }
+    if (!ok) {
+        set_error("libnpm_b200 is built for sm_100a (B200) only; current device is not compute capability 10.x");
+        return NPM_ERR_UNSUPPORTED;
+    }
+    return NPM_OK;
+}
+
+int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
+    NPM_REQUIRE(d.a && d.b && d.c, "gemm: NULL operand");
+    NPM_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem m=%lld n=%lld k=%lld", (long long)d.m,
+                (long long)d.n, (long long)d.k);
+    NPM_REQUIRE((d.a_rs == 1 || d.a_cs == 1) && (d.b_rs == 1 || d.b_cs == 1),
+                "gemm: A and B need one unit stride each");
+    int rc = require_sm100();
+    if (rc) return rc;
+    int prec = d.precision >= 0 ? d.precision : g_precision.load();
+    if (prec != NPM_PREC_FP32 && gemm_tc_supported(d)) return gemm_tc_launch(d, prec, stream);
+    return gemm_simt_launch(d, stream);
+}
+
+static npm_gemm_desc blank_desc() {
+    npm_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.nb1 = d.nb2 = 1;
+    d.alpha = 1.0f;
+    d.precision = -1;
+    return d;
+}
+
+}  // namespace npm
+
+using namespace npm;
+
+extern "C" {
+
+const char* npm_last_error(void) { return g_err; }
+int npm_version(void) { return 100; }
+uint64_t npm_launch_count(void) { return g_launches.load(); }
+void npm_reset_launch_count(void) { g_launches.store(0); }
+int npm_set_precision(int precision) {
+    if (precision < NPM_PREC_TF32 || precision > NPM_PREC_FP32) return g_precision.load();
+    return g_precision.exchange(precision);
+}
+int npm_get_precision(void) { return g_precision.load(); }
+int npm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0, a = 0, b = 0, c = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+        set_error("device query failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return NPM_ERR_CUDA;
+    }
+    if (sm_count) *sm_count = a;
+    if (cc_major) *cc_major = b;
+    if (cc_minor) *cc_minor = c;
+    return NPM_OK;
+}
+
+int npm_gemm(const npm_gemm_desc* d, npm_stream_t stream) {
+    NPM_REQUIRE(d != nullptr, "gemm: NULL descriptor");
+    return gemm_dispatch(*d, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ Linear
+int npm_linear_fwd(const float* x, const float* w, const float* b, float* y, int64_t m, int64_t k, int64_t n,
+                   int w_out_major, int relu, npm_stream_t stream) {
+    npm_gemm_desc d = blank_desc();
+    d.a = x; d.b = w; d.c = y; d.bias = b;
+    d.m = m; d.n = n; d.k = k;
+    d.a_rs = k; d.a_cs = 1;
+    if (w_out_major) { d.b_rs = 1; d.b_cs = k; }   // W[n,k]: B(k,n) at n*k + k
+    else             { d.b_rs = n; d.b_cs = 1; }   // W[k,n]
+    d.ldc = n;
+    d.flags = relu ? NPM_GEMM_RELU : 0;
+    return gemm_dispatch(d, (cudaStream_t)stream);
+}
+
+int npm_linear_bwd_dx(const float* dy, const float* w, float* dx, int64_t m, int64_t k, int64_t n, int w_out_major,
+                      npm_stream_t stream) {
+    // dx[m,k] = sum_n dy[m,n] * W(k,n): contraction over n
+    npm_gemm_desc d = blank_desc();
+    d.a = dy; d.b = w; d.c = dx;
+    d.m = m; d.n = k; d.k = n;
+    d.a_rs = n; d.a_cs = 1;
+    if (w_out_major) { d.b_rs = k; d.b_cs = 1; }   // B(kk=n, nn=k) = W[n,k] at n*k + k
+    else             { d.b_rs = 1; d.b_cs = n; }   // B(kk=n, nn=k) = W[k,n] at k*n + n
+    d.ldc = k;
+    return gemm_dispatch(d, (cudaStream_t)stream);
+}
+
+int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db, int64_t m, int64_t k, int64_t n,
+                         int w_out_major, void* workspace, npm_stream_t stream) {
+    npm_gemm_desc d = blank_desc();
+    if (!w_out_major) {
+        // dw[k,n] = sum_m x[m,k] * dy[m,n]
+        d.a = x; d.b = dy; d.c = dw;
+        d.m = k; d.n = n; d.k = m;
+        d.a_rs = 1; d.a_cs = k;    // A(kk, mm) = x[mm, kk]
+        d.b_rs = n; d.b_cs = 1;
+        d.ldc = n;
+    } else {
+        // dw[n,k] = sum_m dy[m,n] * x[m,k]
+        d.a = dy; d.b = x; d.c = dw;
+        d.m = n; d.n = k; d.k = m;
+        d.a_rs = 1; d.a_cs = n;
+        d.b_rs = k; d.b_cs = 1;
+        d.ldc = k;
+    }
+    int rc = gemm_dispatch(d, (cudaStream_t)stream);
+    if (rc || db == nullptr) return rc;
+    return colsum_launch(dy, db, m, n, workspace, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------- attention core
+// Round-1 implementation: the batched products run on the tcgen05 GEMM with the scores
+// materialised ([B,H,Sq,Skv], as the reference does at attentions.py:103-111); `saved` holds the
+// probabilities P.  A fused online-softmax kernel can replace this behind the same ABI.
+size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t, int64_t) {
+    return (size_t)B * H * Sq * Skv * sizeof(float);
+}
+size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t, int64_t) {
+    return (size_t)B * H * Sq * Skv * sizeof(float);   // dP / dS
+}
+
+int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o, void* saved, int64_t B, int64_t H,
+                     int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream) {
+    NPM_REQUIRE(q && k && v && o && saved, "mha_core_fwd: NULL pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* P = reinterpret_cast<float*>(saved);
+    // S[b,h] = (1/sqrt(dk)) q[b,:,h,:] k[b,:,h,:]^T
+    npm_gemm_desc d = blank_desc();
+    d.a = q; d.b = k; d.c = P;
+    d.m = Sq; d.n = Skv; d.k = dk;
+    d.a_rs = H * dk; d.a_cs = 1;
+    d.b_rs = 1; d.b_cs = H * dk;          // B(c, t) = k[t, h, c]
+    d.ldc = Skv;
+    d.nb1 = (int)H; d.nb2 = (int)B;
+    d.a_bs1 = dk; d.a_bs2 = Sq * H * dk;
+    d.b_bs1 = dk; d.b_bs2 = Skv * H * dk;
+    d.c_bs1 = Sq * Skv; d.c_bs2 = H * Sq * Skv;
+    d.alpha = (float)(1.0 / sqrt((double)dk));
+    int rc = gemm_dispatch(d, s);
+    if (rc) return rc;
+    rc = npm_softmax_fwd(P, P, B * H * Sq, Skv, stream);
+    if (rc) return rc;
+    // o[b,:,h,:] = P[b,h] v[b,:,h,:]
+    npm_gemm_desc e = blank_desc();
+    e.a = P; e.b = v; e.c = o;
+    e.m = Sq; e.n = dv; e.k = Skv;
+    e.a_rs = Skv; e.a_cs = 1;
+    e.b_rs = H * dv; e.b_cs = 1;          // B(t, c) = v[t, h, c]
+    e.ldc = H * dv;
+    e.nb1 = (int)H; e.nb2 = (int)B;
+    e.a_bs1 = Sq * Skv; e.a_bs2 = H * Sq * Skv;
+    e.b_bs1 = dv; e.b_bs2 = Skv * H * dv;
+    e.c_bs1 = dv; e.c_bs2 = Sq * H * dv;
+    return gemm_dispatch(e, s);
+}
+
+int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
+                     const void* saved, float* dq, float* dk_out, float* dv_out, void* scratch, int64_t B, int64_t H,
+                     int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream) {
+    (void)o;
+    NPM_REQUIRE(q && k && v && d_o && saved && dq && dk_out && dv_out && scratch, "mha_core_bwd: NULL pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const float* P = reinterpret_cast<const float*>(saved);
+    float* dP = reinterpret_cast<float*>(scratch);
+    int rc;
+    {   // dV[b,:,h,:] = P[b,h]^T dO[b,:,h,:]                      attentions.py:147-148
+        npm_gemm_desc d = blank_desc();
+        d.a = P; d.b = d_o; d.c = dv_out;
+        d.m = Skv; d.n = dv; d.k = Sq;
+        d.a_rs = 1; d.a_cs = Skv;            // A(t, s) = P[s, t]
+        d.b_rs = H * dv; d.b_cs = 1;         // B(s, c) = dO[s, h, c]
+        d.ldc = H * dv;
+        d.nb1 = (int)H; d.nb2 = (int)B;
+        d.a_bs1 = Sq * Skv; d.a_bs2 = H * Sq * Skv;
+        d.b_bs1 = dv; d.b_bs2 = Sq * H * dv;
+        d.c_bs1 = dv; d.c_bs2 = Skv * H * dv;
+        if ((rc = gemm_dispatch(d, s))) return rc;
+    }
+    {   // dP[b,h] = dO[b,:,h,:] v[b,:,h,:]^T                      attentions.py:146
+        npm_gemm_desc d = blank_desc();
+        d.a = d_o; d.b = v; d.c = dP;
+        d.m = Sq; d.n = Skv; d.k = dv;
+        d.a_rs = H * dv; d.a_cs = 1;
+        d.b_rs = 1; d.b_cs = H * dv;         // B(c, t) = v[t, h, c]
+        d.ldc = Skv;
+        d.nb1 = (int)H; d.nb2 = (int)B;
+        d.a_bs1 = dv; d.a_bs2 = Sq * H * dv;
+        d.b_bs1 = dv; d.b_bs2 = Skv * H * dv;
+        d.c_bs1 = Sq * Skv; d.c_bs2 = H * Sq * Skv;
+        if ((rc = gemm_dispatch(d, s))) return rc;
+    }
+    // dS = P * (dP - rowsum(dP * P)) / sqrt(dk)                    attentions.py:150-155
+    if ((rc = npm_softmax_bwd(P, dP, dP, B * H * Sq, Skv, (float)(1.0 / sqrt((double)dk)), stream))) return rc;
+    {   // dQ[b,:,h,:] = dS[b,h] k[b,:,h,:]                         attentions.py:161
+        npm_gemm_desc d = blank_desc();
+        d.a = dP; d.b = k; d.c = dq;
+        d.m = Sq; d.n = dk; d.k = Skv;
+        d.a_rs = Skv; d.a_cs = 1;
+        d.b_rs = H * dk; d.b_cs = 1;         // B(t, c) = k[t, h, c]
+        d.ldc = H * dk;
+        d.nb1 = (int)H; d.nb2 = (int)B;
+        d.a_bs1 = Sq * Skv; d.a_bs2 = H * Sq * Skv;
+        d.b_bs1 = dk; d.b_bs2 = Skv * H * dk;
+        d.c_bs1 = dk; d.c_bs2 = Sq * H * dk;
+        if ((rc = gemm_dispatch(d, s))) return rc;
+    }
+    {   // dK[b,:,h,:] = dS[b,h]^T q[b,:,h,:]                       attentions.py:162
+        npm_gemm_desc d = blank_desc();
+        d.a = dP; d.b = q; d.c = dk_out;
+        d.m = Skv; d.n = dk; d.k = Sq;
+        d.a_rs = 1; d.a_cs = Skv;            // A(t, s) = dS[s, t]
+        d.b_rs = H * dk; d.b_cs = 1;         // B(s, c) = q[s, h, c]
+        d.ldc = H * dk;
+        d.nb1 = (int)H; d.nb2 = (int)B;
+        d.a_bs1 = Sq * Skv; d.a_bs2 = H * Sq * Skv;
+        d.b_bs1 = dk; d.b_bs2 = Sq * H * dk;
+        d.c_bs1 = dk; d.c_bs2 = Skv * H * dk;
+        if ((rc = gemm_dispatch(d, s))) return rc;
+    }
+    return NPM_OK;
+}
+
+int npm_mha_core_scores(const void* saved, float* p_out, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
+                        npm_stream_t stream) {
+    NPM_REQUIRE(saved && p_out, "mha_core_scores: NULL pointer");
+    cudaError_t e = cudaMemcpyAsync(p_out, saved, (size_t)B * H * Sq * Skv * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("mha_core_scores: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+    return NPM_OK;
+}
+
+}  // extern "C"

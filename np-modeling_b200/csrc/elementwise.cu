@@ -1,0 +1,236 @@
+// elementwise.cu — HBM-bound elementwise kernels: ReLU fwd/bwd, DropOut fwd/bwd (Philox),
+// residual add, 3-way add, scale, fill.
+//
+// All are grid-stride loops over 128-bit vectors (scalar head-free tail only), grids sized to
+// a whole number of waves of the 148 SMs, streaming loads/stores that bypass L1.
+// Algorithmic bytes per element (fp32): relu fwd 8, relu bwd 12, dropout fwd/bwd 8 (mask is
+// recomputed from the Philox counter, never stored), add_inplace 12, add3 12/16.
+#include "common.cuh"
+
+namespace npm {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <class F>
+__global__ void __launch_bounds__(kThreads) ew1_kernel(const float* x, float* y,
+                                                       int64_t n, F f) {
+    const int64_t nv = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float4 v = ld_stream(reinterpret_cast<const float4*>(x) + i);
+        v.x = f(v.x); v.y = f(v.y); v.z = f(v.z); v.w = f(v.w);
+        st_stream(reinterpret_cast<float4*>(y) + i, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (nv << 2) + threadIdx.x;
+        y[i] = f(x[i]);
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kThreads) ew2_kernel(const float* a, const float* b, float* y, int64_t n, F f) {
+    const int64_t nv = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 u = ld_stream(reinterpret_cast<const float4*>(a) + i);
+        const float4 w = ld_stream(reinterpret_cast<const float4*>(b) + i);
+        float4 v;
+        v.x = f(u.x, w.x); v.y = f(u.y, w.y); v.z = f(u.z, w.z); v.w = f(u.w, w.w);
+        st_stream(reinterpret_cast<float4*>(y) + i, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (nv << 2) + threadIdx.x;
+        y[i] = f(a[i], b[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) add3_kernel(const float* a, const float* b, const float* c, float* y, int64_t n) {
+    const int64_t nv = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 u = ld_stream(reinterpret_cast<const float4*>(a) + i);
+        const float4 w = ld_stream(reinterpret_cast<const float4*>(b) + i);
+        const float4 q = ld_stream(reinterpret_cast<const float4*>(c) + i);
+        float4 v;
+        v.x = (u.x + w.x) + q.x; v.y = (u.y + w.y) + q.y; v.z = (u.z + w.z) + q.z; v.w = (u.w + w.w) + q.w;
+        st_stream(reinterpret_cast<float4*>(y) + i, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (nv << 2) + threadIdx.x;
+        y[i] = (a[i] + b[i]) + c[i];
+    }
+}
+
+// Scalar fallbacks for pointers that are not 16-byte aligned (views at odd offsets).
+template <class F>
+__global__ void ew1_scalar_kernel(const float* x, float* y, int64_t n, F f) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = f(x[i]);
+}
+template <class F>
+__global__ void ew2_scalar_kernel(const float* a, const float* b, float* y, int64_t n, F f) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = f(a[i], b[i]);
+}
+
+template <class F>
+int launch_ew1(const char* name, const float* x, float* y, int64_t n, F f, cudaStream_t s) {
+    if (n <= 0) return NPM_OK;
+    if (aligned16(x) && aligned16(y)) {
+        ew1_kernel<<<bw_grid((n + 3) / 4, kThreads), kThreads, 0, s>>>(x, y, n, f);
+    } else {
+        ew1_scalar_kernel<<<bw_grid(n, kThreads), kThreads, 0, s>>>(x, y, n, f);
+    }
+    count_launch();
+    return check_launch(name);
+}
+template <class F>
+int launch_ew2(const char* name, const float* a, const float* b, float* y, int64_t n, F f, cudaStream_t s) {
+    if (n <= 0) return NPM_OK;
+    if (aligned16(a) && aligned16(b) && aligned16(y)) {
+        ew2_kernel<<<bw_grid((n + 3) / 4, kThreads), kThreads, 0, s>>>(a, b, y, n, f);
+    } else {
+        ew2_scalar_kernel<<<bw_grid(n, kThreads), kThreads, 0, s>>>(a, b, y, n, f);
+    }
+    count_launch();
+    return check_launch(name);
+}
+
+struct ReluF { __device__ float operator()(float x) const { return x < 0.0f ? 0.0f : x; } };
+struct ReluB { __device__ float operator()(float x, float dy) const { return x >= 0.0f ? dy : 0.0f; } };
+struct AddF  { __device__ float operator()(float a, float b) const { return a + b; } };
+struct ScaleF { float s; __device__ float operator()(float x) const { return x * s; } };
+
+__global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ x, float v, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
+}
+
+// ---------------------------------------------------------------- dropout
+// keep element g  <=>  philox(g >> 2)[g & 3] < thr, thr = floor(keep_prob * 2^32).
+__device__ __forceinline__ uint32_t pick(const Philox4& p, int lane) {
+    return lane == 0 ? p.x : lane == 1 ? p.y : lane == 2 ? p.z : p.w;
+}
+
+template <bool kExtMask, bool kWriteMask>
+__global__ void __launch_bounds__(kThreads) dropout_kernel(const float* x, float* y,
+                                                           uint8_t* __restrict__ mask_out, int64_t n,
+                                                           float keep_prob, uint64_t thr, uint64_t seed,
+                                                           uint64_t offset, const uint8_t* __restrict__ ext) {
+    const int64_t ngroups = (n + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec_ok = aligned16(x) && aligned16(y);
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += stride) {
+        const int64_t i0 = gi << 2;
+        bool keep[4];
+        if (kExtMask) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) keep[e] = (i0 + e < n) ? (ext[i0 + e] != 0) : false;
+        } else {
+            const uint64_t g0 = offset + (uint64_t)i0;
+            const Philox4 p0 = philox4x32_10(g0 >> 2, seed);
+            if ((g0 & 3) == 0) {
+                keep[0] = p0.x < thr; keep[1] = p0.y < thr; keep[2] = p0.z < thr; keep[3] = p0.w < thr;
+            } else {
+                const Philox4 p1 = philox4x32_10((g0 >> 2) + 1, seed);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint64_t g = g0 + e;
+                    const uint32_t r = ((g >> 2) == (g0 >> 2)) ? pick(p0, (int)(g & 3)) : pick(p1, (int)(g & 3));
+                    keep[e] = r < thr;
+                }
+            }
+        }
+        if (kWriteMask) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i0 + e < n) mask_out[i0 + e] = keep[e] ? 1 : 0;
+        } else if (vec_ok && i0 + 3 < n) {
+            float4 v = ld_stream(reinterpret_cast<const float4*>(x + i0));
+            v.x = keep[0] ? __fdiv_rn(v.x, keep_prob) : 0.0f;
+            v.y = keep[1] ? __fdiv_rn(v.y, keep_prob) : 0.0f;
+            v.z = keep[2] ? __fdiv_rn(v.z, keep_prob) : 0.0f;
+            v.w = keep[3] ? __fdiv_rn(v.w, keep_prob) : 0.0f;
+            st_stream(reinterpret_cast<float4*>(y + i0), v);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i0 + e < n) y[i0 + e] = keep[e] ? __fdiv_rn(x[i0 + e], keep_prob) : 0.0f;
+        }
+    }
+}
+
+int dropout_apply(const float* x, float* y, int64_t n, float keep_prob, uint64_t seed, uint64_t offset,
+                  const uint8_t* ext, cudaStream_t s) {
+    if (n <= 0) return NPM_OK;
+    NPM_REQUIRE(keep_prob > 0.0f && keep_prob <= 1.0f, "dropout: keep_prob %g out of (0,1]", keep_prob);
+    const uint64_t thr = (uint64_t)((double)keep_prob * 4294967296.0);
+    const int grid = bw_grid((n + 3) / 4, kThreads);
+    if (ext)
+        dropout_kernel<true, false><<<grid, kThreads, 0, s>>>(x, y, nullptr, n, keep_prob, thr, seed, offset, ext);
+    else
+        dropout_kernel<false, false><<<grid, kThreads, 0, s>>>(x, y, nullptr, n, keep_prob, thr, seed, offset, nullptr);
+    count_launch();
+    return check_launch("dropout_kernel");
+}
+
+}  // namespace
+}  // namespace npm
+
+using namespace npm;
+
+extern "C" {
+
+int npm_relu_fwd(const float* x, float* y, int64_t n, npm_stream_t stream) {
+    return launch_ew1("relu_fwd", x, y, n, ReluF{}, (cudaStream_t)stream);
+}
+int npm_relu_bwd(const float* x, const float* dy, float* dx, int64_t n, npm_stream_t stream) {
+    return launch_ew2("relu_bwd", x, dy, dx, n, ReluB{}, (cudaStream_t)stream);
+}
+int npm_add_inplace(float* y, const float* x, int64_t n, npm_stream_t stream) {
+    return launch_ew2("add_inplace", y, x, y, n, AddF{}, (cudaStream_t)stream);
+}
+int npm_add3(const float* a, const float* b, const float* c, float* out, int64_t n, npm_stream_t stream) {
+    if (c == nullptr) return launch_ew2("add2", a, b, out, n, AddF{}, (cudaStream_t)stream);
+    if (n <= 0) return NPM_OK;
+    if (aligned16(a) && aligned16(b) && aligned16(c) && aligned16(out)) {
+        add3_kernel<<<bw_grid((n + 3) / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(a, b, c, out, n);
+        count_launch();
+        return check_launch("add3_kernel");
+    }
+    int rc = launch_ew2("add3a", a, b, out, n, AddF{}, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_ew2("add3b", out, c, out, n, AddF{}, (cudaStream_t)stream);
+}
+int npm_scale(float* x, float s, int64_t n, npm_stream_t stream) {
+    return launch_ew1("scale", x, x, n, ScaleF{s}, (cudaStream_t)stream);
+}
+int npm_fill(float* x, float v, int64_t n, npm_stream_t stream) {
+    if (n <= 0) return NPM_OK;
+    fill_kernel<<<bw_grid(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(x, v, n);
+    count_launch();
+    return check_launch("fill_kernel");
+}
+
+int npm_dropout_fwd(const float* x, float* y, int64_t n, float keep_prob, uint64_t seed, uint64_t offset,
+                    const uint8_t* ext_mask, npm_stream_t stream) {
+    return dropout_apply(x, y, n, keep_prob, seed, offset, ext_mask, (cudaStream_t)stream);
+}
+int npm_dropout_bwd(const float* dy, float* dx, int64_t n, float keep_prob, uint64_t seed, uint64_t offset,
+                    const uint8_t* ext_mask, npm_stream_t stream) {
+    // where(mask, dy / keep, 0) — the same map as forward (normalizations.py:25-30)
+    return dropout_apply(dy, dx, n, keep_prob, seed, offset, ext_mask, (cudaStream_t)stream);
+}
+int npm_dropout_mask(uint8_t* mask, int64_t n, float keep_prob, uint64_t seed, uint64_t offset,
+                     npm_stream_t stream) {
+    if (n <= 0) return NPM_OK;
+    NPM_REQUIRE(keep_prob > 0.0f && keep_prob <= 1.0f, "dropout: keep_prob %g out of (0,1]", keep_prob);
+    const uint64_t thr = (uint64_t)((double)keep_prob * 4294967296.0);
+    dropout_kernel<false, true><<<bw_grid((n + 3) / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        nullptr, nullptr, mask, n, keep_prob, thr, seed, offset, nullptr);
+    count_launch();
+    return check_launch("dropout_mask_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,492 @@
+// gemm_tc.cu — persistent, warp-specialised TF32 / 3xTF32 GEMM on tcgen05 + TMEM + TMA.
+//
+//   C[z][m,n] (=|+=) alpha * sum_k A[z][m,k] * B[z][k,n] (+ bias[n]) (ReLU)
+//
+// This single kernel family serves every contraction of the reference hot path:
+// Linear fwd/dX/dW (layers/mlp.py:21-40), the MultiHeadAttention projections and
+// the batched QK^T / PV / dP / dV / dQ / dK products (layers/attentions.py:88-184).
+//
+// Design (one CTA per SM, 128 x BLOCK_N output tile, K step of 32 fp32 = one
+// 128-byte swizzle span):
+//   warp 4      TMA producer   : cp.async.bulk.tensor → smem ring (mbarrier full/empty)
+//   warp 5      MMA issuer     : one lane issues tcgen05.mma kind::tf32, accumulators in TMEM
+//                                (two accumulator buffers so the epilogue of tile i overlaps
+//                                the main loop of tile i+1)
+//   warps 0-3   epilogue       : tcgen05.ld → alpha/bias/ReLU → swizzled smem → TMA store
+//                                (or TMA reduce-add for C += ...)
+//   warps 6-9   split (3xTF32) : rewrite each landed fp32 tile as hi = trunc_tf32(x) in place
+//                                and lo = x - hi beside it; the issuer then runs
+//                                lo*hi + hi*lo + hi*hi, recovering ~fp32 accuracy.
+// Operands may be K-major or MN-major ("transposed"): the UMMA descriptors take the
+// 128B-swizzled tiles exactly as TMA lands them, so no transposes are ever materialised.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace npm {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;   // fp32 elements per K step (128 bytes)
+constexpr int kUmmaK  = 8;    // K of one tcgen05.mma kind::tf32
+
+struct GemmTcArgs {
+    int M, N, K;
+    int tiles_m, tiles_n, nb1, total_tiles;
+    float alpha;
+    const float* bias;
+    int relu, accum;
+};
+
+template <int BLOCK_N, int NPASS>
+struct TcCfg {
+    static constexpr int kABytes     = kBlockM * kBlockK * 4;           // 16 KB
+    static constexpr int kBBytes     = BLOCK_N * kBlockK * 4;
+    static constexpr int kRawBytes   = kABytes + kBBytes;
+    static constexpr int kStageBytes = kRawBytes * (NPASS == 3 ? 2 : 1);  // + lo copies
+    static constexpr int kEpiBytes   = 4 * 2 * 4096;                    // 4 warps x 2 buffers
+    static constexpr int kBarBytes   = 512;
+    static constexpr int kBudget     = 232448 - 1024;                   // 227 KB minus align slack
+    static constexpr int kStagesRaw  = (kBudget - kEpiBytes - kBarBytes) / kStageBytes;
+    static constexpr int kStages     = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSmemBytes  = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+    static constexpr int kTmemCols   = 2 * BLOCK_N;                     // 128 / 256 / 512
+    static constexpr int kThreads    = NPASS == 3 ? 320 : 192;
+    static_assert(kStages >= 2, "need at least a double-buffered ring");
+    static_assert(kTmemCols >= 32 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "");
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int NPASS>
+__global__ void __launch_bounds__(TcCfg<BLOCK_N, NPASS>::kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmTcArgs args) {
+    using Cfg = TcCfg<BLOCK_N, NPASS>;
+    constexpr int S = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+
+    const uint32_t stage_addr = base_addr;                         // S x kStageBytes
+    const uint32_t epi_addr   = base_addr + S * Cfg::kStageBytes;  // 1024-aligned (stage sizes are)
+    const uint32_t bar_addr   = epi_addr + Cfg::kEpiBytes;
+    // barrier slots (8 bytes each)
+    auto full_bar   = [&](int s) { return bar_addr + 8u * s; };
+    auto xf_bar     = [&](int s) { return bar_addr + 8u * (S + s); };
+    auto empty_bar  = [&](int s) { return bar_addr + 8u * (2 * S + s); };
+    auto tfull_bar  = [&](int a) { return bar_addr + 8u * (3 * S + a); };
+    auto tempty_bar = [&](int a) { return bar_addr + 8u * (3 * S + 2 + a); };
+    volatile uint32_t* tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes +
+                                             8 * (3 * S + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = (args.K + kBlockK - 1) / kBlockK;
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&tmC);
+    }
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s) {
+                ptx::mbar_init(full_bar(s), 1);
+                ptx::mbar_init(xf_bar(s), 128);
+                ptx::mbar_init(empty_bar(s), 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                ptx::mbar_init(tfull_bar(a), 1);
+                ptx::mbar_init(tempty_bar(a), 4);
+            }
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_mn = args.tiles_m * args.tiles_n;
+
+    if (warp == 4) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+                const int z  = tile / tiles_mn;
+                const int r  = tile - z * tiles_mn;
+                const int m0 = (r % args.tiles_m) * kBlockM;
+                const int n0 = (r / args.tiles_m) * BLOCK_N;
+                const int z1 = z % args.nb1, z2 = z / args.nb1;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                    const uint32_t sB = sA + Cfg::kABytes;
+                    const uint32_t fb = full_bar(stage);
+                    ptx::mbar_arrive_expect_tx(fb, Cfg::kRawBytes);
+                    const int k0 = kb * kBlockK;
+                    if (!A_MN) {
+                        ptx::tma_load_4d(sA, &tmA, fb, k0, m0, z1, z2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kBlockM / 32; ++c)
+                            ptx::tma_load_4d(sA + c * 4096, &tmA, fb, m0 + c * 32, k0, z1, z2);
+                    }
+                    if (!B_MN) {
+                        ptx::tma_load_4d(sB, &tmB, fb, k0, n0, z1, z2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_N / 32; ++c)
+                            ptx::tma_load_4d(sB + c * 4096, &tmB, fb, n0 + c * 32, k0, z1, z2);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ============================= MMA issuer =============================
+        constexpr uint32_t idesc = ptx::umma_idesc_tf32(kBlockM, BLOCK_N, A_MN, B_MN);
+        // K-major: 8-row groups 1024 B apart (SBO), LBO unused (canonical 1).
+        // MN-major: 32-element MN chunks 4096 B apart (LBO), 8-row K groups 1024 B apart (SBO).
+        constexpr uint64_t descA = A_MN ? ptx::umma_desc_base_sw128(4096, 1024)
+                                        : ptx::umma_desc_base_sw128(16, 1024);
+        constexpr uint64_t descB = B_MN ? ptx::umma_desc_base_sw128(4096, 1024)
+                                        : ptx::umma_desc_base_sw128(16, 1024);
+        constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;   // bytes per UMMA_K (8) step
+        constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(NPASS == 3 ? xf_bar(stage) : full_bar(stage), phase);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                    const uint32_t sB = sA + Cfg::kABytes;
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+                        const uint64_t da = ptx::umma_desc(descA, sA + kk * a_kstep);
+                        const uint64_t db = ptx::umma_desc(descB, sB + kk * b_kstep);
+                        const uint32_t first = (kb | kk) != 0 ? 1u : 0u;
+                        if (NPASS == 1) {
+                            ptx::umma_tf32(d_tmem, da, db, idesc, first);
+                        } else {
+                            const uint64_t da_lo =
+                                ptx::umma_desc(descA, sA + Cfg::kRawBytes + kk * a_kstep);
+                            const uint64_t db_lo =
+                                ptx::umma_desc(descB, sB + Cfg::kRawBytes + kk * b_kstep);
+                            ptx::umma_tf32(d_tmem, da_lo, db, idesc, first);   // lo * hi
+                            ptx::umma_tf32(d_tmem, da, db_lo, idesc, 1u);      // hi * lo
+                            ptx::umma_tf32(d_tmem, da, db, idesc, 1u);         // hi * hi
+                        }
+                    }
+                    ptx::umma_commit(empty_bar(stage));            // smem slot reusable
+                    if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(acc));  // accumulator ready
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else if (warp < 4) {
+        // ============================== epilogue ==============================
+        uint8_t* stg_base = base_ptr + S * Cfg::kStageBytes + warp * 2 * 4096;
+        const uint32_t stg_addr = epi_addr + warp * 2 * 4096;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t nstore = 0;
+        for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+            const int z  = tile / tiles_mn;
+            const int r  = tile - z * tiles_mn;
+            const int m0 = (r % args.tiles_m) * kBlockM;
+            const int n0 = (r / args.tiles_m) * BLOCK_N;
+            const int z1 = z % args.nb1, z2 = z / args.nb1;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const bool rows_live = (m0 + warp * 32) < args.M;
+#pragma unroll 1
+            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                const int nc = n0 + chunk * 32;
+                if (nc >= args.N || !rows_live) break;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(tmem_base + (uint32_t(warp * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+                ptx::tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
+                if (args.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nc + j < args.N) f[j] += __ldg(args.bias + nc + j);
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                const uint32_t buf = nstore & 1u;
+                // the store that last read this buffer (two stores ago) must have drained
+                if (lane == 0) ptx::tma_wait_group_read<1>();
+                __syncwarp();
+                uint8_t* row = stg_base + buf * 4096 + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = o;
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (args.accum)
+                        ptx::tma_reduce_add_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
+                    else
+                        ptx::tma_store_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
+                    ptx::tma_commit_group();
+                }
+                ++nstore;
+            }
+            // every tcgen05.ld of this accumulator has completed (wait::ld above)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (lane == 0) ptx::tma_wait_group<0>();
+    } else if (NPASS == 3) {
+        // ===================== 3xTF32 operand split (warps 6-9) ================
+        const int t = threadIdx.x - 192;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                uint8_t* raw = base_ptr + stage * Cfg::kStageBytes;
+#pragma unroll 4
+                for (int i = t; i < Cfg::kRawBytes / 16; i += 128) {
+                    float4 x = *reinterpret_cast<float4*>(raw + i * 16);
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                    hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                    hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                    hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                    lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+                    *reinterpret_cast<float4*>(raw + i * 16) = hi;
+                    *reinterpret_cast<float4*>(raw + Cfg::kRawBytes + i * 16) = lo;
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(xf_bar(stage));
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+// 4-D fp32 tensor map: dims (d0 contiguous, d1, d2, d3), strides in ELEMENTS for d1..d3,
+// box (b0, b1, 1, 1), 128-byte swizzle, zero fill out of bounds.
+int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t d3, uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1,
+                       bool round_tf32) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return NPM_ERR_CUDA;
+    }
+    cuuint64_t dims[4]    = {d0, d1, d2, d3};
+    cuuint64_t strides[3] = {s1 * 4, s2 * 4, s3 * 4};
+    cuuint32_t box[4]     = {b0, b1, 1, 1};
+    cuuint32_t estr[4]    = {1, 1, 1, 1};
+    CUresult rc = fn(tm, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                     4, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
+                  "box=(%u,%u) base=%p",
+                  (int)rc, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                  (unsigned long long)d3, (unsigned long long)s1, (unsigned long long)s2,
+                  (unsigned long long)s3, b0, b1, (const void*)base);
+        return NPM_ERR_CUDA;
+    }
+    return NPM_OK;
+}
+
+namespace {
+
+template <int BN, bool AMN, bool BMN, int NP>
+int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmTcArgs& args,
+               int grid, cudaStream_t stream) {
+    using Cfg = TcCfg<BN, NP>;
+    auto kern = gemm_tc_kernel<BN, AMN, BMN, NP>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+            return NPM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(a, b, c, args);
+    count_launch();
+    return check_launch("gemm_tc_kernel");
+}
+
+template <int BN, int NP>
+int launch_major(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                 const GemmTcArgs& args, int grid, cudaStream_t s) {
+    if (!amn && !bmn) return launch_one<BN, false, false, NP>(a, b, c, args, grid, s);
+    if (!amn && bmn) return launch_one<BN, false, true, NP>(a, b, c, args, grid, s);
+    if (amn && !bmn) return launch_one<BN, true, false, NP>(a, b, c, args, grid, s);
+    return launch_one<BN, true, true, NP>(a, b, c, args, grid, s);
+}
+
+inline bool mult4(int64_t v) { return (v & 3) == 0; }
+
+}  // namespace
+
+// Can the tensor-core path take this problem?  TMA needs 16-byte aligned bases and
+// 16-byte multiples for every non-contiguous stride.
+bool gemm_tc_supported(const npm_gemm_desc& d) {
+    if (d.m <= 0 || d.n <= 0 || d.k <= 0) return false;
+    if (!aligned16(d.a) || !aligned16(d.b) || !aligned16(d.c)) return false;
+    const int64_t a_ld = d.a_cs == 1 ? d.a_rs : d.a_cs;
+    const int64_t b_ld = d.b_rs == 1 ? d.b_cs : d.b_rs;
+    if (!(d.a_cs == 1 || d.a_rs == 1) || !(d.b_cs == 1 || d.b_rs == 1)) return false;
+    if (!mult4(a_ld) || !mult4(b_ld) || !mult4(d.ldc)) return false;
+    if (a_ld <= 0 || b_ld <= 0 || d.ldc < d.n) return false;
+    if (d.nb1 > 1 && !(mult4(d.a_bs1) && mult4(d.b_bs1) && mult4(d.c_bs1))) return false;
+    if (d.nb2 > 1 && !(mult4(d.a_bs2) && mult4(d.b_bs2) && mult4(d.c_bs2))) return false;
+    if (d.m > (1ll << 31) - 256 || d.n > (1ll << 31) - 256 || d.k > (1ll << 31) - 256) return false;
+    return true;
+}
+
+static bool env_flag(const char* name, bool dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return v[0] != '0';
+}
+
+int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
+    const int nb1 = d.nb1 > 0 ? d.nb1 : 1, nb2 = d.nb2 > 0 ? d.nb2 : 1;
+    // A is "MN-major" when m is the contiguous index of A[m,k]; when both strides are 1 the
+    // matrix is a vector and either reading works — prefer K-major.
+    const bool a_mn = !(d.a_cs == 1);
+    const bool b_mn = !(d.b_rs == 1);   // B[k,n]: K-major when k is contiguous
+    const int npass = precision == NPM_PREC_3XTF32 ? 3 : 1;
+    // In single-pass mode let TMA round fp32 → tf32 (nearest) instead of the MMA truncating.
+    static const bool tma_round = env_flag("NPM_TF32_TMA_ROUND", true);
+    const bool round_ab = (npass == 1) && tma_round;
+
+    // ---- tile shape: minimise (waves x tile cost) ----
+    const int sms = num_sms();
+    const int64_t tiles_m = (d.m + kBlockM - 1) / kBlockM;
+    int best_bn = 64;
+    {
+        static const int forced = getenv("NPM_GEMM_BLOCK_N") ? atoi(getenv("NPM_GEMM_BLOCK_N")) : 0;
+        double best_cost = 1e300;
+        const int cands[3] = {256, 128, 64};
+        for (int i = 0; i < 3; ++i) {
+            const int bn = cands[i];
+            if (forced && bn != forced) continue;
+            const int64_t tn = (d.n + bn - 1) / bn;
+            const int64_t tiles = tiles_m * tn * nb1 * nb2;
+            const int64_t waves = (tiles + sms - 1) / sms;
+            // cost ~ waves * (MMA time ∝ bn  +  fixed per-tile overhead)
+            const double cost = double(waves) * (double(bn) + 24.0);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+        }
+    }
+    const int bn = best_bn;
+    const int64_t tiles_n = (d.n + bn - 1) / bn;
+    const int64_t total = tiles_m * tiles_n * nb1 * nb2;
+    if (total > (1ll << 30)) { set_error("gemm: too many tiles"); return NPM_ERR_INVALID; }
+
+    // ---- tensor maps ----
+    CUtensorMap tmA, tmB, tmC;
+    int rc;
+    const uint64_t M = d.m, N = d.n, K = d.k;
+    auto bs = [](int nb, int64_t s, uint64_t natural) -> uint64_t { return nb > 1 ? (uint64_t)s : natural; };
+    if (!a_mn) {
+        const uint64_t ld = d.a_rs;
+        const uint64_t s2 = bs(nb1, d.a_bs1, ld * M), s3 = bs(nb2, d.a_bs2, s2 * nb1);
+        rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockK, kBlockM, round_ab);
+    } else {
+        const uint64_t ld = d.a_cs;
+        const uint64_t s2 = bs(nb1, d.a_bs1, ld * K), s3 = bs(nb2, d.a_bs2, s2 * nb1);
+        rc = make_tensor_map_4d(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab);
+    }
+    if (rc) return rc;
+    if (!b_mn) {
+        const uint64_t ld = d.b_cs;
+        const uint64_t s2 = bs(nb1, d.b_bs1, ld * N), s3 = bs(nb2, d.b_bs2, s2 * nb1);
+        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, bn, round_ab);
+    } else {
+        const uint64_t ld = d.b_rs;
+        const uint64_t s2 = bs(nb1, d.b_bs1, ld * K), s3 = bs(nb2, d.b_bs2, s2 * nb1);
+        rc = make_tensor_map_4d(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab);
+    }
+    if (rc) return rc;
+    {
+        const uint64_t ld = d.ldc;
+        const uint64_t s2 = bs(nb1, d.c_bs1, ld * M), s3 = bs(nb2, d.c_bs2, s2 * nb1);
+        rc = make_tensor_map_4d(&tmC, d.c, N, M, nb1, nb2, ld, s2, s3, 32, 32, false);
+    }
+    if (rc) return rc;
+
+    GemmTcArgs args;
+    args.M = (int)d.m; args.N = (int)d.n; args.K = (int)d.k;
+    args.tiles_m = (int)tiles_m; args.tiles_n = (int)tiles_n; args.nb1 = nb1;
+    args.total_tiles = (int)total;
+    args.alpha = d.alpha;
+    args.bias = d.bias;
+    args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
+    args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
+    const int grid = (int)(total < sms ? total : sms);
+
+    if (npass == 1) {
+        if (bn == 256) return launch_major<256, 1>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+        if (bn == 128) return launch_major<128, 1>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+        return launch_major<64, 1>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+    } else {
+        if (bn == 256) return launch_major<256, 3>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+        if (bn == 128) return launch_major<128, 3>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+        return launch_major<64, 3>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+    }
+}
+
+}  // namespace npm

@@ -1,0 +1,92 @@
+"""Linear / Dense — drop-in for layers/mlp.py; GEMMs run on tcgen05 (csrc/gemm_tc.cu)."""
+from typing import Optional
+
+import optimizer
+from layers import activations, layer
+from npm_b200 import device
+from npm_b200._lib import C
+
+
+class Linear(layer.StatefulLayer):
+    def __init__(self, units: int, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._output_units = units
+
+    def initialize(self, x) -> None:
+        self._input_units = x.shape[-1]
+        self._w = self._initializer([self._input_units, self._output_units])
+        self._b = self._initializer([self._output_units])
+
+    def forward(self, x, _relu: bool = False):
+        x = device.asdevice(x)
+        assert x.ndim == 2, 'Linear takes [m, k] inputs (mlp.py:33)'
+        self._x = x
+        w, b = self._p('_w'), self._p('_b')
+        m, k = x.shape
+        n = w.shape[1]
+        assert w.shape[0] == k, f'{w.shape} vs input features {k}'
+        y = device.empty((m, n))
+        C.npm_linear_fwd(x.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 0, 1 if _relu else 0, device.stream())
+        return y
+
+    def backward(self, dy, optimizer_: optimizer.Optimizer):
+        # dy: [m, n]   b/db: [n]   w/dw: [k, n]   x/dx: [m, k]
+        dy = device.asdevice(dy)
+        w = self._p('_w')
+        self._p('_b')
+        x = self._x
+        assert dy.shape == (x.shape[0], w.shape[1])
+        m, k = x.shape
+        n = w.shape[1]
+        s = device.stream()
+        db = optimizer_.grad_buffer(self, '_b', (n,))
+        dw = optimizer_.grad_buffer(self, '_w', (k, n))
+        ws = device.workspace(C.npm_colsum_workspace(m, n))
+        C.npm_linear_bwd_dw_db(x.ptr, dy.ptr, dw.ptr, db.ptr, m, k, n, 0, ws.data_ptr(), s)
+        dx = device.empty((m, k))
+        C.npm_linear_bwd_dx(dy.ptr, w.ptr, dx.ptr, m, k, n, 0, s)
+        assert dx.shape == x.shape
+        optimizer_.update(self, '_w', dw)
+        optimizer_.update(self, '_b', db)
+        return dx
+
+    @property
+    def w(self):
+        assert self._initialized
+        return self._w
+
+    @property
+    def b(self):
+        assert self._initialized
+        return self._b
+
+
+class Dense(layer.StatefulLayer):
+    """Dense w/ ReLU activation."""
+    def __init__(self,
+                 units: int,
+                 activation: Optional[activations.Activation] = None,
+                 *args,
+                 **kwargs):
+        super().__init__(*args, **kwargs)
+        self._linear = Linear(units=units)
+        self._activation = activation or activations.ReLU()
+
+    def initialize(self, x) -> None:
+        self._linear.initialize(x)
+        self._linear._initialized = True
+        self._activation.initialize()
+        self._activation._initialized = True
+
+    def forward(self, x):
+        y = self._linear.forward(x)
+        return self._activation.forward(y)
+
+    def backward(self, dy, optimizer_: optimizer.Optimizer):
+        dy = self._activation.backward(dy)
+        return self._linear.backward(dy, optimizer_)
+
+    @property
+    def linear(self) -> Linear:
+        assert self._initialized
+        return self._linear

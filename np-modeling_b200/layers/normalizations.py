@@ -1,0 +1,129 @@
+"""DropOut / LayerNormalization — drop-in for layers/normalizations.py."""
+import itertools
+
+import numpy as np
+import torch
+
+import optimizer
+from layers import layer
+from npm_b200 import device
+from npm_b200._lib import C
+
+# Process-wide Philox state: every DropOut.forward consumes a fresh counter range of the stream
+# keyed by `seed`; `set_dropout_seed` restarts it (the analogue of np.random.seed for the
+# reference's legacy-MT19937 binomial stream, normalizations.py:20).
+_philox = {'seed': 0x5EED5EED, 'offset': 0}
+
+
+def set_dropout_seed(seed: int, offset: int = 0) -> None:
+    _philox['seed'] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _philox['offset'] = int(offset)
+
+
+class DropOut(layer.Layer):
+    def __init__(self, drop_prob: float, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._drop_prob = drop_prob
+        self._ext_mask = None    # injected mask (uint8 device tensor) — parity path
+        self._rng = None         # (seed, offset, n) of the last Philox forward
+        self._shape = None
+
+    def forward(self, x, training: bool = True):
+        if training and self._drop_prob != 0.0:
+            x = device.asdevice(x)
+            keep_prob = np.float32(1 - self._drop_prob)
+            y = device.empty(x.shape)
+            self._shape = x.shape
+            if self._ext_mask is not None:
+                assert self._ext_mask.numel() == x.size, 'injected mask has the wrong size'
+                C.npm_dropout_fwd(x.ptr, y.ptr, x.size, keep_prob, 0, 0, self._ext_mask.data_ptr(), device.stream())
+            else:
+                seed, offset = _philox['seed'], _philox['offset']
+                # keep counters 4-aligned so each 128-bit vector is one Philox call
+                _philox['offset'] = offset + (x.size + 3) // 4 * 4
+                self._rng = (seed, offset)
+                C.npm_dropout_fwd(x.ptr, y.ptr, x.size, keep_prob, seed, offset, None, device.stream())
+            return y
+        return x
+
+    def backward(self, dl_dy, *args, **kwargs):
+        if self._drop_prob != 0.0:
+            # Backward pass only run in training.
+            dl_dy = device.asdevice(dl_dy)
+            keep_prob = np.float32(1 - self._drop_prob)
+            dx = device.empty(dl_dy.shape)
+            if self._ext_mask is not None:
+                C.npm_dropout_bwd(dl_dy.ptr, dx.ptr, dl_dy.size, keep_prob, 0, 0, self._ext_mask.data_ptr(),
+                                  device.stream())
+            else:
+                seed, offset = self._rng
+                C.npm_dropout_bwd(dl_dy.ptr, dx.ptr, dl_dy.size, keep_prob, seed, offset, None, device.stream())
+            return dx
+        return dl_dy
+
+    # The reference stores an int64 mask array (normalizations.py:20); here the mask is a pure
+    # function of (seed, offset) and is only materialised when somebody looks at it.
+    @property
+    def _mask(self):
+        if self._ext_mask is not None:
+            return self._ext_mask.cpu().numpy().astype(np.int64).reshape(self._shape or -1)
+        if self._rng is None:
+            raise AttributeError('_mask')
+        n = int(np.prod(self._shape))
+        m = torch.empty(n, dtype=torch.uint8, device=device._device())
+        C.npm_dropout_mask(m.data_ptr(), n, np.float32(1 - self._drop_prob), self._rng[0], self._rng[1],
+                           device.stream())
+        return m.cpu().numpy().astype(np.int64).reshape(self._shape)
+
+    @_mask.setter
+    def _mask(self, value):
+        """Inject a mask (what the reference's own test does, normalizations_test.py:28)."""
+        if value is None:
+            self._ext_mask = None
+            return
+        host = np.ascontiguousarray(np.asarray(value) != 0).astype(np.uint8)
+        self._ext_mask = torch.from_numpy(host.reshape(-1)).to(device._device())
+        self._shape = tuple(np.asarray(value).shape)
+
+
+class LayerNormalization(layer.StatefulLayer):
+    def __init__(self, epsilon: float = 1e-3, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._epsilon = epsilon
+
+    def initialize(self, x):
+        self._col = x.shape[-1]
+        self._gamma = self._initializer([self._col])
+        self._beta = self._initializer([self._col])
+
+    def forward(self, x):
+        x = device.asdevice(x)
+        self._x = x
+        cols = x.shape[-1]
+        rows = x.size // cols
+        gamma, beta = self._p('_gamma'), self._p('_beta')
+        out = device.empty(x.shape)
+        self._mean = device.empty((rows,))
+        self._rstd = device.empty((rows,))
+        C.npm_layernorm_fwd(x.ptr, gamma.ptr, beta.ptr, out.ptr, self._mean.ptr, self._rstd.ptr, rows, cols,
+                            float(self._epsilon), device.stream())
+        return out
+
+    def backward(self, dl_dz, optimizer_: optimizer.Optimizer):
+        dl_dz = device.asdevice(dl_dz)
+        x = self._x
+        assert dl_dz.shape == x.shape, f'{dl_dz.shape} vs {x.shape}'
+        cols = x.shape[-1]
+        rows = x.size // cols
+        gamma = self._p('_gamma')
+        self._p('_beta')
+        dx = device.empty(x.shape)
+        dgamma = optimizer_.grad_buffer(self, '_gamma', (cols,))
+        dbeta = optimizer_.grad_buffer(self, '_beta', (cols,))
+        ws = device.workspace(C.npm_layernorm_bwd_workspace(rows, cols))
+        # closed form of the [..., C, C] Jacobian einsum (normalizations.py:60-71)
+        C.npm_layernorm_bwd(dl_dz.ptr, x.ptr, gamma.ptr, self._mean.ptr, self._rstd.ptr, dx.ptr, dgamma.ptr,
+                            dbeta.ptr, rows, cols, ws.data_ptr(), device.stream())
+        optimizer_.update(self, '_gamma', dgamma)
+        optimizer_.update(self, '_beta', dbeta)
+        return dx

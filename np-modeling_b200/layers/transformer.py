@@ -1,0 +1,211 @@
+"""TransformerEncoder / TransformerDecoder — drop-in for layers/transformer.py (:8-203).
+
+Glue only, exactly the reference's dataflow (pre-norm = DropOut → LayerNorm → sublayer → +skip;
+post-norm = sublayer → +skip → DropOut → LayerNorm; no causal mask), over device buffers: every
+`+=`, reshape and gradient sum below is a device operation.
+"""
+from layers import attentions, layer, mlp, normalizations
+from npm_b200 import device
+from npm_b200._lib import C
+
+
+def _sum3(t):
+    """np.sum(dy, axis=0) over MultiHeadAttention.backward's 3-tuple (transformer.py:85,196)."""
+    a, b, c = t
+    out = device.empty(a.shape)
+    C.npm_add3(a.ptr, b.ptr, c.ptr, out.ptr, a.size, device.stream())
+    return out
+
+
+class TransformerEncoder(layer.Layer):
+    def __init__(self,
+                 num_heads: int,
+                 hidden_units: int,
+                 norm_first: bool,
+                 drop_rate: float = 0.0,
+                 *args,
+                 **kwargs):
+        super().__init__(*args, **kwargs)
+        self._self_attention = attentions.MultiHeadAttention(num_heads)
+        self._dense1 = mlp.Dense(units=hidden_units)
+        self._norm1 = normalizations.LayerNormalization()
+        self._norm2 = normalizations.LayerNormalization()
+        self._norm_first = norm_first
+        self._dropout1 = normalizations.DropOut(drop_rate)
+        self._dropout2 = normalizations.DropOut(drop_rate)
+
+    def initialize(self, qkv):
+        features = qkv.shape[-1]
+        self._dense2 = mlp.Linear(units=features)  # No activation
+
+    def forward(self, qkv):
+        qkv = device.asdevice(qkv)
+        batch, seq_len_q, features = qkv.shape
+
+        skip = qkv
+        if self._norm_first:
+            qkv = self._dropout1(qkv)
+            qkv = self._norm1(qkv)
+        out = self._self_attention(qkv)
+        out += skip
+        if not self._norm_first:
+            out = self._dropout1(out)
+            out = self._norm1(out)
+
+        # Linear takes 2-D inputs only (mlp.py:33)
+        out = out.reshape(-1, features)
+        skip = out
+
+        if self._norm_first:
+            out = self._dropout2(out)
+            out = self._norm2(out)
+        out = self._dense1(out)
+        out = self._dense2(out)
+        out += skip
+        if not self._norm_first:
+            out = self._dropout2(out)
+            out = self._norm2(out)
+
+        return out.reshape(batch, seq_len_q, features)
+
+    def backward(self, dy, optimizer_):
+        dy = device.asdevice(dy)
+        batch, seq_len_q, features = dy.shape
+
+        dy = dy.reshape(-1, features)
+        if not self._norm_first:
+            dy = self._norm2.backward(dy, optimizer_)
+            dy = self._dropout2.backward(dy)
+        dskip = dy
+        dy = self._dense2.backward(dy, optimizer_)
+        dy = self._dense1.backward(dy, optimizer_)
+        if self._norm_first:
+            dy = self._norm2.backward(dy, optimizer_)
+            dy = self._dropout2.backward(dy)
+
+        dy += dskip
+        dy = dy.reshape(batch, seq_len_q, features)
+
+        if not self._norm_first:
+            dy = self._norm1.backward(dy, optimizer_)
+            dy = self._dropout1.backward(dy)
+        dskip = dy
+        dy = self._self_attention.backward(dy, optimizer_)
+        dy = _sum3(dy)
+        if self._norm_first:
+            dy = self._norm1.backward(dy, optimizer_)
+            dy = self._dropout1.backward(dy)
+
+        dy += dskip
+
+        return dy
+
+
+class TransformerDecoder(layer.Layer):
+    def __init__(self,
+                 num_heads: int,
+                 hidden_units: int,
+                 norm_first: bool,
+                 drop_rate: float = 0.0,
+                 *args,
+                 **kwargs):
+        super().__init__(*args, **kwargs)
+        self._self_attention = attentions.MultiHeadAttention(num_heads)
+        self._cross_attention = attentions.MultiHeadAttention(num_heads)
+        self._dense1 = mlp.Dense(units=hidden_units)
+        self._norm1 = normalizations.LayerNormalization()
+        self._norm2 = normalizations.LayerNormalization()
+        self._norm3 = normalizations.LayerNormalization()
+        self._norm_first = norm_first
+        self._dropout1 = normalizations.DropOut(drop_rate)
+        self._dropout2 = normalizations.DropOut(drop_rate)
+        self._dropout3 = normalizations.DropOut(drop_rate)
+
+    def initialize(self, q, kv):
+        features = q.shape[-1]
+        self._dense2 = mlp.Linear(units=features)  # No activation
+
+    def forward(self, q, kv):
+        q = device.asdevice(q)
+        kv = device.asdevice(kv)
+        batch, seq_len_q, features = q.shape
+
+        skip = q
+        if self._norm_first:
+            q = self._dropout1(q)
+            q = self._norm1(q)
+        out = self._self_attention(q)
+        out += skip
+        if not self._norm_first:
+            out = self._dropout1(out)
+            out = self._norm1(out)
+
+        skip = out
+
+        if self._norm_first:
+            out = self._dropout2(out)
+            out = self._norm2(out)
+        out = self._cross_attention(out, kv)
+        out += skip
+        if not self._norm_first:
+            out = self._dropout2(out)
+            out = self._norm2(out)
+
+        out = out.reshape(-1, features)
+        skip = out
+
+        if self._norm_first:
+            out = self._dropout3(out)
+            out = self._norm3(out)
+        out = self._dense1(out)
+        out = self._dense2(out)
+        out += skip
+        if not self._norm_first:
+            out = self._dropout3(out)
+            out = self._norm3(out)
+
+        return out.reshape(batch, seq_len_q, features)
+
+    def backward(self, dy, optimizer_):
+        dy = device.asdevice(dy)
+        batch, seq_len_q, features = dy.shape
+
+        dy = dy.reshape(-1, features)
+        if not self._norm_first:
+            dy = self._norm3.backward(dy, optimizer_)
+            dy = self._dropout3.backward(dy)
+        dskip = dy
+        dy = self._dense2.backward(dy, optimizer_)
+        dy = self._dense1.backward(dy, optimizer_)
+        if self._norm_first:
+            dy = self._norm3.backward(dy, optimizer_)
+            dy = self._dropout3.backward(dy)
+
+        dy += dskip
+        dy = dy.reshape(batch, seq_len_q, features)
+
+        if not self._norm_first:
+            dy = self._norm2.backward(dy, optimizer_)
+            dy = self._dropout2.backward(dy)
+        dskip = dy
+        dy = self._cross_attention.backward(dy, optimizer_)
+        dkv = dy[1] + dy[2]          # np.sum(dy[1:3], axis=0) (transformer.py:184)
+        dy = dy[0]
+        if self._norm_first:
+            dy = self._norm2.backward(dy, optimizer_)
+            dy = self._dropout2.backward(dy)
+
+        dy += dskip
+        if not self._norm_first:
+            dy = self._norm1.backward(dy, optimizer_)
+            dy = self._dropout1.backward(dy)
+        dskip = dy
+        dy = self._self_attention.backward(dy, optimizer_)
+        dy = _sum3(dy)
+        if self._norm_first:
+            dy = self._norm1.backward(dy, optimizer_)
+            dy = self._dropout1.backward(dy)
+
+        dy += dskip
+
+        return dy, dkv

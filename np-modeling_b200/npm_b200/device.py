@@ -1,0 +1,197 @@
+"""DeviceArray — the ndarray stand-in that flows between layers.
+
+The reference passes NumPy arrays between `Layer.forward/backward` calls
+(layers/layer.py:19-25).  Here the same objects flow, but the bytes live in B200
+HBM: a DeviceArray is a thin owner of a contiguous fp32 CUDA buffer (allocated
+through torch's caching allocator — torch is plumbing only) exposing the small
+ndarray surface the reference's glue code uses (`shape`, `size`, `reshape`,
+`+=`, indexing on the leading axis, `np.asarray(x)`).
+
+Every arithmetic operation on it is one of this repo's CUDA kernels, reached
+through the C-ABI; nothing here computes on the host.
+"""
+import numpy as np
+import torch
+
+from ._lib import C
+
+
+def stream():
+    """cudaStream_t (as int) all kernels are enqueued on: torch's current stream."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('np-modeling_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class DeviceArray:
+    __slots__ = ('t',)
+    __array_priority__ = 1000
+
+    def __init__(self, t: torch.Tensor):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'DeviceArray wraps contiguous fp32 CUDA'
+        self.t = t
+
+    # ---- ndarray-like surface -------------------------------------------------
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    @property
+    def ndim(self):
+        return self.t.dim()
+
+    @property
+    def size(self):
+        return self.t.numel()
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    def __len__(self):
+        return self.t.shape[0]
+
+    def numpy(self):
+        return self.t.detach().cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __repr__(self):
+        return f'DeviceArray(shape={self.shape}, device={self.t.device})'
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return DeviceArray(self.t.view(*shape))
+
+    def copy(self):
+        return DeviceArray(self.t.clone())
+
+    def __deepcopy__(self, memo):
+        return self.copy()
+
+    def __getitem__(self, idx):
+        v = self.t[idx]
+        if not v.is_contiguous():
+            raise IndexError('DeviceArray only supports contiguous (leading-axis) views')
+        return DeviceArray(v)
+
+    def __iadd__(self, other):
+        other = asdevice(other)
+        assert other.shape == self.shape, f'{other.shape} vs {self.shape}'
+        C.npm_add_inplace(self.ptr, other.ptr, self.size, stream())
+        return self
+
+    def __add__(self, other):
+        other = asdevice(other)
+        assert other.shape == self.shape, f'{other.shape} vs {self.shape}'
+        out = empty(self.shape)
+        C.npm_add3(self.ptr, other.ptr, None, out.ptr, self.size, stream())
+        return out
+
+    def item(self):
+        return float(self.t.item())
+
+    def __float__(self):
+        return self.item()
+
+    def copy_from(self, src):
+        """In-place overwrite from a host array or another DeviceArray (keeps the buffer identity)."""
+        if isinstance(src, DeviceArray):
+            self.t.copy_(src.t.view(self.t.shape))
+        else:
+            host = np.ascontiguousarray(np.asarray(src), dtype=np.float32).reshape(self.shape)
+            self.t.copy_(torch.from_numpy(host), non_blocking=False)
+        return self
+
+
+def asdevice(x) -> DeviceArray:
+    """np.ndarray / scalar sequence / torch tensor / DeviceArray → DeviceArray (fp32, on the current GPU)."""
+    if isinstance(x, DeviceArray):
+        return x
+    if isinstance(x, torch.Tensor):
+        return DeviceArray(x.detach().to(device=_device(), dtype=torch.float32).contiguous())
+    host = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+    return DeviceArray(torch.from_numpy(host).to(_device(), non_blocking=False))
+
+
+def from_pinned(host_pinned: torch.Tensor) -> DeviceArray:
+    """Asynchronous H2D copy from a pinned host tensor on the current stream."""
+    return DeviceArray(host_pinned.to(_device(), non_blocking=True))
+
+
+def empty(shape) -> DeviceArray:
+    if isinstance(shape, int):
+        shape = (shape,)
+    return DeviceArray(torch.empty(tuple(int(s) for s in shape), dtype=torch.float32, device=_device()))
+
+
+def zeros(shape) -> DeviceArray:
+    if isinstance(shape, int):
+        shape = (shape,)
+    return DeviceArray(torch.zeros(tuple(int(s) for s in shape), dtype=torch.float32, device=_device()))
+
+
+def workspace(nbytes: int) -> torch.Tensor:
+    """Scratch bytes for a *_workspace() query (caller-owned, per the C-ABI contract)."""
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=_device())
+
+
+def param(x):
+    """Normalise a parameter attribute: users may assign NumPy arrays (as the reference's tests do,
+    layers/utils.py:41-101); they are moved to the device on first use."""
+    return x if isinstance(x, DeviceArray) else asdevice(x)
+
+
+class DeviceScalar:
+    """A loss value still on the device.  Behaves like the Python float the reference returns
+    (loss.py:25,36) but only synchronises with the GPU when somebody looks at it."""
+    __slots__ = ('_t', '_v')
+    __array_priority__ = 1000
+
+    def __init__(self, arr: DeviceArray):
+        self._t = arr.t
+        self._v = None
+
+    def __float__(self):
+        if self._v is None:
+            self._v = float(self._t.item())
+        return self._v
+
+    def item(self):
+        return float(self)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(float(self), dtype=dtype or np.float32)
+
+    def __repr__(self):
+        return repr(float(self))
+
+    __str__ = __repr__
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __add__(self, o): return float(self) + float(o)
+    __radd__ = __add__
+    def __sub__(self, o): return float(self) - float(o)
+    def __rsub__(self, o): return float(o) - float(self)
+    def __mul__(self, o): return float(self) * float(o)
+    __rmul__ = __mul__
+    def __truediv__(self, o): return float(self) / float(o)
+    def __lt__(self, o): return float(self) < float(o)
+    def __le__(self, o): return float(self) <= float(o)
+    def __gt__(self, o): return float(self) > float(o)
+    def __ge__(self, o): return float(self) >= float(o)
+    def __eq__(self, o): return float(self) == float(o)
+    def __hash__(self): return hash(float(self))

@@ -1,0 +1,179 @@
+"""Trainer — drop-in for the reference's `train` module (train.py:13-46), made batch-sharded
+data parallel.
+
+Single process: identical to the reference loop (forward chain → loss → `loss(backprop=True)` →
+reverse chain with `optimizer_`), printing `Step:` / `Loss:` each step.  Inputs arrive as host
+arrays and are copied host→device every step; the loss is read back every step.
+
+Data parallel (one process per GPU, `torch.distributed` initialised with NCCL — or gloo for the
+CPU tests of this logic): rank r trains on rows [r*B/n, (r+1)*B/n) of `inputs`/`targets`.  Parameters
+are broadcast from rank 0 after the lazy initialisation of step 0; gradients, which the optimizer keeps
+in a flat arena, are all-reduced (SUM) block by block right before the fused update and scaled by
+1/n when the loss is a mean over the local shard (MSELoss) or by 1 when it is a sum
+(CrossEntropyLoss) — so the update equals the single-process one on the full batch
+(SURVEY.md §8e).  The printed loss is the global one.
+"""
+import logging
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import loss
+import optimizer
+from layers import layer
+from npm_b200 import device
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def iter_parameters(obj, _seen=None):
+    """Yield (owner, attribute) for every parameter reachable from a layer (depth-first, attribute
+    order = creation order, identical on every rank)."""
+    if _seen is None:
+        _seen = set()
+    if id(obj) in _seen:
+        return
+    _seen.add(id(obj))
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            yield from iter_parameters(o, _seen)
+        return
+    if not isinstance(obj, layer.Layer):
+        return
+    for name, value in list(vars(obj).items()):
+        if isinstance(value, (layer.Layer, list, tuple)):
+            yield from iter_parameters(value, _seen)
+        elif isinstance(obj, layer.StatefulLayer) and name in getattr(obj, 'PARAMETERS', _DEFAULT_PARAMS):
+            if isinstance(value, (device.DeviceArray, np.ndarray)):
+                yield obj, name
+
+
+_DEFAULT_PARAMS = ('_w', '_b', '_gamma', '_beta', '_wq', '_wk', '_wv', '_wo', '_bq', '_bk', '_bv', '_bo')
+
+
+class Trainer:
+    def __init__(self,
+                 layers: Sequence[layer.Layer],
+                 loss_: Optional[loss.Loss] = None,
+                 verbose: bool = True):
+        self._layers = layers
+        self._loss = loss_ or loss.MSELoss()
+        self._verbose = verbose
+        self._synced = False
+        self._pinned = {}
+
+    # ---- host → device staging ------------------------------------------------------------
+    def _shard(self, a):
+        rank, world = _world()
+        if world == 1 or isinstance(a, device.DeviceArray):
+            return a
+        n = a.shape[0]
+        assert n % world == 0, f'batch {n} is not divisible by world size {world}'
+        per = n // world
+        return a[rank * per:(rank + 1) * per]
+
+    def _to_device(self, key, a):
+        """Copy one step's host input into HBM through a reusable pinned staging buffer."""
+        if isinstance(a, device.DeviceArray):
+            return a
+        a = np.asarray(a)
+        if not torch.cuda.is_available():
+            raise RuntimeError('np-modeling_b200 needs a CUDA device; there is no CPU fallback')
+        pin = self._pinned.get(key)
+        if pin is None or tuple(pin.shape) != a.shape:
+            pin = torch.empty(a.shape, dtype=torch.float32).pin_memory()
+            self._pinned[key] = pin
+        pin.numpy()[...] = a
+        return device.from_pinned(pin)
+
+    # ---- data-parallel plumbing -----------------------------------------------------------
+    def _broadcast_parameters(self):
+        rank, world = _world()
+        if world == 1 or self._synced:
+            return
+        for owner, name in iter_parameters(list(self._layers)):
+            p = owner._p(name) if hasattr(owner, '_p') else device.asdevice(getattr(owner, name))
+            dist.broadcast(p.t, src=0)
+        self._synced = True
+
+    def _install_grad_sync(self, optimizer_):
+        rank, world = _world()
+        if world == 1 or not isinstance(optimizer_, optimizer._FusedOptimizer):
+            return
+        optimizer_.grad_scale = (1.0 / world) if getattr(self._loss, 'dp_mean', True) else 1.0
+
+        def sync(opt):
+            for view in opt._arena.used_views():
+                dist.all_reduce(view, op=dist.ReduceOp.SUM)
+            # gradients that did not come from the arena (user-supplied buffers)
+            arena_ptrs = [(b[0].data_ptr(), b[0].data_ptr() + b[0].numel() * 4) for b in opt._arena.blocks]
+            for _, _, g in opt._pending:
+                if not any(lo <= g.ptr < hi for lo, hi in arena_ptrs):
+                    dist.all_reduce(g.t, op=dist.ReduceOp.SUM)
+
+        optimizer_.grad_sync = sync
+
+    def _global_loss(self, l):
+        rank, world = _world()
+        if world == 1:
+            return l
+        t = l._t.clone() if isinstance(l, device.DeviceScalar) else torch.tensor([float(l)], device=device._device())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if getattr(self._loss, 'dp_mean', True):
+            t /= world
+        return device.DeviceScalar(device.DeviceArray(t))
+
+    # ---- the reference loop (train.py:20-39) ------------------------------------------------
+    def train(self, inputs, targets, steps: int, optimizer_: optimizer.Optimizer) -> None:
+        inputs, targets = self._shard(inputs), self._shard(targets)
+        self._install_grad_sync(optimizer_)
+        fused = isinstance(optimizer_, optimizer.Optimizer)
+
+        for i in range(steps):
+            if self._verbose:
+                print('Step: ', i)
+
+            logging.info('Running forward pass')
+            y = self._to_device('inputs', inputs)
+            t = self._to_device('targets', targets)
+            for layer_ in self._layers:
+                y = layer_(y)
+            self._broadcast_parameters()
+            if not self._synced and _world()[1] > 1:
+                raise RuntimeError('parameter broadcast failed')
+            l = self._loss(y, t)
+
+            logging.info('Running backward pass')
+            dy = self._loss(backprop=True)
+            # One bracket around the whole reverse chain: every layer's updates are applied by a
+            # single fused kernel (after one gradient all-reduce when data parallel).
+            if fused:
+                optimizer_._enter()
+            try:
+                for layer_ in reversed(self._layers):
+                    dy = layer_(dy, backprop=True, optimizer_=optimizer_)
+            finally:
+                if fused:
+                    optimizer_._exit()
+            self.last_loss = self._global_loss(l)
+            if self._verbose:
+                # printed after the backward pass is enqueued so the host never stalls the GPU
+                # mid-step; the text is the reference's (train.py:32)
+                print('Loss: ', self.last_loss)
+
+    def eval(self, inputs, targets) -> None:
+        inputs, targets = self._shard(inputs), self._shard(targets)
+        y = self._to_device('inputs', inputs)
+        t = self._to_device('targets', targets)
+        for layer_ in self._layers:
+            y = layer_(y)
+        l = self._global_loss(self._loss(y, t))
+        self.last_loss = l
+        if self._verbose:
+            print('Loss: ', l)
