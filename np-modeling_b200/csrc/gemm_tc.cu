@@ -36,6 +36,7 @@ struct GemmTcArgs {
     float alpha;
     const float* bias;
     int relu, accum;
+    uint64_t desc_a, desc_b;   // UMMA shared-memory descriptor templates (start address = 0)
 };
 
 template <int BLOCK_N, int NPASS>
@@ -153,12 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 5) {
         // ============================= MMA issuer =============================
         constexpr uint32_t idesc = ptx::umma_idesc_tf32(kBlockM, BLOCK_N, A_MN, B_MN);
-        // K-major: 8-row groups 1024 B apart (SBO), LBO unused (canonical 1).
-        // MN-major: 32-element MN chunks 4096 B apart (LBO), 8-row K groups 1024 B apart (SBO).
-        constexpr uint64_t descA = A_MN ? ptx::umma_desc_base_sw128(4096, 1024)
-                                        : ptx::umma_desc_base_sw128(16, 1024);
-        constexpr uint64_t descB = B_MN ? ptx::umma_desc_base_sw128(4096, 1024)
-                                        : ptx::umma_desc_base_sw128(16, 1024);
+        const uint64_t descA = args.desc_a, descB = args.desc_b;   // see gemm_tc_launch()
         constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;   // bytes per UMMA_K (8) step
         constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
         int stage = 0, acc = 0;
@@ -320,7 +316,7 @@ EncodeTiledFn encode_fn() {
 // box (b0, b1, 1, 1), 128-byte swizzle, zero fill out of bounds.
 int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2,
                        uint64_t d3, uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1,
-                       bool round_tf32) {
+                       bool round_tf32, bool atom32b) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -332,7 +328,8 @@ int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t
     cuuint32_t estr[4]    = {1, 1, 1, 1};
     CUresult rc = fn(tm, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                      4, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
@@ -444,27 +441,27 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     if (!a_mn) {
         const uint64_t ld = d.a_rs;
         const uint64_t s2 = bs(nb1, d.a_bs1, ld * M), s3 = bs(nb2, d.a_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockK, kBlockM, round_ab);
+        rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockK, kBlockM, round_ab, false);
     } else {
         const uint64_t ld = d.a_cs;
         const uint64_t s2 = bs(nb1, d.a_bs1, ld * K), s3 = bs(nb2, d.a_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab);
+        rc = make_tensor_map_4d(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
     }
     if (rc) return rc;
     if (!b_mn) {
         const uint64_t ld = d.b_cs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * N), s3 = bs(nb2, d.b_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, bn, round_ab);
+        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, bn, round_ab, false);
     } else {
         const uint64_t ld = d.b_rs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * K), s3 = bs(nb2, d.b_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab);
+        rc = make_tensor_map_4d(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
     }
     if (rc) return rc;
     {
         const uint64_t ld = d.ldc;
         const uint64_t s2 = bs(nb1, d.c_bs1, ld * M), s3 = bs(nb2, d.c_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmC, d.c, N, M, nb1, nb2, ld, s2, s3, 32, 32, false);
+        rc = make_tensor_map_4d(&tmC, d.c, N, M, nb1, nb2, ld, s2, s3, 32, 32, false, false);
     }
     if (rc) return rc;
 
@@ -476,6 +473,20 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     args.bias = d.bias;
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
     args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
+    // Shared-memory descriptors.
+    //  K-major operand : TMA box {32 k, rows} with the 128B swizzle (16 B atoms) lands rows of 128 B;
+    //                    UMMA layout SWIZZLE_128B, 8-row groups 1024 B apart (SBO), LBO unused (1).
+    //  MN-major operand: fp32/tf32 MN-major only exists with 32-byte swizzle atoms (a 4-byte element
+    //                    cannot be transposed at 16 B granularity): TMA SWIZZLE_128B_ATOM_32B lands
+    //                    each {32 mn, 32 k} box as 32 K-rows of 128 B; UMMA layout
+    //                    SWIZZLE_128B_BASE32B, 32-element MN chunks 4096 B apart (LBO), 4-row K groups
+    //                    512 B apart (SBO).
+    static const uint32_t mn_lbo = getenv("NPM_MN_LBO") ? (uint32_t)atoi(getenv("NPM_MN_LBO")) : 4096u;
+    static const uint32_t mn_sbo = getenv("NPM_MN_SBO") ? (uint32_t)atoi(getenv("NPM_MN_SBO")) : 512u;
+    const uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
+    const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, mn_lbo, mn_sbo);
+    args.desc_a = a_mn ? desc_mn : desc_k;
+    args.desc_b = b_mn ? desc_mn : desc_k;
     const int grid = (int)(total < sms ? total : sms);
 
     if (npass == 1) {

@@ -168,11 +168,13 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 // ------------------------------------------------- UMMA descriptors (sm_100)
-// Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout=2
-__host__ __device__ constexpr uint64_t umma_desc_base_sw128(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
+//   layout type: 0 none, 1 SWIZZLE_128B_BASE32B, 2 SWIZZLE_128B, 4 SWIZZLE_64B, 6 SWIZZLE_32B
+__host__ __device__ constexpr uint64_t umma_desc_base(uint32_t layout_type, uint32_t lbo_bytes,
+                                                      uint32_t sbo_bytes) {
     return (uint64_t((lbo_bytes >> 4) & 0x3fffu) << 16) | (uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32) |
-           (uint64_t(1) << 46) | (uint64_t(2) << 61);
+           (uint64_t(1) << 46) | (uint64_t(layout_type & 7u) << 61);
 }
 __device__ __forceinline__ uint64_t umma_desc(uint64_t base, uint32_t smem_addr) {
     return base | uint64_t((smem_addr >> 4) & 0x3fffu);

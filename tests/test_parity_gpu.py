@@ -1,0 +1,464 @@
+"""GPU parity: every layer of the hot path, driven through the reference's own Layer API, against the
+golden vectors produced by the unmodified reference (tests/golden) and against the oracle on fresh
+seeded inputs.  Tolerances are north_star's: rtol 1e-3 / atol 1e-4 for tensor-core contractions
+(3xTF32), 1e-5 elementwise, masks bit-exact."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, sub
+from helpers import EW, TC, Recorder, bind, close, grads_of, param_values
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _precision():
+    import npm_b200
+    npm_b200.set_precision('3xtf32')
+    yield
+
+
+def test_library_loaded_and_device():
+    import ctypes
+    from npm_b200 import _lib
+    lib = _lib.load()
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.npm_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)) == 0
+    assert major.value == 10, 'these kernels are sm_100a only'
+    assert sm.value >= 100
+
+
+# ------------------------------------------------------------------ Dense / Linear
+def test_dense_golden():
+    import optimizer
+    from layers import Dense
+    g = load_golden('dense')
+    layer = Dense(16)
+    layer(g['x'])
+    bind(layer, sub(g, 'p.'))
+    close(layer(g['x']), g['y'])
+    rec = Recorder()
+    dx = layer(g['dy'], backprop=True, optimizer_=rec)
+    close(dx, g['dx'])
+    got = grads_of(layer, rec, sub(g, 'g.').keys())
+    for k, v in sub(g, 'g.').items():
+        close(got[k], v)
+    # parameters are untouched by the recorder
+    close(layer.linear.w, g['p._linear._w'], rtol=0, atol=0)
+
+    # real SGD step through `learning_rate=` sugar; an alias captured before sees the update
+    sgd = Dense(16)
+    sgd(g['x'])
+    bind(sgd, sub(g, 'p.'))
+    sgd(g['x'])
+    w_alias = sgd.linear.w
+    sgd(g['dy'], backprop=True, learning_rate=0.05)
+    close(w_alias, g['sgd._linear._w'])
+    close(sgd.linear.b, g['sgd._linear._b'])
+
+    adam = Dense(16)
+    adam(g['x'])
+    bind(adam, sub(g, 'p.'))
+    opt = optimizer.AdamOptimizer(learning_rate=0.01)
+    for _ in range(3):
+        adam(g['x'])
+        adam(g['dy'], backprop=True, optimizer_=opt)
+    close(adam.linear.w, g['adam3._linear._w'], rtol=1e-3, atol=2e-4)
+    close(adam.linear.b, g['adam3._linear._b'], rtol=1e-3, atol=2e-4)
+
+
+def test_layer_protocol_errors():
+    import optimizer
+    from layers import Dense
+    layer = Dense(4)
+    x = np.ones((3, 5), np.float32)
+    layer(x)
+    with pytest.raises(ValueError):
+        layer(np.ones((3, 4), np.float32), backprop=True, learning_rate=0.1, optimizer_=optimizer.SGDOptimizer(0.1))
+    with pytest.raises(AssertionError):
+        layer(np.ones((2, 4), np.float32), backprop=True, learning_rate=0.1)   # wrong batch
+
+
+@pytest.mark.parametrize('m,k,n', [(64, 784, 256), (64, 256, 10), (513, 100, 36), (1, 8, 4), (300, 1024, 520)])
+def test_linear_vs_oracle_shapes(m, k, n):
+    from layers import Linear
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(m * 7 + n)
+    x = rng.standard_normal((m, k), dtype=np.float32)
+    dy = rng.standard_normal((m, n), dtype=np.float32)
+    w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    layer = Linear(n)
+    layer(x)
+    bind(layer, {'_w': w, '_b': b})
+    close(layer(x), O.linear_fwd(x, w, b))
+    rec = Recorder()
+    dx = layer(dy, backprop=True, optimizer_=rec)
+    odx, odw, odb = O.linear_bwd(x, w, dy)
+    close(dx, odx)
+    g = grads_of(layer, rec, ['_w', '_b'])
+    close(g['_w'], odw, rtol=1e-3, atol=1e-4 * np.sqrt(m))
+    close(g['_b'], odb, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ activations / norm / dropout
+def test_activations_golden():
+    from layers import ReLU, Softmax
+    g = load_golden('activations')
+    sm = Softmax()
+    close(sm(g['sm_x']), g['sm_y'], **EW)
+    close(sm(g['sm_dy'], backprop=True), g['sm_dx'], **EW)
+    r = ReLU()
+    close(r(g['relu_x']), g['relu_y'], rtol=0, atol=0)
+    close(r.backward(g['relu_dy']), g['relu_dx'], rtol=0, atol=0)     # includes the x == 0 branch
+
+
+@pytest.mark.parametrize('rows,cols', [(64, 10), (33, 1000), (128, 1024), (7, 4100), (5, 3)])
+def test_softmax_shapes(rows, cols):
+    from layers import Softmax
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(rows + cols)
+    x = (rng.standard_normal((rows, cols)) * 3).astype(np.float32)
+    dy = rng.standard_normal((rows, cols)).astype(np.float32)
+    sm = Softmax()
+    y = sm(x)
+    close(y, O.softmax_fwd(x), **EW)
+    close(np.asarray(y).sum(-1), np.ones(rows), rtol=1e-5, atol=1e-5)
+    close(sm(dy, backprop=True), O.softmax_bwd(O.softmax_fwd(x), dy), **EW)
+
+
+def test_layernorm_golden():
+    from layers import LayerNormalization
+    g = load_golden('layernorm')
+    for sfx, eps in (('', 1e-3), ('3', 1e-6)):
+        layer = LayerNormalization(epsilon=eps)
+        layer(g['x' + sfx])
+        bind(layer, sub(g, f'p{sfx}.'))
+        close(layer(g['x' + sfx]), g['z' + sfx], **EW)
+        rec = Recorder()
+        close(layer(g['dz' + sfx], backprop=True, optimizer_=rec), g['dx' + sfx], rtol=1e-4, atol=1e-5)
+        got = grads_of(layer, rec, ['_gamma', '_beta'])
+        close(got['_gamma'], g[f'g{sfx}._gamma'], rtol=1e-4, atol=1e-4)
+        close(got['_beta'], g[f'g{sfx}._beta'], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('rows,cols', [(4096, 1024), (1000, 768), (50, 36), (3, 2050), (17, 7)])
+def test_layernorm_shapes(rows, cols):
+    from layers import LayerNormalization
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(rows * 3 + cols)
+    x = (rng.standard_normal((rows, cols)) * 2 + 0.5).astype(np.float32)
+    dz = rng.standard_normal((rows, cols)).astype(np.float32)
+    gamma = rng.standard_normal(cols).astype(np.float32)
+    beta = rng.standard_normal(cols).astype(np.float32)
+    layer = LayerNormalization()
+    layer(x)
+    bind(layer, {'_gamma': gamma, '_beta': beta})
+    close(layer(x), O.layernorm_fwd(x, gamma, beta)[0], rtol=1e-4, atol=1e-5)
+    rec = Recorder()
+    dx = layer(dz, backprop=True, optimizer_=rec)
+    odx, odg, odb = O.layernorm_bwd(x, gamma, dz)
+    close(dx, odx, rtol=1e-4, atol=1e-5)
+    got = grads_of(layer, rec, ['_gamma', '_beta'])
+    close(got['_gamma'], odg, rtol=1e-4, atol=1e-5 * np.sqrt(rows) * 4)
+    close(got['_beta'], odb, rtol=1e-4, atol=1e-5 * np.sqrt(rows) * 4)
+
+
+def test_dropout_mask_injection_golden():
+    from layers.normalizations import DropOut
+    g = load_golden('dropout')
+    layer = DropOut(0.5)
+    layer._mask = g['mask']
+    close(layer(g['x']), g['y'], rtol=0, atol=0)
+    close(layer(g['dy'], backprop=True), g['dx'], rtol=0, atol=0)
+    assert np.array_equal(layer._mask, g['mask'])
+    layer2 = DropOut(0.1)
+    layer2._mask = g['mask2']
+    close(layer2(g['x']), g['y2'], rtol=0, atol=0)   # x / float32(0.9), correctly rounded division
+
+
+@pytest.mark.parametrize('n,offset', [(4096, 0), (1001, 0), (777, 5), (64, 2 ** 33 + 3)])
+def test_dropout_philox_bit_exact(n, offset):
+    """The GPU mask equals the CPU Philox restatement bit for bit for a given (seed, offset)."""
+    import torch
+    from npm_b200 import device
+    from npm_b200._lib import C
+    from oracle import philox
+    seed = 0x1234ABCD5678EF01
+    keep = np.float32(0.9)
+    x = np.random.default_rng(0).standard_normal(n).astype(np.float32)
+    xd = device.asdevice(x)
+    yd = device.empty((n,))
+    C.npm_dropout_fwd(xd.ptr, yd.ptr, n, keep, seed, offset, None, device.stream())
+    mask = philox.dropout_mask(n, keep, seed, offset)
+    want = np.where(mask != 0, x / keep, np.float32(0)).astype(np.float32)
+    assert np.array_equal(np.asarray(yd), want)
+    md = torch.empty(n, dtype=torch.uint8, device='cuda')
+    C.npm_dropout_mask(md.data_ptr(), n, keep, seed, offset, device.stream())
+    assert np.array_equal(md.cpu().numpy(), mask)
+    # backward applies the same mask
+    dd = device.empty((n,))
+    C.npm_dropout_bwd(xd.ptr, dd.ptr, n, keep, seed, offset, None, device.stream())
+    assert np.array_equal(np.asarray(dd), want)
+
+
+def test_dropout_layer_semantics():
+    from layers.normalizations import DropOut, set_dropout_seed
+    x = np.random.default_rng(1).standard_normal((64, 48)).astype(np.float32)
+    set_dropout_seed(42)
+    a = DropOut(0.25)
+    ya = np.asarray(a(x))
+    set_dropout_seed(42)
+    b = DropOut(0.25)
+    yb = np.asarray(b(x))
+    assert np.array_equal(ya, yb)                           # same seed → same mask
+    yc = np.asarray(b(x))
+    assert not np.array_equal(yb, yc)                       # the stream advances between calls
+    m = a._mask
+    assert m.dtype == np.int64 and m.shape == x.shape and 0.6 < m.mean() < 0.9
+    assert np.array_equal(ya != 0, m != 0)
+    dy = np.ones_like(x)
+    assert np.array_equal(np.asarray(a(dy, backprop=True)) != 0, m != 0)
+    ident = DropOut(0.0)
+    assert ident(x) is x                                    # identity when drop_prob == 0 (:14,23)
+    assert np.array_equal(np.asarray(DropOut(0.5).forward(x, training=False)), x)
+
+
+# ------------------------------------------------------------------ attention / transformer
+@pytest.mark.parametrize('tag', ['self', 'cross'])
+def test_mha_golden(tag):
+    from layers import MultiHeadAttention
+    from oracle import np_oracle as O
+    g = load_golden('mha_' + tag)
+    layer = MultiHeadAttention(2)
+    args = (g['query'],) if tag == 'self' else (g['query'], g['kv'])
+    layer(*args)
+    bind(layer, sub(g, 'p.'))
+    close(layer(*args), g['out'])
+    close(layer._attention_scores, g['scores'], rtol=1e-3, atol=1e-5)
+    rec = Recorder()
+    dq, dk, dv = layer(g['dy'], backprop=True, optimizer_=rec)
+    close(dq, g['dquery']); close(dk, g['dkey']); close(dv, g['dvalue'])
+    got = grads_of(layer, rec, O.MHA_PARAMS)
+    for k in O.MHA_PARAMS:
+        assert got[k].shape == g['g.' + k].shape
+        close(got[k], g['g.' + k])
+    assert copy.deepcopy(layer) is not layer                # attentions_test.py:72 deep-copies layers
+
+
+def test_mha_mask_raises():
+    from layers import MultiHeadAttention
+    layer = MultiHeadAttention(2)
+    q = np.zeros((1, 4, 8), np.float32)
+    with pytest.raises(ValueError):
+        layer(q, mask=np.ones((1, 2, 4, 4)))
+
+
+def _transformer_case(kind, norm, drop):
+    from layers import TransformerDecoder, TransformerEncoder
+    g = load_golden(f'{kind}_{norm}_{drop}')
+    cls = TransformerEncoder if kind == 'encoder' else TransformerDecoder
+    layer = cls(2, 32, norm == 'pre', 0.25 if drop == 'drop' else 0.0)
+    args = (g['q'],) if kind == 'encoder' else (g['q'], g['kv'])
+    layer(*args)
+    bind(layer, sub(g, 'p.'))
+    if drop == 'drop':
+        for i in (1, 2, 3):
+            if f'mask{i}' in g:
+                getattr(layer, f'_dropout{i}')._mask = g[f'mask{i}']
+    close(layer(*args), g['out'])
+    rec = Recorder()
+    res = layer(g['dy'], backprop=True, optimizer_=rec)
+    if kind == 'encoder':
+        close(res, g['dq'])
+    else:
+        assert isinstance(res, tuple) and len(res) == 2
+        close(res[0], g['dq']); close(res[1], g['dkv'])
+    gg = sub(g, 'g.')
+    got = grads_of(layer, rec, gg.keys())
+    for k, v in gg.items():
+        close(got[k], v, rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize('norm', ['pre', 'post'])
+@pytest.mark.parametrize('drop', ['nodrop', 'drop'])
+def test_encoder_golden(norm, drop):
+    _transformer_case('encoder', norm, drop)
+
+
+@pytest.mark.parametrize('norm', ['pre', 'post'])
+@pytest.mark.parametrize('drop', ['nodrop', 'drop'])
+def test_decoder_golden(norm, drop):
+    _transformer_case('decoder', norm, drop)
+
+
+def test_decoder_vs_oracle_medium():
+    """A decoder layer at a size the oracle finishes in seconds (B2, Sq 64, Skv 96, D 256, H 4, F 512),
+    with Philox dropout: the GPU's own masks are injected into the oracle (normalizations_test.py:28)."""
+    import optimizer
+    from layers import TransformerDecoder
+    from layers.normalizations import set_dropout_seed
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(11)
+    b, sq, skv, d, h, f = 2, 64, 96, 256, 4, 512
+    q = rng.standard_normal((b, sq, d)).astype(np.float32)
+    kv = rng.standard_normal((b, skv, d)).astype(np.float32)
+    dy = rng.standard_normal((b, sq, d)).astype(np.float32)
+    layer = TransformerDecoder(h, f, True, 0.1)
+    set_dropout_seed(5)
+    layer(q, kv)
+    # fan-in scaled weights so deep paths stay O(1)
+    from train import iter_parameters
+    params = {}
+    for owner, name in iter_parameters(layer):
+        v = np.asarray(getattr(owner, name))
+        if name.startswith('_w'):
+            fan_in = v.shape[-1] if v.ndim == 3 and name != '_wo' else (v.shape[1] * v.shape[2] if name == '_wo' else v.shape[0])
+            v = (v / np.sqrt(fan_in)).astype(np.float32)
+            setattr(owner, name, v)
+    set_dropout_seed(6)
+    out = layer(q, kv)
+    masks = tuple(getattr(layer, f'_dropout{i}')._mask for i in (1, 2, 3))
+    p = {}
+    for path in ['_self_attention.' + k for k in O.MHA_PARAMS] + ['_cross_attention.' + k for k in O.MHA_PARAMS] + \
+            ['_dense1._linear._w', '_dense1._linear._b', '_dense2._w', '_dense2._b'] + \
+            [f'_norm{i}.{n}' for i in (1, 2, 3) for n in ('_gamma', '_beta')]:
+        p[path] = param_values(layer, [path])[path]
+    keep = np.float32(0.9)
+    oout, cache = O.decoder_fwd(p, q, kv, True, masks, keep)
+    close(out, oout)
+    rec = Recorder()
+    dq, dkv = layer(dy, backprop=True, optimizer_=rec)
+    (odq, odkv), ograds = O.decoder_bwd(p, cache, dy, True, masks, keep)
+    close(dq, odq); close(dkv, odkv)
+    got = grads_of(layer, rec, ograds.keys())
+    for k, v in ograds.items():
+        close(got[k], v, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(v).max()))
+
+
+# ------------------------------------------------------------------ conv
+@pytest.mark.parametrize('tag', ['c3', 'c8', 'k5', 'k1'])
+def test_conv_golden(tag):
+    from layers import Conv2D
+    g = load_golden('conv_' + tag)
+    k, _, _, c1 = g['p._w'].shape
+    layer = Conv2D(c1, k)
+    layer(g['x'])
+    bind(layer, sub(g, 'p.'))
+    close(layer(g['x']), g['y'])
+    rec = Recorder()
+    close(layer(g['dy'], backprop=True, optimizer_=rec), g['dx'])
+    got = grads_of(layer, rec, ['_w', '_b'])
+    close(got['_w'], g['g._w']); close(got['_b'], g['g._b'])
+
+
+@pytest.mark.parametrize('shape', [(4, 32, 32, 3, 64, 3), (2, 32, 32, 64, 128, 3), (3, 9, 7, 16, 20, 5), (2, 16, 16, 32, 32, 1)])
+def test_conv_vs_oracle(shape):
+    from layers import Conv2D
+    from oracle import np_oracle as O
+    n, hh, ww, c0, c1, k = shape
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal((n, hh, ww, c0)).astype(np.float32)
+    dy = rng.standard_normal((n, hh, ww, c1)).astype(np.float32)
+    f = (rng.standard_normal((k, k, c0, c1)) / np.sqrt(k * k * c0)).astype(np.float32)
+    b = rng.standard_normal(c1).astype(np.float32)
+    layer = Conv2D(c1, k)
+    layer(x)
+    bind(layer, {'_w': f, '_b': b})
+    y, z = O.conv_layer_fwd(x, f, b)
+    close(layer(x), y)
+    rec = Recorder()
+    dx = layer(dy, backprop=True, optimizer_=rec)
+    odx, odw, odb = O.conv_layer_bwd(x, f, z, dy)
+    close(dx, odx)
+    got = grads_of(layer, rec, ['_w', '_b'])
+    close(got['_w'], odw, rtol=1e-3, atol=1e-4 * np.sqrt(n * hh * ww))
+    close(got['_b'], odb, rtol=1e-4, atol=1e-4 * np.sqrt(n * hh * ww))
+
+
+# ------------------------------------------------------------------ losses / optimizers / trainer
+def test_losses_golden():
+    import loss
+    g = load_golden('loss')
+    mse = loss.MSELoss()
+    close(float(mse(g['y'], g['t'])), g['mse'], rtol=1e-5, atol=1e-6)
+    close(mse(backprop=True), g['mse_dy'], **EW)
+    ce = loss.CrossEntropyLoss()
+    close(float(ce(g['prob'], g['onehot'])), g['ce'], rtol=1e-5, atol=1e-5)
+    close(ce(backprop=True), g['ce_dy'], **EW)
+
+
+def test_optimizers_golden():
+    import optimizer
+    from npm_b200 import device
+    g = load_golden('optimizer')
+
+    class Box:
+        pass
+
+    box = Box()
+    box.w = device.asdevice(g['w0'])
+    optimizer.SGDOptimizer(0.1).update(box, 'w', g['grads'][0])
+    close(box.w, g['sgd'], rtol=1e-6, atol=1e-6)
+    box.w = device.asdevice(g['w0'])
+    adam = optimizer.AdamOptimizer(learning_rate=0.01)
+    for t, grad in enumerate(g['grads']):
+        adam.update(box, 'w', grad)
+        close(box.w, g['adam'][t], rtol=1e-5, atol=2e-6)
+
+
+def test_adam_many_tensors_one_launch():
+    """The fused update touches tensors of ragged sizes (incl. non-multiples of 4 and > one chunk)."""
+    import npm_b200
+    import optimizer
+    from npm_b200 import device
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(3)
+    sizes = [1, 3, 7, 64, 1000, 8192, 8193, 50000, 12]
+
+    class Box:
+        pass
+
+    box = Box()
+    host = {}
+    for i, n in enumerate(sizes):
+        host[f'p{i}'] = rng.standard_normal(n).astype(np.float32)
+        setattr(box, f'p{i}', device.asdevice(host[f'p{i}']))
+    opt = optimizer.AdamOptimizer(learning_rate=0.05)
+    state = {k: (np.zeros_like(v, np.float64), np.zeros_like(v, np.float64)) for k, v in host.items()}
+    for t in (1, 2):
+        grads = {k: rng.standard_normal(v.shape).astype(np.float32) for k, v in host.items()}
+        opt._enter()
+        for k in host:
+            opt.update(box, k, grads[k])
+        before = npm_b200.launch_count()
+        opt._exit()
+        assert npm_b200.launch_count() - before == 1       # ONE multi-tensor kernel
+        for k in host:
+            host[k], m, v = O.adam_step(host[k], grads[k], *state[k], t, 0.05)
+            state[k] = (m, v)
+            close(getattr(box, k), host[k], rtol=1e-5, atol=2e-6)
+
+
+def test_trainer_mlp_golden(capsys):
+    import loss
+    import optimizer
+    from layers import Dense, Softmax
+    from train import Trainer
+    g = load_golden('trainer_mlp')
+    layers = [Dense(8), Dense(4, activation=Softmax())]
+    trainer = Trainer(layers, loss.CrossEntropyLoss())
+    trainer.eval(g['x'], g['t'])
+    for i, layer in enumerate(layers):
+        bind(layer, sub(g, f'p0.{i}.'))
+    capsys.readouterr()
+    trainer.train(g['x'], g['t'], 4, optimizer.SGDOptimizer(1e-2))
+    out = capsys.readouterr().out.splitlines()
+    assert [line.split()[0] for line in out] == ['Step:', 'Loss:'] * 4     # train.py:24,32
+    losses = [float(line.split()[-1]) for line in out if line.startswith('Loss')]
+    close(losses, g['losses'], rtol=1e-4, atol=1e-4)
+    for i, layer in enumerate(layers):
+        for k, v in sub(g, f'p1.{i}.').items():
+            close(param_values(layer, [k])[k], v, rtol=1e-3, atol=1e-4)
