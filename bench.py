@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+  metric : TransformerDecoder train-step tokens/sec (fwd + bwd + Adam, + gradient all-reduce when N > 1)
+  config : cfg5 — 24 x TransformerDecoder(16 heads, 4096 hidden, pre-norm, drop 0.1), d_model 1024,
+           Sq = Skv = 1024, per-GPU batch 8 (8192 tokens / GPU / step), MSELoss, AdamOptimizer(1e-4),
+           synthetic N(0,1) inputs / memory / targets, fan-in scaled random weights.
+
+`python bench.py --gpus N --steps K --warmup W` (torchrun for N > 1) prints ONE JSON line on rank 0:
+  value    : tokens/s with the step's inputs already resident in HBM (CUDA-event timed, max over ranks)
+  e2e      : the same through Trainer.train() with pinned HOST inputs copied in and the loss read back each step
+  roofline : the dominant kernel (tcgen05 TF32 GEMM at the FFN shape) timed live with CUDA events
+  cpu_baseline : the NumPy oracle (port of the reference algorithm) on this host's cores, bounded sample
+`--impl reference` times that CPU path alone with the same metric/config/unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'np-modeling_b200'))
+sys.path.insert(0, ROOT)
+
+METRIC = 'TransformerDecoder train-step tokens/sec'
+UNIT = 'tokens/s'
+FLOP_PER_TOKEN_LAYER = lambda d, s, f: 3 * (16 * d * d + 8 * s * d + 4 * d * f)   # fwd+bwd, SURVEY §8d
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('NPM_BENCH_PRECISION', 'tf32'), choices=['tf32', '3xtf32'])
+    ap.add_argument('--layers', type=int, default=24)
+    ap.add_argument('--d-model', type=int, default=1024)
+    ap.add_argument('--heads', type=int, default=16)
+    ap.add_argument('--hidden', type=int, default=4096)
+    ap.add_argument('--seq', type=int, default=1024)
+    ap.add_argument('--batch', type=int, default=8, help='per-GPU batch (weak scaling)')
+    ap.add_argument('--no-alt', action='store_true', help='skip the secondary 3xTF32 measurement')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(hbm=p['hbm_gbs'], bf16=p['bf16_tflops'], bf16_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    src='MEASURED_PEAKS.json')
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_decoder_layer_sample(args, seq, repeats=1):
+    """One decoder layer fwd + bwd + Adam on the oracle (NumPy port of the reference algorithm;
+    closed-form softmax/LayerNorm backward — the reference's Jacobian route cannot run at this
+    width), B=1, Sq=Skv=seq.  Returns seconds per sample."""
+    import numpy as np
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(0)
+    d, h, f = args.d_model, args.heads, args.hidden
+    p = {}
+    for a in ('_self_attention.', '_cross_attention.'):
+        for w in ('_wq', '_wk', '_wv'):
+            p[a + w] = rng.standard_normal((h, d // h, d)) / np.sqrt(d)
+        p[a + '_wo'] = rng.standard_normal((d, h, d // h)) / np.sqrt(d)
+        for b in ('_bq', '_bk', '_bv'):
+            p[a + b] = rng.standard_normal((h, d // h)) * 0.1
+        p[a + '_bo'] = rng.standard_normal(d) * 0.1
+    p['_dense1._linear._w'] = rng.standard_normal((d, f)) / np.sqrt(d)
+    p['_dense1._linear._b'] = rng.standard_normal(f) * 0.1
+    p['_dense2._w'] = rng.standard_normal((f, d)) / np.sqrt(f)
+    p['_dense2._b'] = rng.standard_normal(d) * 0.1
+    for i in (1, 2, 3):
+        p[f'_norm{i}._gamma'] = np.ones(d)
+        p[f'_norm{i}._beta'] = np.zeros(d)
+    q = rng.standard_normal((1, seq, d))
+    kv = rng.standard_normal((1, seq, d))
+    t = rng.standard_normal((1, seq, d))
+    masks = tuple((rng.random((1, seq, d)) < 0.9).astype(np.uint8) for _ in range(3))
+    state = {k: (np.zeros_like(v), np.zeros_like(v)) for k, v in p.items()}
+    best = None
+    for it in range(repeats + 1):          # first pass = warm-up
+        t0 = time.perf_counter()
+        out, cache = O.decoder_fwd(p, q, kv, True, masks, 0.9)
+        dy = O.mse_bwd(out, t)
+        _, grads = O.decoder_bwd(p, cache, dy, True, masks, 0.9)
+        for k in p:
+            p[k], m, v = O.adam_step(p[k], grads[k], *state[k], it + 1, 1e-4)
+            state[k] = (m, v)
+        dt = time.perf_counter() - t0
+        if it > 0:
+            best = dt if best is None else min(best, dt)
+    return best
+
+
+def cpu_arm(args, seq, repeats):
+    sec = cpu_decoder_layer_sample(args, seq, repeats)
+    tokens_per_s = seq / (sec * args.layers)       # one layer timed; the stack is `layers` of them
+    cores = os.cpu_count()
+    return dict(value=tokens_per_s, unit=UNIT, cores=cores, kind='port',
+                sample=f'oracle/np_oracle.py (NumPy float64, BLAS on {cores} threads): one decoder layer fwd+bwd+Adam, '
+                       f'B=1, Sq=Skv={seq}, d={args.d_model}, {sec:.2f} s; tokens/s = {seq} / ({sec:.2f} s x {args.layers} layers)')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    seq = min(args.seq, 512)
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.warmup):
+        cpu_decoder_layer_sample(args, min(seq, 128), 0) if False else None
+    base = None
+    for _ in range(max(1, args.steps)):
+        base = cpu_arm(args, seq, 1)
+        vals.append(base['value'])
+        if time.perf_counter() - t_all > 150:
+            break
+    v = sum(vals) / len(vals)
+    base['value'] = v
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(vals), warmup=args.warmup,
+                ms_per_step=1e3 * args.batch * args.seq * args.gpus / v, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
+                config=dict(workload=f'cfg5 TransformerDecoder x{args.layers} d{args.d_model} h{args.heads} '
+                                     f'f{args.hidden} Sq=Skv={args.seq} batch {args.batch}/GPU; CPU sample: {base["sample"]}'),
+                cpu_baseline=base,
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index),
+                 '--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+                 'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    power_w_max=max(pw) if pw else None, samples=len(sm))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import npm_b200
+    import loss as loss_mod
+    import optimizer as opt_mod
+    from layers import adapters
+    from layers.normalizations import set_dropout_seed
+    from npm_b200 import device
+    from npm_b200._lib import C, GemmDesc
+    from train import Trainer, iter_parameters
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N > 1)'
+
+    B, S, D, H, F, L = args.batch, args.seq, args.d_model, args.heads, args.hidden, args.layers
+    tokens_per_step = B * S * world
+    pk = peaks()
+
+    def build(precision):
+        npm_b200.set_precision(precision)
+        np.random.seed(0)
+        set_dropout_seed(1234 + rank)
+        stack = adapters.DecoderStack(L, H, F, True, 0.1)
+        trainer = Trainer([stack], loss_mod.MSELoss(), verbose=False, shard_inputs=False)
+        return stack, trainer
+
+    g = torch.Generator(device='cuda').manual_seed(100 + rank)
+    q_d = device.DeviceArray(torch.randn(B, S, D, generator=g, device='cuda'))
+    kv_d = device.DeviceArray(torch.randn(B, S, D, generator=g, device='cuda'))
+    t_d = device.DeviceArray(torch.randn(B, S, D, generator=g, device='cuda'))
+    q_h, kv_h, t_h = (x.t.cpu().pin_memory() for x in (q_d, kv_d, t_d))
+
+    def init_weights(stack):
+        """Lazy-initialise with one forward (reference init, layer.py:57-60), then overwrite with the
+        fan-in scaled synthetic weights of SURVEY §8d, in place (same buffers)."""
+        stack(q_d, kv_d)
+        gw = torch.Generator(device='cuda').manual_seed(7)      # same on every rank
+        for owner, name in iter_parameters(stack):
+            p = owner._p(name).t
+            if name.startswith('_w'):
+                fan_in = p.shape[-1] if name in ('_wq', '_wk', '_wv') else (p.shape[1] * p.shape[2] if name == '_wo' else p.shape[0])
+                p.copy_(torch.randn(p.shape, generator=gw, device='cuda') / fan_in ** 0.5)
+            elif name == '_gamma':
+                p.fill_(1.0)
+            elif name == '_beta':
+                p.zero_()
+            else:
+                p.copy_(torch.randn(p.shape, generator=gw, device='cuda') * 0.02)
+        torch.cuda.synchronize()
+
+    def timed(trainer, adam, inputs, targets, steps, read_loss):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            trainer.train(inputs, targets, 1, adam)
+            if read_loss:
+                float(trainer.last_loss)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
+    def measure(precision, steps, warmup, with_e2e):
+        stack, trainer = build(precision)
+        init_weights(stack)
+        adam = opt_mod.AdamOptimizer(learning_rate=1e-4)
+        for _ in range(warmup):
+            trainer.train((q_d, kv_d), t_d, 1, adam)
+        torch.cuda.synchronize()
+        npm_b200.reset_launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms = timed(trainer, adam, (q_d, kv_d), t_d, steps, read_loss=False)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = npm_b200.launch_count()
+        out = dict(ms_per_step=ms / steps, value=tokens_per_step * steps / (ms / 1e3), launches=launches, clocks=clocks,
+                   loss=float(trainer.last_loss))
+        if with_e2e:
+            trainer.train((q_h, kv_h), t_h, 1, adam)          # warm the pinned path
+            float(trainer.last_loss)
+            ms2 = timed(trainer, adam, (q_h, kv_h), t_h, steps, read_loss=True)
+            out['e2e'] = dict(value=tokens_per_step * steps / (ms2 / 1e3), unit=UNIT,
+                              h2d_bytes_per_step=int(3 * B * S * D * 4), d2h_bytes_per_step=4,
+                              ms_per_step=ms2 / steps)
+        del stack, trainer, adam
+        torch.cuda.empty_cache()
+        return out
+
+    main = measure(args.precision, args.steps, max(args.warmup, 3), with_e2e=True)
+
+    # ---- roofline of the dominant kernel: tcgen05 GEMM at the FFN up-projection shape ----------
+    def gemm_roofline(precision):
+        npm_b200.set_precision(precision)
+        M, K, N = B * S, D, F
+        x = torch.randn(M, K, device='cuda')
+        w = torch.randn(K, N, device='cuda') / K ** 0.5
+        bias = torch.zeros(N, device='cuda')
+        y = torch.empty(M, N, device='cuda')
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')   # > 126 MB L2
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            C.npm_linear_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), M, K, N, 0, 0, st)
+        times = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            C.npm_linear_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), M, K, N, 0, 0, st)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        return 2.0 * M * K * N / (ms * 1e-3) / 1e12, ms
+
+    tf, gemm_ms = gemm_roofline(args.precision)
+    tf32_peak = pk['bf16'] / 2.0          # kind::tf32 runs at half the bf16 rate; burst figure: kernel timed alone
+    flop_per_token = L * FLOP_PER_TOKEN_LAYER(D, S, F)
+    roofline = dict(bound='tensor', achieved=tf, peak=tf32_peak, unit='TFLOP/s', frac=tf / tf32_peak, traffic=None,
+                    kernel=f'gemm_tc_kernel ({args.precision}) linear_fwd M={B * S} K={D} N={F}',
+                    launch_ms=gemm_ms, l2='flushed between launches (256 MiB write)',
+                    peak_basis=f'{pk["src"]} bf16_tflops/2 (tf32 = half the bf16 tensor rate)',
+                    step_model_flops_frac=main['value'] * flop_per_token / world / 1e12 / (pk['bf16_sustained'] / 2.0))
+
+    alt = None
+    if not args.no_alt:
+        other = '3xtf32' if args.precision == 'tf32' else 'tf32'
+        a = measure(other, max(2, args.steps // 2), 3, with_e2e=False)
+        atf, _ = gemm_roofline(other)
+        alt = dict(precision=other, value=a['value'], ms_per_step=a['ms_per_step'], gemm_tflops=atf)
+    npm_b200.set_precision(args.precision)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_arm(args, 256, 1)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=main['value'], unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=main['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype=args.precision, data='synthetic',
+                    config=dict(workload=f'cfg5: {L} x TransformerDecoder(heads {H}, hidden {F}, pre-norm, drop 0.1), d_model {D}, '
+                                         f'Sq=Skv={S}, batch {B}/GPU, MSELoss, Adam(1e-4)',
+                                global_batch=B * world, seq_len=S, parallelism=f'dp{world}',
+                                l2_policy='per-step working set (> 40 GB of activations) far exceeds the 126 MB L2',
+                                precision=f'{args.precision} contractions, fp32 accumulate/storage'),
+                    e2e=main['e2e'], gpu_launches=int(main['launches']), clocks=main['clocks'], roofline=roofline,
+                    cpu_baseline=cpu, alt=alt, final_loss=main['loss'])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

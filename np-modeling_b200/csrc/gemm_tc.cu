@@ -414,7 +414,8 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     const int64_t tiles_m = (d.m + kBlockM - 1) / kBlockM;
     int best_bn = 64;
     {
-        static const int forced = getenv("NPM_GEMM_BLOCK_N") ? atoi(getenv("NPM_GEMM_BLOCK_N")) : 0;
+        const char* fe = getenv("NPM_GEMM_BLOCK_N_DYN");
+        const int forced = fe ? atoi(fe) : 0;   // tuning hook (tools/gemm_bench.py)
         double best_cost = 1e300;
         const int cands[3] = {256, 128, 64};
         for (int i = 0; i < 3; ++i) {

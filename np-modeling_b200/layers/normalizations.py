@@ -7,6 +7,7 @@ import torch
 import optimizer
 from layers import layer
 from npm_b200 import device
+from npm_b200 import dist as npm_dist
 from npm_b200._lib import C
 
 # Process-wide Philox state: every DropOut.forward consumes a fresh counter range of the stream
@@ -38,9 +39,9 @@ class DropOut(layer.Layer):
                 assert self._ext_mask.numel() == x.size, 'injected mask has the wrong size'
                 C.npm_dropout_fwd(x.ptr, y.ptr, x.size, keep_prob, 0, 0, self._ext_mask.data_ptr(), device.stream())
             else:
-                seed, offset = _philox['seed'], _philox['offset']
-                # keep counters 4-aligned so each 128-bit vector is one Philox call
-                _philox['offset'] = offset + (x.size + 3) // 4 * 4
+                seed = _philox['seed']
+                # this rank's slice of the global tensor's counter range (world-size independent)
+                offset, _philox['offset'] = npm_dist.dropout_range(x.size, _philox['offset'], *npm_dist.world())
                 self._rng = (seed, offset)
                 C.npm_dropout_fwd(x.ptr, y.ptr, x.size, keep_prob, seed, offset, None, device.stream())
             return y

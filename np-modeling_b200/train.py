@@ -24,12 +24,9 @@ import loss
 import optimizer
 from layers import layer
 from npm_b200 import device
+from npm_b200 import dist as npm_dist
 
-
-def _world():
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
-    return 0, 1
+_world = npm_dist.world
 
 
 def iter_parameters(obj, _seen=None):
@@ -61,27 +58,36 @@ class Trainer:
     def __init__(self,
                  layers: Sequence[layer.Layer],
                  loss_: Optional[loss.Loss] = None,
-                 verbose: bool = True):
+                 verbose: bool = True,
+                 shard_inputs: bool = True):
+        """`verbose=False` silences the reference's Step/Loss prints; `shard_inputs=False` says the
+        arrays passed to train()/eval() already are this rank's shard.  Extension over the reference:
+        `inputs` may be a tuple — it is splatted into the first layer (e.g. `(q, kv)` for a
+        DecoderStack), and a tuple gradient is reduced to its first element between layers."""
         self._layers = layers
         self._loss = loss_ or loss.MSELoss()
         self._verbose = verbose
+        self._shard_inputs = shard_inputs
         self._synced = False
         self._pinned = {}
 
     # ---- host → device staging ------------------------------------------------------------
     def _shard(self, a):
         rank, world = _world()
-        if world == 1 or isinstance(a, device.DeviceArray):
+        if isinstance(a, tuple):
+            return tuple(self._shard(x) for x in a)
+        if world == 1 or not self._shard_inputs or isinstance(a, device.DeviceArray):
             return a
-        n = a.shape[0]
-        assert n % world == 0, f'batch {n} is not divisible by world size {world}'
-        per = n // world
-        return a[rank * per:(rank + 1) * per]
+        return npm_dist.shard_rows(a, rank, world)
 
     def _to_device(self, key, a):
         """Copy one step's host input into HBM through a reusable pinned staging buffer."""
+        if isinstance(a, tuple):
+            return tuple(self._to_device(f'{key}.{i}', x) for i, x in enumerate(a))
         if isinstance(a, device.DeviceArray):
             return a
+        if isinstance(a, torch.Tensor) and a.is_pinned() and a.dtype == torch.float32:
+            return device.from_pinned(a)        # already page-locked: one async H2D copy
         a = np.asarray(a)
         if not torch.cuda.is_available():
             raise RuntimeError('np-modeling_b200 needs a CUDA device; there is no CPU fallback')
@@ -97,25 +103,21 @@ class Trainer:
         rank, world = _world()
         if world == 1 or self._synced:
             return
-        for owner, name in iter_parameters(list(self._layers)):
-            p = owner._p(name) if hasattr(owner, '_p') else device.asdevice(getattr(owner, name))
-            dist.broadcast(p.t, src=0)
+        npm_dist.broadcast_from_rank0([owner._p(name).t for owner, name in iter_parameters(list(self._layers))])
         self._synced = True
 
     def _install_grad_sync(self, optimizer_):
         rank, world = _world()
         if world == 1 or not isinstance(optimizer_, optimizer._FusedOptimizer):
             return
-        optimizer_.grad_scale = (1.0 / world) if getattr(self._loss, 'dp_mean', True) else 1.0
+        optimizer_.grad_scale = npm_dist.grad_scale(getattr(self._loss, 'dp_mean', True), world)
 
         def sync(opt):
-            for view in opt._arena.used_views():
-                dist.all_reduce(view, op=dist.ReduceOp.SUM)
+            npm_dist.allreduce_sum(opt._arena.used_views())
             # gradients that did not come from the arena (user-supplied buffers)
             arena_ptrs = [(b[0].data_ptr(), b[0].data_ptr() + b[0].numel() * 4) for b in opt._arena.blocks]
-            for _, _, g in opt._pending:
-                if not any(lo <= g.ptr < hi for lo, hi in arena_ptrs):
-                    dist.all_reduce(g.t, op=dist.ReduceOp.SUM)
+            npm_dist.allreduce_sum([g.t for _, _, g in opt._pending
+                                    if not any(lo <= g.ptr < hi for lo, hi in arena_ptrs)])
 
         optimizer_.grad_sync = sync
 
@@ -123,17 +125,24 @@ class Trainer:
         rank, world = _world()
         if world == 1:
             return l
-        t = l._t.clone() if isinstance(l, device.DeviceScalar) else torch.tensor([float(l)], device=device._device())
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        if getattr(self._loss, 'dp_mean', True):
-            t /= world
-        return device.DeviceScalar(device.DeviceArray(t))
+        t = l._t if isinstance(l, device.DeviceScalar) else torch.tensor([float(l)], device=device._device())
+        return device.DeviceScalar(device.DeviceArray(npm_dist.global_loss(t, getattr(self._loss, 'dp_mean', True))))
+
+    def _forward(self, y):
+        for i, layer_ in enumerate(self._layers):
+            y = layer_(*y) if (i == 0 and isinstance(y, tuple)) else layer_(y)
+        return y
 
     # ---- the reference loop (train.py:20-39) ------------------------------------------------
     def train(self, inputs, targets, steps: int, optimizer_: optimizer.Optimizer) -> None:
         inputs, targets = self._shard(inputs), self._shard(targets)
         self._install_grad_sync(optimizer_)
         fused = isinstance(optimizer_, optimizer.Optimizer)
+        if _world()[1] > 1 and not self._synced:
+            # parameters are created lazily by the first forward (layers/layer.py:33-35): run one
+            # untrained forward so they exist, then make every rank start from rank 0's values
+            self._forward(self._to_device('inputs', inputs))
+            self._broadcast_parameters()
 
         for i in range(steps):
             if self._verbose:
@@ -142,11 +151,7 @@ class Trainer:
             logging.info('Running forward pass')
             y = self._to_device('inputs', inputs)
             t = self._to_device('targets', targets)
-            for layer_ in self._layers:
-                y = layer_(y)
-            self._broadcast_parameters()
-            if not self._synced and _world()[1] > 1:
-                raise RuntimeError('parameter broadcast failed')
+            y = self._forward(y)
             l = self._loss(y, t)
 
             logging.info('Running backward pass')
@@ -158,6 +163,8 @@ class Trainer:
             try:
                 for layer_ in reversed(self._layers):
                     dy = layer_(dy, backprop=True, optimizer_=optimizer_)
+                    if isinstance(dy, tuple):
+                        dy = dy[0]
             finally:
                 if fused:
                     optimizer_._exit()
@@ -171,8 +178,7 @@ class Trainer:
         inputs, targets = self._shard(inputs), self._shard(targets)
         y = self._to_device('inputs', inputs)
         t = self._to_device('targets', targets)
-        for layer_ in self._layers:
-            y = layer_(y)
+        y = self._forward(y)
         l = self._global_loss(self._loss(y, t))
         self.last_loss = l
         if self._verbose:

@@ -28,6 +28,12 @@ def _f(x):
     return np.asarray(x, dtype=F64)
 
 
+def _es(spec, *ops):
+    """np.einsum as the reference calls it, routed through BLAS (optimize=True) so the CPU baseline
+    is not handicapped by einsum's scalar loops."""
+    return np.einsum(spec, *ops, optimize=True)
+
+
 # ----------------------------------------------------------------------------- Linear / Dense
 def linear_fwd(x, w, b):
     """y = x @ w + b                                                    layers/mlp.py:21-25"""
@@ -120,13 +126,13 @@ def mha_fwd(p, query, key=None, value=None):
     value = key if value is None else _f(value)
     wq, wk, wv, wo = (_f(p[k]) for k in ('_wq', '_wk', '_wv', '_wo'))
     dk = wq.shape[1]
-    q = np.einsum('bsd,hkd->bshk', query, wq) + _f(p['_bq'])          # :90-92
-    k = np.einsum('btd,hkd->bthk', key, wk) + _f(p['_bk'])            # :94-96
-    v = np.einsum('btd,hcd->bthc', value, wv) + _f(p['_bv'])          # :98-100
-    s = np.einsum('bshk,bthk->bhst', q, k) / np.sqrt(dk)              # :103-104
+    q = _es('bsd,hkd->bshk', query, wq) + _f(p['_bq'])          # :90-92
+    k = _es('btd,hkd->bthk', key, wk) + _f(p['_bk'])            # :94-96
+    v = _es('btd,hcd->bthc', value, wv) + _f(p['_bv'])          # :98-100
+    s = _es('bshk,bthk->bhst', q, k) / np.sqrt(dk)              # :103-104
     prob = softmax_fwd(s)                                             # :108
-    vals = np.einsum('bhst,bthc->bhsc', prob, v)                      # :112
-    out = np.einsum('bhsc,dhc->bsd', vals, wo) + _f(p['_bo'])         # :116-117
+    vals = _es('bhst,bthc->bhsc', prob, v)                      # :112
+    out = _es('bhsc,dhc->bsd', vals, wo) + _f(p['_bo'])         # :116-117
     cache = dict(query=query, key=key, value=value, q=q, k=k, v=v, prob=prob, vals=vals)
     return out, cache
 
@@ -140,19 +146,19 @@ def mha_bwd(p, cache, dy):
     c = cache
     g = {}
     g['_bo'] = dy.sum(axis=(0, 1))                                    # :129
-    g['_wo'] = np.einsum('bhsc,bsd->dhc', c['vals'], dy)              # :133-135 (batch-summed)
-    dvals = np.einsum('bsd,dhc->bhsc', dy, wo)                        # :136
-    dprob = np.einsum('bhsc,bthc->bhst', dvals, c['v'])               # :146
-    dv = np.einsum('bhst,bhsc->bthc', c['prob'], dvals)               # :147-148
+    g['_wo'] = _es('bhsc,bsd->dhc', c['vals'], dy)              # :133-135 (batch-summed)
+    dvals = _es('bsd,dhc->bhsc', dy, wo)                        # :136
+    dprob = _es('bhsc,bthc->bhst', dvals, c['v'])               # :146
+    dv = _es('bhst,bhsc->bthc', c['prob'], dvals)               # :147-148
     ds = softmax_bwd(c['prob'], dprob) / np.sqrt(dk_dim)              # :150-155
-    dq = np.einsum('bhst,bthk->bshk', ds, c['k'])                     # :161
-    dk = np.einsum('bshk,bhst->bthk', c['q'], ds)                     # :162
-    g['_wq'] = np.einsum('bsd,bshk->hkd', c['query'], dq)             # :169-171
-    dquery = np.einsum('bshk,hkd->bsd', dq, wq)                       # :172
-    g['_wk'] = np.einsum('btd,bthk->hkd', c['key'], dk)               # :173-175
-    dkey = np.einsum('bthk,hkd->btd', dk, wk)                         # :176
-    g['_wv'] = np.einsum('btd,bthc->hcd', c['value'], dv)             # :181-183
-    dvalue = np.einsum('bthc,hcd->btd', dv, wv)                       # :184
+    dq = _es('bhst,bthk->bshk', ds, c['k'])                     # :161
+    dk = _es('bshk,bhst->bthk', c['q'], ds)                     # :162
+    g['_wq'] = _es('bsd,bshk->hkd', c['query'], dq)             # :169-171
+    dquery = _es('bshk,hkd->bsd', dq, wq)                       # :172
+    g['_wk'] = _es('btd,bthk->hkd', c['key'], dk)               # :173-175
+    dkey = _es('bthk,hkd->btd', dk, wk)                         # :176
+    g['_wv'] = _es('btd,bthc->hcd', c['value'], dv)             # :181-183
+    dvalue = _es('bthc,hcd->btd', dv, wv)                       # :184
     g['_bq'] = dq.sum(axis=(0, 1))                                    # :186
     g['_bk'] = dk.sum(axis=(0, 1))                                    # :187
     g['_bv'] = dv.sum(axis=(0, 1))                                    # :188

@@ -1,0 +1,193 @@
+"""BASELINE-size checks through size-independent properties (the oracle cannot run these sizes in
+seconds): checksum-of-checksums for the GEMMs, row-stochastic attention, normalisation moments,
+mask idempotence; plus the TF32 single-pass mode against the oracle with ITS stated tolerance."""
+import numpy as np
+import pytest
+
+from helpers import Recorder, bind, close, grads_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _precision():
+    import npm_b200
+    npm_b200.set_precision('3xtf32')
+    yield
+    npm_b200.set_precision('3xtf32')
+
+
+@pytest.mark.parametrize('precision', ['3xtf32', 'tf32'])
+def test_linear_cfg5_checksums(precision):
+    """cfg5 FFN shapes, M = 8192 tokens: 1^T(XW + b) = (1^T X)W + M b, and the same identities for
+    dX and dW — every output element enters a checksum that a float64 host GEMV can verify."""
+    import npm_b200
+    from layers import Linear
+    npm_b200.set_precision(precision)
+    rng = np.random.default_rng(0)
+    m, k, n = 8192, 1024, 4096
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    dy = rng.standard_normal((m, n)).astype(np.float32)
+    w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    layer = Linear(n)
+    layer(x)
+    bind(layer, {'_w': w, '_b': b})
+    y = np.asarray(layer(x)).astype(np.float64)
+    rec = Recorder()
+    dx = np.asarray(layer(dy, backprop=True, optimizer_=rec)).astype(np.float64)
+    g = grads_of(layer, rec, ['_w', '_b'])
+    x64, dy64, w64 = x.astype(np.float64), dy.astype(np.float64), w.astype(np.float64)
+    tol = dict(rtol=2e-4, atol=2e-2) if precision == '3xtf32' else dict(rtol=5e-3, atol=1.0)
+    close(y.sum(0), x64.sum(0) @ w64 + m * b.astype(np.float64), **tol)                 # column checksum
+    close(y.sum(1), x64 @ w64.sum(1) + b.astype(np.float64).sum(), **tol)               # row checksum
+    close(dx.sum(0), dy64.sum(0) @ w64.T, **tol)
+    close(dx.sum(1), dy64 @ w64.sum(0), **tol)
+    close(g['_w'].astype(np.float64).sum(0), x64.sum(0) @ dy64, rtol=tol['rtol'], atol=tol['atol'] * 10)
+    close(g['_w'].astype(np.float64).sum(1), x64.T @ dy64.sum(1), rtol=tol['rtol'], atol=tol['atol'] * 10)
+    close(g['_b'], dy64.sum(0), rtol=1e-4, atol=1e-2)
+
+
+def test_attention_core_cfg5_properties():
+    """B8 H16 S1024 dk64: probabilities are row-stochastic; a constant value vector passes through
+    unchanged; dV checksum equals the checksum of dO (columns of P^T sum the rows of P)."""
+    import torch
+    from npm_b200 import device
+    from npm_b200._lib import C
+    B, H, S, dk = 8, 16, 1024, 64
+    g = torch.Generator(device='cuda').manual_seed(0)
+    q = torch.randn(B, S, H, dk, generator=g, device='cuda')
+    k = torch.randn(B, S, H, dk, generator=g, device='cuda')
+    v = torch.randn(1, 1, H, dk, generator=g, device='cuda').expand(B, S, H, dk).contiguous()   # constant over t
+    o = torch.empty(B, S, H, dk, device='cuda')
+    saved = device.workspace(C.npm_mha_core_saved_bytes(B, H, S, S, dk, dk))
+    st = device.stream()
+    C.npm_mha_core_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), saved.data_ptr(), B, H, S, S, dk, dk, st)
+    torch.cuda.synchronize()
+    assert torch.allclose(o, v, rtol=1e-4, atol=1e-4)                 # sum_t P[s,t] v = v
+    p = torch.empty(B, H, S, S, device='cuda')
+    C.npm_mha_core_scores(saved.data_ptr(), p.data_ptr(), B, H, S, S, st)
+    rows = p.sum(-1)
+    assert torch.allclose(rows, torch.ones_like(rows), rtol=1e-5, atol=1e-5)
+    assert float(p.min()) >= 0.0
+    # backward: dV[b,t,h,:] = sum_s P[s,t] dO[s]; summing over t gives sum_s dO[s]
+    do = torch.randn(B, S, H, dk, generator=g, device='cuda')
+    dq, dk_, dv = (torch.empty(B, S, H, dk, device='cuda') for _ in range(3))
+    scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes(B, H, S, S, dk, dk))
+    C.npm_mha_core_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), saved.data_ptr(),
+                       dq.data_ptr(), dk_.data_ptr(), dv.data_ptr(), scratch.data_ptr(), B, H, S, S, dk, dk, st)
+    torch.cuda.synchronize()
+    assert torch.allclose(dv.sum(1), do.sum(1), rtol=1e-3, atol=2e-3)
+    # softmax backward output sums to zero over t, so dQ for constant-over-t K... use the row identity:
+    # sum_t dS[s,t] = 0  =>  with k constant over t, dQ = 0.  (checked on a fresh call)
+    kc = torch.randn(1, 1, H, dk, generator=g, device='cuda').expand(B, S, H, dk).contiguous()
+    C.npm_mha_core_fwd(q.data_ptr(), kc.data_ptr(), v.data_ptr(), o.data_ptr(), saved.data_ptr(), B, H, S, S, dk, dk, st)
+    C.npm_mha_core_bwd(q.data_ptr(), kc.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), saved.data_ptr(),
+                       dq.data_ptr(), dk_.data_ptr(), dv.data_ptr(), scratch.data_ptr(), B, H, S, S, dk, dk, st)
+    torch.cuda.synchronize()
+    assert float(dq.abs().max()) < 1e-4
+
+
+def test_layernorm_dropout_cfg5_properties():
+    from layers import LayerNormalization
+    from layers.normalizations import DropOut, set_dropout_seed
+    rng = np.random.default_rng(1)
+    rows, cols = 8192, 1024
+    x = (rng.standard_normal((rows, cols)) * 3 + 1).astype(np.float32)
+    ln = LayerNormalization()
+    ln(x)
+    bind(ln, {'_gamma': np.ones(cols, np.float32), '_beta': np.zeros(cols, np.float32)})
+    z = np.asarray(ln(x)).astype(np.float64)
+    close(z.mean(-1), np.zeros(rows), rtol=0, atol=1e-5)
+    close((z ** 2).mean(-1), x.astype(np.float64).var(-1) / (x.astype(np.float64).var(-1) + 1e-3), rtol=1e-4, atol=1e-5)
+    rec = Recorder()
+    dz = rng.standard_normal((rows, cols)).astype(np.float32)
+    dx = np.asarray(ln(dz, backprop=True, optimizer_=rec)).astype(np.float64)
+    close(dx.sum(-1), np.zeros(rows), rtol=0, atol=1e-3)            # LN backward removes the row mean
+    g = grads_of(ln, rec, ['_gamma', '_beta'])
+    close(g['_beta'], dz.astype(np.float64).sum(0), rtol=1e-4, atol=1e-3)
+    close(g['_gamma'], (dz.astype(np.float64) * z).sum(0), rtol=1e-4, atol=2e-3)
+
+    set_dropout_seed(9)
+    d = DropOut(0.1)
+    y1 = np.asarray(d(x))
+    kept = y1 != 0
+    assert abs(kept.mean() - 0.9) < 2e-3
+    close(y1[kept], (x / np.float32(0.9))[kept], rtol=0, atol=0)
+    back = np.asarray(d(np.ones_like(x), backprop=True))
+    assert np.array_equal(back != 0, kept)                           # same mask forward and backward
+    set_dropout_seed(9)
+    assert np.array_equal(np.asarray(DropOut(0.1)(x)), y1)           # idempotent for a given seed
+
+
+def test_adam_cfg5_layer_sized_update_matches_closed_form():
+    """One decoder layer's worth of parameters (16.8 M) in a single fused launch vs the formula."""
+    import torch
+    import optimizer
+    from npm_b200 import device
+    sizes = [1024 * 1024] * 8 + [1024 * 4096] * 2 + [4096, 1024] + [1024] * 14
+
+    class Box:
+        pass
+
+    box = Box()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    ps, gs = [], []
+    for i, n in enumerate(sizes):
+        p = torch.randn(n, generator=g, device='cuda')
+        ps.append(p.clone())
+        setattr(box, f'p{i}', device.DeviceArray(p))
+        gs.append(torch.randn(n, generator=g, device='cuda'))
+    opt = optimizer.AdamOptimizer(learning_rate=1e-3)
+    opt._enter()
+    for i in range(len(sizes)):
+        opt.update(box, f'p{i}', device.DeviceArray(gs[i]))
+    opt._exit()
+    for i in range(len(sizes)):
+        m = 0.1 * gs[i].double()
+        v = 0.001 * gs[i].double() ** 2
+        want = ps[i].double() - 1e-3 * (m / 0.1) / torch.sqrt(v / 0.001 + 1e-7)
+        assert torch.allclose(getattr(box, f'p{i}').t.double(), want, rtol=1e-5, atol=1e-6)
+
+
+def test_tf32_mode_stated_tolerance():
+    """bench.py's default contraction mode is ONE tcgen05 kind::tf32 pass with operands rounded to
+    nearest by TMA.  Its stated tolerance against the float64 oracle: every tensor within 2e-3 of
+    its own max magnitude (10-bit mantissas); 3xTF32 on the same inputs is >= 30x tighter."""
+    import npm_b200
+    from layers import TransformerDecoder
+    from oracle import np_oracle as O
+    from train import iter_parameters
+    rng = np.random.default_rng(2)
+    b, sq, skv, d, h, f = 2, 64, 64, 256, 4, 512
+    q = rng.standard_normal((b, sq, d)).astype(np.float32)
+    kv = rng.standard_normal((b, skv, d)).astype(np.float32)
+    dy = rng.standard_normal((b, sq, d)).astype(np.float32)
+    errs = {}
+    for mode in ('tf32', '3xtf32'):
+        npm_b200.set_precision(mode)
+        np.random.seed(0)
+        layer = TransformerDecoder(h, f, True, 0.0)
+        layer(q, kv)
+        p = {}
+        for owner, name in iter_parameters(layer):
+            v = np.asarray(getattr(owner, name))
+            if name.startswith('_w'):
+                v = (v / np.sqrt(d)).astype(np.float32)
+                setattr(owner, name, v)
+        names = {id(getattr(layer, a)): a for a in vars(layer)}
+        for owner, name in iter_parameters(layer):
+            path = names.get(id(owner))
+            if path is None:     # Dense._linear
+                path = '_dense1._linear'
+            p[f'{path}.{name}'] = np.asarray(getattr(owner, name))
+        out = np.asarray(layer(q, kv))
+        ref, cache = O.decoder_fwd(p, q, kv, True)
+        rec = Recorder()
+        dq, dkv = layer(dy, backprop=True, optimizer_=rec)
+        (rdq, rdkv), _ = O.decoder_bwd(p, cache, dy, True)
+        errs[mode] = max(np.abs(out - ref).max() / np.abs(ref).max(), np.abs(np.asarray(dq) - rdq).max() / np.abs(rdq).max(),
+                         np.abs(np.asarray(dkv) - rdkv).max() / np.abs(rdkv).max())
+    assert errs['tf32'] < 2e-3, errs
+    assert errs['3xtf32'] < 2e-5, errs
+    assert errs['3xtf32'] * 30 < errs['tf32'], errs
