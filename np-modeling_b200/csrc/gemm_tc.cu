@@ -33,6 +33,7 @@ constexpr int kUmmaK  = 8;    // K of one tcgen05.mma kind::tf32
 struct GemmTcArgs {
     int M, N, K;
     int tiles_m, tiles_n, nb1, total_tiles;
+    int splits, kb_per_split, items_per_split;   // split-K: work item = (split, batch, n-tile, m-tile); partials are TMA-reduced into C
     float alpha;
     const float* bias;
     int relu, accum;
@@ -121,12 +122,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-                const int z  = tile / tiles_mn;
-                const int r  = tile - z * tiles_mn;
+                const int sp = tile / args.items_per_split, t2 = tile - sp * args.items_per_split;
+                const int z  = t2 / tiles_mn;
+                const int r  = t2 - z * tiles_mn;
+                const int kb0 = sp * args.kb_per_split;
+                const int kb1 = min(num_kb, kb0 + args.kb_per_split);
                 const int m0 = (r % args.tiles_m) * kBlockM;
                 const int n0 = (r / args.tiles_m) * BLOCK_N;
                 const int z1 = z % args.nb1, z2 = z / args.nb1;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
                     const uint32_t sB = sA + Cfg::kABytes;
@@ -160,10 +164,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+            const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
+            const int kb1 = min(num_kb, kb0 + args.kb_per_split);
             ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(NPASS == 3 ? xf_bar(stage) : full_bar(stage), phase);
                 ptx::tc_fence_after();
                 if (lane == 0) {
@@ -173,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                         const uint64_t da = ptx::umma_desc(descA, sA + kk * a_kstep);
                         const uint64_t db = ptx::umma_desc(descB, sB + kk * b_kstep);
-                        const uint32_t first = (kb | kk) != 0 ? 1u : 0u;
+                        const uint32_t first = (kb != kb0 || kk != 0) ? 1u : 0u;
                         if (NPASS == 1) {
                             ptx::umma_tf32(d_tmem, da, db, idesc, first);
                         } else {
@@ -187,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     ptx::umma_commit(empty_bar(stage));            // smem slot reusable
-                    if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(acc));  // accumulator ready
+                    if (kb == kb1 - 1) ptx::umma_commit(tfull_bar(acc));  // accumulator ready
                 }
                 __syncwarp();
                 if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -203,8 +209,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         uint32_t nstore = 0;
         for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-            const int z  = tile / tiles_mn;
-            const int r  = tile - z * tiles_mn;
+            const int sp = tile / args.items_per_split, t2 = tile - sp * args.items_per_split;
+            const int z  = t2 / tiles_mn;
+            const int r  = t2 - z * tiles_mn;
             const int m0 = (r % args.tiles_m) * kBlockM;
             const int n0 = (r / args.tiles_m) * BLOCK_N;
             const int z1 = z % args.nb1, z2 = z / args.nb1;
@@ -221,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
-                if (args.bias != nullptr) {
+                if (args.bias != nullptr && sp == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (nc + j < args.N) f[j] += __ldg(args.bias + nc + j);
@@ -243,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (args.accum)
+                    if (args.accum || args.splits > 1)
                         ptx::tma_reduce_add_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
                     else
                         ptx::tma_store_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
@@ -265,7 +272,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
+            const int kb1 = min(num_kb, kb0 + args.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(full_bar(stage), phase);
                 uint8_t* raw = base_ptr + stage * Cfg::kStageBytes;
 #pragma unroll 4
@@ -409,30 +418,47 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     static const bool tma_round = env_flag("NPM_TF32_TMA_ROUND", true);
     const bool round_ab = (npass == 1) && tma_round;
 
-    // ---- tile shape: minimise (waves x tile cost) ----
+    // ---- tile shape and split-K: minimise waves x (main-loop + per-tile overhead), in SM cycles ----
+    // Per K-step (32 fp32) cost of one CTA: the MMA floor is 2*BLOCK_N cycles; narrow tiles re-read
+    // more operand bytes per flop from L2 and measured slower than that floor (profiles/r01_gemm_bench.txt).
     const int sms = num_sms();
     const int64_t tiles_m = (d.m + kBlockM - 1) / kBlockM;
-    int best_bn = 64;
+    const int num_kb_total = (int)((d.k + kBlockK - 1) / kBlockK);
+    const bool c_dense = (d.ldc == d.n) && (nb1 == 1 || d.c_bs1 == d.m * d.n) && (nb2 == 1 || d.c_bs2 == d.m * d.n * nb1);
+    const bool may_split = c_dense && !(d.flags & (NPM_GEMM_RELU | NPM_GEMM_ACCUM)) && !getenv("NPM_GEMM_NO_SPLITK");
+    int best_bn = 64, best_splits = 1;
     {
         const char* fe = getenv("NPM_GEMM_BLOCK_N_DYN");
         const int forced = fe ? atoi(fe) : 0;   // tuning hook (tools/gemm_bench.py)
         double best_cost = 1e300;
         const int cands[3] = {256, 128, 64};
+        const double kstep[3] = {512.0, 400.0, 300.0};
         for (int i = 0; i < 3; ++i) {
             const int bn = cands[i];
             if (forced && bn != forced) continue;
             const int64_t tn = (d.n + bn - 1) / bn;
             const int64_t tiles = tiles_m * tn * nb1 * nb2;
-            const int64_t waves = (tiles + sms - 1) / sms;
-            // cost ~ waves * (MMA time ∝ bn  +  fixed per-tile overhead)
-            const double cost = double(waves) * (double(bn) + 24.0);
-            if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+            for (int sp = 1; sp <= (may_split ? 16 : 1); sp *= 2) {
+                const int kbs = (num_kb_total + sp - 1) / sp;
+                if (sp > 1 && kbs < 16) break;
+                const int64_t waves = (tiles * sp + sms - 1) / sms;
+                double cost = double(waves) * (kbs * kstep[i] * npass + 1500.0 + 8.0 * bn);
+                if (sp > 1) cost = cost * 1.08 + 3000.0;   // zero-fill + reduce traffic: split only for a clear win
+                if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_splits = sp; }
+            }
         }
     }
     const int bn = best_bn;
+    const int kb_per_split = (num_kb_total + best_splits - 1) / best_splits;
+    const int splits = (num_kb_total + kb_per_split - 1) / kb_per_split;
     const int64_t tiles_n = (d.n + bn - 1) / bn;
-    const int64_t total = tiles_m * tiles_n * nb1 * nb2;
+    const int64_t items_per_split = tiles_m * tiles_n * nb1 * nb2;
+    const int64_t total = items_per_split * splits;
     if (total > (1ll << 30)) { set_error("gemm: too many tiles"); return NPM_ERR_INVALID; }
+    if (splits > 1) {
+        cudaError_t e = cudaMemsetAsync(d.c, 0, sizeof(float) * (size_t)d.m * d.n * nb1 * nb2, stream);
+        if (e != cudaSuccess) { set_error("gemm split-K memset: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+    }
 
     // ---- tensor maps ----
     CUtensorMap tmA, tmB, tmC;
@@ -470,6 +496,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     args.M = (int)d.m; args.N = (int)d.n; args.K = (int)d.k;
     args.tiles_m = (int)tiles_m; args.tiles_n = (int)tiles_n; args.nb1 = nb1;
     args.total_tiles = (int)total;
+    args.splits = splits; args.kb_per_split = kb_per_split; args.items_per_split = (int)items_per_split;
     args.alpha = d.alpha;
     args.bias = d.bias;
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
