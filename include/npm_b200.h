@@ -156,7 +156,10 @@ int npm_fill(float* x, float v, int64_t n, npm_stream_t stream);
 /* q [B,Sq,H,dk], k [B,Skv,H,dk], v [B,Skv,H,dv]  → o [B,Sq,H,dv]
  * o = softmax(q k^T / sqrt(dk)) v per (b,h); unmasked (the reference's mask
  * path raises, attentions.py:84).  `saved` (npm_mha_core_saved_bytes) must be
- * kept by the caller from fwd to bwd; its content is private to the library. */
+ * kept by the caller from fwd to bwd; its content is private to the library
+ * (TF32 mode with dk = dv = 64: the fused tcgen05 kernels, `saved` = one
+ * log-sum-exp per row; otherwise the probabilities P).  The size queries, fwd
+ * and bwd of one attention call must run under the same precision mode. */
 size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv,
                                 int64_t dk, int64_t dv);
 size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq,
@@ -169,10 +172,13 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v,
                      float* dq, float* dk_out, float* dv_out, void* scratch,
                      int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk,
                      int64_t dv, npm_stream_t stream);
-/* Copies the attention probabilities [B,H,Sq,Skv] out of `saved` (debug /
- * parity with MultiHeadAttention._attention_scores). */
-int npm_mha_core_scores(const void* saved, float* p_out, int64_t B, int64_t H,
-                        int64_t Sq, int64_t Skv, npm_stream_t stream);
+/* Writes the attention probabilities [B,H,Sq,Skv] to p_out (debug / parity with
+ * MultiHeadAttention._attention_scores, attentions.py:108-111): copied out of
+ * `saved` when it holds them, recomputed from q, k and the saved log-sum-exp
+ * when the fused kernels ran. */
+int npm_mha_core_scores(const float* q, const float* k, const void* saved,
+                        float* p_out, int64_t B, int64_t H, int64_t Sq,
+                        int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream);
 
 /* ---- Conv2D (layers/conv.py) ---------------------------------------------- */
 /* NHWC activations, HWIO filters, SAME padding, stride 1, odd ksize.

@@ -1,6 +1,8 @@
 // api.cu — library state, error plumbing, GEMM dispatch and the Linear / attention-core
 // entry points of the C-ABI (include/npm_b200.h).
+#include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -46,6 +48,15 @@ bool gemm_tc_supported(const npm_gemm_desc& d);
 int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream);
 int gemm_simt_launch(const npm_gemm_desc& d, cudaStream_t stream);
 size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
+// attn_fwd.cu / attn_bwd.cu
+bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv);
+int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
+                    int64_t Sq, int64_t Skv, cudaStream_t stream);
+size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq);
+int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
+                    float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
+                    cudaStream_t stream);
+int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
 
 static int require_sm100() {
@@ -77,6 +88,14 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     int prec = d.precision >= 0 ? d.precision : g_precision.load();
     if (prec != NPM_PREC_FP32 && gemm_tc_supported(d)) return gemm_tc_launch(d, prec, stream);
     return gemm_simt_launch(d, stream);
+}
+
+// The fused attention kernels serve head dim 64 in TF32 mode (the throughput mode); the 3xTF32 /
+// fp32 modes and other head dims run the batched-GEMM + softmax chain below.  fwd, bwd and the size
+// queries must be called under the same precision mode.
+static bool attn_fused(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    const bool off = getenv("NPM_ATTN_UNFUSED") != nullptr;     // A/B switch for tools/ and tests
+    return !off && g_precision.load() == NPM_PREC_TF32 && attn_fused_supported(B, H, Sq, Skv, dk, dv);
 }
 
 static npm_gemm_desc blank_desc() {
@@ -177,10 +196,12 @@ int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db, 
 // Round-1 implementation: the batched products run on the tcgen05 GEMM with the scores
 // materialised ([B,H,Sq,Skv], as the reference does at attentions.py:103-111); `saved` holds the
 // probabilities P.  A fused online-softmax kernel can replace this behind the same ABI.
-size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t, int64_t) {
-    return (size_t)B * H * Sq * Skv * sizeof(float);
+size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    if (attn_fused(B, H, Sq, Skv, dk, dv)) return (size_t)B * H * Sq * sizeof(float);   // log-sum-exp per row
+    return (size_t)B * H * Sq * Skv * sizeof(float);                                      // P
 }
-size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t, int64_t) {
+size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_bwd_scratch_bytes(B, H, Sq);      // D = rowsum(dO o O)
     return (size_t)B * H * Sq * Skv * sizeof(float);   // dP / dS
 }
 
@@ -189,6 +210,7 @@ int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o, v
     NPM_REQUIRE(q && k && v && o && saved, "mha_core_fwd: NULL pointer");
     cudaStream_t s = (cudaStream_t)stream;
     float* P = reinterpret_cast<float*>(saved);
+    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, s);
     // S[b,h] = (1/sqrt(dk)) q[b,:,h,:] k[b,:,h,:]^T
     npm_gemm_desc d = blank_desc();
     d.a = q; d.b = k; d.c = P;
@@ -222,9 +244,11 @@ int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o, v
 int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
                      const void* saved, float* dq, float* dk_out, float* dv_out, void* scratch, int64_t B, int64_t H,
                      int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream) {
-    (void)o;
     NPM_REQUIRE(q && k && v && d_o && saved && dq && dk_out && dv_out && scratch, "mha_core_bwd: NULL pointer");
     cudaStream_t s = (cudaStream_t)stream;
+    if (attn_fused(B, H, Sq, Skv, dk, dv))
+        return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
+                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, s);
     const float* P = reinterpret_cast<const float*>(saved);
     float* dP = reinterpret_cast<float*>(scratch);
     int rc;
@@ -285,11 +309,29 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float
     return NPM_OK;
 }
 
-int npm_mha_core_scores(const void* saved, float* p_out, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                        npm_stream_t stream) {
+int npm_mha_core_scores(const float* q, const float* k, const void* saved, float* p_out, int64_t B, int64_t H,
+                        int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream) {
     NPM_REQUIRE(saved && p_out, "mha_core_scores: NULL pointer");
-    cudaError_t e = cudaMemcpyAsync(p_out, saved, (size_t)B * H * Sq * Skv * sizeof(float), cudaMemcpyDeviceToDevice,
-                                    (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (attn_fused(B, H, Sq, Skv, dk, dv)) {
+        // recompute P = exp(q k^T / sqrt(dk) - lse) from the saved log-sum-exp
+        NPM_REQUIRE(q && k, "mha_core_scores: q and k are needed to recompute the probabilities");
+        npm_gemm_desc d = blank_desc();
+        d.a = q; d.b = k; d.c = p_out;
+        d.m = Sq; d.n = Skv; d.k = dk;
+        d.a_rs = H * dk; d.a_cs = 1;
+        d.b_rs = 1; d.b_cs = H * dk;
+        d.ldc = Skv;
+        d.nb1 = (int)H; d.nb2 = (int)B;
+        d.a_bs1 = dk; d.a_bs2 = Sq * H * dk;
+        d.b_bs1 = dk; d.b_bs2 = Skv * H * dk;
+        d.c_bs1 = Sq * Skv; d.c_bs2 = H * Sq * Skv;
+        d.alpha = (float)(1.0 / sqrt((double)dk));
+        int rc = gemm_dispatch(d, s);
+        if (rc) return rc;
+        return attn_scores_from_lse_launch(p_out, reinterpret_cast<const float*>(saved), B * H * Sq, Skv, s);
+    }
+    cudaError_t e = cudaMemcpyAsync(p_out, saved, (size_t)B * H * Sq * Skv * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) { set_error("mha_core_scores: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
     return NPM_OK;
 }

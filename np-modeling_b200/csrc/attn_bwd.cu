@@ -1,0 +1,609 @@
+// attn_bwd.cu — fused attention core backward on tcgen05 / TMEM / TMA (TF32, head dim 64).
+//
+// Replaces the reference's  dV = P^T dO, dP = dO V^T, Softmax.backward Jacobian einsum, dQ = dS K,
+// dK = dS^T Q  (layers/attentions.py:146-162, layers/activations.py:33-45) without ever
+// materialising P, dP or dS in HBM.  P is recomputed from the saved log-sum-exp:
+//     P = exp2(c * Q K^T - L),   dS = P o (dP - D) / sqrt(dk),   D = rowsum(dO o O)
+// Two persistent kernels, each shaped like the forward one (TMA producers / one MMA issuer /
+// four softmax warps owning one TMEM lane each):
+//   attn_bwd_dkdv : work item = (b, h, 128 kv rows), loops over 128-row q blocks, works on the
+//                   TRANSPOSED score tile S^T = K Q^T (TMEM lane = kv row) so that P^T and dS^T are
+//                   directly the TMEM A operands of  dV += P^T dO  and  dK += dS^T Q.
+//   attn_bwd_dq   : work item = (b, h, 128 q rows), loops over kv blocks, S = Q K^T (lane = q row),
+//                   dS is the TMEM A operand of  dQ += dS K.
+// A [rows, 64] fp32 tile that is contracted over its 64 columns is landed with the plain 128-byte
+// swizzle ("R" image, K-major operand); contracted over its rows it is landed with 32-byte swizzle
+// atoms ("T" image, MN-major operand) — tf32 operands cannot be transposed at 16-byte granularity.
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace npm {
+
+int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                       uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, bool round_tf32,
+                       bool atom32b);
+
+namespace {
+
+constexpr int kBlk = 128;         // rows of every tile (q rows and kv rows)
+constexpr int kD   = 64;          // head dim
+constexpr int kTileBytes  = kBlk * kD * 4;   // 32 KB
+constexpr int kChunkBytes = 16384;           // one {32 d, 128 rows} TMA box
+constexpr int kThreads = 256;
+
+struct BwdArgs {
+    int B, H, Sq, Skv;
+    int n_q, n_kv, total_items;
+    float c;                  // log2(e) / sqrt(dk)
+    float scale;              // 1 / sqrt(dk)
+    const float* lse;         // [B, H, Sq]  (log2 domain)
+    const float* dsum;        // [B, H, Sq]  D = rowsum(dO o O)
+    float* dq;                // [B, Sq, H, 64]
+    float* dk;                // [B, Skv, H, 64]
+    float* dv;                // [B, Skv, H, 64]
+};
+
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void bar_sync_128(int id) {
+    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+// both 16 KB boxes of a [128 rows, 64] tile
+__device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int row0, int h, int b) {
+    ptx::tma_load_4d(dst, tm, bar, 0, row0, h, b);
+    ptx::tma_load_4d(dst + kChunkBytes, tm, bar, 32, row0, h, b);
+}
+// D[tmem] (=|+=) A[smem, K-major R image] * B[smem, K-major R image]^T over the 64-wide head dim
+__device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc) {
+    const uint64_t desc_k = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            ptx::umma_tf32(d_tmem, ptx::umma_desc(desc_k, a_addr + kb * kChunkBytes + kk * 32),
+                           ptx::umma_desc(desc_k, b_addr + kb * kChunkBytes + kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
+}
+// D[tmem, 128 x 64] (=|+=) A[tmem, 128 lanes x 128 cols] * B[smem T image: 128 rows (k) x 64 (n)]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+    const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, kChunkBytes, 512);
+#pragma unroll
+    for (int kk = 0; kk < kBlk / 8; ++kk)
+        ptx::umma_tf32_ts(d_tmem, a_tmem + kk * 8, ptx::umma_desc(desc_mn, b_addr + kk * 1024), idesc,
+                          (accumulate || kk != 0) ? 1u : 0u);
+}
+// one accumulator row (64 fp32 in TMEM) → 256 contiguous bytes of global memory
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool live) {
+    uint32_t o[kD];
+    ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+    ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+    ptx::tmem_ld_wait();
+    if (live) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int k = 0; k < kD / 4; ++k)
+            d4[k] = make_float4(__uint_as_float(o[4 * k]), __uint_as_float(o[4 * k + 1]), __uint_as_float(o[4 * k + 2]),
+                                __uint_as_float(o[4 * k + 3]));
+    }
+}
+
+// =============================================================================== dK, dV
+// smem: K_R, V_R (resident per item) | Q_R, dO_R, Q_T, dO_T (one q block each) | L/D staging | barriers
+constexpr int kKvSmem = 6 * kTileBytes + 2 * 2 * kBlk * 4 + 1024 + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmQt,
+                     const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmVr,
+                     const __grid_constant__ CUtensorMap tmDOr, const __grid_constant__ CUtensorMap tmDOt,
+                     const BwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+
+    const uint32_t kr_addr = base_addr, vr_addr = kr_addr + kTileBytes;
+    const uint32_t qr_addr = vr_addr + kTileBytes, dor_addr = qr_addr + kTileBytes;
+    const uint32_t qt_addr = dor_addr + kTileBytes, dot_addr = qt_addr + kTileBytes;
+    float* lsm = reinterpret_cast<float*>(base_ptr + 6 * kTileBytes);   // [2][128] L, then [2][128] D
+    float* dsm = lsm + 2 * kBlk;
+    const uint32_t bar_addr = base_addr + 6 * kTileBytes + 2 * 2 * kBlk * 4;
+    enum { KV_FULL = 0, KV_EMPTY, QR_FULL, QR_EMPTY, DOR_FULL, DOR_EMPTY, QT_FULL, QT_EMPTY, DOT_FULL, DOT_EMPTY,
+           ST_FULL0, ST_FULL1, P_READY0, P_READY1, DPT_FULL, DS_READY, ACC_DONE, NBAR };
+    auto bar = [&](int i) { return bar_addr + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 6 * kTileBytes + 2 * 2 * kBlk * 4 + 8 * NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmQr); ptx::prefetch_tensormap(&tmQt); ptx::prefetch_tensormap(&tmKr);
+        ptx::prefetch_tensormap(&tmVr); ptx::prefetch_tensormap(&tmDOr); ptx::prefetch_tensormap(&tmDOt);
+    }
+    if (warp == 3) {
+        if (lane == 0) {
+            for (int i = 0; i < NBAR; ++i)
+                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DS_READY) ? 128 : 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_dpt = tmem_base + 256, tm_dv = tmem_base + 384, tm_dk = tmem_base + 448;
+
+    const int n_q = args.n_q;
+    const int my_items = (args.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t G = (uint32_t)my_items * (uint32_t)n_q;     // q blocks this CTA walks, over all its items
+
+    if (warp == 0) {
+        // ============ producer: K_R, V_R per item; Q_R, dO_R per q block ============
+        if (lane == 0) {
+            uint32_t g = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+                const int nt = item % args.n_kv;
+                const int bh = item / args.n_kv;
+                const int h = bh % args.H, b = bh / args.H;
+                ptx::mbar_wait(bar(KV_EMPTY), (it & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(bar(KV_FULL), 2 * kTileBytes);
+                load_tile(kr_addr, &tmKr, bar(KV_FULL), nt * kBlk, h, b);
+                load_tile(vr_addr, &tmVr, bar(KV_FULL), nt * kBlk, h, b);
+                for (int i = 0; i < n_q; ++i, ++g) {
+                    ptx::mbar_wait(bar(QR_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(QR_FULL), kTileBytes);
+                    load_tile(qr_addr, &tmQr, bar(QR_FULL), i * kBlk, h, b);
+                    ptx::mbar_wait(bar(DOR_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(DOR_FULL), kTileBytes);
+                    load_tile(dor_addr, &tmDOr, bar(DOR_FULL), i * kBlk, h, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============ producer: dO_T, Q_T per q block ============
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+                const int bh = item / args.n_kv;
+                const int h = bh % args.H, b = bh / args.H;
+                for (int i = 0; i < n_q; ++i, ++g) {
+                    ptx::mbar_wait(bar(DOT_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(DOT_FULL), kTileBytes);
+                    load_tile(dot_addr, &tmDOt, bar(DOT_FULL), i * kBlk, h, b);
+                    ptx::mbar_wait(bar(QT_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(QT_FULL), kTileBytes);
+                    load_tile(qt_addr, &tmQt, bar(QT_FULL), i * kBlk, h, b);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ============ MMA issuer ============
+        if (lane == 0) {
+            constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
+            constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
+            auto issue_st = [&](uint32_t g) {        // S^T(g) = K Q^T
+                const int it = g / n_q, i = g - it * n_q;
+                if (i == 0) ptx::mbar_wait(bar(KV_FULL), it & 1);
+                ptx::mbar_wait(bar(QR_FULL), g & 1);
+                ptx::tc_fence_after();
+                mma_rr(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s);
+                ptx::umma_commit(bar(QR_EMPTY));
+                ptx::umma_commit(bar(ST_FULL0 + (g & 1u)));
+            };
+            auto issue_dpt = [&](uint32_t g) {       // dP^T(g) = V dO^T
+                const int it = g / n_q, i = g - it * n_q;
+                ptx::mbar_wait(bar(DOR_FULL), g & 1);
+                ptx::tc_fence_after();
+                mma_rr(tm_dpt, vr_addr, dor_addr, idesc_s);
+                ptx::umma_commit(bar(DOR_EMPTY));
+                ptx::umma_commit(bar(DPT_FULL));
+                if (i == n_q - 1) ptx::umma_commit(bar(KV_EMPTY));
+            };
+            if (G > 0) { issue_st(0); issue_dpt(0); }
+            if (G > 1) issue_st(1);
+            for (uint32_t g = 0; g < G; ++g) {
+                const int i = g % n_q;
+                ptx::mbar_wait(bar(P_READY0 + (g & 1u)), (g >> 1) & 1);
+                ptx::mbar_wait(bar(DOT_FULL), g & 1);
+                ptx::tc_fence_after();
+                mma_ts(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, i != 0);    // dV += P^T dO
+                ptx::umma_commit(bar(DOT_EMPTY));
+                ptx::mbar_wait(bar(DS_READY), g & 1);
+                ptx::mbar_wait(bar(QT_FULL), g & 1);
+                ptx::tc_fence_after();
+                mma_ts(tm_dk, tm_dpt, qt_addr, idesc_ts, i != 0);                          // dK += dS^T Q
+                ptx::umma_commit(bar(QT_EMPTY));
+                if (i == n_q - 1) ptx::umma_commit(bar(ACC_DONE));
+                if (g + 1 < G) issue_dpt(g + 1);
+                if (g + 2 < G) issue_st(g + 2);
+            }
+        }
+    } else if (warp >= 4) {
+        // ============ softmax / dS warps: thread = kv row ============
+        const int wq = warp & 3;
+        const int tid = wq * 32 + lane;
+        const uint32_t lane_off = uint32_t(wq * 32) << 16;
+        const float c = args.c, scale = args.scale;
+        uint32_t g = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+            const int nt = item % args.n_kv;
+            const int bh = item / args.n_kv;
+            const int h = bh % args.H, b = bh / args.H;
+            const float* Lrow = args.lse + (size_t)bh * args.Sq;
+            const float* Drow = args.dsum + (size_t)bh * args.Sq;
+            for (int i = 0; i < n_q; ++i, ++g) {
+                const uint32_t buf = g & 1u;
+                {   // stage this q block's L and D (the columns of the transposed tile)
+                    const int qi = i * kBlk + tid;
+                    const bool live = qi < args.Sq;
+                    lsm[buf * kBlk + tid] = live ? __ldg(Lrow + qi) : INFINITY;    // exp2(-inf) = 0 for padded q
+                    dsm[buf * kBlk + tid] = live ? __ldg(Drow + qi) : 0.0f;
+                    bar_sync_128(1);
+                }
+                const float4* L4 = reinterpret_cast<const float4*>(lsm + buf * kBlk);
+                const float4* D4 = reinterpret_cast<const float4*>(dsm + buf * kBlk);
+                ptx::mbar_wait(bar(ST_FULL0 + buf), (g >> 1) & 1);
+                ptx::tc_fence_after();
+                float p[kBlk];
+                const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    ptx::tmem_ld_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[ch * 32]));
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < kBlk; k += 4) {
+                    const float4 l4 = L4[k >> 2];
+                    p[k]     = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k], c, -l4.x))));
+                    p[k + 1] = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k + 1], c, -l4.y))));
+                    p[k + 2] = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k + 2], c, -l4.z))));
+                    p[k + 3] = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k + 3], c, -l4.w))));
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    ptx::tmem_st_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[ch * 32]));
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar(P_READY0 + buf));
+
+                ptx::mbar_wait(bar(DPT_FULL), g & 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t dp[32];
+                    ptx::tmem_ld_32x32(tm_dpt + lane_off + ch * 32, dp);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        const float4 d4 = D4[(ch * 32 + k) >> 2];
+                        dp[k]     = cvt_tf32(p[ch * 32 + k]     * (__uint_as_float(dp[k])     - d4.x) * scale);
+                        dp[k + 1] = cvt_tf32(p[ch * 32 + k + 1] * (__uint_as_float(dp[k + 1]) - d4.y) * scale);
+                        dp[k + 2] = cvt_tf32(p[ch * 32 + k + 2] * (__uint_as_float(dp[k + 2]) - d4.z) * scale);
+                        dp[k + 3] = cvt_tf32(p[ch * 32 + k + 3] * (__uint_as_float(dp[k + 3]) - d4.w) * scale);
+                    }
+                    ptx::tmem_st_32x32(tm_dpt + lane_off + ch * 32, dp);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar(DS_READY));
+            }
+            // ---- epilogue: dV, dK rows of this kv tile ----
+            ptx::mbar_wait(bar(ACC_DONE), it & 1);
+            ptx::tc_fence_after();
+            const int t = nt * kBlk + tid;
+            const bool live = t < args.Skv;
+            const size_t off = (((size_t)b * args.Skv + (live ? t : 0)) * args.H + h) * kD;
+            store_acc_row(tm_dv + lane_off, args.dv + off, live);
+            store_acc_row(tm_dk + lane_off, args.dk + off, live);
+            ptx::tc_fence_before();
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 3) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================== dQ
+// smem: Q_R, dO_R (double buffered across items) | K_R, V_R, K_T (one kv block each) | barriers
+constexpr int kDqSmem = 7 * kTileBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmDOr,
+                   const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmKt,
+                   const __grid_constant__ CUtensorMap tmVr, const BwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+
+    const uint32_t qr_addr = base_addr;                       // 2 x 32 KB
+    const uint32_t dor_addr = qr_addr + 2 * kTileBytes;       // 2 x 32 KB
+    const uint32_t kr_addr = dor_addr + 2 * kTileBytes, vr_addr = kr_addr + kTileBytes, kt_addr = vr_addr + kTileBytes;
+    const uint32_t bar_addr = base_addr + 7 * kTileBytes;
+    enum { QDO_FULL0 = 0, QDO_FULL1, QDO_EMPTY0, QDO_EMPTY1, KR_FULL, KR_EMPTY, VR_FULL, VR_EMPTY, KT_FULL, KT_EMPTY,
+           S_FULL0, S_FULL1, DP_FULL, DS_READY, ACC_DONE, NBAR };
+    auto bar = [&](int i) { return bar_addr + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 7 * kTileBytes + 8 * NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmQr); ptx::prefetch_tensormap(&tmDOr); ptx::prefetch_tensormap(&tmKr);
+        ptx::prefetch_tensormap(&tmKt); ptx::prefetch_tensormap(&tmVr);
+    }
+    if (warp == 3) {
+        if (lane == 0) {
+            for (int i = 0; i < NBAR; ++i) ptx::mbar_init(bar(i), i == DS_READY ? 128 : 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_dp = tmem_base + 256, tm_dq = tmem_base + 384;
+
+    const int n_kv = args.n_kv;
+    const int my_items = (args.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t G = (uint32_t)my_items * (uint32_t)n_kv;
+
+    if (warp == 0) {
+        // ============ producer: Q_R + dO_R per item; K_R, V_R per kv block ============
+        if (lane == 0) {
+            uint32_t g = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+                const int mt = item % args.n_q;
+                const int bh = item / args.n_q;
+                const int h = bh % args.H, b = bh / args.H;
+                const int qb = it & 1;
+                ptx::mbar_wait(bar(QDO_EMPTY0 + qb), ((it >> 1) & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(bar(QDO_FULL0 + qb), 2 * kTileBytes);
+                load_tile(qr_addr + qb * kTileBytes, &tmQr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
+                load_tile(dor_addr + qb * kTileBytes, &tmDOr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
+                for (int j = 0; j < n_kv; ++j, ++g) {
+                    ptx::mbar_wait(bar(KR_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(KR_FULL), kTileBytes);
+                    load_tile(kr_addr, &tmKr, bar(KR_FULL), j * kBlk, h, b);
+                    ptx::mbar_wait(bar(VR_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(VR_FULL), kTileBytes);
+                    load_tile(vr_addr, &tmVr, bar(VR_FULL), j * kBlk, h, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============ producer: K_T per kv block ============
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+                const int bh = item / args.n_q;
+                const int h = bh % args.H, b = bh / args.H;
+                for (int j = 0; j < n_kv; ++j, ++g) {
+                    ptx::mbar_wait(bar(KT_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(KT_FULL), kTileBytes);
+                    load_tile(kt_addr, &tmKt, bar(KT_FULL), j * kBlk, h, b);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ============ MMA issuer ============
+        if (lane == 0) {
+            constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
+            constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
+            auto issue_s = [&](uint32_t g) {         // S(g) = Q K^T
+                const int it = g / n_kv, j = g - it * n_kv;
+                if (j == 0) ptx::mbar_wait(bar(QDO_FULL0 + (it & 1)), (it >> 1) & 1);
+                ptx::mbar_wait(bar(KR_FULL), g & 1);
+                ptx::tc_fence_after();
+                mma_rr(tmem_base + (g & 1u) * kBlk, qr_addr + (it & 1) * kTileBytes, kr_addr, idesc_s);
+                ptx::umma_commit(bar(KR_EMPTY));
+                ptx::umma_commit(bar(S_FULL0 + (g & 1u)));
+            };
+            auto issue_dp = [&](uint32_t g) {        // dP(g) = dO V^T
+                const int it = g / n_kv, j = g - it * n_kv;
+                ptx::mbar_wait(bar(VR_FULL), g & 1);
+                ptx::tc_fence_after();
+                mma_rr(tm_dp, dor_addr + (it & 1) * kTileBytes, vr_addr, idesc_s);
+                ptx::umma_commit(bar(VR_EMPTY));
+                ptx::umma_commit(bar(DP_FULL));
+                if (j == n_kv - 1) ptx::umma_commit(bar(QDO_EMPTY0 + (it & 1)));
+            };
+            if (G > 0) { issue_s(0); issue_dp(0); }
+            if (G > 1) issue_s(1);
+            for (uint32_t g = 0; g < G; ++g) {
+                const int j = g % n_kv;
+                ptx::mbar_wait(bar(DS_READY), g & 1);
+                ptx::mbar_wait(bar(KT_FULL), g & 1);
+                ptx::tc_fence_after();
+                mma_ts(tm_dq, tm_dp, kt_addr, idesc_ts, j != 0);                           // dQ += dS K
+                ptx::umma_commit(bar(KT_EMPTY));
+                if (j == n_kv - 1) ptx::umma_commit(bar(ACC_DONE));
+                if (g + 1 < G) issue_dp(g + 1);
+                if (g + 2 < G) issue_s(g + 2);
+            }
+        }
+    } else if (warp >= 4) {
+        // ============ softmax / dS warps: thread = q row ============
+        const int wq = warp & 3;
+        const int tid = wq * 32 + lane;
+        const uint32_t lane_off = uint32_t(wq * 32) << 16;
+        const float c = args.c, scale = args.scale;
+        uint32_t g = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+            const int mt = item % args.n_q;
+            const int bh = item / args.n_q;
+            const int h = bh % args.H, b = bh / args.H;
+            const int sq = mt * kBlk + tid;
+            const bool live = sq < args.Sq;
+            const float L = live ? __ldg(args.lse + (size_t)bh * args.Sq + sq) : INFINITY;
+            const float Dr = live ? __ldg(args.dsum + (size_t)bh * args.Sq + sq) : 0.0f;
+            for (int j = 0; j < n_kv; ++j, ++g) {
+                const uint32_t buf = g & 1u;
+                ptx::mbar_wait(bar(S_FULL0 + buf), (g >> 1) & 1);
+                ptx::tc_fence_after();
+                float p[kBlk];
+                const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    ptx::tmem_ld_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[ch * 32]));
+                ptx::tmem_ld_wait();
+                const int kv_left = args.Skv - j * kBlk;
+#pragma unroll
+                for (int k = 0; k < kBlk; ++k) {
+                    const float e = ptx::ex2(fmaf(p[k], c, -L));
+                    p[k] = (k < kv_left) ? e : 0.0f;
+                }
+                ptx::mbar_wait(bar(DP_FULL), g & 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t dp[32];
+                    ptx::tmem_ld_32x32(tm_dp + lane_off + ch * 32, dp);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        dp[k] = cvt_tf32(p[ch * 32 + k] * (__uint_as_float(dp[k]) - Dr) * scale);
+                    ptx::tmem_st_32x32(tm_dp + lane_off + ch * 32, dp);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar(DS_READY));
+            }
+            // ---- epilogue: dQ rows of this q tile ----
+            ptx::mbar_wait(bar(ACC_DONE), it & 1);
+            ptx::tc_fence_after();
+            store_acc_row(tm_dq + lane_off, args.dq + (((size_t)b * args.Sq + (live ? sq : 0)) * args.H + h) * kD, live);
+            ptx::tc_fence_before();
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 3) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// D[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]: 16 lanes x float4 per (b,s,h) row
+__global__ void __launch_bounds__(256) attn_dsum_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
+                                                        float* __restrict__ dsum, int B, int H, int Sq) {
+    const int64_t rows = (int64_t)B * Sq * H;
+    const int sub = threadIdx.x & 15;
+    const int64_t step = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    // r0 is warp-uniform up to the +1 of the upper half-warp, so every lane runs the same trip count
+    for (int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 4; r0 < rows; r0 += step) {
+        const int64_t r = r0 + ((threadIdx.x >> 4) & 1);
+        const bool ok = r < rows;
+        float v = 0.0f;
+        if (ok) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(d_o + r * kD) + sub);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(o + r * kD) + sub);
+            // dO rounded exactly as the tensor core will see it: D then equals sum_t P dP for the dP the
+            // MMA computes, so the common-mode part of its TF32 error cancels in dS = P o (dP - D)
+            v = __uint_as_float(cvt_tf32(a.x)) * bb.x + __uint_as_float(cvt_tf32(a.y)) * bb.y +
+                __uint_as_float(cvt_tf32(a.z)) * bb.z + __uint_as_float(cvt_tf32(a.w)) * bb.w;
+        }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (ok && sub == 0) {
+            const int h = (int)(r % H);
+            const int64_t bs = r / H;
+            const int s = (int)(bs % Sq), b = (int)(bs / Sq);
+            dsum[((size_t)b * H + h) * Sq + s] = v;
+        }
+    }
+}
+
+// p[bh, s, t] = exp2(log2(e) * x[bh, s, t] - L[bh, s]) in place (x = scaled scores): debug view of P
+__global__ void __launch_bounds__(256) attn_scores_from_lse_kernel(float* __restrict__ p, const float* __restrict__ lse,
+                                                                   int64_t rows, int64_t cols) {
+    const int64_t n = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = exp2f(fmaf(p[i], 1.4426950408889634f, -lse[i / cols]));
+}
+
+}  // namespace
+
+size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq) { return (size_t)B * H * Sq * sizeof(float); }
+
+int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream) {
+    attn_scores_from_lse_kernel<<<bw_grid((size_t)(rows * cols), 256), 256, 0, stream>>>(p, lse, rows, cols);
+    count_launch();
+    return check_launch("attn_scores_from_lse_kernel");
+}
+
+int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
+                    float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
+                    cudaStream_t stream) {
+    NPM_REQUIRE(o != nullptr, "mha_core_bwd: the fused path needs the forward output o");
+    NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
+                aligned16(dk) && aligned16(dv), "mha_core_bwd: pointers must be 16-byte aligned");
+    const uint64_t HD = (uint64_t)H * kD;
+    CUtensorMap tQr, tQt, tKr, tKt, tVr, tDOr, tDOt;
+    int rc;
+    if ((rc = make_tensor_map_4d(&tQr, q, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tQt, q, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, true))) return rc;
+    if ((rc = make_tensor_map_4d(&tKr, k, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tKt, k, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBlk, true, true))) return rc;
+    if ((rc = make_tensor_map_4d(&tVr, v, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tDOr, d_o, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tDOt, d_o, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, true))) return rc;
+
+    BwdArgs a;
+    a.B = (int)B; a.H = (int)H; a.Sq = (int)Sq; a.Skv = (int)Skv;
+    a.n_q = (int)((Sq + kBlk - 1) / kBlk);
+    a.n_kv = (int)((Skv + kBlk - 1) / kBlk);
+    a.c = (float)(1.4426950408889634 / sqrt((double)kD));
+    a.scale = (float)(1.0 / sqrt((double)kD));
+    a.lse = lse; a.dsum = dsum; a.dq = dq; a.dk = dk; a.dv = dv;
+
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+        if (e != cudaSuccess) { set_error("attn_bwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+        configured = true;
+    }
+    {
+        const int64_t rows = B * Sq * H;
+        int grid = (int)((rows * 16 + 255) / 256);
+        const int cap = num_sms() * 8;
+        if (grid > cap) grid = cap;
+        attn_dsum_kernel<<<grid, 256, 0, stream>>>(d_o, o, dsum, (int)B, (int)H, (int)Sq);
+        count_launch();
+        if ((rc = check_launch("attn_dsum_kernel"))) return rc;
+    }
+    {
+        const int64_t items = B * H * a.n_kv;
+        NPM_REQUIRE(items < (1ll << 30), "mha_core_bwd: too many tiles");
+        a.total_items = (int)items;
+        const int grid = (int)(items < num_sms() ? items : num_sms());
+        attn_bwd_dkdv_kernel<<<grid, kThreads, kKvSmem, stream>>>(tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        count_launch();
+        if ((rc = check_launch("attn_bwd_dkdv_kernel"))) return rc;
+    }
+    {
+        const int64_t items = B * H * a.n_q;
+        NPM_REQUIRE(items < (1ll << 30), "mha_core_bwd: too many tiles");
+        a.total_items = (int)items;
+        const int grid = (int)(items < num_sms() ? items : num_sms());
+        attn_bwd_dq_kernel<<<grid, kThreads, kDqSmem, stream>>>(tQr, tDOr, tKr, tKt, tVr, a);
+        count_launch();
+        if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
+    }
+    return NPM_OK;
+}
+
+}  // namespace npm

@@ -1,0 +1,341 @@
+// attn_fwd.cu — fused attention core forward on tcgen05 / TMEM / TMA (TF32, head dim 64).
+//
+//   o[b,s,h,:] = softmax_t( q[b,s,h,:] . k[b,t,h,:] / sqrt(dk) ) v[b,t,h,:]
+//
+// replaces the reference's materialised  einsum → Softmax → einsum  chain
+// (layers/attentions.py:103-112): the [B,H,Sq,Skv] score tensor never exists in HBM; only the
+// per-row log-sum-exp is saved for the backward pass.
+//
+// One persistent CTA per SM; a work item is (batch, head, 128 query rows).  Per 128-row KV block:
+//   warp 0   TMA producer: Q tile (double buffered across items) and the K ring
+//   warp 1   TMA producer: the V ring (landed with 32-byte swizzle atoms = an MN-major B operand)
+//   warp 2   MMA issuer  : S = Q K^T          (tcgen05.mma kind::tf32, A/B from smem, D in TMEM)
+//                          O += P V           (A = P read straight from TMEM, B = V from smem)
+//   warps 4-7 softmax    : thread t owns query row t = TMEM lane t: tcgen05.ld the S row, online
+//                          max / exp2 / sum, write P back over S with tcgen05.st.  The running
+//                          maximum is only raised when it grew by more than 2^8 (the O accumulator
+//                          is then rescaled in TMEM), so the rescale is off the critical path.
+// S/P is double buffered in TMEM so that S(j+1) is computed while the softmax of block j runs.
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace npm {
+
+int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                       uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, bool round_tf32,
+                       bool atom32b);
+
+namespace {
+
+constexpr int kBM = 128;          // query rows per work item
+constexpr int kBN = 128;          // kv rows per block
+constexpr int kD  = 64;           // head dim (dk = dv)
+constexpr int kTileBytes = kBM * kD * 4;     // 32 KB: two {32 d, 128 rows} boxes of 16 KB
+constexpr int kChunkBytes = 16384;
+constexpr int kKS = 2, kVS = 2;              // K / V ring depth
+constexpr int kSmemBytes = (2 + kKS + kVS) * kTileBytes + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int kThreads = 256;
+constexpr float kRescaleThreshold = 8.0f;    // log2 units
+
+struct FwdArgs {
+    int B, H, Sq, Skv;
+    int q_tiles, n_kv, total_items;
+    float c;                 // log2(e) / sqrt(dk)
+    float* o;                // [B, Sq, H, 64]
+    float* lse;              // [B, H, Sq]  log2-domain: m + log2(sum)
+};
+
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+
+    const uint32_t q_addr = base_addr;                              // 2 x 32 KB
+    const uint32_t k_addr = q_addr + 2 * kTileBytes;                // kKS x 32 KB
+    const uint32_t v_addr = k_addr + kKS * kTileBytes;              // kVS x 32 KB
+    const uint32_t bar_addr = v_addr + kVS * kTileBytes;
+    auto q_full   = [&](int i) { return bar_addr + 8u * i; };
+    auto q_empty  = [&](int i) { return bar_addr + 8u * (2 + i); };
+    auto k_full   = [&](int i) { return bar_addr + 8u * (4 + i); };
+    auto k_empty  = [&](int i) { return bar_addr + 8u * (4 + kKS + i); };
+    auto v_full   = [&](int i) { return bar_addr + 8u * (4 + 2 * kKS + i); };
+    auto v_empty  = [&](int i) { return bar_addr + 8u * (4 + 2 * kKS + kVS + i); };
+    const uint32_t misc = bar_addr + 8u * (4 + 2 * kKS + 2 * kVS);
+    auto s_full   = [&](int i) { return misc + 8u * i; };
+    auto p_ready  = [&](int i) { return misc + 8u * (2 + i); };
+    const uint32_t o_done = misc + 8u * 4;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
+        base_ptr + (2 + kKS + kVS) * kTileBytes + 8 * (4 + 2 * kKS + 2 * kVS + 5));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmK);
+        ptx::prefetch_tensormap(&tmV);
+    }
+    if (warp == 3) {
+        if (lane == 0) {
+            for (int i = 0; i < 2; ++i) { ptx::mbar_init(q_full(i), 1); ptx::mbar_init(q_empty(i), 1); }
+            for (int i = 0; i < kKS; ++i) { ptx::mbar_init(k_full(i), 1); ptx::mbar_init(k_empty(i), 1); }
+            for (int i = 0; i < kVS; ++i) { ptx::mbar_init(v_full(i), 1); ptx::mbar_init(v_empty(i), 1); }
+            for (int i = 0; i < 2; ++i) { ptx::mbar_init(s_full(i), 1); ptx::mbar_init(p_ready(i), 128); }
+            ptx::mbar_init(o_done, 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + 256;          // S/P buffers at columns [0,128) and [128,256)
+
+    const int n_kv = args.n_kv;
+
+    if (warp == 0) {
+        // ===================== Q + K producer =====================
+        if (lane == 0) {
+            uint32_t gk = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+                const int mt = item % args.q_tiles;
+                const int bh = item / args.q_tiles;
+                const int h = bh % args.H, b = bh / args.H;
+                const int qb = it & 1;
+                ptx::mbar_wait(q_empty(qb), ((it >> 1) & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(q_full(qb), kTileBytes);
+                ptx::tma_load_4d(q_addr + qb * kTileBytes, &tmQ, q_full(qb), 0, mt * kBM, h, b);
+                ptx::tma_load_4d(q_addr + qb * kTileBytes + kChunkBytes, &tmQ, q_full(qb), 32, mt * kBM, h, b);
+                for (int j = 0; j < n_kv; ++j, ++gk) {
+                    const int st = gk % kKS;
+                    ptx::mbar_wait(k_empty(st), ((gk / kKS) & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(k_full(st), kTileBytes);
+                    ptx::tma_load_4d(k_addr + st * kTileBytes, &tmK, k_full(st), 0, j * kBN, h, b);
+                    ptx::tma_load_4d(k_addr + st * kTileBytes + kChunkBytes, &tmK, k_full(st), 32, j * kBN, h, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= V producer =======================
+        if (lane == 0) {
+            uint32_t gv = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+                const int bh = item / args.q_tiles;
+                const int h = bh % args.H, b = bh / args.H;
+                for (int j = 0; j < n_kv; ++j, ++gv) {
+                    const int st = gv % kVS;
+                    ptx::mbar_wait(v_empty(st), ((gv / kVS) & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(v_full(st), kTileBytes);
+                    ptx::tma_load_4d(v_addr + st * kTileBytes, &tmV, v_full(st), 0, j * kBN, h, b);
+                    ptx::tma_load_4d(v_addr + st * kTileBytes + kChunkBytes, &tmV, v_full(st), 32, j * kBN, h, b);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBM, kBN, false, false);
+            constexpr uint32_t idesc_pv = ptx::umma_idesc_tf32(kBM, kD, false, true);
+            const uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
+            const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, kChunkBytes, 512);
+            const int my_items = (args.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const uint32_t total_blocks = (uint32_t)my_items * (uint32_t)n_kv;
+
+            // S(gs): the score block of global index gs (item gs / n_kv, kv block gs % n_kv)
+            auto issue_s = [&](uint32_t gs) {
+                const int it = gs / n_kv, j = gs - it * n_kv;
+                const int qb = it & 1;
+                if (j == 0) ptx::mbar_wait(q_full(qb), (it >> 1) & 1);
+                const int st = gs % kKS;
+                ptx::mbar_wait(k_full(st), (gs / kKS) & 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (gs & 1u) * kBN;
+                const uint32_t qa = q_addr + qb * kTileBytes, ka = k_addr + st * kTileBytes;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t da = ptx::umma_desc(desc_k, qa + kb * kChunkBytes + kk * 32);
+                        const uint64_t db = ptx::umma_desc(desc_k, ka + kb * kChunkBytes + kk * 32);
+                        ptx::umma_tf32(d_tmem, da, db, idesc_s, (kb | kk) != 0 ? 1u : 0u);
+                    }
+                ptx::umma_commit(k_empty(st));
+                ptx::umma_commit(s_full(gs & 1u));
+                if (j == n_kv - 1) ptx::umma_commit(q_empty(qb));
+            };
+
+            if (total_blocks > 0) issue_s(0);
+            for (uint32_t g = 0; g < total_blocks; ++g) {
+                if (g + 1 < total_blocks) issue_s(g + 1);
+                const int j = g % n_kv;
+                const int st = g % kVS;
+                ptx::mbar_wait(p_ready(g & 1u), (g >> 1) & 1);
+                ptx::mbar_wait(v_full(st), (g / kVS) & 1);
+                ptx::tc_fence_after();
+                const uint32_t p_tmem = tmem_base + (g & 1u) * kBN;
+                const uint32_t va = v_addr + st * kTileBytes;
+#pragma unroll
+                for (int kk = 0; kk < kBN / 8; ++kk) {
+                    const uint64_t db = ptx::umma_desc(desc_mn, va + kk * 1024);
+                    ptx::umma_tf32_ts(tmem_o, p_tmem + kk * 8, db, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(v_empty(st));
+                ptx::umma_commit(o_done);
+            }
+        }
+    } else if (warp >= 4) {
+        // ========================= softmax =========================
+        const int wq = warp & 3;                         // TMEM lane quarter this warp may access
+        const int row = wq * 32 + lane;                  // query row within the tile
+        const uint32_t lane_off = uint32_t(wq * 32) << 16;
+        const float c = args.c;
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+            const int mt = item % args.q_tiles;
+            const int bh = item / args.q_tiles;
+            const int h = bh % args.H, b = bh / args.H;
+            float m_ref = -INFINITY, l = 0.0f;
+            for (int j = 0; j < n_kv; ++j, ++g) {
+                const uint32_t buf = g & 1u;
+                ptx::mbar_wait(s_full(buf), (g >> 1) & 1);
+                ptx::tc_fence_after();
+                float s[kBN];
+                const uint32_t s_tmem = tmem_base + lane_off + buf * kBN;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    ptx::tmem_ld_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]));
+                ptx::tmem_ld_wait();
+                const int kv_left = args.Skv - j * kBN;
+                if (kv_left < kBN) {
+#pragma unroll
+                    for (int k = 0; k < kBN; ++k)
+                        if (k >= kv_left) s[k] = -INFINITY;
+                }
+                float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+                for (int k = 4; k < kBN; k += 4) {
+                    mx0 = fmaxf(mx0, s[k]); mx1 = fmaxf(mx1, s[k + 1]);
+                    mx2 = fmaxf(mx2, s[k + 2]); mx3 = fmaxf(mx3, s[k + 3]);
+                }
+                const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+                // PV(g-1) must have landed in O before O is rescaled (and, trivially, before P(g) is used)
+                if (g > 0) ptx::mbar_wait(o_done, (g - 1) & 1);
+                const bool need = mb > m_ref + kRescaleThreshold;
+                if (__any_sync(0xffffffffu, need)) {
+                    float alpha = 1.0f;
+                    if (need) {
+                        alpha = ptx::ex2(m_ref - mb);      // 0 on the first block (m_ref = -inf)
+                        m_ref = mb;
+                        l *= alpha;
+                    }
+                    if (j > 0) {
+                        ptx::tc_fence_after();
+                        uint32_t o[kD];
+                        ptx::tmem_ld_32x32(tmem_o + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+                        ptx::tmem_ld_32x32(tmem_o + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < kD; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                        ptx::tmem_st_32x32(tmem_o + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+                        ptx::tmem_st_32x32(tmem_o + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+                    }
+                }
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < kBN; k += 4) {
+                    const uint32_t p0 = cvt_tf32(ptx::ex2(fmaf(s[k], c, -m_ref)));
+                    const uint32_t p1 = cvt_tf32(ptx::ex2(fmaf(s[k + 1], c, -m_ref)));
+                    const uint32_t p2 = cvt_tf32(ptx::ex2(fmaf(s[k + 2], c, -m_ref)));
+                    const uint32_t p3 = cvt_tf32(ptx::ex2(fmaf(s[k + 3], c, -m_ref)));
+                    l0 += __uint_as_float(p0); l1 += __uint_as_float(p1);
+                    l2 += __uint_as_float(p2); l3 += __uint_as_float(p3);
+                    s[k] = __uint_as_float(p0); s[k + 1] = __uint_as_float(p1);
+                    s[k + 2] = __uint_as_float(p2); s[k + 3] = __uint_as_float(p3);
+                }
+                l += (l0 + l1) + (l2 + l3);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    ptx::tmem_st_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]));
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(p_ready(buf));
+            }
+            // ---- epilogue: O / l → global, log-sum-exp → saved ----
+            ptx::mbar_wait(o_done, (g - 1) & 1);
+            ptx::tc_fence_after();
+            uint32_t o[kD];
+            ptx::tmem_ld_32x32(tmem_o + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+            ptx::tmem_ld_32x32(tmem_o + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            const int sq = mt * kBM + row;
+            if (sq < args.Sq) {
+                const float inv = 1.0f / l;
+                float4* dst = reinterpret_cast<float4*>(args.o + (((size_t)b * args.Sq + sq) * args.H + h) * kD);
+#pragma unroll
+                for (int k = 0; k < kD / 4; ++k)
+                    dst[k] = make_float4(__uint_as_float(o[4 * k]) * inv, __uint_as_float(o[4 * k + 1]) * inv,
+                                         __uint_as_float(o[4 * k + 2]) * inv, __uint_as_float(o[4 * k + 3]) * inv);
+                args.lse[((size_t)b * args.H + h) * args.Sq + sq] = m_ref + ptx::lg2(l);
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 3) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    return dk == kD && dv == kD && B > 0 && H > 0 && Sq > 0 && Skv > 0 && B < 65536 && H < 65536 &&
+           Sq < (1ll << 30) && Skv < (1ll << 30);
+}
+
+int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
+                    int64_t Sq, int64_t Skv, cudaStream_t stream) {
+    NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "mha_core_fwd: pointers must be 16-byte aligned");
+    CUtensorMap tmQ, tmK, tmV;
+    int rc;
+    const uint64_t HD = (uint64_t)H * kD;
+    if ((rc = make_tensor_map_4d(&tmQ, q, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBM, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tmK, k, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBN, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tmV, v, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBN, true, true))) return rc;
+    FwdArgs a;
+    a.B = (int)B; a.H = (int)H; a.Sq = (int)Sq; a.Skv = (int)Skv;
+    a.q_tiles = (int)((Sq + kBM - 1) / kBM);
+    a.n_kv = (int)((Skv + kBN - 1) / kBN);
+    const int64_t items = B * H * a.q_tiles;
+    NPM_REQUIRE(items < (1ll << 30), "mha_core_fwd: too many tiles");
+    a.total_items = (int)items;
+    a.c = (float)(1.4426950408889634 / sqrt((double)kD));
+    a.o = o; a.lse = lse;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) { set_error("attn_fwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+        configured = true;
+    }
+    const int grid = (int)(items < num_sms() ? items : num_sms());
+    attn_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
+    count_launch();
+    return check_launch("attn_fwd_kernel");
+}
+
+}  // namespace npm

@@ -461,6 +461,10 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     }
 
     // ---- tensor maps ----
+    // Probe knob: land K-major operands with the 32-byte-atom swizzle too and read them through a
+    // SWIZZLE_128B_BASE32B descriptor (the attention kernels use one smem image of a [rows, d] tile
+    // both as a K-major and as an MN-major operand).
+    static const bool k_atom32 = env_flag("NPM_KMAJOR_ATOM32", false);
     CUtensorMap tmA, tmB, tmC;
     int rc;
     const uint64_t M = d.m, N = d.n, K = d.k;
@@ -468,7 +472,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     if (!a_mn) {
         const uint64_t ld = d.a_rs;
         const uint64_t s2 = bs(nb1, d.a_bs1, ld * M), s3 = bs(nb2, d.a_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockK, kBlockM, round_ab, false);
+        rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockK, kBlockM, round_ab, k_atom32);
     } else {
         const uint64_t ld = d.a_cs;
         const uint64_t s2 = bs(nb1, d.a_bs1, ld * K), s3 = bs(nb2, d.a_bs2, s2 * nb1);
@@ -478,7 +482,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     if (!b_mn) {
         const uint64_t ld = d.b_cs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * N), s3 = bs(nb2, d.b_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, bn, round_ab, false);
+        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, bn, round_ab, k_atom32);
     } else {
         const uint64_t ld = d.b_rs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * K), s3 = bs(nb2, d.b_bs2, s2 * nb1);
@@ -511,7 +515,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     //                    512 B apart (SBO).
     static const uint32_t mn_lbo = getenv("NPM_MN_LBO") ? (uint32_t)atoi(getenv("NPM_MN_LBO")) : 4096u;
     static const uint32_t mn_sbo = getenv("NPM_MN_SBO") ? (uint32_t)atoi(getenv("NPM_MN_SBO")) : 512u;
-    const uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
+    const uint64_t desc_k  = k_atom32 ? ptx::umma_desc_base(1, 16, 1024) : ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
     const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, mn_lbo, mn_sbo);
     args.desc_a = a_mn ? desc_mn : desc_k;
     args.desc_b = b_mn ? desc_mn : desc_k;

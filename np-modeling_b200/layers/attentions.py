@@ -164,7 +164,8 @@ class MultiHeadAttention(layer.StatefulLayer):
         """softmax probabilities [B, H, Sq, Skv] (attentions.py:108-111)."""
         b, sq, h, _ = self._q.shape
         out = device.empty((b, h, sq, self._seq_len_kv))
-        C.npm_mha_core_scores(self._saved.data_ptr(), out.ptr, b, h, sq, self._seq_len_kv, device.stream())
+        C.npm_mha_core_scores(self._q.ptr, self._k.ptr, self._saved.data_ptr(), out.ptr, b, h, sq, self._seq_len_kv,
+                              self._key_dim, self._value_dim, device.stream())
         return out
 
     @property

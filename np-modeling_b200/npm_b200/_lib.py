@@ -75,7 +75,7 @@ SIGNATURES = {
     'npm_mha_core_bwd_scratch_bytes': (c_size_t, [I64] * 6),
     'npm_mha_core_fwd': (c_int, [P, P, P, P, P] + [I64] * 6 + [P]),
     'npm_mha_core_bwd': (c_int, [P] * 10 + [I64] * 6 + [P]),
-    'npm_mha_core_scores': (c_int, [P, P, I64, I64, I64, I64, P]),
+    'npm_mha_core_scores': (c_int, [P, P, P, P] + [I64] * 6 + [P]),
     'npm_conv2d_workspace': (c_size_t, [I64, I64, I64, I64, I64, I]),
     'npm_conv2d_fwd': (c_int, [P, P, P, P, I64, I64, I64, I64, I64, I, I, P, P]),
     'npm_conv2d_bwd_dx': (c_int, [P, P, P, I64, I64, I64, I64, I64, I, P, P]),

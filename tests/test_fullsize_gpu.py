@@ -48,12 +48,17 @@ def test_linear_cfg5_checksums(precision):
     close(g['_b'], dy64.sum(0), rtol=1e-4, atol=1e-2)
 
 
-def test_attention_core_cfg5_properties():
+@pytest.mark.parametrize('precision', ['3xtf32', 'tf32'])
+def test_attention_core_cfg5_properties(precision):
     """B8 H16 S1024 dk64: probabilities are row-stochastic; a constant value vector passes through
-    unchanged; dV checksum equals the checksum of dO (columns of P^T sum the rows of P)."""
+    unchanged; dV checksum equals the checksum of dO (columns of P^T sum the rows of P).
+    'tf32' runs the fused tcgen05 attention kernels (attn_fwd.cu / attn_bwd.cu), '3xtf32' the
+    batched-GEMM + softmax chain."""
     import torch
+    import npm_b200
     from npm_b200 import device
     from npm_b200._lib import C
+    npm_b200.set_precision(precision)
     B, H, S, dk = 8, 16, 1024, 64
     g = torch.Generator(device='cuda').manual_seed(0)
     q = torch.randn(B, S, H, dk, generator=g, device='cuda')
@@ -64,11 +69,13 @@ def test_attention_core_cfg5_properties():
     st = device.stream()
     C.npm_mha_core_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), saved.data_ptr(), B, H, S, S, dk, dk, st)
     torch.cuda.synchronize()
-    assert torch.allclose(o, v, rtol=1e-4, atol=1e-4)                 # sum_t P[s,t] v = v
+    tf32 = precision == 'tf32'
+    # sum_t P[s,t] v = v (in TF32 mode v itself is rounded to 10 mantissa bits on load)
+    assert torch.allclose(o, v, rtol=1e-3 if tf32 else 1e-4, atol=1e-4)
     p = torch.empty(B, H, S, S, device='cuda')
-    C.npm_mha_core_scores(saved.data_ptr(), p.data_ptr(), B, H, S, S, st)
+    C.npm_mha_core_scores(q.data_ptr(), k.data_ptr(), saved.data_ptr(), p.data_ptr(), B, H, S, S, dk, dk, st)
     rows = p.sum(-1)
-    assert torch.allclose(rows, torch.ones_like(rows), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(rows, torch.ones_like(rows), rtol=1e-5, atol=2e-3 if tf32 else 1e-5)
     assert float(p.min()) >= 0.0
     # backward: dV[b,t,h,:] = sum_s P[s,t] dO[s]; summing over t gives sum_s dO[s]
     do = torch.randn(B, S, H, dk, generator=g, device='cuda')
@@ -77,7 +84,7 @@ def test_attention_core_cfg5_properties():
     C.npm_mha_core_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), saved.data_ptr(),
                        dq.data_ptr(), dk_.data_ptr(), dv.data_ptr(), scratch.data_ptr(), B, H, S, S, dk, dk, st)
     torch.cuda.synchronize()
-    assert torch.allclose(dv.sum(1), do.sum(1), rtol=1e-3, atol=2e-3)
+    assert torch.allclose(dv.sum(1), do.sum(1), rtol=1e-3, atol=6e-2 if tf32 else 2e-3)   # tf32: 1024 operand roundings of 2^-11 each
     # softmax backward output sums to zero over t, so dQ for constant-over-t K... use the row identity:
     # sum_t dS[s,t] = 0  =>  with k constant over t, dQ = 0.  (checked on a fresh call)
     kc = torch.randn(1, 1, H, dk, generator=g, device='cuda').expand(B, S, H, dk).contiguous()
@@ -85,7 +92,7 @@ def test_attention_core_cfg5_properties():
     C.npm_mha_core_bwd(q.data_ptr(), kc.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), saved.data_ptr(),
                        dq.data_ptr(), dk_.data_ptr(), dv.data_ptr(), scratch.data_ptr(), B, H, S, S, dk, dk, st)
     torch.cuda.synchronize()
-    assert float(dq.abs().max()) < 1e-4
+    assert float(dq.abs().max()) < (2e-3 if tf32 else 1e-4)
 
 
 def test_layernorm_dropout_cfg5_properties():
@@ -152,8 +159,10 @@ def test_adam_cfg5_layer_sized_update_matches_closed_form():
 
 def test_tf32_mode_stated_tolerance():
     """bench.py's default contraction mode is ONE tcgen05 kind::tf32 pass with operands rounded to
-    nearest by TMA.  Its stated tolerance against the float64 oracle: every tensor within 2e-3 of
-    its own max magnitude (10-bit mantissas); 3xTF32 on the same inputs is >= 30x tighter."""
+    nearest by TMA.  Its stated tolerance against the float64 oracle: relative Frobenius error of
+    every tensor below 2e-3 (10-bit mantissas; a max-norm bound would be ill-posed here: a 1e-4
+    perturbation of a pre-activation that sits at zero flips its ReLU gate, activations.py:19, and
+    moves one gradient element by O(1)); 3xTF32 on the same inputs is >= 30x tighter."""
     import npm_b200
     from layers import TransformerDecoder
     from oracle import np_oracle as O
@@ -186,8 +195,50 @@ def test_tf32_mode_stated_tolerance():
         rec = Recorder()
         dq, dkv = layer(dy, backprop=True, optimizer_=rec)
         (rdq, rdkv), _ = O.decoder_bwd(p, cache, dy, True)
-        errs[mode] = max(np.abs(out - ref).max() / np.abs(ref).max(), np.abs(np.asarray(dq) - rdq).max() / np.abs(rdq).max(),
-                         np.abs(np.asarray(dkv) - rdkv).max() / np.abs(rdkv).max())
+        fro = lambda a, r: float(np.linalg.norm(np.asarray(a, dtype=np.float64) - r) / np.linalg.norm(r))
+        errs[mode] = max(fro(out, ref), fro(dq, rdq), fro(dkv, rdkv))
     assert errs['tf32'] < 2e-3, errs
-    assert errs['3xtf32'] < 2e-5, errs
+    assert errs['3xtf32'] < 1e-5, errs
     assert errs['3xtf32'] * 30 < errs['tf32'], errs
+
+
+@pytest.mark.parametrize('B,H,Sq,Skv', [(1, 1, 128, 128), (2, 4, 256, 384), (2, 3, 200, 300), (1, 2, 1, 130), (3, 2, 129, 64)])
+def test_fused_attention_vs_oracle(B, H, Sq, Skv):
+    """The fused tcgen05 attention kernels (TF32 mode, dk = dv = 64) against the float64 oracle
+    (oracle/np_oracle.py softmax / closed-form softmax backward), ragged sequence lengths included.
+    Stated TF32 tolerance: within 2e-3 of each tensor's max magnitude."""
+    import torch
+    import npm_b200
+    from npm_b200 import device
+    from npm_b200._lib import C
+    from oracle import np_oracle as O
+    npm_b200.set_precision('tf32')
+    D = 64
+    rng = np.random.default_rng(B * 1000 + Sq)
+    q, do = (rng.standard_normal((B, Sq, H, D)).astype(np.float32) for _ in range(2))
+    k, v = (rng.standard_normal((B, Skv, H, D)).astype(np.float32) for _ in range(2))
+    tq, tk, tv, tdo = (torch.from_numpy(a).cuda() for a in (q, k, v, do))
+    o = torch.full((B, Sq, H, D), float('nan'), device='cuda')
+    st = device.stream()
+    assert C.npm_mha_core_saved_bytes(B, H, Sq, Skv, D, D) == B * H * Sq * 4       # only the log-sum-exp is saved
+    saved = device.workspace(C.npm_mha_core_saved_bytes(B, H, Sq, Skv, D, D))
+    C.npm_mha_core_fwd(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), o.data_ptr(), saved.data_ptr(), B, H, Sq, Skv, D, D, st)
+    dq, dk, dv = (torch.full(s, float('nan'), device='cuda') for s in ((B, Sq, H, D), (B, Skv, H, D), (B, Skv, H, D)))
+    scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes(B, H, Sq, Skv, D, D))
+    C.npm_mha_core_bwd(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), o.data_ptr(), tdo.data_ptr(), saved.data_ptr(),
+                       dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), scratch.data_ptr(), B, H, Sq, Skv, D, D, st)
+    p = torch.empty(B, H, Sq, Skv, device='cuda')
+    C.npm_mha_core_scores(tq.data_ptr(), tk.data_ptr(), saved.data_ptr(), p.data_ptr(), B, H, Sq, Skv, D, D, st)
+    torch.cuda.synchronize()
+    q64, k64, v64, do64 = (a.astype(np.float64) for a in (q, k, v, do))
+    s = np.einsum('bshd,bthd->bhst', q64, k64) / np.sqrt(D)
+    P = O.softmax_fwd(s)
+    ro = np.einsum('bhst,bthd->bshd', P, v64)
+    rdv = np.einsum('bhst,bshd->bthd', P, do64)
+    ds = O.softmax_bwd(P, np.einsum('bshd,bthd->bhst', do64, v64)) / np.sqrt(D)
+    rdq = np.einsum('bhst,bthd->bshd', ds, k64)
+    rdk = np.einsum('bhst,bshd->bthd', ds, q64)
+    for name, got, want in (('o', o, ro), ('dq', dq, rdq), ('dk', dk, rdk), ('dv', dv, rdv), ('p', p, P)):
+        got = got.cpu().numpy().astype(np.float64)
+        assert np.isfinite(got).all(), name
+        assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())
