@@ -50,6 +50,8 @@ __device__ __forceinline__ uint32_t cvt_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// fp32 → tf32 round-to-nearest on the integer ALU (kind::tf32 ignores the low 13 bits); see attn_fwd.cu
+__device__ __forceinline__ uint32_t rna_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
 __device__ __forceinline__ void bar_sync_128(int id) {
     asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
@@ -261,10 +263,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < kBlk; k += 4) {
                     const float4 l4 = L4[k >> 2];
-                    p[k]     = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k], c, -l4.x))));
-                    p[k + 1] = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k + 1], c, -l4.y))));
-                    p[k + 2] = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k + 2], c, -l4.z))));
-                    p[k + 3] = __uint_as_float(cvt_tf32(ptx::ex2(fmaf(p[k + 3], c, -l4.w))));
+                    p[k]     = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -l4.x))));
+                    p[k + 1] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 1], c, -l4.y))));
+                    p[k + 2] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 2], c, -l4.z))));
+                    p[k + 3] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 3], c, -l4.w))));
                 }
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch)
@@ -283,10 +285,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
                         const float4 d4 = D4[(ch * 32 + k) >> 2];
-                        dp[k]     = cvt_tf32(p[ch * 32 + k]     * (__uint_as_float(dp[k])     - d4.x) * scale);
-                        dp[k + 1] = cvt_tf32(p[ch * 32 + k + 1] * (__uint_as_float(dp[k + 1]) - d4.y) * scale);
-                        dp[k + 2] = cvt_tf32(p[ch * 32 + k + 2] * (__uint_as_float(dp[k + 2]) - d4.z) * scale);
-                        dp[k + 3] = cvt_tf32(p[ch * 32 + k + 3] * (__uint_as_float(dp[k + 3]) - d4.w) * scale);
+                        dp[k]     = rna_tf32(p[ch * 32 + k]     * (__uint_as_float(dp[k])     - d4.x) * scale);
+                        dp[k + 1] = rna_tf32(p[ch * 32 + k + 1] * (__uint_as_float(dp[k + 1]) - d4.y) * scale);
+                        dp[k + 2] = rna_tf32(p[ch * 32 + k + 2] * (__uint_as_float(dp[k + 2]) - d4.z) * scale);
+                        dp[k + 3] = rna_tf32(p[ch * 32 + k + 3] * (__uint_as_float(dp[k + 3]) - d4.w) * scale);
                     }
                     ptx::tmem_st_32x32(tm_dpt + lane_off + ch * 32, dp);
                 }
@@ -475,7 +477,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int k = 0; k < 32; ++k)
-                        dp[k] = cvt_tf32(p[ch * 32 + k] * (__uint_as_float(dp[k]) - Dr) * scale);
+                        dp[k] = rna_tf32(p[ch * 32 + k] * (__uint_as_float(dp[k]) - Dr) * scale);
                     ptx::tmem_st_32x32(tm_dp + lane_off + ch * 32, dp);
                 }
                 ptx::tmem_st_wait();

@@ -34,7 +34,7 @@ constexpr int kBN = 128;          // kv rows per block
 constexpr int kD  = 64;           // head dim (dk = dv)
 constexpr int kTileBytes = kBM * kD * 4;     // 32 KB: two {32 d, 128 rows} boxes of 16 KB
 constexpr int kChunkBytes = 16384;
-constexpr int kKS = 2, kVS = 2;              // K / V ring depth
+constexpr int kKS = 3, kVS = 2;              // K / V ring depth (K is consumed one block ahead of V)
 constexpr int kSmemBytes = (2 + kKS + kVS) * kTileBytes + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int kThreads = 256;
 constexpr float kRescaleThreshold = 8.0f;    // log2 units
@@ -47,11 +47,10 @@ struct FwdArgs {
     float* lse;              // [B, H, Sq]  log2-domain: m + log2(sum)
 };
 
-__device__ __forceinline__ uint32_t cvt_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// Round-to-nearest (ties away) fp32 → tf32 on the integer ALU: kind::tf32 reads only the upper 19 bits
+// of each operand, so adding half a tf32 ulp to the bit pattern is the whole rounding.  (cvt.rna.tf32
+// issues on the XU pipe, which the ex2 of the softmax already saturates.)
+__device__ __forceinline__ uint32_t rna_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -233,8 +232,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     mx2 = fmaxf(mx2, s[k + 2]); mx3 = fmaxf(mx3, s[k + 3]);
                 }
                 const float mb = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
-                // PV(g-1) must have landed in O before O is rescaled (and, trivially, before P(g) is used)
-                if (g > 0) ptx::mbar_wait(o_done, (g - 1) & 1);
                 const bool need = mb > m_ref + kRescaleThreshold;
                 if (__any_sync(0xffffffffu, need)) {
                     float alpha = 1.0f;
@@ -244,6 +241,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         l *= alpha;
                     }
                     if (j > 0) {
+                        // PV(g-1) must have landed in O before O is rescaled.  o_done is only waited on
+                        // here (rare) and in the epilogue, so PV(g-1) overlaps the exponentials of block
+                        // g.  Skipping waits is phase-safe: s_full(g) (observed above) was committed
+                        // after PV(g-2), and PV(g) cannot start before this thread's p_ready(g), so the
+                        // barrier has completed either g-1 or g phases — parity (g-1)&1 is unambiguous.
+                        ptx::mbar_wait(o_done, (g - 1) & 1);
                         ptx::tc_fence_after();
                         uint32_t o[kD];
                         ptx::tmem_ld_32x32(tmem_o + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
@@ -258,14 +261,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
                 for (int k = 0; k < kBN; k += 4) {
-                    const uint32_t p0 = cvt_tf32(ptx::ex2(fmaf(s[k], c, -m_ref)));
-                    const uint32_t p1 = cvt_tf32(ptx::ex2(fmaf(s[k + 1], c, -m_ref)));
-                    const uint32_t p2 = cvt_tf32(ptx::ex2(fmaf(s[k + 2], c, -m_ref)));
-                    const uint32_t p3 = cvt_tf32(ptx::ex2(fmaf(s[k + 3], c, -m_ref)));
-                    l0 += __uint_as_float(p0); l1 += __uint_as_float(p1);
-                    l2 += __uint_as_float(p2); l3 += __uint_as_float(p3);
-                    s[k] = __uint_as_float(p0); s[k + 1] = __uint_as_float(p1);
-                    s[k + 2] = __uint_as_float(p2); s[k + 3] = __uint_as_float(p3);
+                    const float p0 = ptx::ex2(fmaf(s[k], c, -m_ref));
+                    const float p1 = ptx::ex2(fmaf(s[k + 1], c, -m_ref));
+                    const float p2 = ptx::ex2(fmaf(s[k + 2], c, -m_ref));
+                    const float p3 = ptx::ex2(fmaf(s[k + 3], c, -m_ref));
+                    l0 += p0; l1 += p1; l2 += p2; l3 += p3;       // rounding to nearest is zero-mean: sum the exact p
+                    s[k] = __uint_as_float(rna_tf32(p0)); s[k + 1] = __uint_as_float(rna_tf32(p1));
+                    s[k + 2] = __uint_as_float(rna_tf32(p2)); s[k + 3] = __uint_as_float(rna_tf32(p3));
                 }
                 l += (l0 + l1) + (l2 + l3);
 #pragma unroll
