@@ -4,8 +4,9 @@
 // dK = dS^T Q  (layers/attentions.py:146-162, layers/activations.py:33-45) without ever
 // materialising P, dP or dS in HBM.  P is recomputed from the saved log-sum-exp:
 //     P = exp2(c * Q K^T - L),   dS = P o (dP - D) / sqrt(dk),   D = rowsum(dO o O)
-// Two persistent kernels, each shaped like the forward one (TMA producers / one MMA issuer /
-// four softmax warps owning one TMEM lane each):
+// Two persistent kernels, each shaped like the forward one: TMA producers / one MMA issuer / four
+// "exp" warps (P from S, in place in TMEM) / four "dS" warps (dS from P and dP, in place over dP),
+// every thread of the last two groups owning one TMEM lane:
 //   attn_bwd_dkdv : work item = (b, h, 128 kv rows), loops over 128-row q blocks, works on the
 //                   TRANSPOSED score tile S^T = K Q^T (TMEM lane = kv row) so that P^T and dS^T are
 //                   directly the TMEM A operands of  dV += P^T dO  and  dK += dS^T Q.
@@ -31,7 +32,7 @@ constexpr int kBlk = 128;         // rows of every tile (q rows and kv rows)
 constexpr int kD   = 64;          // head dim
 constexpr int kTileBytes  = kBlk * kD * 4;   // 32 KB
 constexpr int kChunkBytes = 16384;           // one {32 d, 128 rows} TMA box
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;       // 4 control warps + 4 exp warps + 4 dS warps
 
 struct BwdArgs {
     int B, H, Sq, Skv;
@@ -113,8 +114,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
     float* lsm = reinterpret_cast<float*>(base_ptr + 6 * kTileBytes);   // [2][128] L, then [2][128] D
     float* dsm = lsm + 2 * kBlk;
     const uint32_t bar_addr = base_addr + 6 * kTileBytes + 2 * 2 * kBlk * 4;
-    enum { KV_FULL = 0, KV_EMPTY, QR_FULL, QR_EMPTY, DOR_FULL, DOR_EMPTY, QT_FULL, QT_EMPTY, DOT_FULL, DOT_EMPTY,
-           ST_FULL0, ST_FULL1, P_READY0, P_READY1, DPT_FULL, DS_READY, ACC_DONE, NBAR };
+    enum { K_FULL = 0, K_EMPTY, V_FULL, V_EMPTY, QR_FULL, QR_EMPTY, DOR_FULL, DOR_EMPTY, QT_FULL, QT_EMPTY, DOT_FULL,
+           DOT_EMPTY, ST_FULL0, ST_FULL1, P_READY0, P_READY1, DPT_FULL, DS_READY, DV_DONE, DK_DONE, NBAR };
     auto bar = [&](int i) { return bar_addr + 8u * i; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 6 * kTileBytes + 2 * 2 * kBlk * 4 + 8 * NBAR);
 
@@ -147,6 +148,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
 
     if (warp == 0) {
         // ============ producer: K_R, V_R per item; Q_R, dO_R per q block ============
+        // K_R is released by the LAST S^T of an item (issued two blocks early) and V_R by its last
+        // dP^T, so the next item's K / V land while the current item is still finishing; V is queued
+        // behind Q_R(0) because S^T(0) of the next item is issued before V_R is free.
         if (lane == 0) {
             uint32_t g = 0;
             int it = 0;
@@ -154,14 +158,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 const int nt = item % args.n_kv;
                 const int bh = item / args.n_kv;
                 const int h = bh % args.H, b = bh / args.H;
-                ptx::mbar_wait(bar(KV_EMPTY), (it & 1) ^ 1u);
-                ptx::mbar_arrive_expect_tx(bar(KV_FULL), 2 * kTileBytes);
-                load_tile(kr_addr, &tmKr, bar(KV_FULL), nt * kBlk, h, b);
-                load_tile(vr_addr, &tmVr, bar(KV_FULL), nt * kBlk, h, b);
+                ptx::mbar_wait(bar(K_EMPTY), (it & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(bar(K_FULL), kTileBytes);
+                load_tile(kr_addr, &tmKr, bar(K_FULL), nt * kBlk, h, b);
                 for (int i = 0; i < n_q; ++i, ++g) {
                     ptx::mbar_wait(bar(QR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(QR_FULL), kTileBytes);
                     load_tile(qr_addr, &tmQr, bar(QR_FULL), i * kBlk, h, b);
+                    if (i == 0) {
+                        ptx::mbar_wait(bar(V_EMPTY), (it & 1) ^ 1u);
+                        ptx::mbar_arrive_expect_tx(bar(V_FULL), kTileBytes);
+                        load_tile(vr_addr, &tmVr, bar(V_FULL), nt * kBlk, h, b);
+                    }
                     ptx::mbar_wait(bar(DOR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(DOR_FULL), kTileBytes);
                     load_tile(dor_addr, &tmDOr, bar(DOR_FULL), i * kBlk, h, b);
@@ -192,21 +200,23 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
             auto issue_st = [&](uint32_t g) {        // S^T(g) = K Q^T
                 const int it = g / n_q, i = g - it * n_q;
-                if (i == 0) ptx::mbar_wait(bar(KV_FULL), it & 1);
+                if (i == 0) ptx::mbar_wait(bar(K_FULL), it & 1);
                 ptx::mbar_wait(bar(QR_FULL), g & 1);
                 ptx::tc_fence_after();
                 mma_rr(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s);
                 ptx::umma_commit(bar(QR_EMPTY));
                 ptx::umma_commit(bar(ST_FULL0 + (g & 1u)));
+                if (i == n_q - 1) ptx::umma_commit(bar(K_EMPTY));
             };
             auto issue_dpt = [&](uint32_t g) {       // dP^T(g) = V dO^T
                 const int it = g / n_q, i = g - it * n_q;
+                if (i == 0) ptx::mbar_wait(bar(V_FULL), it & 1);
                 ptx::mbar_wait(bar(DOR_FULL), g & 1);
                 ptx::tc_fence_after();
                 mma_rr(tm_dpt, vr_addr, dor_addr, idesc_s);
                 ptx::umma_commit(bar(DOR_EMPTY));
                 ptx::umma_commit(bar(DPT_FULL));
-                if (i == n_q - 1) ptx::umma_commit(bar(KV_EMPTY));
+                if (i == n_q - 1) ptx::umma_commit(bar(V_EMPTY));
             };
             if (G > 0) { issue_st(0); issue_dpt(0); }
             if (G > 1) issue_st(1);
@@ -217,93 +227,111 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 ptx::tc_fence_after();
                 mma_ts(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, i != 0);    // dV += P^T dO
                 ptx::umma_commit(bar(DOT_EMPTY));
+                if (i == n_q - 1) ptx::umma_commit(bar(DV_DONE));
                 ptx::mbar_wait(bar(DS_READY), g & 1);
                 ptx::mbar_wait(bar(QT_FULL), g & 1);
                 ptx::tc_fence_after();
                 mma_ts(tm_dk, tm_dpt, qt_addr, idesc_ts, i != 0);                          // dK += dS^T Q
                 ptx::umma_commit(bar(QT_EMPTY));
-                if (i == n_q - 1) ptx::umma_commit(bar(ACC_DONE));
+                if (i == n_q - 1) ptx::umma_commit(bar(DK_DONE));
                 if (g + 1 < G) issue_dpt(g + 1);
                 if (g + 2 < G) issue_st(g + 2);
             }
         }
     } else if (warp >= 4) {
-        // ============ softmax / dS warps: thread = kv row ============
+        // ============ warps 4-7: P^T = exp2(c S^T - L[q]) in place.  warps 8-11: dS^T = P^T o (dP^T - D[q]) / sqrt(dk)
+        // in place over dP^T.  Thread = kv row = TMEM lane; the two groups run one block apart, so the
+        // exponentials of block g+1 overlap the dS / dK / dP^T chain of block g. ============
+        const bool exp_group = warp < 8;
         const int wq = warp & 3;
-        const int tid = wq * 32 + lane;
+        const int tid = wq * 32 + lane;             // kv row within the tile (also: which q column's L / D this thread stages)
         const uint32_t lane_off = uint32_t(wq * 32) << 16;
         const float c = args.c, scale = args.scale;
+        const float* vec = exp_group ? args.lse : args.dsum;      // per-q-row vector this group consumes
+        float* stage = exp_group ? lsm : dsm;
+        const float pad = exp_group ? INFINITY : 0.0f;            // exp2(-inf) = 0 for padded q columns
+        const int bar_id = exp_group ? 1 : 2;
+        auto fetch = [&](int item, int i) -> float {
+            const int bh = item / args.n_kv;
+            const int qi = i * kBlk + tid;
+            return qi < args.Sq ? __ldg(vec + (size_t)bh * args.Sq + qi) : pad;
+        };
         uint32_t g = 0;
         int it = 0;
+        float next = (int)blockIdx.x < args.total_items ? fetch(blockIdx.x, 0) : 0.0f;
         for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
             const int nt = item % args.n_kv;
             const int bh = item / args.n_kv;
             const int h = bh % args.H, b = bh / args.H;
-            const float* Lrow = args.lse + (size_t)bh * args.Sq;
-            const float* Drow = args.dsum + (size_t)bh * args.Sq;
             for (int i = 0; i < n_q; ++i, ++g) {
                 const uint32_t buf = g & 1u;
-                {   // stage this q block's L and D (the columns of the transposed tile)
-                    const int qi = i * kBlk + tid;
-                    const bool live = qi < args.Sq;
-                    lsm[buf * kBlk + tid] = live ? __ldg(Lrow + qi) : INFINITY;    // exp2(-inf) = 0 for padded q
-                    dsm[buf * kBlk + tid] = live ? __ldg(Drow + qi) : 0.0f;
-                    bar_sync_128(1);
+                // stage this block's L (or D) — fetched one block ago — and prefetch the next block's
+                stage[buf * kBlk + tid] = next;
+                {
+                    int ni = i + 1, nitem = item;
+                    if (ni == n_q) { ni = 0; nitem = item + gridDim.x; }
+                    if (nitem < args.total_items) next = fetch(nitem, ni);
                 }
-                const float4* L4 = reinterpret_cast<const float4*>(lsm + buf * kBlk);
-                const float4* D4 = reinterpret_cast<const float4*>(dsm + buf * kBlk);
-                ptx::mbar_wait(bar(ST_FULL0 + buf), (g >> 1) & 1);
-                ptx::tc_fence_after();
-                float p[kBlk];
-                const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
+                bar_sync_128(bar_id);
+                const float4* V4 = reinterpret_cast<const float4*>(stage + buf * kBlk);
+                if (exp_group) {
+                    ptx::mbar_wait(bar(ST_FULL0 + buf), (g >> 1) & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                    ptx::tmem_ld_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[ch * 32]));
-                ptx::tmem_ld_wait();
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float p[64];
+                        ptx::tmem_ld_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_ld_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                for (int k = 0; k < kBlk; k += 4) {
-                    const float4 l4 = L4[k >> 2];
-                    p[k]     = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -l4.x))));
-                    p[k + 1] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 1], c, -l4.y))));
-                    p[k + 2] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 2], c, -l4.z))));
-                    p[k + 3] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 3], c, -l4.w))));
-                }
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                    ptx::tmem_st_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[ch * 32]));
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(bar(P_READY0 + buf));
-
-                ptx::mbar_wait(bar(DPT_FULL), g & 1);
-                ptx::tc_fence_after();
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t dp[32];
-                    ptx::tmem_ld_32x32(tm_dpt + lane_off + ch * 32, dp);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int k = 0; k < 32; k += 4) {
-                        const float4 d4 = D4[(ch * 32 + k) >> 2];
-                        dp[k]     = rna_tf32(p[ch * 32 + k]     * (__uint_as_float(dp[k])     - d4.x) * scale);
-                        dp[k + 1] = rna_tf32(p[ch * 32 + k + 1] * (__uint_as_float(dp[k + 1]) - d4.y) * scale);
-                        dp[k + 2] = rna_tf32(p[ch * 32 + k + 2] * (__uint_as_float(dp[k + 2]) - d4.z) * scale);
-                        dp[k + 3] = rna_tf32(p[ch * 32 + k + 3] * (__uint_as_float(dp[k + 3]) - d4.w) * scale);
+                        for (int k = 0; k < 64; k += 4) {
+                            const float4 l4 = V4[(hf * 64 + k) >> 2];
+                            p[k]     = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -l4.x))));
+                            p[k + 1] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 1], c, -l4.y))));
+                            p[k + 2] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 2], c, -l4.z))));
+                            p[k + 3] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 3], c, -l4.w))));
+                        }
+                        ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
                     }
-                    ptx::tmem_st_32x32(tm_dpt + lane_off + ch * 32, dp);
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(bar(P_READY0 + buf));
+                } else {
+                    ptx::mbar_wait(bar(P_READY0 + buf), (g >> 1) & 1);
+                    ptx::mbar_wait(bar(DPT_FULL), g & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t p_tmem = tmem_base + lane_off + buf * kBlk;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t pp[32], dp[32];
+                        ptx::tmem_ld_32x32(p_tmem + ch * 32, pp);
+                        ptx::tmem_ld_32x32(tm_dpt + lane_off + ch * 32, dp);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) {
+                            const float4 d4 = V4[(ch * 32 + k) >> 2];
+                            dp[k]     = rna_tf32(__uint_as_float(pp[k])     * ((__uint_as_float(dp[k])     - d4.x) * scale));
+                            dp[k + 1] = rna_tf32(__uint_as_float(pp[k + 1]) * ((__uint_as_float(dp[k + 1]) - d4.y) * scale));
+                            dp[k + 2] = rna_tf32(__uint_as_float(pp[k + 2]) * ((__uint_as_float(dp[k + 2]) - d4.z) * scale));
+                            dp[k + 3] = rna_tf32(__uint_as_float(pp[k + 3]) * ((__uint_as_float(dp[k + 3]) - d4.w) * scale));
+                        }
+                        ptx::tmem_st_32x32(tm_dpt + lane_off + ch * 32, dp);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(bar(DS_READY));
                 }
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(bar(DS_READY));
             }
-            // ---- epilogue: dV, dK rows of this kv tile ----
-            ptx::mbar_wait(bar(ACC_DONE), it & 1);
+            // ---- epilogue: the exp warps store this kv tile's dV rows, the dS warps its dK rows ----
+            ptx::mbar_wait(bar(exp_group ? DV_DONE : DK_DONE), it & 1);
             ptx::tc_fence_after();
             const int t = nt * kBlk + tid;
             const bool live = t < args.Skv;
             const size_t off = (((size_t)b * args.Skv + (live ? t : 0)) * args.H + h) * kD;
-            store_acc_row(tm_dv + lane_off, args.dv + off, live);
-            store_acc_row(tm_dk + lane_off, args.dk + off, live);
+            if (exp_group) store_acc_row(tm_dv + lane_off, args.dv + off, live);
+            else           store_acc_row(tm_dk + lane_off, args.dk + off, live);
             ptx::tc_fence_before();
         }
     }
@@ -331,7 +359,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
     const uint32_t kr_addr = dor_addr + 2 * kTileBytes, vr_addr = kr_addr + kTileBytes, kt_addr = vr_addr + kTileBytes;
     const uint32_t bar_addr = base_addr + 7 * kTileBytes;
     enum { QDO_FULL0 = 0, QDO_FULL1, QDO_EMPTY0, QDO_EMPTY1, KR_FULL, KR_EMPTY, VR_FULL, VR_EMPTY, KT_FULL, KT_EMPTY,
-           S_FULL0, S_FULL1, DP_FULL, DS_READY, ACC_DONE, NBAR };
+           S_FULL0, S_FULL1, P_READY0, P_READY1, DP_FULL, DS_READY, ACC_DONE, NBAR };
     auto bar = [&](int i) { return bar_addr + 8u * i; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 7 * kTileBytes + 8 * NBAR);
 
@@ -344,7 +372,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
     }
     if (warp == 3) {
         if (lane == 0) {
-            for (int i = 0; i < NBAR; ++i) ptx::mbar_init(bar(i), i == DS_READY ? 128 : 1);
+            for (int i = 0; i < NBAR; ++i)
+                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DS_READY) ? 128 : 1);
             ptx::fence_mbar_init();
         }
         __syncwarp();
@@ -437,58 +466,82 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        // ============ softmax / dS warps: thread = q row ============
+        // ============ warps 4-7: P = exp2(c S - L) in place.  warps 8-11: dS = P o (dP - D) / sqrt(dk) in place over
+        // dP, then the dQ epilogue.  Thread = q row = TMEM lane; the groups run one block apart. ============
+        const bool exp_group = warp < 8;
         const int wq = warp & 3;
         const int tid = wq * 32 + lane;
         const uint32_t lane_off = uint32_t(wq * 32) << 16;
         const float c = args.c, scale = args.scale;
+        const float* vec = exp_group ? args.lse : args.dsum;
+        const float pad = exp_group ? INFINITY : 0.0f;
+        auto fetch = [&](int item) -> float {
+            const int sq = (item % args.n_q) * kBlk + tid;
+            return sq < args.Sq ? __ldg(vec + (size_t)(item / args.n_q) * args.Sq + sq) : pad;
+        };
         uint32_t g = 0;
         int it = 0;
+        float next = (int)blockIdx.x < args.total_items ? fetch(blockIdx.x) : 0.0f;
         for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
             const int mt = item % args.n_q;
             const int bh = item / args.n_q;
             const int h = bh % args.H, b = bh / args.H;
-            const int sq = mt * kBlk + tid;
-            const bool live = sq < args.Sq;
-            const float L = live ? __ldg(args.lse + (size_t)bh * args.Sq + sq) : INFINITY;
-            const float Dr = live ? __ldg(args.dsum + (size_t)bh * args.Sq + sq) : 0.0f;
+            const float mine = next;                              // L (exp warps) or D (dS warps) of this thread's q row
+            if (item + (int)gridDim.x < args.total_items) next = fetch(item + gridDim.x);
             for (int j = 0; j < n_kv; ++j, ++g) {
                 const uint32_t buf = g & 1u;
-                ptx::mbar_wait(bar(S_FULL0 + buf), (g >> 1) & 1);
-                ptx::tc_fence_after();
-                float p[kBlk];
                 const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
+                if (exp_group) {
+                    ptx::mbar_wait(bar(S_FULL0 + buf), (g >> 1) & 1);
+                    ptx::tc_fence_after();
+                    const int kv_left = args.Skv - j * kBlk;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                    ptx::tmem_ld_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[ch * 32]));
-                ptx::tmem_ld_wait();
-                const int kv_left = args.Skv - j * kBlk;
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float p[64];
+                        ptx::tmem_ld_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_ld_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                for (int k = 0; k < kBlk; ++k) {
-                    const float e = ptx::ex2(fmaf(p[k], c, -L));
-                    p[k] = (k < kv_left) ? e : 0.0f;
+                        for (int k = 0; k < 64; ++k) {
+                            const float e = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -mine))));
+                            p[k] = (hf * 64 + k < kv_left) ? e : 0.0f;       // zero-filled K rows past Skv
+                        }
+                        ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(bar(P_READY0 + buf));
+                } else {
+                    ptx::mbar_wait(bar(P_READY0 + buf), (g >> 1) & 1);
+                    ptx::mbar_wait(bar(DP_FULL), g & 1);
+                    ptx::tc_fence_after();
+                    const float dscale = mine * scale;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t pp[32], dp[32];
+                        ptx::tmem_ld_32x32(s_tmem + ch * 32, pp);
+                        ptx::tmem_ld_32x32(tm_dp + lane_off + ch * 32, dp);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            dp[k] = rna_tf32(__uint_as_float(pp[k]) * fmaf(__uint_as_float(dp[k]), scale, -dscale));
+                        ptx::tmem_st_32x32(tm_dp + lane_off + ch * 32, dp);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(bar(DS_READY));
                 }
-                ptx::mbar_wait(bar(DP_FULL), g & 1);
-                ptx::tc_fence_after();
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t dp[32];
-                    ptx::tmem_ld_32x32(tm_dp + lane_off + ch * 32, dp);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        dp[k] = rna_tf32(p[ch * 32 + k] * (__uint_as_float(dp[k]) - Dr) * scale);
-                    ptx::tmem_st_32x32(tm_dp + lane_off + ch * 32, dp);
-                }
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(bar(DS_READY));
             }
-            // ---- epilogue: dQ rows of this q tile ----
-            ptx::mbar_wait(bar(ACC_DONE), it & 1);
-            ptx::tc_fence_after();
-            store_acc_row(tm_dq + lane_off, args.dq + (((size_t)b * args.Sq + (live ? sq : 0)) * args.H + h) * kD, live);
-            ptx::tc_fence_before();
+            if (!exp_group) {
+                // ---- epilogue: dQ rows of this q tile ----
+                ptx::mbar_wait(bar(ACC_DONE), it & 1);
+                ptx::tc_fence_after();
+                const int sq = mt * kBlk + tid;
+                const bool live = sq < args.Sq;
+                store_acc_row(tm_dq + lane_off, args.dq + (((size_t)b * args.Sq + (live ? sq : 0)) * args.H + h) * kD, live);
+                ptx::tc_fence_before();
+            }
         }
     }
 

@@ -301,6 +301,235 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 5) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ===========================================================================================
+// CTA-pair variant (TF32 single pass): two CTAs of a cluster compute one 256 x BLOCK_N tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages only ITS 128 rows of A and ITS half of B's columns
+// (32 KB per K step instead of 48 KB), the tensor cores of both SMs read both halves of B — shared
+// memory bandwidth, the limiter of fp32-operand MMA, is spent on 1/3 fewer bytes per flop, and the
+// ring is 6 stages deep.  The leader CTA (rank 0) issues every MMA; a multicast tcgen05.commit
+// releases the ring slot / publishes the accumulator in both CTAs; both CTAs run their own
+// producer and their own epilogue (TMEM lanes = their 128 rows).
+// ===========================================================================================
+template <int BLOCK_N>
+struct Tc2Cfg {
+    static constexpr int kHalfN      = BLOCK_N / 2;
+    static constexpr int kABytes     = kBlockM * kBlockK * 4;           // 16 KB
+    static constexpr int kBBytes     = kHalfN * kBlockK * 4;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kEpiBytes   = 4 * 2 * 4096;
+    static constexpr int kBarBytes   = 512;
+    static constexpr int kBudget     = 232448 - 1024;
+    static constexpr int kStagesRaw  = (kBudget - kEpiBytes - kBarBytes) / kStageBytes;
+    static constexpr int kStages     = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSmemBytes  = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+    static constexpr int kTmemCols   = 2 * BLOCK_N;
+    static constexpr int kThreads    = 192;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const GemmTcArgs args) {
+    using Cfg = Tc2Cfg<BLOCK_N>;
+    constexpr int S = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+
+    const uint32_t stage_addr = base_addr;
+    const uint32_t epi_addr   = base_addr + S * Cfg::kStageBytes;
+    const uint32_t bar_addr   = epi_addr + Cfg::kEpiBytes;
+    auto full_bar   = [&](int s) { return bar_addr + 8u * s; };
+    auto empty_bar  = [&](int s) { return bar_addr + 8u * (S + s); };
+    auto tfull_bar  = [&](int a) { return bar_addr + 8u * (2 * S + a); };
+    auto tempty_bar = [&](int a) { return bar_addr + 8u * (2 * S + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
+        base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + 8 * (2 * S + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();          // 0 = pair leader
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_kb = (args.K + kBlockK - 1) / kBlockK;
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&tmC);
+    }
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s) {
+                ptx::mbar_init(full_bar(s), 1);       // the leader's arrive.expect_tx (bytes of both CTAs)
+                ptx::mbar_init(empty_bar(s), 1);      // one multicast commit
+            }
+            for (int a = 0; a < 2; ++a) {
+                ptx::mbar_init(tfull_bar(a), 1);
+                ptx::mbar_init(tempty_bar(a), 8);     // 4 epilogue warps of each CTA (leader's copy is the one used)
+            }
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc_2sm(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_mn = args.tiles_m * args.tiles_n;      // tiles_m counts 256-row tiles here
+
+    if (warp == 4) {
+        // ============================ TMA producer (both CTAs) ============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+                const int sp = tile / args.items_per_split, t2 = tile - sp * args.items_per_split;
+                const int z  = t2 / tiles_mn;
+                const int r  = t2 - z * tiles_mn;
+                const int kb0 = sp * args.kb_per_split;
+                const int kb1 = min(num_kb, kb0 + args.kb_per_split);
+                const int m0 = (r % args.tiles_m) * (2 * kBlockM) + (int)rank * kBlockM;
+                const int n0 = (r / args.tiles_m) * BLOCK_N + (int)rank * Cfg::kHalfN;
+                const int z1 = z % args.nb1, z2 = z / args.nb1;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                    const uint32_t sB = sA + Cfg::kABytes;
+                    const uint32_t fb = ptx::mapa(full_bar(stage), 0);       // the leader's barrier
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                    const int k0 = kb * kBlockK;
+                    if (!A_MN) {
+                        ptx::tma_load_4d_2sm(sA, &tmA, fb, k0, m0, z1, z2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kBlockM / 32; ++c)
+                            ptx::tma_load_4d_2sm(sA + c * 4096, &tmA, fb, m0 + c * 32, k0, z1, z2);
+                    }
+                    if (!B_MN) {
+                        ptx::tma_load_4d_2sm(sB, &tmB, fb, k0, n0, z1, z2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < Cfg::kHalfN / 32; ++c)
+                            ptx::tma_load_4d_2sm(sB + c * 4096, &tmB, fb, n0 + c * 32, k0, z1, z2);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ============================= MMA issuer (leader CTA) =============================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * kBlockM, BLOCK_N, A_MN, B_MN);
+            const uint64_t descA = args.desc_a, descB = args.desc_b;
+            constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;
+            constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+                const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
+                const int kb1 = min(num_kb, kb0 + args.kb_per_split);
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                    const uint32_t sB = sA + Cfg::kABytes;
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+                        const uint64_t da = ptx::umma_desc(descA, sA + kk * a_kstep);
+                        const uint64_t db = ptx::umma_desc(descB, sB + kk * b_kstep);
+                        ptx::umma_tf32_2sm(d_tmem, da, db, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit_2sm(empty_bar(stage), 3);                    // slot reusable in both CTAs
+                    if (kb == kb1 - 1) ptx::umma_commit_2sm(tfull_bar(acc), 3);   // accumulator ready in both CTAs
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp < 4) {
+        // ============================== epilogue (both CTAs) ==============================
+        uint8_t* stg_base = base_ptr + S * Cfg::kStageBytes + warp * 2 * 4096;
+        const uint32_t stg_addr = epi_addr + warp * 2 * 4096;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t nstore = 0;
+        for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+            const int sp = tile / args.items_per_split, t2 = tile - sp * args.items_per_split;
+            const int z  = t2 / tiles_mn;
+            const int r  = t2 - z * tiles_mn;
+            const int m0 = (r % args.tiles_m) * (2 * kBlockM) + (int)rank * kBlockM;
+            const int n0 = (r / args.tiles_m) * BLOCK_N;
+            const int z1 = z % args.nb1, z2 = z / args.nb1;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const bool rows_live = (m0 + warp * 32) < args.M;
+#pragma unroll 1
+            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                const int nc = n0 + chunk * 32;
+                if (nc >= args.N || !rows_live) break;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(tmem_base + (uint32_t(warp * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+                ptx::tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
+                if (args.bias != nullptr && sp == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nc + j < args.N) f[j] += __ldg(args.bias + nc + j);
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                const uint32_t buf = nstore & 1u;
+                if (lane == 0) ptx::tma_wait_group_read<1>();
+                __syncwarp();
+                uint8_t* row = stg_base + buf * 4096 + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = o;
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (args.accum || args.splits > 1)
+                        ptx::tma_reduce_add_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
+                    else
+                        ptx::tma_store_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
+                    ptx::tma_commit_group();
+                }
+                ++nstore;
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+                else           ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(acc), 0));
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (lane == 0) ptx::tma_wait_group<0>();
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();       // the peer's barriers / TMEM must outlive every remote arrive and multicast commit
+    if (warp == 5) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -381,6 +610,46 @@ int launch_major(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap& b,
     return launch_one<BN, true, true, NP>(a, b, c, args, grid, s);
 }
 
+
+template <int BN, bool AMN, bool BMN>
+int launch_one2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmTcArgs& args,
+                int grid, cudaStream_t stream) {
+    using Cfg = Tc2Cfg<BN>;
+    auto kern = gemm_tc2_kernel<BN, AMN, BMN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+            return NPM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, c, args);
+    count_launch();
+    if (e != cudaSuccess) { set_error("gemm_tc2_kernel launch: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+    return check_launch("gemm_tc2_kernel");
+}
+
+template <int BN>
+int launch_major2(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                  const GemmTcArgs& args, int grid, cudaStream_t s) {
+    if (!amn && !bmn) return launch_one2<BN, false, false>(a, b, c, args, grid, s);
+    if (!amn && bmn) return launch_one2<BN, false, true>(a, b, c, args, grid, s);
+    if (amn && !bmn) return launch_one2<BN, true, false>(a, b, c, args, grid, s);
+    return launch_one2<BN, true, true>(a, b, c, args, grid, s);
+}
+
 inline bool mult4(int64_t v) { return (v & 3) == 0; }
 
 }  // namespace
@@ -422,7 +691,12 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     // Per K-step (32 fp32) cost of one CTA: the MMA floor is 2*BLOCK_N cycles; narrow tiles re-read
     // more operand bytes per flop from L2 and measured slower than that floor (profiles/r01_gemm_bench.txt).
     const int sms = num_sms();
-    const int64_t tiles_m = (d.m + kBlockM - 1) / kBlockM;
+    // CTA-pair kernel (256-row tiles) for single-pass TF32 whenever there are at least two row tiles
+    static const bool pair_off = env_flag("NPM_GEMM_1CTA", false);
+    const bool pair = (npass == 1) && !pair_off && d.m > kBlockM;
+    const int tile_m = pair ? 2 * kBlockM : kBlockM;
+    const int units = pair ? sms / 2 : sms;        // concurrently running tiles
+    const int64_t tiles_m = (d.m + tile_m - 1) / tile_m;
     const int num_kb_total = (int)((d.k + kBlockK - 1) / kBlockK);
     const bool c_dense = (d.ldc == d.n) && (nb1 == 1 || d.c_bs1 == d.m * d.n) && (nb2 == 1 || d.c_bs2 == d.m * d.n * nb1);
     const bool may_split = c_dense && !(d.flags & (NPM_GEMM_RELU | NPM_GEMM_ACCUM)) && !getenv("NPM_GEMM_NO_SPLITK");
@@ -433,7 +707,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
         double best_cost = 1e300;
         const int cands[3] = {256, 128, 64};
         const double kstep[3] = {512.0, 400.0, 300.0};
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < (pair ? 2 : 3); ++i) {
             const int bn = cands[i];
             if (forced && bn != forced) continue;
             const int64_t tn = (d.n + bn - 1) / bn;
@@ -441,7 +715,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
             for (int sp = 1; sp <= (may_split ? 16 : 1); sp *= 2) {
                 const int kbs = (num_kb_total + sp - 1) / sp;
                 if (sp > 1 && kbs < 16) break;
-                const int64_t waves = (tiles * sp + sms - 1) / sms;
+                const int64_t waves = (tiles * sp + units - 1) / units;
                 double cost = double(waves) * (kbs * kstep[i] * npass + 1500.0 + 8.0 * bn);
                 if (sp > 1) cost = cost * 1.08 + 3000.0;   // zero-fill + reduce traffic: split only for a clear win
                 if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_splits = sp; }
@@ -482,7 +756,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     if (!b_mn) {
         const uint64_t ld = d.b_cs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * N), s3 = bs(nb2, d.b_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, bn, round_ab, k_atom32);
+        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, pair ? bn / 2 : bn, round_ab, k_atom32);
     } else {
         const uint64_t ld = d.b_rs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * K), s3 = bs(nb2, d.b_bs2, s2 * nb1);
@@ -519,6 +793,11 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, mn_lbo, mn_sbo);
     args.desc_a = a_mn ? desc_mn : desc_k;
     args.desc_b = b_mn ? desc_mn : desc_k;
+    if (pair) {
+        const int grid2 = 2 * (int)(total < units ? total : units);
+        if (bn == 256) return launch_major2<256>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
+        return launch_major2<128>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
+    }
     const int grid = (int)(total < sms ? total : sms);
 
     if (npass == 1) {

@@ -63,8 +63,13 @@ def main():
              ('attn dV=P^TdO', 'mm', 1024, 64, 1024, 128), ('attn dQ=dS K', 'km', 1024, 64, 1024, 128)]
     for name, mj, M, N, K, nb in cases:
         row = f'{name:26s} {mj} M={M:5d} N={N:5d} K={K:5d} nb={nb:3d} :'
+        if nb == 1:      # cuBLAS TF32 on the same shape / operand majors: the practical ceiling
+            a_ = torch.randn(M, K, device='cuda') if mj[0] == 'k' else torch.randn(K, M, device='cuda').t()
+            b_ = torch.randn(N, K, device='cuda').t() if mj[1] == 'k' else torch.randn(K, N, device='cuda')
+            ms = time_fn(lambda: torch.matmul(a_, b_))
+            row += f'  cublas: {2.0 * M * N * K / ms / 1e9:7.1f} TF ({ms:.3f} ms)'
         for prec in ('tf32', '3xtf32'):
-            for bn in (0, 128, 256) if N >= 256 else (0,):
+            for bn in (0,):
                 if bn:
                     os.environ['NPM_GEMM_BLOCK_N_DYN'] = str(bn)
                 else:
