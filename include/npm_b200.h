@@ -109,6 +109,16 @@ int npm_relu_fwd(const float* x, float* y, int64_t n, npm_stream_t stream);     
 /* dx = dy where x >= 0 else 0 (note >=, activations.py:19) */
 int npm_relu_bwd(const float* x, const float* dy, float* dx, int64_t n,
                  npm_stream_t stream);
+/* ReLU.backward from the OUTPUT of a fused Dense forward (npm_linear_fwd with
+ * relu != 0): dx = dy where the sign bit of y is clear, else 0. */
+int npm_relu_bwd_y(const float* y, const float* dy, float* dx, int64_t n,
+                   npm_stream_t stream);
+/* The same on a [rows, cols] matrix, fused with the bias gradient that follows
+ * it in Dense.backward (mlp.py:74-77 → :34): db[c] = sum_r dx[r,c].
+ * workspace: npm_colsum_workspace(rows, cols) bytes. */
+int npm_relu_bwd_colsum(const float* y, const float* dy, float* dx, float* db,
+                        int64_t rows, int64_t cols, void* workspace,
+                        npm_stream_t stream);
 /* row softmax over the last axis, max-shifted (activations.py:23-31). In place ok. */
 int npm_softmax_fwd(const float* x, float* y, int64_t rows, int64_t cols,
                     npm_stream_t stream);
@@ -128,6 +138,34 @@ int npm_layernorm_bwd(const float* dz, const float* x, const float* gamma,
                       const float* mean, const float* rstd, float* dx,
                       float* dgamma, float* dbeta, int64_t rows, int64_t cols,
                       void* workspace, npm_stream_t stream);
+
+/* DropOut -> LayerNormalization fused (the pre-norm blocks of
+ * layers/transformer.py:35-37,48-50,125-127,136-138,149-151 call them back to
+ * back): out = LN(dropout(x)) without writing the dropped tensor; the mask is
+ * the Philox mask of npm_dropout_fwd for (keep_prob, seed, offset).  Backward:
+ * dx = dropout_bwd(LN_bwd(dz)) + dskip (dskip may be NULL; it is the residual
+ * branch the reference adds right after, transformer.py:176,190,201).
+ * Served when npm_dropout_layernorm_fused(rows, cols) != 0 (cols % 4 == 0,
+ * cols <= 1024), offset % 4 == 0 and pointers are 16-byte aligned; otherwise
+ * NPM_ERR_UNSUPPORTED and the caller runs the two layers separately.
+ * workspace: npm_layernorm_bwd_workspace(rows, cols) bytes. */
+int npm_dropout_layernorm_fused(int64_t rows, int64_t cols);
+/* `maskbits` (npm_dropout_layernorm_mask_bytes): the keep bits, bit-packed by
+ * the forward kernel and consumed by the backward one (private layout). */
+size_t npm_dropout_layernorm_mask_bytes(int64_t rows, int64_t cols);
+int npm_dropout_layernorm_fwd(const float* x, const float* gamma,
+                              const float* beta, float* out, float* mean,
+                              float* rstd, uint32_t* maskbits, int64_t rows,
+                              int64_t cols, float epsilon, float keep_prob,
+                              uint64_t seed, uint64_t offset,
+                              npm_stream_t stream);
+int npm_dropout_layernorm_bwd(const float* dz, const float* x,
+                              const float* gamma, const float* mean,
+                              const float* rstd, const uint32_t* maskbits,
+                              const float* dskip, float* dx, float* dgamma,
+                              float* dbeta, int64_t rows, int64_t cols,
+                              float keep_prob, void* workspace,
+                              npm_stream_t stream);
 
 /* ---- DropOut (layers/normalizations.py:9-30) ------------------------------ */
 /* Element i is kept iff philox4x32_10(counter=(offset+i)/4, key=seed)[(offset+i)%4]

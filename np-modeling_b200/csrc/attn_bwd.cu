@@ -16,6 +16,7 @@
 // swizzle ("R" image, K-major operand); contracted over its rows it is landed with 32-byte swizzle
 // atoms ("T" image, MN-major operand) — tf32 operands cannot be transposed at 16-byte granularity.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -44,6 +45,7 @@ struct BwdArgs {
     float* dq;                // [B, Sq, H, 64]
     float* dk;                // [B, Skv, H, 64]
     float* dv;                // [B, Skv, H, 64]
+    int debug_skip;           // tools only: 1 = exp warps do no work, 2 = dS warps do no work, 3 = both (timing experiments)
 };
 
 __device__ __forceinline__ uint32_t cvt_tf32(float x) {
@@ -280,6 +282,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
+                        if (args.debug_skip & 1) break;
                         float p[64];
                         ptx::tmem_ld_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
                         ptx::tmem_ld_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
@@ -305,6 +308,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     const uint32_t p_tmem = tmem_base + lane_off + buf * kBlk;
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
+                        if (args.debug_skip & 2) break;
                         uint32_t pp[32], dp[32];
                         ptx::tmem_ld_32x32(p_tmem + ch * 32, pp);
                         ptx::tmem_ld_32x32(tm_dpt + lane_off + ch * 32, dp);
@@ -622,6 +626,7 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
     a.c = (float)(1.4426950408889634 / sqrt((double)kD));
     a.scale = (float)(1.0 / sqrt((double)kD));
     a.lse = lse; a.dsum = dsum; a.dq = dq; a.dk = dk; a.dv = dv;
+    a.debug_skip = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
 
     static bool configured = false;
     if (!configured) {

@@ -99,6 +99,8 @@ int launch_ew2(const char* name, const float* a, const float* b, float* y, int64
 
 struct ReluF { __device__ float operator()(float x) const { return x < 0.0f ? 0.0f : x; } };
 struct ReluB { __device__ float operator()(float x, float dy) const { return x >= 0.0f ? dy : 0.0f; } };
+// ReLU.backward from the fused Dense output: the GEMM epilogue stored -0.0 for x < 0 and +0.0 for x == 0
+struct ReluBY { __device__ float operator()(float y, float dy) const { return (__float_as_uint(y) >> 31) ? 0.0f : dy; } };
 struct AddF  { __device__ float operator()(float a, float b) const { return a + b; } };
 struct ScaleF { float s; __device__ float operator()(float x) const { return x * s; } };
 
@@ -184,6 +186,9 @@ extern "C" {
 
 int npm_relu_fwd(const float* x, float* y, int64_t n, npm_stream_t stream) {
     return launch_ew1("relu_fwd", x, y, n, ReluF{}, (cudaStream_t)stream);
+}
+int npm_relu_bwd_y(const float* y, const float* dy, float* dx, int64_t n, npm_stream_t stream) {
+    return launch_ew2("relu_bwd_y", y, dy, dx, n, ReluBY{}, (cudaStream_t)stream);
 }
 int npm_relu_bwd(const float* x, const float* dy, float* dx, int64_t n, npm_stream_t stream) {
     return launch_ew2("relu_bwd", x, dy, dx, n, ReluB{}, (cudaStream_t)stream);

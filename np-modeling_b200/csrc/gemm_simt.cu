@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs p) {
             if (gn >= p.n) continue;
             float v = acc[i][j] * p.alpha;
             if (p.bias) v += __ldg(p.bias + gn);
-            if (p.relu) v = fmaxf(v, 0.0f);
+            if (p.relu) v = v < 0.0f ? -0.0f : v;
             float* dst = C + gm * p.ldc + gn;
             *dst = p.accum ? (*dst + v) : v;
         }

@@ -235,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (args.relu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? -0.0f : f[j];   // -0.0 keeps "x < 0" for ReLU.backward
                 }
                 const uint32_t buf = nstore & 1u;
                 // the store that last read this buffer (two stores ago) must have drained
@@ -491,7 +491,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (args.relu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? -0.0f : f[j];   // -0.0 keeps "x < 0" for ReLU.backward
                 }
                 const uint32_t buf = nstore & 1u;
                 if (lane == 0) ptx::tma_wait_group_read<1>();

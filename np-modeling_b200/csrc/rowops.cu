@@ -5,6 +5,8 @@
 // are warp shuffles.  Rows wider than that (or with a width that is not a multiple of 4) take a
 // multi-pass variant of the same kernels.  Algorithmic bytes per element: softmax fwd 8, bwd 12;
 // layernorm fwd 8 (+8 B/row statistics), bwd 12 (+8 B/row, + 2*C*4 B of parameter gradients).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace npm {
@@ -124,17 +126,44 @@ inline int nv_for(int64_t cols) {   // float4 per lane needed to hold a row, rou
 }
 
 // ============================================================= layernorm
-template <int NV>
+// Optional DropOut fused in front of the normalisation (the pre-norm blocks of layers/transformer.py run
+// DropOut -> LayerNormalization back to back, :35-37): the dropped tensor is never written, forward and
+// backward recompute the Philox mask of elementwise.cu's dropout_kernel from (seed, offset + element index).
+struct DropArgs {
+    float keep_prob;      // 0 = no dropout
+    float inv_keep;       // 1 / keep_prob rounded to fp32: the fused kernels scale by it (<= 1 ulp from x / keep_prob;
+                          // the stand-alone DropOut kernel keeps the exact division of normalizations.py:22)
+    uint64_t thr, seed, offset;   // offset is a multiple of 4: one Philox call per float4
+};
+// applies the mask to one float4 whose first element has global index e; returns the 4 keep bits
+__device__ __forceinline__ uint32_t drop4(float4& v, const DropArgs& d, uint64_t e) {
+    const Philox4 p = philox4x32_10((d.offset + e) >> 2, d.seed);
+    const uint32_t k = (p.x < d.thr ? 1u : 0u) | (p.y < d.thr ? 2u : 0u) | (p.z < d.thr ? 4u : 0u) | (p.w < d.thr ? 8u : 0u);
+    v.x = (k & 1u) ? v.x * d.inv_keep : 0.0f; v.y = (k & 2u) ? v.y * d.inv_keep : 0.0f;
+    v.z = (k & 4u) ? v.z * d.inv_keep : 0.0f; v.w = (k & 8u) ? v.w * d.inv_keep : 0.0f;
+    return k;
+}
+template <int NV, bool DROP = false>
 __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, float* __restrict__ out,
                                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                                    int64_t rows, int cols, float eps) {
+                                                                    int64_t rows, int cols, float eps, DropArgs drop = DropArgs{},
+                                                                    uint32_t* __restrict__ maskbits = nullptr) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (row >= rows) return;
     RowRegs<NV> r;
     r.load(x + row * cols, cols, lane, 0.0f);
+    if (DROP) {
+        uint32_t keep_bits = 0;      // 4 bits per float4 of this lane; saved so that backward need not redo Philox
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < cols) keep_bits |= drop4(r.v[i], drop, (uint64_t)row * cols + c) << (4 * i);
+        }
+        maskbits[row * 32 + lane] = keep_bits;
+    }
     float s = 0.0f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
@@ -188,27 +217,44 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_generic(const float
 // dgamma/dbeta in registers; warps of a CTA are combined through shared memory and each CTA
 // writes one partial row pair to the workspace [grid][2][cols]; colsum-style second stage
 // finishes the reduction (no atomics → deterministic).
-template <int NV>
-__global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x,
+template <int NV, bool DROP = false>
+__global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     float* __restrict__ dx, float* __restrict__ partial,
-                                                                    int64_t rows, int cols) {
+                                                                    int64_t rows, int cols, DropArgs drop = DropArgs{},
+                                                                    const float* __restrict__ dskip = nullptr,
+                                                                    const uint32_t* __restrict__ maskbits = nullptr) {
     extern __shared__ float sred[];   // [kWarpsPerCta][2][cols_padded]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 dg[NV], db[NV], g[NV];
+    // dgamma / dbeta of this warp's rows accumulate in the warp's own shared-memory slice and gamma is
+    // re-read through L1 for every row: with only the two row images in registers two CTAs fit an SM,
+    // and 16 warps of loads in flight are what a latency-bound row kernel needs to approach HBM speed.
+    constexpr int cpad = NV * 128;
+    float* my = sred + (size_t)warp * 2 * cpad;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        dg[i] = make_float4(0, 0, 0, 0);
-        db[i] = make_float4(0, 0, 0, 0);
         const int c = (i * 32 + lane) * 4;
-        g[i] = (c < cols) ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(my + c) = make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(my + cpad + c) = make_float4(0, 0, 0, 0);
     }
     const float inv_c = 1.0f / (float)cols;
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < rows; row += (int64_t)gridDim.x * kWarpsPerCta) {
         RowRegs<NV> rx, rz;
         rx.load(x + row * cols, cols, lane, 0.0f);
         rz.load(dz + row * cols, cols, lane, 0.0f);
+        uint32_t keep_bits = 0;          // 4 bits per float4 of this lane (NV <= 8), written by the fused forward
+        if (DROP) {
+            keep_bits = __ldg(maskbits + row * 32 + lane);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const uint32_t k = keep_bits >> (4 * i);
+                rx.v[i].x = (k & 1u) ? rx.v[i].x * drop.inv_keep : 0.0f;
+                rx.v[i].y = (k & 2u) ? rx.v[i].y * drop.inv_keep : 0.0f;
+                rx.v[i].z = (k & 4u) ? rx.v[i].z * drop.inv_keep : 0.0f;
+                rx.v[i].w = (k & 8u) ? rx.v[i].w * drop.inv_keep : 0.0f;
+            }
+        }
         const float mu = mean[row], rs = rstd[row];
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
@@ -218,10 +264,14 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float*
                 // rx ← y_hat ; rz stays dz
                 rx.v[i].x = (rx.v[i].x - mu) * rs; rx.v[i].y = (rx.v[i].y - mu) * rs;
                 rx.v[i].z = (rx.v[i].z - mu) * rs; rx.v[i].w = (rx.v[i].w - mu) * rs;
-                dg[i].x += rz.v[i].x * rx.v[i].x; dg[i].y += rz.v[i].y * rx.v[i].y;
-                dg[i].z += rz.v[i].z * rx.v[i].z; dg[i].w += rz.v[i].w * rx.v[i].w;
-                db[i].x += rz.v[i].x; db[i].y += rz.v[i].y; db[i].z += rz.v[i].z; db[i].w += rz.v[i].w;
-                const float gx = rz.v[i].x * g[i].x, gy = rz.v[i].y * g[i].y, gz = rz.v[i].z * g[i].z, gw = rz.v[i].w * g[i].w;
+                float4 dg = *reinterpret_cast<float4*>(my + c), db = *reinterpret_cast<float4*>(my + cpad + c);
+                dg.x += rz.v[i].x * rx.v[i].x; dg.y += rz.v[i].y * rx.v[i].y;
+                dg.z += rz.v[i].z * rx.v[i].z; dg.w += rz.v[i].w * rx.v[i].w;
+                db.x += rz.v[i].x; db.y += rz.v[i].y; db.z += rz.v[i].z; db.w += rz.v[i].w;
+                *reinterpret_cast<float4*>(my + c) = dg;
+                *reinterpret_cast<float4*>(my + cpad + c) = db;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+                const float gx = rz.v[i].x * g.x, gy = rz.v[i].y * g.y, gz = rz.v[i].z * g.z, gw = rz.v[i].w * g.w;
                 s1 += (gx + gy) + (gz + gw);
                 s2 += (gx * rx.v[i].x + gy * rx.v[i].y) + (gz * rx.v[i].z + gw * rx.v[i].w);
                 rz.v[i] = make_float4(gx, gy, gz, gw);   // rz ← g = dz * gamma
@@ -234,17 +284,29 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float*
             rz.v[i].x = rs * (rz.v[i].x - s1 - rx.v[i].x * s2); rz.v[i].y = rs * (rz.v[i].y - s1 - rx.v[i].y * s2);
             rz.v[i].z = rs * (rz.v[i].z - s1 - rx.v[i].z * s2); rz.v[i].w = rs * (rz.v[i].w - s1 - rx.v[i].w * s2);
         }
+        if (DROP) {       // DropOut.backward (normalizations.py:25-30) on the way out, then the residual branch
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const uint32_t k = keep_bits >> (4 * i);
+                rz.v[i].x = (k & 1u) ? rz.v[i].x * drop.inv_keep : 0.0f;
+                rz.v[i].y = (k & 2u) ? rz.v[i].y * drop.inv_keep : 0.0f;
+                rz.v[i].z = (k & 4u) ? rz.v[i].z * drop.inv_keep : 0.0f;
+                rz.v[i].w = (k & 8u) ? rz.v[i].w * drop.inv_keep : 0.0f;
+            }
+        }
+        if (dskip != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                if (c < cols) {
+                    const float4 a = ld_stream(reinterpret_cast<const float4*>(dskip + row * cols + c));
+                    rz.v[i].x += a.x; rz.v[i].y += a.y; rz.v[i].z += a.z; rz.v[i].w += a.w;
+                }
+            }
+        }
         rz.store(dx + row * cols, cols, lane);
     }
     // CTA reduce of the parameter-gradient partials
-    const int cpad = NV * 128;
-    float* my = sred + (size_t)warp * 2 * cpad;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        *reinterpret_cast<float4*>(my + c) = dg[i];
-        *reinterpret_cast<float4*>(my + cpad + c) = db[i];
-    }
     __syncthreads();
     for (int c = threadIdx.x; c < 2 * cpad; c += kRowThreads) {
         float acc = 0.0f;
@@ -299,11 +361,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_param_generic(const float* 
 // out[c] = sum_s partial[s*slab_stride + c]  — second stage of every column reduction here.
 // 32 columns x 8 slab lanes per CTA: coalesced 128-byte rows, the slab chain is 8x shorter than a
 // thread-per-column loop, combined through shared memory.
+// blockIdx.y = 1 (LayerNorm: dbeta) reads the partials `cols` further on and writes out2.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                                              int64_t cols, int nslabs, int64_t slab_stride) {
+                                                              int64_t cols, int nslabs, int64_t slab_stride,
+                                                              float* __restrict__ out2 = nullptr) {
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+    if (blockIdx.y == 1) { partial += cols; out = out2; }
     float acc = 0.0f;
     if (c < cols)
         for (int s = ty; s < nslabs; s += 8) acc += partial[(size_t)s * slab_stride + c];
@@ -317,18 +382,54 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 }
 
 // ================================================================ colsum
-// stage 1: CTA = 8 warps; a warp row covers 128 columns (float4 per lane); warps stride rows.
-__global__ void __launch_bounds__(kRowThreads) colsum_stage1(const float* __restrict__ x, float* __restrict__ partial,
-                                                            int64_t rows, int64_t cols, int64_t rows_per_slab) {
+// One launch.  CTA = 8 warps over a slab of rows; a warp row covers 128 columns (float4 per lane).  Every
+// CTA writes its partial row to the workspace; the LAST CTA of a column group to arrive (ticket counter)
+// adds the partial rows in slab order — a fixed order, so the result is deterministic — and resets the
+// counter.  `relu_y` != nullptr fuses ReLU.backward (activations.py:17-19): the value summed and written
+// to `masked` is x where the forward output's sign bit is clear (the fused Dense epilogue stores -0.0 for
+// negative pre-activations, +0.0 for zero ones, so "x >= 0" survives in the sign of y).
+constexpr int kTicketSlots = 64, kTicketCols = 128;
+__device__ unsigned int g_colsum_tickets[kTicketSlots * kTicketCols];
+
+__global__ void __launch_bounds__(kRowThreads) colsum_kernel(const float* __restrict__ x, float* __restrict__ partial,
+                                                            float* __restrict__ out, int64_t rows, int64_t cols,
+                                                            int64_t rows_per_slab, unsigned ticket_base,
+                                                            const float* __restrict__ relu_y, float* __restrict__ masked) {
     __shared__ float4 sm[kWarpsPerCta][32];
+    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t c = ((int64_t)blockIdx.x * 32 + lane) * 4;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
     const int64_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
     float4 acc = make_float4(0, 0, 0, 0);
     if (c < cols) {
-        for (int64_t r = r0 + warp; r < r1; r += kWarpsPerCta) {
-            const float4 v = ld_stream(reinterpret_cast<const float4*>(x + r * cols + c));
+        constexpr int U = 4;       // rows in flight per thread: the loads of a batch are all issued before the adds
+        int64_t r = r0 + warp;
+        for (; r + (U - 1) * kWarpsPerCta < r1; r += U * kWarpsPerCta) {
+            float4 v[U], y[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const float4*>(x + (r + u * kWarpsPerCta) * cols + c));
+            if (relu_y != nullptr) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) y[u] = ld_stream(reinterpret_cast<const float4*>(relu_y + (r + u * kWarpsPerCta) * cols + c));
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    v[u].x = (__float_as_uint(y[u].x) >> 31) ? 0.0f : v[u].x; v[u].y = (__float_as_uint(y[u].y) >> 31) ? 0.0f : v[u].y;
+                    v[u].z = (__float_as_uint(y[u].z) >> 31) ? 0.0f : v[u].z; v[u].w = (__float_as_uint(y[u].w) >> 31) ? 0.0f : v[u].w;
+                    st_stream(reinterpret_cast<float4*>(masked + (r + u * kWarpsPerCta) * cols + c), v[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; r < r1; r += kWarpsPerCta) {
+            float4 v = ld_stream(reinterpret_cast<const float4*>(x + r * cols + c));
+            if (relu_y != nullptr) {
+                const float4 y = ld_stream(reinterpret_cast<const float4*>(relu_y + r * cols + c));
+                v.x = (__float_as_uint(y.x) >> 31) ? 0.0f : v.x; v.y = (__float_as_uint(y.y) >> 31) ? 0.0f : v.y;
+                v.z = (__float_as_uint(y.z) >> 31) ? 0.0f : v.z; v.w = (__float_as_uint(y.w) >> 31) ? 0.0f : v.w;
+                st_stream(reinterpret_cast<float4*>(masked + r * cols + c), v);
+            }
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
     }
@@ -342,6 +443,32 @@ __global__ void __launch_bounds__(kRowThreads) colsum_stage1(const float* __rest
         }
         *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * cols + c) = acc;
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&g_colsum_tickets[ticket_base + blockIdx.x], 1u);
+        is_last = (t == gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    acc = make_float4(0, 0, 0, 0);
+    if (c < cols)
+        for (int sl = warp; sl < (int)gridDim.y; sl += kWarpsPerCta) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (size_t)sl * cols + c));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    sm[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c < cols) {
+#pragma unroll
+        for (int w = 1; w < kWarpsPerCta; ++w) {
+            const float4 v = sm[w][lane];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + c) = acc;
+    }
+    if (threadIdx.x == 0) g_colsum_tickets[ticket_base + blockIdx.x] = 0;     // ready for the next launch on this slot
 }
 __global__ void __launch_bounds__(256) colsum_generic(const float* x, float* partial, int64_t rows, int64_t cols,
                                                       int64_t rows_per_slab) {
@@ -370,23 +497,40 @@ inline int colsum_slabs(int64_t rows, int64_t cols) {
 size_t colsum_workspace_bytes(int64_t rows, int64_t cols) {
     return (size_t)colsum_slabs(rows, cols) * (size_t)cols * sizeof(float);
 }
-int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s) {
+static unsigned next_ticket_base(int64_t col_ctas) {
+    static std::atomic<unsigned> n{0};
+    (void)col_ctas;
+    return (n.fetch_add(1u) % kTicketSlots) * kTicketCols;
+}
+
+// out[c] = sum_r x[r,c]; with relu_y/masked: out[c] = sum_r m[r,c], m = x where sign(relu_y) clear else 0, m → masked
+int colsum_relu_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, const float* relu_y,
+                       float* masked, cudaStream_t s) {
     NPM_REQUIRE(rows > 0 && cols > 0, "colsum: empty input");
     NPM_REQUIRE(workspace != nullptr, "colsum: workspace is NULL");
     const int slabs = colsum_slabs(rows, cols);
     const int64_t rps = (rows + slabs - 1) / slabs;
     float* partial = reinterpret_cast<float*>(workspace);
-    if ((cols & 3) == 0 && aligned16(x) && aligned16(partial)) {
-        colsum_stage1<<<dim3((unsigned)((cols + 127) / 128), slabs), kRowThreads, 0, s>>>(x, partial, rows, cols, rps);
-    } else {
-        colsum_generic<<<dim3((unsigned)((cols + 255) / 256), slabs), 256, 0, s>>>(x, partial, rows, cols, rps);
+    const int64_t col_ctas = (cols + 127) / 128;
+    const bool vec = (cols & 3) == 0 && aligned16(x) && aligned16(partial) && aligned16(out) &&
+                     (relu_y == nullptr || (aligned16(relu_y) && aligned16(masked)));
+    if (vec && col_ctas <= kTicketCols) {
+        colsum_kernel<<<dim3((unsigned)col_ctas, slabs), kRowThreads, 0, s>>>(x, partial, out, rows, cols, rps,
+                                                                            next_ticket_base(col_ctas), relu_y, masked);
+        count_launch();
+        return check_launch("colsum_kernel");
     }
+    NPM_REQUIRE(relu_y == nullptr, "relu_bwd_colsum: needs 16-byte aligned pointers and cols %% 4 == 0");
+    colsum_generic<<<dim3((unsigned)((cols + 255) / 256), slabs), 256, 0, s>>>(x, partial, rows, cols, rps);
     count_launch();
-    int rc = check_launch("colsum_stage1");
+    int rc = check_launch("colsum_generic");
     if (rc) return rc;
     reduce_partials_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, s>>>(partial, out, cols, slabs, cols);
     count_launch();
     return check_launch("reduce_partials_kernel");
+}
+int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s) {
+    return colsum_relu_launch(x, out, rows, cols, workspace, nullptr, nullptr, s);
 }
 
 }  // namespace npm
@@ -411,6 +555,18 @@ size_t npm_colsum_workspace(int64_t rows, int64_t cols) {
 }
 int npm_colsum(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, npm_stream_t stream) {
     return colsum_launch(x, out, rows, cols, workspace, (cudaStream_t)stream);
+}
+
+int npm_relu_bwd_colsum(const float* y, const float* dy, float* dx, float* db, int64_t rows, int64_t cols,
+                        void* workspace, npm_stream_t stream) {
+    NPM_REQUIRE(y && dy && dx && db, "relu_bwd_colsum: NULL pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = (cols & 3) == 0 && cols <= (int64_t)kTicketCols * 128 && aligned16(y) && aligned16(dy) &&
+                     aligned16(dx) && aligned16(db) && aligned16(workspace);
+    if (vec) return colsum_relu_launch(dy, db, rows, cols, workspace, y, dx, s);
+    int rc = npm_relu_bwd_y(y, dy, dx, rows * cols, stream);
+    if (rc) return rc;
+    return colsum_launch(dx, db, rows, cols, workspace, s);
 }
 
 int npm_softmax_fwd(const float* x, float* y, int64_t rows, int64_t cols, npm_stream_t stream) {
@@ -473,7 +629,7 @@ int npm_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
 
 static int ln_bwd_grid(int64_t rows) {
     int64_t g = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int64_t cap = (int64_t)num_sms() * 2;
+    const int64_t cap = (int64_t)num_sms() * 2;      // two resident CTAs per SM, one wave
     return (int)(g < cap ? g : cap);
 }
 static int ln_generic_slabs(int64_t rows) {
@@ -538,10 +694,95 @@ int npm_layernorm_bwd(const float* dz, const float* x, const float* gamma, const
         if (rc) return rc;
     }
     const unsigned g2 = (unsigned)((cols + 31) / 32);
-    reduce_partials_kernel<<<g2, 256, 0, s>>>(partial, dgamma, cols, slabs, 2 * cols);
-    reduce_partials_kernel<<<g2, 256, 0, s>>>(partial + cols, dbeta, cols, slabs, 2 * cols);
-    count_launch(2);
+    reduce_partials_kernel<<<dim3(g2, 2), 256, 0, s>>>(partial, dgamma, cols, slabs, 2 * cols, dbeta);
+    count_launch();
     return check_launch("layernorm_bwd_reduce");
+}
+
+// ---- DropOut -> LayerNormalization fused (pre-norm transformer blocks) ----
+int npm_dropout_layernorm_fused(int64_t rows, int64_t cols) {
+    (void)rows;
+    return ln_fast(cols) && nv_for(cols) > 0 ? 1 : 0;
+}
+
+static DropArgs make_drop(float keep_prob, uint64_t seed, uint64_t offset) {
+    DropArgs d;
+    d.keep_prob = keep_prob;
+    d.inv_keep = 1.0f / keep_prob;
+    d.thr = (uint64_t)((double)keep_prob * 4294967296.0);
+    d.seed = seed;
+    d.offset = offset;
+    return d;
+}
+
+size_t npm_dropout_layernorm_mask_bytes(int64_t rows, int64_t cols) {
+    (void)cols;
+    return rows > 0 ? (size_t)rows * 32 * sizeof(uint32_t) : 0;     // 4 keep bits per float4, one word per lane and row
+}
+
+int npm_dropout_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
+                              uint32_t* maskbits, int64_t rows, int64_t cols, float epsilon, float keep_prob, uint64_t seed,
+                              uint64_t offset, npm_stream_t stream) {
+    NPM_REQUIRE(maskbits != nullptr, "dropout_layernorm_fwd: maskbits is NULL");
+    if (rows <= 0 || cols <= 0) return NPM_OK;
+    NPM_REQUIRE(keep_prob > 0.0f && keep_prob <= 1.0f, "dropout_layernorm: keep_prob %g out of (0,1]", keep_prob);
+    if (!(npm_dropout_layernorm_fused(rows, cols) && (offset & 3) == 0 && aligned16(x) && aligned16(out) &&
+          aligned16(gamma) && aligned16(beta))) {
+        set_error("dropout_layernorm_fwd: needs cols %% 4 == 0, cols <= 1024, offset %% 4 == 0 and 16-byte aligned pointers");
+        return NPM_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+    const DropArgs d = make_drop(keep_prob, seed, offset);
+    switch (nv_for(cols)) {
+        case 1: layernorm_fwd_kernel<1, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
+        case 2: layernorm_fwd_kernel<2, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
+        case 4: layernorm_fwd_kernel<4, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
+        default: layernorm_fwd_kernel<8, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
+    }
+    count_launch();
+    return check_launch("dropout_layernorm_fwd");
+}
+
+int npm_dropout_layernorm_bwd(const float* dz, const float* x, const float* gamma, const float* mean, const float* rstd,
+                              const uint32_t* maskbits, const float* dskip, float* dx, float* dgamma, float* dbeta,
+                              int64_t rows, int64_t cols, float keep_prob, void* workspace, npm_stream_t stream) {
+    NPM_REQUIRE(maskbits != nullptr, "dropout_layernorm_bwd: maskbits is NULL");
+    const uint64_t seed = 0, offset = 0;      // the mask comes from the forward pass
+    if (rows <= 0 || cols <= 0) return NPM_OK;
+    NPM_REQUIRE(workspace != nullptr, "dropout_layernorm_bwd: workspace is NULL");
+    NPM_REQUIRE(keep_prob > 0.0f && keep_prob <= 1.0f, "dropout_layernorm: keep_prob %g out of (0,1]", keep_prob);
+    if (!(npm_dropout_layernorm_fused(rows, cols) && (offset & 3) == 0 && aligned16(dz) && aligned16(x) &&
+          aligned16(gamma) && aligned16(dx) && (dskip == nullptr || aligned16(dskip)))) {
+        set_error("dropout_layernorm_bwd: needs cols %% 4 == 0, cols <= 1024, offset %% 4 == 0 and 16-byte aligned pointers");
+        return NPM_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    float* partial = reinterpret_cast<float*>(workspace);
+    const int slabs = ln_bwd_grid(rows);
+    const int nv = nv_for(cols);
+    const size_t smem = (size_t)kWarpsPerCta * 2 * nv * 128 * sizeof(float);
+    const DropArgs d = make_drop(keep_prob, seed, offset);
+    switch (nv) {
+        case 1: layernorm_bwd_kernel<1, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits); break;
+        case 2: layernorm_bwd_kernel<2, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits); break;
+        case 4: layernorm_bwd_kernel<4, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits); break;
+        default: {
+            static bool configured = false;
+            if (!configured) {
+                cudaFuncSetAttribute(layernorm_bwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                configured = true;
+            }
+            layernorm_bwd_kernel<8, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
+        } break;
+    }
+    count_launch();
+    int rc = check_launch("dropout_layernorm_bwd");
+    if (rc) return rc;
+    const unsigned g2 = (unsigned)((cols + 31) / 32);
+    reduce_partials_kernel<<<dim3(g2, 2), 256, 0, s>>>(partial, dgamma, cols, slabs, 2 * cols, dbeta);
+    count_launch();
+    return check_launch("dropout_layernorm_bwd_reduce");
 }
 
 }  // extern "C"

@@ -29,8 +29,9 @@ class Linear(layer.StatefulLayer):
         C.npm_linear_fwd(x.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 0, 1 if _relu else 0, device.stream())
         return y
 
-    def backward(self, dy, optimizer_: optimizer.Optimizer):
+    def backward(self, dy, optimizer_: optimizer.Optimizer, _db=None):
         # dy: [m, n]   b/db: [n]   w/dw: [k, n]   x/dx: [m, k]
+        # _db: bias gradient already computed by the caller (Dense fuses it with ReLU.backward)
         dy = device.asdevice(dy)
         w = self._p('_w')
         self._p('_b')
@@ -39,10 +40,14 @@ class Linear(layer.StatefulLayer):
         m, k = x.shape
         n = w.shape[1]
         s = device.stream()
-        db = optimizer_.grad_buffer(self, '_b', (n,))
         dw = optimizer_.grad_buffer(self, '_w', (k, n))
-        ws = device.workspace(C.npm_colsum_workspace(m, n))
-        C.npm_linear_bwd_dw_db(x.ptr, dy.ptr, dw.ptr, db.ptr, m, k, n, 0, ws.data_ptr(), s)
+        if _db is None:
+            db = optimizer_.grad_buffer(self, '_b', (n,))
+            ws = device.workspace(C.npm_colsum_workspace(m, n))
+            C.npm_linear_bwd_dw_db(x.ptr, dy.ptr, dw.ptr, db.ptr, m, k, n, 0, ws.data_ptr(), s)
+        else:
+            db = _db
+            C.npm_linear_bwd_dw_db(x.ptr, dy.ptr, dw.ptr, None, m, k, n, 0, None, s)
         dx = device.empty((m, k))
         C.npm_linear_bwd_dx(dy.ptr, w.ptr, dx.ptr, m, k, n, 0, s)
         assert dx.shape == x.shape
@@ -78,11 +83,30 @@ class Dense(layer.StatefulLayer):
         self._activation.initialize()
         self._activation._initialized = True
 
+    def _fused_relu(self):
+        # The default activation is fused into the GEMM epilogue (bias + ReLU, pre-activation never
+        # written); anything else (e.g. Softmax, a user subclass) runs as its own layer.
+        return type(self._activation) is activations.ReLU
+
     def forward(self, x):
+        if self._fused_relu():
+            self._y = self._linear.forward(x, _relu=True)
+            return self._y
         y = self._linear.forward(x)
         return self._activation.forward(y)
 
     def backward(self, dy, optimizer_: optimizer.Optimizer):
+        if self._fused_relu():
+            # ReLU.backward (activations.py:17-19) and the bias gradient (mlp.py:34) in one pass over dy
+            dy = device.asdevice(dy)
+            y = self._y
+            assert dy.shape == y.shape, f'{dy.shape} vs {y.shape}'
+            m, n = y.shape
+            db = optimizer_.grad_buffer(self._linear, '_b', (n,))
+            dz = device.empty((m, n))
+            ws = device.workspace(C.npm_colsum_workspace(m, n))
+            C.npm_relu_bwd_colsum(y.ptr, dy.ptr, dz.ptr, db.ptr, m, n, ws.data_ptr(), device.stream())
+            return self._linear.backward(dz, optimizer_, _db=db)
         dy = self._activation.backward(dy)
         return self._linear.backward(dy, optimizer_)
 

@@ -100,6 +100,7 @@ class LayerNormalization(layer.StatefulLayer):
     def forward(self, x):
         x = device.asdevice(x)
         self._x = x
+        self._fused = None      # set by dropout_layernorm_forward when DropOut ran inside the kernel
         cols = x.shape[-1]
         rows = x.size // cols
         gamma, beta = self._p('_gamma'), self._p('_beta')
@@ -128,3 +129,59 @@ class LayerNormalization(layer.StatefulLayer):
         optimizer_.update(self, '_gamma', dgamma)
         optimizer_.update(self, '_beta', dbeta)
         return dx
+
+
+# ---- DropOut -> LayerNormalization as ONE kernel (pre-norm transformer blocks) ----------------------
+# layers/transformer.py calls `dropout(x)` then `norm(x)` back to back (:35-37, :125-127, ...) and, in
+# backward, norm.backward -> dropout.backward -> `dy += dskip` (:90-92, :199-201).  These two helpers are
+# result-identical to those call sequences (same Philox mask, same arithmetic) but never write the dropped
+# tensor: 1 launch instead of 2 forward, 1 instead of 3 backward.  They fall back to the plain sequence
+# whenever the fused kernel does not apply (no dropout, injected mask, wide or unaligned rows).
+def dropout_layernorm_forward(drop: DropOut, norm: LayerNormalization, x):
+    x = device.asdevice(x)
+    if not norm._initialized:
+        norm.initialize(x)
+        norm._initialized = True
+    cols = x.shape[-1]
+    rows = x.size // cols
+    if drop._drop_prob == 0.0 or drop._ext_mask is not None or not C.npm_dropout_layernorm_fused(rows, cols):
+        return norm(drop(x))
+    keep_prob = np.float32(1 - drop._drop_prob)
+    seed = _philox['seed']
+    offset, _philox['offset'] = npm_dist.dropout_range(x.size, _philox['offset'], *npm_dist.world())
+    drop._rng, drop._shape = (seed, offset), x.shape
+    gamma, beta = norm._p('_gamma'), norm._p('_beta')
+    out = device.empty(x.shape)
+    norm._x = x                               # the PRE-dropout input: backward re-applies the mask
+    norm._mean, norm._rstd = device.empty((rows,)), device.empty((rows,))
+    norm._maskbits = device.workspace(C.npm_dropout_layernorm_mask_bytes(rows, cols))   # bit-packed keep mask
+    norm._fused = (keep_prob, seed, offset)
+    C.npm_dropout_layernorm_fwd(x.ptr, gamma.ptr, beta.ptr, out.ptr, norm._mean.ptr, norm._rstd.ptr,
+                                norm._maskbits.data_ptr(), rows, cols, float(norm._epsilon), keep_prob, seed, offset,
+                                device.stream())
+    return out
+
+
+def dropout_layernorm_backward(drop: DropOut, norm: LayerNormalization, dz, dskip, optimizer_):
+    """dropout.backward(norm.backward(dz)) + dskip"""
+    dz = device.asdevice(dz)
+    if getattr(norm, '_fused', None) is None:
+        dy = drop.backward(norm.backward(dz, optimizer_))
+        dy += dskip
+        return dy
+    keep_prob, seed, offset = norm._fused
+    x = norm._x
+    assert dz.size == x.size and dskip.size == x.size, f'{dz.shape} / {dskip.shape} vs {x.shape}'
+    cols = x.shape[-1]
+    rows = x.size // cols
+    gamma = norm._p('_gamma')
+    dx = device.empty(dz.shape)
+    dgamma = optimizer_.grad_buffer(norm, '_gamma', (cols,))
+    dbeta = optimizer_.grad_buffer(norm, '_beta', (cols,))
+    ws = device.workspace(C.npm_layernorm_bwd_workspace(rows, cols))
+    C.npm_dropout_layernorm_bwd(dz.ptr, x.ptr, gamma.ptr, norm._mean.ptr, norm._rstd.ptr, norm._maskbits.data_ptr(),
+                                dskip.ptr, dx.ptr, dgamma.ptr, dbeta.ptr, rows, cols, keep_prob, ws.data_ptr(),
+                                device.stream())
+    optimizer_.update(norm, '_gamma', dgamma)
+    optimizer_.update(norm, '_beta', dbeta)
+    return dx

@@ -44,8 +44,7 @@ class TransformerEncoder(layer.Layer):
 
         skip = qkv
         if self._norm_first:
-            qkv = self._dropout1(qkv)
-            qkv = self._norm1(qkv)
+            qkv = normalizations.dropout_layernorm_forward(self._dropout1, self._norm1, qkv)
         out = self._self_attention(qkv)
         out += skip
         if not self._norm_first:
@@ -57,8 +56,7 @@ class TransformerEncoder(layer.Layer):
         skip = out
 
         if self._norm_first:
-            out = self._dropout2(out)
-            out = self._norm2(out)
+            out = normalizations.dropout_layernorm_forward(self._dropout2, self._norm2, out)
         out = self._dense1(out)
         out = self._dense2(out)
         out += skip
@@ -80,10 +78,9 @@ class TransformerEncoder(layer.Layer):
         dy = self._dense2.backward(dy, optimizer_)
         dy = self._dense1.backward(dy, optimizer_)
         if self._norm_first:
-            dy = self._norm2.backward(dy, optimizer_)
-            dy = self._dropout2.backward(dy)
-
-        dy += dskip
+            dy = normalizations.dropout_layernorm_backward(self._dropout2, self._norm2, dy, dskip, optimizer_)
+        else:
+            dy += dskip
         dy = dy.reshape(batch, seq_len_q, features)
 
         if not self._norm_first:
@@ -93,10 +90,9 @@ class TransformerEncoder(layer.Layer):
         dy = self._self_attention.backward(dy, optimizer_)
         dy = _sum3(dy)
         if self._norm_first:
-            dy = self._norm1.backward(dy, optimizer_)
-            dy = self._dropout1.backward(dy)
-
-        dy += dskip
+            dy = normalizations.dropout_layernorm_backward(self._dropout1, self._norm1, dy, dskip, optimizer_)
+        else:
+            dy += dskip
 
         return dy
 
@@ -132,8 +128,7 @@ class TransformerDecoder(layer.Layer):
 
         skip = q
         if self._norm_first:
-            q = self._dropout1(q)
-            q = self._norm1(q)
+            q = normalizations.dropout_layernorm_forward(self._dropout1, self._norm1, q)
         out = self._self_attention(q)
         out += skip
         if not self._norm_first:
@@ -143,8 +138,7 @@ class TransformerDecoder(layer.Layer):
         skip = out
 
         if self._norm_first:
-            out = self._dropout2(out)
-            out = self._norm2(out)
+            out = normalizations.dropout_layernorm_forward(self._dropout2, self._norm2, out)
         out = self._cross_attention(out, kv)
         out += skip
         if not self._norm_first:
@@ -155,8 +149,7 @@ class TransformerDecoder(layer.Layer):
         skip = out
 
         if self._norm_first:
-            out = self._dropout3(out)
-            out = self._norm3(out)
+            out = normalizations.dropout_layernorm_forward(self._dropout3, self._norm3, out)
         out = self._dense1(out)
         out = self._dense2(out)
         out += skip
@@ -178,10 +171,9 @@ class TransformerDecoder(layer.Layer):
         dy = self._dense2.backward(dy, optimizer_)
         dy = self._dense1.backward(dy, optimizer_)
         if self._norm_first:
-            dy = self._norm3.backward(dy, optimizer_)
-            dy = self._dropout3.backward(dy)
-
-        dy += dskip
+            dy = normalizations.dropout_layernorm_backward(self._dropout3, self._norm3, dy, dskip, optimizer_)
+        else:
+            dy += dskip
         dy = dy.reshape(batch, seq_len_q, features)
 
         if not self._norm_first:
@@ -192,10 +184,9 @@ class TransformerDecoder(layer.Layer):
         dkv = dy[1] + dy[2]          # np.sum(dy[1:3], axis=0) (transformer.py:184)
         dy = dy[0]
         if self._norm_first:
-            dy = self._norm2.backward(dy, optimizer_)
-            dy = self._dropout2.backward(dy)
-
-        dy += dskip
+            dy = normalizations.dropout_layernorm_backward(self._dropout2, self._norm2, dy, dskip, optimizer_)
+        else:
+            dy += dskip
         if not self._norm_first:
             dy = self._norm1.backward(dy, optimizer_)
             dy = self._dropout1.backward(dy)
@@ -203,9 +194,8 @@ class TransformerDecoder(layer.Layer):
         dy = self._self_attention.backward(dy, optimizer_)
         dy = _sum3(dy)
         if self._norm_first:
-            dy = self._norm1.backward(dy, optimizer_)
-            dy = self._dropout1.backward(dy)
-
-        dy += dskip
+            dy = normalizations.dropout_layernorm_backward(self._dropout1, self._norm1, dy, dskip, optimizer_)
+        else:
+            dy += dskip
 
         return dy, dkv

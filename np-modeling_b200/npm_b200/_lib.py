@@ -59,11 +59,17 @@ SIGNATURES = {
     'npm_colsum': (c_int, [P, P, I64, I64, P, P]),
     'npm_relu_fwd': (c_int, [P, P, I64, P]),
     'npm_relu_bwd': (c_int, [P, P, P, I64, P]),
+    'npm_relu_bwd_y': (c_int, [P, P, P, I64, P]),
+    'npm_relu_bwd_colsum': (c_int, [P, P, P, P, I64, I64, P, P]),
     'npm_softmax_fwd': (c_int, [P, P, I64, I64, P]),
     'npm_softmax_bwd': (c_int, [P, P, P, I64, I64, F, P]),
     'npm_layernorm_fwd': (c_int, [P, P, P, P, P, P, I64, I64, F, P]),
     'npm_layernorm_bwd_workspace': (c_size_t, [I64, I64]),
     'npm_layernorm_bwd': (c_int, [P, P, P, P, P, P, P, P, I64, I64, P, P]),
+    'npm_dropout_layernorm_fused': (c_int, [I64, I64]),
+    'npm_dropout_layernorm_mask_bytes': (c_size_t, [I64, I64]),
+    'npm_dropout_layernorm_fwd': (c_int, [P, P, P, P, P, P, P, I64, I64, F, F, U64, U64, P]),
+    'npm_dropout_layernorm_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, I64, I64, F, P, P]),
     'npm_dropout_fwd': (c_int, [P, P, I64, F, U64, U64, P, P]),
     'npm_dropout_bwd': (c_int, [P, P, I64, F, U64, U64, P, P]),
     'npm_dropout_mask': (c_int, [P, I64, F, U64, U64, P]),
@@ -125,7 +131,7 @@ class _Calls:
         lib = load()
         fn = getattr(lib, name)
         res = SIGNATURES[name][0]
-        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision'):
+        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision', 'npm_dropout_layernorm_fused'):
             def call(*args, _fn=fn, _name=name):
                 rc = _fn(*args)
                 if rc != NPM_OK:

@@ -462,3 +462,95 @@ def test_trainer_mlp_golden(capsys):
     for i, layer in enumerate(layers):
         for k, v in sub(g, f'p1.{i}.').items():
             close(param_values(layer, [k])[k], v, rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------ fused bandwidth kernels
+def test_dense_fused_relu_keeps_reference_gradient_at_zero():
+    """Dense's default ReLU runs in the GEMM epilogue (pre-activation never written).  The reference's
+    backward passes the gradient where x >= 0 (activations.py:19) — including x == 0 exactly, which
+    the epilogue keeps apart from x < 0 through the sign of the stored zero."""
+    from layers import Dense
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(5)
+    m, k, n = 96, 64, 48
+    x = rng.standard_normal((m, k)).astype(np.float32)
+    w = rng.standard_normal((k, n)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    w[:, :8] = 0.0
+    b[:8] = 0.0                                   # pre-activation exactly 0 in the first 8 columns
+    dy = rng.standard_normal((m, n)).astype(np.float32)
+    layer = Dense(n)
+    layer(x)
+    bind(layer, {'_linear._w': w, '_linear._b': b})
+    y = np.asarray(layer(x))
+    z = O.linear_fwd(x, w, b)
+    close(y, np.maximum(z, 0.0))
+    assert (y >= 0).all() and (y[:, :8] == 0).all()
+    rec = Recorder()
+    dx = layer(dy, backprop=True, optimizer_=rec)
+    dz = np.where(z >= 0.0, dy.astype(np.float64), 0.0)          # gradient passes in the zero columns
+    assert (dz[:, :8] == dy[:, :8]).all()
+    odx, odw, odb = O.linear_bwd(x, w, dz)
+    close(dx, odx)
+    g = grads_of(layer, rec, ['_linear._w', '_linear._b'])
+    close(g['_linear._w'], odw, rtol=1e-3, atol=1e-3)
+    close(g['_linear._b'], odb, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('rows,cols', [(1, 4), (8192, 1024), (8192, 4096), (333, 260), (70, 130), (5000, 36)])
+def test_colsum_single_launch_matches_numpy_and_is_deterministic(rows, cols):
+    import torch
+    from npm_b200 import device
+    from npm_b200._lib import C
+    rng = np.random.default_rng(rows + cols)
+    x = rng.standard_normal((rows, cols)).astype(np.float32)
+    tx = torch.from_numpy(x).cuda()
+    outs = []
+    for _ in range(3):
+        out = torch.full((cols,), float('nan'), device='cuda')
+        ws = device.workspace(C.npm_colsum_workspace(rows, cols))
+        C.npm_colsum(tx.data_ptr(), out.data_ptr(), rows, cols, ws.data_ptr(), device.stream())
+        outs.append(out.cpu().numpy())
+    close(outs[0], x.astype(np.float64).sum(0), rtol=1e-5, atol=1e-3)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])     # fixed summation order
+
+
+@pytest.mark.parametrize('shape', [(4, 32, 128), (2, 100, 1024), (64, 260)])
+def test_fused_dropout_layernorm_equals_the_two_layers(shape):
+    """dropout_layernorm_forward/backward (one kernel each) == DropOut then LayerNormalization, backward then
+    `+= dskip`: the same Philox mask bit for bit; values to within the 1 ulp that separates the fused
+    kernels' multiply by fl(1 / keep) from DropOut's exact division (normalizations.py:22)."""
+    from layers.normalizations import (DropOut, LayerNormalization, dropout_layernorm_backward,
+                                       dropout_layernorm_forward, set_dropout_seed)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(shape).astype(np.float32)
+    dz = rng.standard_normal(shape).astype(np.float32)
+    dskip = rng.standard_normal(shape).astype(np.float32)
+    gamma = rng.standard_normal(shape[-1]).astype(np.float32)
+    beta = rng.standard_normal(shape[-1]).astype(np.float32)
+
+    def run(fused):
+        set_dropout_seed(77, 40)
+        drop, norm = DropOut(0.25), LayerNormalization()
+        norm(x)
+        bind(norm, {'_gamma': gamma, '_beta': beta})
+        set_dropout_seed(77, 40)
+        rec = Recorder()
+        if fused:
+            y = dropout_layernorm_forward(drop, norm, x)
+            assert norm._fused is not None
+            dx = dropout_layernorm_backward(drop, norm, dz, dskip_d(), rec)
+        else:
+            y = norm(drop(x))
+            dx = drop.backward(norm.backward(dz, rec))
+            dx += dskip_d()
+        g = grads_of(norm, rec, ['_gamma', '_beta'])
+        return np.asarray(y), np.asarray(dx), g['_gamma'], g['_beta'], drop._mask
+
+    from npm_b200 import device
+    dskip_d = lambda: device.asdevice(dskip)
+    a, b = run(True), run(False)
+    assert np.array_equal(a[4], b[4])
+    for u, v in zip(a[:4], b[:4]):
+        np.testing.assert_allclose(u, v, rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(v).max())))
+    assert abs(a[4].mean() - 0.75) < 0.05
