@@ -30,6 +30,8 @@ int check_launch(const char* what) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+int current_precision() { return g_precision.load(); }
+
 int num_sms() {
     static int sms = 0;
     if (sms == 0) {

@@ -10,9 +10,24 @@
 // K slices, 4x4 register micro-tile) that serves every shape, including channel counts TMA cannot
 // describe (Cin = 3: 12-byte pixel stride); wgrad is split over pixel slabs and combined with
 // fp32 atomics into a zero-initialised dw.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace npm {
+int current_precision();
+// conv_tc.cu: tcgen05 implicit GEMM (TF32 mode)
+bool conv_tc_supported(const void* p0, const void* p1, const void* p2, int64_t N, int64_t H, int64_t W, int64_t Cin,
+                       int64_t Cout, int ks);
+int conv_tc_fprop_dgrad(bool dgrad, const float* act, const float* f, const float* bias, float* out, int64_t N, int64_t H,
+                        int64_t W, int64_t Cin, int64_t Cout, int ks, int relu, cudaStream_t stream);
+int conv_tc_wgrad(const float* x, const float* dy, float* dw, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                  int ks, cudaStream_t stream);
+static bool use_tc(const void* p0, const void* p1, const void* p2, int64_t N, int64_t H, int64_t W, int64_t Cin,
+                   int64_t Cout, int ks) {
+    return current_precision() == NPM_PREC_TF32 && getenv("NPM_CONV_SIMT") == nullptr &&
+           conv_tc_supported(p0, p1, p2, N, H, W, Cin, Cout, ks);
+}
 size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
 
@@ -170,6 +185,8 @@ int npm_conv2d_fwd(const float* x, const float* f, const float* b, float* y, int
     int rc = check_conv(N, H, W, Cin, Cout, ksize);
     if (rc) return rc;
     NPM_REQUIRE(x && f && y, "conv2d_fwd: NULL pointer");
+    if (use_tc(x, f, y, N, H, W, Cin, Cout, ksize))
+        return conv_tc_fprop_dgrad(false, x, f, b, y, N, H, W, Cin, Cout, ksize, relu, (cudaStream_t)stream);
     ConvArgs a{};
     a.act = x; a.other = f; a.out = y; a.bias = b;
     a.N = (int)N; a.H = (int)H; a.W = (int)W; a.Ca = (int)Cin; a.Co = (int)Cout;
@@ -186,6 +203,8 @@ int npm_conv2d_bwd_dx(const float* dy, const float* f, float* dx, int64_t N, int
     int rc = check_conv(N, H, W, Cin, Cout, ksize);
     if (rc) return rc;
     NPM_REQUIRE(dy && f && dx, "conv2d_bwd_dx: NULL pointer");
+    if (use_tc(dy, f, dx, N, H, W, Cin, Cout, ksize))
+        return conv_tc_fprop_dgrad(true, dy, f, nullptr, dx, N, H, W, Cin, Cout, ksize, 0, (cudaStream_t)stream);
     ConvArgs a{};
     a.act = dy; a.other = f; a.out = dx; a.bias = nullptr;
     a.N = (int)N; a.H = (int)H; a.W = (int)W; a.Ca = (int)Cout; a.Co = (int)Cin;
@@ -205,6 +224,12 @@ int npm_conv2d_bwd_dw_db(const float* x, const float* dy, float* dw, float* db, 
     const int64_t pixels = N * H * W;
     const int64_t Mw = (int64_t)ksize * ksize * Cin;
     if ((rc = npm_fill(dw, 0.0f, Mw * Cout, stream))) return rc;
+    if (use_tc(x, dy, dw, N, H, W, Cin, Cout, ksize)) {
+        if ((rc = conv_tc_wgrad(x, dy, dw, N, H, W, Cin, Cout, ksize, s))) return rc;
+        if (db == nullptr) return NPM_OK;
+        NPM_REQUIRE(workspace != nullptr, "conv2d_bwd_dw_db: workspace is NULL");
+        return colsum_launch(dy, db, pixels, Cout, workspace, s);
+    }
     ConvArgs a{};
     a.act = x; a.other = dy; a.out = dw; a.bias = nullptr;
     a.N = (int)N; a.H = (int)H; a.W = (int)W; a.Ca = (int)Cin; a.Co = (int)Cout;

@@ -580,6 +580,32 @@ int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t
     return NPM_OK;
 }
 
+// General 4-D fp32 tensor map (dims[0] contiguous; strides of dims 1..3 in ELEMENTS; any box).
+int make_tensor_map_4d_box(CUtensorMap* tm, const float* base, const uint64_t dims[4], const uint64_t strides[3],
+                           const uint32_t box[4], bool round_tf32, bool atom32b) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return NPM_ERR_CUDA;
+    }
+    cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t st[3] = {strides[0] * 4, strides[1] * 4, strides[2] * 4};
+    cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult rc = fn(tm, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                     const_cast<float*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u,%u,%u) base=%p",
+                  (int)rc, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                  (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+                  (unsigned long long)strides[2], box[0], box[1], box[2], box[3], (const void*)base);
+        return NPM_ERR_CUDA;
+    }
+    return NPM_OK;
+}
+
 namespace {
 
 template <int BN, bool AMN, bool BMN, int NP>

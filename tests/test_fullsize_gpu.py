@@ -242,3 +242,37 @@ def test_fused_attention_vs_oracle(B, H, Sq, Skv):
         got = got.cpu().numpy().astype(np.float64)
         assert np.isfinite(got).all(), name
         assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32, 64, 128, 3), (3, 12, 28, 16, 20, 5), (2, 16, 16, 32, 32, 1), (2, 9, 8, 8, 260, 3),
+                                   (1, 5, 130, 4, 8, 3), (4, 32, 32, 3, 64, 3)])
+def test_conv_tensor_core_path_vs_oracle(shape):
+    """TF32 mode: Conv2D forward / input gradient / filter gradient run as TMA-staged implicit GEMMs on
+    tcgen05 (csrc/conv_tc.cu) whenever Cin % 4 == Cout % 4 == 0 and W >= 8 (the last shape, Cin = 3, stays on
+    the fp32 kernel).  Stated TF32 tolerance: 2e-3 of each tensor's max magnitude."""
+    import npm_b200
+    from layers import Conv2D
+    from oracle import np_oracle as O
+    npm_b200.set_precision('tf32')
+    n, hh, ww, c0, c1, k = shape
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal((n, hh, ww, c0)).astype(np.float32)
+    dy = rng.standard_normal((n, hh, ww, c1)).astype(np.float32)
+    f = (rng.standard_normal((k, k, c0, c1)) / np.sqrt(k * k * c0)).astype(np.float32)
+    b = rng.standard_normal(c1).astype(np.float32)
+    layer = Conv2D(c1, k)
+    layer(x)
+    bind(layer, {'_w': f, '_b': b})
+    y, z = O.conv_layer_fwd(x, f, b)
+    rec = Recorder()
+    got_y = np.asarray(layer(x))
+    dx = np.asarray(layer(dy, backprop=True, optimizer_=rec))
+    # ReLU gates of pre-activations within TF32 noise of zero may flip: judge dx / dw on the oracle evaluated
+    # with the gates the device actually used
+    gate = got_y > 0
+    odx, odw, odb = O.conv_layer_bwd(x, f, np.where(gate, 1.0, -1.0), dy)
+    g = grads_of(layer, rec, ['_w', '_b'])
+    for name, got, want in (('y', got_y, y), ('dx', dx, odx), ('dw', g['_w'], odw), ('db', g['_b'], odb)):
+        got = np.asarray(got, dtype=np.float64)
+        assert np.isfinite(got).all(), name
+        assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())
