@@ -131,8 +131,10 @@ def run_reference(args):
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=len(vals), warmup=args.warmup,
                 ms_per_step=1e3 * args.batch * args.seq * args.gpus / v, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
-                config=dict(workload=f'cfg5 TransformerDecoder x{args.layers} d{args.d_model} h{args.heads} '
-                                     f'f{args.hidden} Sq=Skv={args.seq} batch {args.batch}/GPU; CPU sample: {base["sample"]}'),
+                config=dict(workload=f'cfg5: {args.layers} x TransformerDecoder(heads {args.heads}, hidden {args.hidden}, pre-norm, '
+                                     f'drop 0.1), d_model {args.d_model}, Sq=Skv={args.seq}, batch {args.batch}/GPU, MSELoss, Adam(1e-4)',
+                            global_batch=args.batch * args.gpus, seq_len=args.seq, parallelism=f'dp{args.gpus}',
+                            note='CPU arm: bounded sample of this workload, see cpu_baseline.sample'),
                 cpu_baseline=base,
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -311,8 +313,12 @@ def run_b200(args):
     tf, gemm_ms = gemm_roofline(args.precision)
     tf32_peak = pk['bf16'] / 2.0          # kind::tf32 runs at half the bf16 rate; burst figure: kernel timed alone
     flop_per_token = L * FLOP_PER_TOKEN_LAYER(D, S, F)
-    roofline = dict(bound='tensor', achieved=tf, peak=tf32_peak, unit='TFLOP/s', frac=tf / tf32_peak, traffic=None,
-                    kernel=f'gemm_tc_kernel ({args.precision}) linear_fwd M={B * S} K={D} N={F}',
+    # DRAM traffic of this launch from the committed ncu --set full capture (profiles/r01_ncu_gemm_tc2_ffn.txt):
+    # 68.8 MB read + 92.1 MB written per launch, against 184.5 MB algorithmic (A + B once, C once; part of C is
+    # still in the 126 MB L2 when the kernel ends) — no re-reads.
+    traffic = 160.9e6 if (B * S, D, F) == (8192, 1024, 4096) else None
+    roofline = dict(bound='tensor', achieved=tf, peak=tf32_peak, unit='TFLOP/s', frac=tf / tf32_peak, traffic=traffic,
+                    kernel=f'gemm_tc2_kernel (CTA-pair tcgen05, {args.precision}) linear_fwd M={B * S} K={D} N={F}',
                     launch_ms=gemm_ms, l2='flushed between launches (256 MiB write)',
                     peak_basis=f'{pk["src"]} bf16_tflops/2 (tf32 = half the bf16 tensor rate)',
                     step_model_flops_frac=main['value'] * flop_per_token / world / 1e12 / (pk['bf16_sustained'] / 2.0))
