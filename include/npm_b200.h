@@ -77,6 +77,10 @@ typedef struct npm_gemm_desc {
     float   alpha;
     int32_t flags;
     int32_t precision;        /* NPM_PREC_* or <0 for the library default       */
+    const float* residual;    /* NULL, or [m, n] (leading dimension ldr) added after bias: the
+                               * `out += skip` of layers/transformer.py:39,53 in the epilogue;
+                               * unbatched problems only                            */
+    int64_t ldr;
 } npm_gemm_desc;
 int npm_gemm(const npm_gemm_desc* d, npm_stream_t stream);
 
@@ -88,6 +92,13 @@ int npm_gemm(const npm_gemm_desc* d, npm_stream_t stream);
 int npm_linear_fwd(const float* x, const float* w, const float* b, float* y,
                    int64_t m, int64_t k, int64_t n, int w_out_major, int relu,
                    npm_stream_t stream);
+/* y = x @ W + b + residual[m,n]: the residual connection that follows the
+ * output projection / second FFN layer in layers/transformer.py:39,53,129,143,
+ * 155, fused into the GEMM epilogue (residual may alias nothing it writes). */
+int npm_linear_fwd_residual(const float* x, const float* w, const float* b,
+                            const float* residual, float* y, int64_t m,
+                            int64_t k, int64_t n, int w_out_major,
+                            npm_stream_t stream);
 /* dx[m,k] = dy[m,n] @ W^T.                                         mlp.py:36 */
 int npm_linear_bwd_dx(const float* dy, const float* w, float* dx,
                       int64_t m, int64_t k, int64_t n, int w_out_major,
@@ -210,6 +221,26 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v,
                      float* dq, float* dk_out, float* dv_out, void* scratch,
                      int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk,
                      int64_t dv, npm_stream_t stream);
+/* Strided variants: q / k / v (and dq / dk / dv) may be column blocks of a wider
+ * row-major buffer, e.g. one [tokens, 3*H*dk] array written by a single packed
+ * q|k|v projection GEMM (the three einsums of attentions.py:90-100 share their
+ * input in self-attention).  Each field is the number of floats between
+ * consecutive tokens (>= H*d, multiple of 4); 0 = dense (H*d); ld == NULL = all
+ * dense.  o and d_o are always dense [B,Sq,H,dv]. */
+typedef struct npm_mha_strides {
+    int64_t q, k, v;          /* inputs                                         */
+    int64_t dq, dk, dv;       /* gradients written by the backward              */
+} npm_mha_strides;
+int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v,
+                             float* o, void* saved, int64_t B, int64_t H,
+                             int64_t Sq, int64_t Skv, int64_t dk, int64_t dv,
+                             const npm_mha_strides* ld, npm_stream_t stream);
+int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v,
+                             const float* o, const float* d_o, const void* saved,
+                             float* dq, float* dk_out, float* dv_out,
+                             void* scratch, int64_t B, int64_t H, int64_t Sq,
+                             int64_t Skv, int64_t dk, int64_t dv,
+                             const npm_mha_strides* ld, npm_stream_t stream);
 /* Writes the attention probabilities [B,H,Sq,Skv] to p_out (debug / parity with
  * MultiHeadAttention._attention_scores, attentions.py:108-111): copied out of
  * `saved` when it holds them, recomputed from q, k and the saved log-sum-exp

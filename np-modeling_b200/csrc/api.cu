@@ -53,11 +53,11 @@ size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
 // attn_fwd.cu / attn_bwd.cu
 bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv);
 int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, cudaStream_t stream);
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, cudaStream_t stream);
 size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq);
 int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    cudaStream_t stream);
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, cudaStream_t stream);
 int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
 
@@ -85,6 +85,8 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
                 (long long)d.n, (long long)d.k);
     NPM_REQUIRE((d.a_rs == 1 || d.a_cs == 1) && (d.b_rs == 1 || d.b_cs == 1),
                 "gemm: A and B need one unit stride each");
+    NPM_REQUIRE(d.residual == nullptr || (d.nb1 <= 1 && d.nb2 <= 1 && d.ldr >= d.n && !(d.flags & NPM_GEMM_RELU)),
+                "gemm: residual needs an unbatched problem, ldr >= n and no ReLU");
     int rc = require_sm100();
     if (rc) return rc;
     int prec = d.precision >= 0 ? d.precision : g_precision.load();
@@ -158,6 +160,18 @@ int npm_linear_fwd(const float* x, const float* w, const float* b, float* y, int
     return gemm_dispatch(d, (cudaStream_t)stream);
 }
 
+int npm_linear_fwd_residual(const float* x, const float* w, const float* b, const float* residual, float* y, int64_t m,
+                            int64_t k, int64_t n, int w_out_major, npm_stream_t stream) {
+    npm_gemm_desc d = blank_desc();
+    d.a = x; d.b = w; d.c = y; d.bias = b;
+    d.m = m; d.n = n; d.k = k;
+    d.a_rs = k; d.a_cs = 1;
+    if (w_out_major) { d.b_rs = 1; d.b_cs = k; } else { d.b_rs = n; d.b_cs = 1; }
+    d.ldc = n;
+    d.residual = residual; d.ldr = n;
+    return gemm_dispatch(d, (cudaStream_t)stream);
+}
+
 int npm_linear_bwd_dx(const float* dy, const float* w, float* dx, int64_t m, int64_t k, int64_t n, int w_out_major,
                       npm_stream_t stream) {
     // dx[m,k] = sum_n dy[m,n] * W(k,n): contraction over n
@@ -209,20 +223,29 @@ size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, int64_t 
 
 int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o, void* saved, int64_t B, int64_t H,
                      int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream) {
+    return npm_mha_core_fwd_strided(q, k, v, o, saved, B, H, Sq, Skv, dk, dv, nullptr, stream);
+}
+
+int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v, float* o, void* saved, int64_t B,
+                             int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, const npm_mha_strides* ld,
+                             npm_stream_t stream) {
     NPM_REQUIRE(q && k && v && o && saved, "mha_core_fwd: NULL pointer");
     cudaStream_t s = (cudaStream_t)stream;
     float* P = reinterpret_cast<float*>(saved);
-    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, s);
+    const int64_t ldq = ld && ld->q ? ld->q : H * dk, ldk = ld && ld->k ? ld->k : H * dk,
+                  ldv = ld && ld->v ? ld->v : H * dv;
+    NPM_REQUIRE(ldq >= H * dk && ldk >= H * dk && ldv >= H * dv, "mha_core_fwd: token strides must be >= H*d");
+    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, s);
     // S[b,h] = (1/sqrt(dk)) q[b,:,h,:] k[b,:,h,:]^T
     npm_gemm_desc d = blank_desc();
     d.a = q; d.b = k; d.c = P;
     d.m = Sq; d.n = Skv; d.k = dk;
-    d.a_rs = H * dk; d.a_cs = 1;
-    d.b_rs = 1; d.b_cs = H * dk;          // B(c, t) = k[t, h, c]
+    d.a_rs = ldq; d.a_cs = 1;
+    d.b_rs = 1; d.b_cs = ldk;             // B(c, t) = k[t, h, c]
     d.ldc = Skv;
     d.nb1 = (int)H; d.nb2 = (int)B;
-    d.a_bs1 = dk; d.a_bs2 = Sq * H * dk;
-    d.b_bs1 = dk; d.b_bs2 = Skv * H * dk;
+    d.a_bs1 = dk; d.a_bs2 = Sq * ldq;
+    d.b_bs1 = dk; d.b_bs2 = Skv * ldk;
     d.c_bs1 = Sq * Skv; d.c_bs2 = H * Sq * Skv;
     d.alpha = (float)(1.0 / sqrt((double)dk));
     int rc = gemm_dispatch(d, s);
@@ -234,11 +257,11 @@ int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o, v
     e.a = P; e.b = v; e.c = o;
     e.m = Sq; e.n = dv; e.k = Skv;
     e.a_rs = Skv; e.a_cs = 1;
-    e.b_rs = H * dv; e.b_cs = 1;          // B(t, c) = v[t, h, c]
+    e.b_rs = ldv; e.b_cs = 1;             // B(t, c) = v[t, h, c]
     e.ldc = H * dv;
     e.nb1 = (int)H; e.nb2 = (int)B;
     e.a_bs1 = Sq * Skv; e.a_bs2 = H * Sq * Skv;
-    e.b_bs1 = dv; e.b_bs2 = Skv * H * dv;
+    e.b_bs1 = dv; e.b_bs2 = Skv * ldv;
     e.c_bs1 = dv; e.c_bs2 = Sq * H * dv;
     return gemm_dispatch(e, s);
 }
@@ -246,11 +269,24 @@ int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o, v
 int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
                      const void* saved, float* dq, float* dk_out, float* dv_out, void* scratch, int64_t B, int64_t H,
                      int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream) {
+    return npm_mha_core_bwd_strided(q, k, v, o, d_o, saved, dq, dk_out, dv_out, scratch, B, H, Sq, Skv, dk, dv, nullptr,
+                                    stream);
+}
+
+int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v, const float* o, const float* d_o,
+                             const void* saved, float* dq, float* dk_out, float* dv_out, void* scratch, int64_t B,
+                             int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, const npm_mha_strides* ld,
+                             npm_stream_t stream) {
     NPM_REQUIRE(q && k && v && d_o && saved && dq && dk_out && dv_out && scratch, "mha_core_bwd: NULL pointer");
     cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ldq = ld && ld->q ? ld->q : H * dk, ldk = ld && ld->k ? ld->k : H * dk,
+                  ldv = ld && ld->v ? ld->v : H * dv, lddq = ld && ld->dq ? ld->dq : H * dk,
+                  lddk = ld && ld->dk ? ld->dk : H * dk, lddv = ld && ld->dv ? ld->dv : H * dv;
+    NPM_REQUIRE(ldq >= H * dk && ldk >= H * dk && ldv >= H * dv && lddq >= H * dk && lddk >= H * dk && lddv >= H * dv,
+                "mha_core_bwd: token strides must be >= H*d");
     if (attn_fused(B, H, Sq, Skv, dk, dv))
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
-                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, s);
+                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, lddq, lddk, lddv, s);
     const float* P = reinterpret_cast<const float*>(saved);
     float* dP = reinterpret_cast<float*>(scratch);
     int rc;
@@ -260,11 +296,11 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float
         d.m = Skv; d.n = dv; d.k = Sq;
         d.a_rs = 1; d.a_cs = Skv;            // A(t, s) = P[s, t]
         d.b_rs = H * dv; d.b_cs = 1;         // B(s, c) = dO[s, h, c]
-        d.ldc = H * dv;
+        d.ldc = lddv;
         d.nb1 = (int)H; d.nb2 = (int)B;
         d.a_bs1 = Sq * Skv; d.a_bs2 = H * Sq * Skv;
         d.b_bs1 = dv; d.b_bs2 = Sq * H * dv;
-        d.c_bs1 = dv; d.c_bs2 = Skv * H * dv;
+        d.c_bs1 = dv; d.c_bs2 = Skv * lddv;
         if ((rc = gemm_dispatch(d, s))) return rc;
     }
     {   // dP[b,h] = dO[b,:,h,:] v[b,:,h,:]^T                      attentions.py:146
@@ -272,11 +308,11 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float
         d.a = d_o; d.b = v; d.c = dP;
         d.m = Sq; d.n = Skv; d.k = dv;
         d.a_rs = H * dv; d.a_cs = 1;
-        d.b_rs = 1; d.b_cs = H * dv;         // B(c, t) = v[t, h, c]
+        d.b_rs = 1; d.b_cs = ldv;            // B(c, t) = v[t, h, c]
         d.ldc = Skv;
         d.nb1 = (int)H; d.nb2 = (int)B;
         d.a_bs1 = dv; d.a_bs2 = Sq * H * dv;
-        d.b_bs1 = dv; d.b_bs2 = Skv * H * dv;
+        d.b_bs1 = dv; d.b_bs2 = Skv * ldv;
         d.c_bs1 = Sq * Skv; d.c_bs2 = H * Sq * Skv;
         if ((rc = gemm_dispatch(d, s))) return rc;
     }
@@ -287,12 +323,12 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float
         d.a = dP; d.b = k; d.c = dq;
         d.m = Sq; d.n = dk; d.k = Skv;
         d.a_rs = Skv; d.a_cs = 1;
-        d.b_rs = H * dk; d.b_cs = 1;         // B(t, c) = k[t, h, c]
-        d.ldc = H * dk;
+        d.b_rs = ldk; d.b_cs = 1;            // B(t, c) = k[t, h, c]
+        d.ldc = lddq;
         d.nb1 = (int)H; d.nb2 = (int)B;
         d.a_bs1 = Sq * Skv; d.a_bs2 = H * Sq * Skv;
-        d.b_bs1 = dk; d.b_bs2 = Skv * H * dk;
-        d.c_bs1 = dk; d.c_bs2 = Sq * H * dk;
+        d.b_bs1 = dk; d.b_bs2 = Skv * ldk;
+        d.c_bs1 = dk; d.c_bs2 = Sq * lddq;
         if ((rc = gemm_dispatch(d, s))) return rc;
     }
     {   // dK[b,:,h,:] = dS[b,h]^T q[b,:,h,:]                       attentions.py:162
@@ -300,12 +336,12 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v, const float
         d.a = dP; d.b = q; d.c = dk_out;
         d.m = Skv; d.n = dk; d.k = Sq;
         d.a_rs = 1; d.a_cs = Skv;            // A(t, s) = dS[s, t]
-        d.b_rs = H * dk; d.b_cs = 1;         // B(s, c) = q[s, h, c]
-        d.ldc = H * dk;
+        d.b_rs = ldq; d.b_cs = 1;            // B(s, c) = q[s, h, c]
+        d.ldc = lddk;
         d.nb1 = (int)H; d.nb2 = (int)B;
         d.a_bs1 = Sq * Skv; d.a_bs2 = H * Sq * Skv;
-        d.b_bs1 = dk; d.b_bs2 = Sq * H * dk;
-        d.c_bs1 = dk; d.c_bs2 = Skv * H * dk;
+        d.b_bs1 = dk; d.b_bs2 = Sq * ldq;
+        d.c_bs1 = dk; d.c_bs2 = Skv * lddk;
         if ((rc = gemm_dispatch(d, s))) return rc;
     }
     return NPM_OK;

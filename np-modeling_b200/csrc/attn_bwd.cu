@@ -42,9 +42,10 @@ struct BwdArgs {
     float scale;              // 1 / sqrt(dk)
     const float* lse;         // [B, H, Sq]  (log2 domain)
     const float* dsum;        // [B, H, Sq]  D = rowsum(dO o O)
-    float* dq;                // [B, Sq, H, 64]
-    float* dk;                // [B, Skv, H, 64]
-    float* dv;                // [B, Skv, H, 64]
+    float* dq;                // [B, Sq, H, 64]   token stride lddq
+    float* dk;                // [B, Skv, H, 64]  token stride lddk
+    float* dv;                // [B, Skv, H, 64]  token stride lddv
+    int64_t lddq, lddk, lddv;
     int debug_skip;           // tools only: 1 = exp warps do no work, 2 = dS warps do no work, 3 = both (timing experiments)
 };
 
@@ -333,9 +334,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             ptx::tc_fence_after();
             const int t = nt * kBlk + tid;
             const bool live = t < args.Skv;
-            const size_t off = (((size_t)b * args.Skv + (live ? t : 0)) * args.H + h) * kD;
-            if (exp_group) store_acc_row(tm_dv + lane_off, args.dv + off, live);
-            else           store_acc_row(tm_dk + lane_off, args.dk + off, live);
+            const size_t tok = (size_t)b * args.Skv + (live ? t : 0);
+            if (exp_group) store_acc_row(tm_dv + lane_off, args.dv + tok * args.lddv + (size_t)h * kD, live);
+            else           store_acc_row(tm_dk + lane_off, args.dk + tok * args.lddk + (size_t)h * kD, live);
             ptx::tc_fence_before();
         }
     }
@@ -543,7 +544,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 ptx::tc_fence_after();
                 const int sq = mt * kBlk + tid;
                 const bool live = sq < args.Sq;
-                store_acc_row(tm_dq + lane_off, args.dq + (((size_t)b * args.Sq + (live ? sq : 0)) * args.H + h) * kD, live);
+                store_acc_row(tm_dq + lane_off, args.dq + ((size_t)b * args.Sq + (live ? sq : 0)) * args.lddq + (size_t)h * kD, live);
                 ptx::tc_fence_before();
             }
         }
@@ -604,18 +605,20 @@ int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_
 
 int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    cudaStream_t stream) {
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, cudaStream_t stream) {
     NPM_REQUIRE(o != nullptr, "mha_core_bwd: the fused path needs the forward output o");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
                 aligned16(dk) && aligned16(dv), "mha_core_bwd: pointers must be 16-byte aligned");
     const uint64_t HD = (uint64_t)H * kD;
     CUtensorMap tQr, tQt, tKr, tKt, tVr, tDOr, tDOt;
     int rc;
-    if ((rc = make_tensor_map_4d(&tQr, q, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tQt, q, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, true))) return rc;
-    if ((rc = make_tensor_map_4d(&tKr, k, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBlk, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tKt, k, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBlk, true, true))) return rc;
-    if ((rc = make_tensor_map_4d(&tVr, v, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBlk, true, false))) return rc;
+    for (int64_t ld : {ldq, ldk, ldv, lddq, lddk, lddv})
+        NPM_REQUIRE(ld >= (int64_t)HD && ld % 4 == 0, "mha_core_bwd: token strides must be >= H*d and multiples of 4 floats");
+    if ((rc = make_tensor_map_4d(&tQr, q, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tQt, q, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBlk, true, true))) return rc;
+    if ((rc = make_tensor_map_4d(&tKr, k, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tKt, k, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBlk, true, true))) return rc;
+    if ((rc = make_tensor_map_4d(&tVr, v, kD, Skv, H, B, ldv, kD, Skv * ldv, 32, kBlk, true, false))) return rc;
     if ((rc = make_tensor_map_4d(&tDOr, d_o, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, false))) return rc;
     if ((rc = make_tensor_map_4d(&tDOt, d_o, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, true))) return rc;
 
@@ -626,6 +629,7 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
     a.c = (float)(1.4426950408889634 / sqrt((double)kD));
     a.scale = (float)(1.0 / sqrt((double)kD));
     a.lse = lse; a.dsum = dsum; a.dq = dq; a.dk = dk; a.dv = dv;
+    a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
     a.debug_skip = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
 
     static bool configured = false;

@@ -311,14 +311,17 @@ bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t
 }
 
 int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, cudaStream_t stream) {
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, cudaStream_t stream) {
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "mha_core_fwd: pointers must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
     int rc;
     const uint64_t HD = (uint64_t)H * kD;
-    if ((rc = make_tensor_map_4d(&tmQ, q, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBM, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tmK, k, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBN, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tmV, v, kD, Skv, H, B, HD, kD, Skv * HD, 32, kBN, true, true))) return rc;
+    NPM_REQUIRE(ldq >= (int64_t)HD && ldk >= (int64_t)HD && ldv >= (int64_t)HD && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0,
+                "mha_core_fwd: token strides must be >= H*d and multiples of 4 floats");
+    // token stride ld*: q / k / v may be column blocks of one packed [tokens, 3*H*d] projection output
+    if ((rc = make_tensor_map_4d(&tmQ, q, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBM, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tmK, k, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBN, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tmV, v, kD, Skv, H, B, ldv, kD, Skv * ldv, 32, kBN, true, true))) return rc;
     FwdArgs a;
     a.B = (int)B; a.H = (int)H; a.Sq = (int)Sq; a.Skv = (int)Skv;
     a.q_tiles = (int)((Sq + kBM - 1) / kBM);

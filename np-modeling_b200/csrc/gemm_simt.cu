@@ -19,6 +19,7 @@ struct SimtArgs {
     int64_t a_bs1, a_bs2, b_bs1, b_bs2, c_bs1, c_bs2;
     float alpha;
     int relu, accum;
+    const float* residual; int64_t ldr;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs p) {
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs p) {
             if (gn >= p.n) continue;
             float v = acc[i][j] * p.alpha;
             if (p.bias) v += __ldg(p.bias + gn);
+            if (p.residual) v += __ldg(p.residual + gm * p.ldr + gn);
             if (p.relu) v = v < 0.0f ? -0.0f : v;
             float* dst = C + gm * p.ldc + gn;
             *dst = p.accum ? (*dst + v) : v;
@@ -108,6 +110,7 @@ int gemm_simt_launch(const npm_gemm_desc& d, cudaStream_t stream) {
     p.alpha = d.alpha;
     p.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
     p.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
+    p.residual = d.residual; p.ldr = d.ldr;
     const int64_t gx = (d.n + TN - 1) / TN, gy = (d.m + TM - 1) / TM, gz = (int64_t)p.nb1 * nb2;
     if (gx > 65535 || gz > 65535) {
         set_error("gemm_simt: grid too large (n tiles %lld, batches %lld)", (long long)gx, (long long)gz);

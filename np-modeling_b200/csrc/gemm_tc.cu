@@ -36,6 +36,8 @@ struct GemmTcArgs {
     int splits, kb_per_split, items_per_split;   // split-K: work item = (split, batch, n-tile, m-tile); partials are TMA-reduced into C
     float alpha;
     const float* bias;
+    const float* residual;     // [M, N] with leading dimension ldr, or nullptr
+    int64_t ldr;
     int relu, accum;
     uint64_t desc_a, desc_b;   // UMMA shared-memory descriptor templates (start address = 0)
 };
@@ -232,6 +234,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (nc + j < args.N) f[j] += __ldg(args.bias + nc + j);
+                }
+                if (args.residual != nullptr && sp == 0) {
+                    const int64_t row_g = (int64_t)m0 + warp * 32 + lane;
+                    if (row_g < args.M) {
+                        const float* rrow = args.residual + row_g * args.ldr + nc;
+                        if (nc + 32 <= args.N && ((reinterpret_cast<uintptr_t>(rrow) & 15u) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+                                f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nc + j < args.N) f[j] += __ldg(rrow + j);
+                        }
+                    }
                 }
                 if (args.relu) {
 #pragma unroll
@@ -488,6 +507,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (nc + j < args.N) f[j] += __ldg(args.bias + nc + j);
+                }
+                if (args.residual != nullptr && sp == 0) {
+                    const int64_t row_g = (int64_t)m0 + warp * 32 + lane;
+                    if (row_g < args.M) {
+                        const float* rrow = args.residual + row_g * args.ldr + nc;
+                        if (nc + 32 <= args.N && ((reinterpret_cast<uintptr_t>(rrow) & 15u) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+                                f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nc + j < args.N) f[j] += __ldg(rrow + j);
+                        }
+                    }
                 }
                 if (args.relu) {
 #pragma unroll
@@ -803,6 +839,8 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     args.splits = splits; args.kb_per_split = kb_per_split; args.items_per_split = (int)items_per_split;
     args.alpha = d.alpha;
     args.bias = d.bias;
+    args.residual = d.residual;
+    args.ldr = d.ldr;
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
     args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
     // Shared-memory descriptors.

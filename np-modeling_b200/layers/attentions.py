@@ -7,12 +7,19 @@ Parameter attributes and layouts are the reference's: `_wq,_wk [H,dk,D]`, `_wv [
 gradients are single tcgen05 GEMMs on the arrays as stored; the attention core runs behind
 `npm_mha_core_fwd/bwd`.
 """
+import ctypes
 from typing import Optional
 
 import optimizer
 from layers import activations, layer
 from npm_b200 import device
-from npm_b200._lib import C
+from npm_b200._lib import C, GemmDesc, MhaStrides
+
+
+def _add3(parts):
+    out = device.empty(parts[0].shape)
+    C.npm_add3(parts[0].ptr, parts[1].ptr, parts[2].ptr, out.ptr, out.size, device.stream())
+    return out
 
 
 class MultiHeadAttention(layer.StatefulLayer):
@@ -53,20 +60,59 @@ class MultiHeadAttention(layer.StatefulLayer):
         self._bv = self._initializer([h, dv])
         self._bo = self._initializer([h * dk])
 
-    def _project(self, x2d, w, b, n):
+    # ---- packed projection parameters --------------------------------------------------------
+    # `_wq,_wk,_wv` ([H,dk,D] each) and `_bq,_bk,_bv` are kept as the three leading-axis slices of one
+    # [3,H,dk,D] / [3,H,dk] block, so that the projections that share an input run as ONE GEMM:
+    # self-attention q|k|v = x @ [Wq;Wk;Wv]^T (N = 3*H*dk), cross-attention k|v (N = 2*H*dk), and in
+    # backward dW / db of the block in one GEMM + one column sum and dx = [dq|dk|dv] @ [Wq;Wk;Wv]
+    # (K = 3*H*dk), which is already the sum the transformer blocks take (transformer.py:85,184,196).
+    # The attribute names, shapes and values are the reference's; only their placement in HBM is chosen.
+    def _packed_params(self):
+        """(w_pack [3,H,dk,D], b_pack [3,H,dk]) with `_wq/_wk/_wv` and `_bq/_bk/_bv` as their slices, or
+        None when dk != dv.  Re-packs when a parameter was rebound (tests assign NumPy arrays by name,
+        layers/utils.py:41-101) or the layer was deep-copied."""
+        if self._key_dim != self._value_dim:
+            return None
+        ws = [self._p(n) for n in ('_wq', '_wk', '_wv')]
+        bs = [self._p(n) for n in ('_bq', '_bk', '_bv')]
+        packs = getattr(self, '_packs', None)
+        if packs is not None:
+            wp, bp = packs
+            wsz, bsz = ws[0].size * 4, bs[0].size * 4
+            if all(w.ptr == wp.ptr + i * wsz and w.size * 4 == wsz for i, w in enumerate(ws)) and \
+               all(b.ptr == bp.ptr + i * bsz and b.size * 4 == bsz for i, b in enumerate(bs)):
+                return packs
+        if len({w.shape for w in ws}) != 1 or len({b.shape for b in bs}) != 1:
+            return None
+        wp = device.empty((3,) + ws[0].shape)
+        bp = device.empty((3,) + bs[0].shape)
+        for i, (wn, bn) in enumerate((('_wq', '_bq'), ('_wk', '_bk'), ('_wv', '_bv'))):
+            setattr(self, wn, wp[i].copy_from(ws[i]))
+            setattr(self, bn, bp[i].copy_from(bs[i]))
+        self._packs = (wp, bp)
+        return self._packs
+
+    def _project(self, x2d, w, b, n, residual=None):
         m, k = x2d.shape
         y = device.empty((m, n))
-        C.npm_linear_fwd(x2d.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 1, 0, device.stream())
+        if residual is not None:
+            assert residual.size == m * n, 'residual must match the attention output'
+            C.npm_linear_fwd_residual(x2d.ptr, w.ptr, b.ptr, residual.ptr, y.ptr, m, k, n, 1, device.stream())
+        else:
+            C.npm_linear_fwd(x2d.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 1, 0, device.stream())
         return y
 
-    def forward(self, query, key=None, value=None, mask=None):
+    def forward(self, query, key=None, value=None, mask=None, _residual=None):
+        # _residual (B200 extension): the `out += skip` of the transformer blocks, run in the epilogue of the
+        # output projection
         if mask is not None:
             # the reference's `if mask:` raises for arrays (attentions.py:84) and its backward is
             # NotImplementedError (:152-153): attention is unmasked.
             raise ValueError('MultiHeadAttention: mask is not supported (reference attentions.py:84,152)')
+        query_in, key_in = query, key
         query = device.asdevice(query)
-        key = query if key is None else device.asdevice(key)
-        value = key if value is None else device.asdevice(value)
+        key = query if (key is None or key is query_in) else device.asdevice(key)
+        value = key if (value is None or value is key_in) else (query if value is query_in else device.asdevice(value))
 
         self._query, self._key, self._value, self._mask = query, key, value, mask
         batch, sq, dmodel = query.shape
@@ -74,50 +120,91 @@ class MultiHeadAttention(layer.StatefulLayer):
         h, dk, dv = self._num_heads, self._key_dim, self._value_dim
         assert sq == self._seq_len_q and skv == self._seq_len_kv, 'sequence lengths are fixed at init (:142-145)'
 
+        packs = self._packed_params()
         wq, wk, wv, wo = self._p('_wq'), self._p('_wk'), self._p('_wv'), self._p('_wo')
         bq, bk, bv, bo = self._p('_bq'), self._p('_bk'), self._p('_bv'), self._p('_bo')
+        hd = h * dk
+        query2 = query.reshape(batch * sq, dmodel)
+        key2 = key.reshape(batch * skv, key.shape[2])
 
-        q2 = self._project(query.reshape(batch * sq, dmodel), wq, bq, h * dk)
-        k2 = self._project(key.reshape(batch * skv, key.shape[2]), wk, bk, h * dk)
-        v2 = self._project(value.reshape(batch * skv, value.shape[2]), wv, bv, h * dv)
-        self._q = q2.reshape(batch, sq, h, dk)
-        self._k = k2.reshape(batch, skv, h, dk)
-        self._v = v2.reshape(batch, skv, h, dv)
+        # input projections (attentions.py:88-100); q/k/v are [B,S,H,dk] row blocks of `bufs`, token stride ld
+        if packs is not None and key is query and value is query:
+            self._mode = 'qkv'
+            qkv = self._project(query2, packs[0], packs[1], 3 * hd)                    # [B*S, 3*H*dk]
+            self._proj = (qkv,)
+            self._qkv_ptrs = (qkv.ptr, qkv.ptr + 4 * hd, qkv.ptr + 8 * hd)
+            self._qkv_ld = (3 * hd, 3 * hd, 3 * hd)
+        elif packs is not None and value is key:
+            self._mode = 'kv'
+            q2 = self._project(query2, wq, bq, hd)
+            kv2 = self._project(key2, packs[0][1:3], packs[1][1:3], 2 * hd)              # [B*Skv, 2*H*dk]
+            self._proj = (q2, kv2)
+            self._qkv_ptrs = (q2.ptr, kv2.ptr, kv2.ptr + 4 * hd)
+            self._qkv_ld = (hd, 2 * hd, 2 * hd)
+        else:
+            self._mode = 'separate'
+            q2 = self._project(query2, wq, bq, hd)
+            k2 = self._project(key2, wk, bk, hd)
+            v2 = self._project(value.reshape(batch * skv, value.shape[2]), wv, bv, h * dv)
+            self._proj = (q2, k2, v2)
+            self._qkv_ptrs = (q2.ptr, k2.ptr, v2.ptr)
+            self._qkv_ld = (hd, hd, h * dv)
 
         self._saved = device.workspace(C.npm_mha_core_saved_bytes(batch, h, sq, skv, dk, dv))
         values = device.empty((batch, sq, h, dv))          # [B, Sq, H, dv] (reference keeps [B,H,Sq,dv])
-        C.npm_mha_core_fwd(q2.ptr, k2.ptr, v2.ptr, values.ptr, self._saved.data_ptr(), batch, h, sq, skv, dk, dv,
-                           device.stream())
+        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2])
+        qp, kp, vp = self._qkv_ptrs
+        C.npm_mha_core_fwd_strided(qp, kp, vp, values.ptr, self._saved.data_ptr(), batch, h, sq, skv, dk, dv,
+                                   ctypes.byref(ld), device.stream())
         self._values = values
 
-        o = self._project(values.reshape(batch * sq, h * dv), wo, bo, wo.shape[0])
+        o = self._project(values.reshape(batch * sq, h * dv), wo, bo, wo.shape[0], _residual)
         return o.reshape(batch, sq, wo.shape[0])
 
-    def backward(self, dy, optimizer_: optimizer.Optimizer):
+    def backward(self, dy, optimizer_: optimizer.Optimizer, _sum_inputs: bool = False):
+        """Returns `(dquery, dkey, dvalue)` (attentions.py:199).  `_sum_inputs=True` (B200 extension used by
+        the transformer blocks, which only ever sum these — transformer.py:85,184-185,196) returns
+        `(dquery + dkey + dvalue, None)` for self-attention and `(dquery, dkey + dvalue)` when key is value,
+        computed by one GEMM over the concatenated contraction instead of separate GEMMs and adds."""
         dy = device.asdevice(dy)
         batch, sq, dmodel = dy.shape
         h, dk, dv = self._num_heads, self._key_dim, self._value_dim
         skv = self._seq_len_kv
         assert sq == self._seq_len_q
         s = device.stream()
+        hd = h * dk
+        mode = self._mode
+        packs = self._packed_params() if mode != 'separate' else None
+        if mode != 'separate' and packs is None:
+            raise RuntimeError('MultiHeadAttention: projection parameters changed shape between forward and backward')
         wq, wk, wv, wo = self._p('_wq'), self._p('_wk'), self._p('_wv'), self._p('_wo')
         for name in ('_bq', '_bk', '_bv', '_bo'):
             self._p(name)
 
-        def grads(x2d, dy2d, w_attr, b_attr):
-            """(dw, db) of y = x @ W^T + b for an output-major W [n, k]."""
+        def grads_into(x2d, dy2d, dw, db):
+            """dw [n, k] (output-major) = dy^T x, db [n] = column sums of dy, for y = x @ W^T + b."""
             m, k = x2d.shape
             n = dy2d.shape[1]
-            dw = optimizer_.grad_buffer(self, w_attr, getattr(self, w_attr).shape)
-            db = optimizer_.grad_buffer(self, b_attr, getattr(self, b_attr).shape)
             ws = device.workspace(C.npm_colsum_workspace(m, n))
             C.npm_linear_bwd_dw_db(x2d.ptr, dy2d.ptr, dw.ptr, db.ptr, m, k, n, 1, ws.data_ptr(), s)
+
+        def grads(x2d, dy2d, w_attr, b_attr):
+            dw = optimizer_.grad_buffer(self, w_attr, getattr(self, w_attr).shape)
+            db = optimizer_.grad_buffer(self, b_attr, getattr(self, b_attr).shape)
+            grads_into(x2d, dy2d, dw, db)
             return dw, db
 
-        def dinput(dy2d, w, k):
-            m, n = dy2d.shape
+        def dinput(dy2d, w, k, n=None, ld=None, ptr=None):
+            """dx [m, k] = dy [m, n] @ W for an output-major W [n, k]; dy may be a column block (ptr, ld)."""
+            m = dy2d.shape[0]
+            n = dy2d.shape[1] if n is None else n
             dx = device.empty((m, k))
-            C.npm_linear_bwd_dx(dy2d.ptr, w.ptr, dx.ptr, m, k, n, 1, s)
+            if ld is None:
+                C.npm_linear_bwd_dx(dy2d.ptr, w.ptr, dx.ptr, m, k, n, 1, s)
+            else:
+                d = GemmDesc(a=ptr, b=w.ptr, c=dx.ptr, bias=None, m=m, n=k, k=n, a_rs=ld, a_cs=1, b_rs=k, b_cs=1,
+                             ldc=k, nb1=1, nb2=1, alpha=1.0, flags=0, precision=-1, residual=None, ldr=0)
+                C.npm_gemm(ctypes.byref(d), s)
             return dx
 
         # output projection (attentions.py:129-136)
@@ -126,26 +213,63 @@ class MultiHeadAttention(layer.StatefulLayer):
         dwo, dbo = grads(values2, dy2, '_wo', '_bo')
         dvalues = dinput(dy2, wo, h * dv)                     # [B*Sq, H*dv]
 
-        # attention core (attentions.py:146-162)
-        dq = device.empty((batch, sq, h, dk))
-        dk_ = device.empty((batch, skv, h, dk))
-        dv_ = device.empty((batch, skv, h, dv))
+        # attention core (attentions.py:146-162): dq / dk / dv are written as row blocks mirroring forward's layout
+        if mode == 'qkv':
+            dqkv = device.empty((batch * sq, 3 * hd))
+            dptrs, dld, dbufs = (dqkv.ptr, dqkv.ptr + 4 * hd, dqkv.ptr + 8 * hd), (3 * hd,) * 3, (dqkv,)
+        elif mode == 'kv':
+            dq2 = device.empty((batch * sq, hd))
+            dkv2 = device.empty((batch * skv, 2 * hd))
+            dptrs, dld, dbufs = (dq2.ptr, dkv2.ptr, dkv2.ptr + 4 * hd), (hd, 2 * hd, 2 * hd), (dq2, dkv2)
+        else:
+            dq2 = device.empty((batch * sq, hd))
+            dk2 = device.empty((batch * skv, hd))
+            dv2 = device.empty((batch * skv, h * dv))
+            dptrs, dld, dbufs = (dq2.ptr, dk2.ptr, dv2.ptr), (hd, hd, h * dv), (dq2, dk2, dv2)
         scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes(batch, h, sq, skv, dk, dv))
-        C.npm_mha_core_bwd(self._q.ptr, self._k.ptr, self._v.ptr, self._values.ptr, dvalues.ptr,
-                           self._saved.data_ptr(), dq.ptr, dk_.ptr, dv_.ptr, scratch.data_ptr(), batch, h, sq, skv,
-                           dk, dv, s)
+        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], dq=dld[0], dk=dld[1], dv=dld[2])
+        qp, kp, vp = self._qkv_ptrs
+        C.npm_mha_core_bwd_strided(qp, kp, vp, self._values.ptr, dvalues.ptr, self._saved.data_ptr(), dptrs[0],
+                                   dptrs[1], dptrs[2], scratch.data_ptr(), batch, h, sq, skv, dk, dv,
+                                   ctypes.byref(ld), s)
 
         # input projections (attentions.py:169-188)
-        dq2, dk2, dv2 = dq.reshape(batch * sq, h * dk), dk_.reshape(batch * skv, h * dk), dv_.reshape(batch * skv, h * dv)
         query2 = self._query.reshape(batch * sq, self._query.shape[2])
         key2 = self._key.reshape(batch * skv, self._key.shape[2])
         value2 = self._value.reshape(batch * skv, self._value.shape[2])
-        dwq, dbq = grads(query2, dq2, '_wq', '_bq')
-        dquery = dinput(dq2, wq, query2.shape[1]).reshape(self._query.shape)
-        dwk, dbk = grads(key2, dk2, '_wk', '_bk')
-        dkey = dinput(dk2, wk, key2.shape[1]).reshape(self._key.shape)
-        dwv, dbv = grads(value2, dv2, '_wv', '_bv')
-        dvalue = dinput(dv2, wv, value2.shape[1]).reshape(self._value.shape)
+        din = query2.shape[1]
+        if mode == 'separate':
+            dwq, dbq = grads(query2, dq2, '_wq', '_bq')
+            dwk, dbk = grads(key2, dk2, '_wk', '_bk')
+            dwv, dbv = grads(value2, dv2, '_wv', '_bv')
+            dquery = dinput(dq2, wq, din).reshape(self._query.shape)
+            dkey = dinput(dk2, wk, key2.shape[1]).reshape(self._key.shape)
+            dvalue = dinput(dv2, wv, value2.shape[1]).reshape(self._value.shape)
+            result = (dquery, dkey, dvalue)
+        else:
+            dwp = optimizer_.grad_buffer_pack(self, ('_wq', '_wk', '_wv'), wq.shape)      # [3,H,dk,D]
+            dbp = optimizer_.grad_buffer_pack(self, ('_bq', '_bk', '_bv'), (h, dk))        # [3,H,dk]
+            (dwq, dwk, dwv), (dbq, dbk, dbv) = (dwp[0], dwp[1], dwp[2]), (dbp[0], dbp[1], dbp[2])
+            if mode == 'qkv':
+                grads_into(query2, dqkv, dwp, dbp)
+                if _sum_inputs:
+                    result = (dinput(dqkv, packs[0], din).reshape(self._query.shape), None)
+                else:
+                    result = tuple(dinput(dqkv, w, din, n=hd, ld=3 * hd, ptr=dptrs[i]).reshape(self._query.shape)
+                                   for i, w in enumerate((wq, wk, wv)))
+            else:
+                grads_into(query2, dq2, dwq, dbq)
+                grads_into(key2, dkv2, dwp[1:3], dbp[1:3])
+                dquery = dinput(dq2, wq, din).reshape(self._query.shape)
+                if _sum_inputs:
+                    result = (dquery, dinput(dkv2, packs[0][1:3], key2.shape[1]).reshape(self._key.shape))
+                else:
+                    result = (dquery,) + tuple(
+                        dinput(dkv2, w, key2.shape[1], n=hd, ld=2 * hd, ptr=dptrs[1 + i]).reshape(self._key.shape)
+                        for i, w in enumerate((wk, wv)))
+        if _sum_inputs and mode == 'separate':
+            assert self._value is self._key, '_sum_inputs is for self-attention and key-is-value cross-attention'
+            result = (result[0], result[1] + result[2]) if self._key is not self._query else (_add3(result), None)
 
         optimizer_.update(self, '_wq', dwq)
         optimizer_.update(self, '_wk', dwk)
@@ -156,17 +280,42 @@ class MultiHeadAttention(layer.StatefulLayer):
         optimizer_.update(self, '_bv', dbv)
         optimizer_.update(self, '_bo', dbo)
 
-        return dquery, dkey, dvalue
+        return result
 
     # ---- views matching the reference's cached intermediates (debug / parity only) ----------
     @property
     def _attention_scores(self):
         """softmax probabilities [B, H, Sq, Skv] (attentions.py:108-111)."""
-        b, sq, h, _ = self._q.shape
+        q, k = self._q, self._k
+        b, sq, h, _ = q.shape
         out = device.empty((b, h, sq, self._seq_len_kv))
-        C.npm_mha_core_scores(self._q.ptr, self._k.ptr, self._saved.data_ptr(), out.ptr, b, h, sq, self._seq_len_kv,
+        C.npm_mha_core_scores(q.ptr, k.ptr, self._saved.data_ptr(), out.ptr, b, h, sq, self._seq_len_kv,
                               self._key_dim, self._value_dim, device.stream())
         return out
+
+    def _block(self, i, seq):
+        """Dense copy of projected q (0) / k (1) / v (2) as [B, S, H, d] (reference `_q,_k,_v`, attentions.py:92-100)."""
+        h, d = self._num_heads, (self._key_dim if i < 2 else self._value_dim)
+        batch = self._query.shape[0]
+        if self._mode == 'qkv':
+            t = self._proj[0].t.view(batch, seq, 3, h, d)[:, :, i]
+        elif self._mode == 'kv' and i > 0:
+            t = self._proj[1].t.view(batch, seq, 2, h, d)[:, :, i - 1]
+        else:
+            t = self._proj[i if self._mode == 'separate' else 0].t.view(batch, seq, h, d)
+        return device.DeviceArray(t.contiguous())
+
+    @property
+    def _q(self):
+        return self._block(0, self._seq_len_q)
+
+    @property
+    def _k(self):
+        return self._block(1, self._seq_len_kv)
+
+    @property
+    def _v(self):
+        return self._block(2, self._seq_len_kv)
 
     @property
     def _attention_values(self):

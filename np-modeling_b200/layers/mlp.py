@@ -12,12 +12,14 @@ class Linear(layer.StatefulLayer):
         super().__init__(*args, **kwargs)
         self._output_units = units
 
-    def initialize(self, x) -> None:
+    def initialize(self, x, **kwargs) -> None:
         self._input_units = x.shape[-1]
         self._w = self._initializer([self._input_units, self._output_units])
         self._b = self._initializer([self._output_units])
 
-    def forward(self, x, _relu: bool = False):
+    def forward(self, x, _relu: bool = False, _residual=None):
+        """_relu / _residual are B200 extensions used by Dense and the transformer blocks: the activation and
+        the `out += skip` that follow this layer in the reference run in the GEMM epilogue."""
         x = device.asdevice(x)
         assert x.ndim == 2, 'Linear takes [m, k] inputs (mlp.py:33)'
         self._x = x
@@ -26,7 +28,11 @@ class Linear(layer.StatefulLayer):
         n = w.shape[1]
         assert w.shape[0] == k, f'{w.shape} vs input features {k}'
         y = device.empty((m, n))
-        C.npm_linear_fwd(x.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 0, 1 if _relu else 0, device.stream())
+        if _residual is not None:
+            assert not _relu and _residual.size == m * n, 'residual must match the output'
+            C.npm_linear_fwd_residual(x.ptr, w.ptr, b.ptr, _residual.ptr, y.ptr, m, k, n, 0, device.stream())
+        else:
+            C.npm_linear_fwd(x.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 0, 1 if _relu else 0, device.stream())
         return y
 
     def backward(self, dy, optimizer_: optimizer.Optimizer, _db=None):

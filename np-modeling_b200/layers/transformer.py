@@ -45,8 +45,7 @@ class TransformerEncoder(layer.Layer):
         skip = qkv
         if self._norm_first:
             qkv = normalizations.dropout_layernorm_forward(self._dropout1, self._norm1, qkv)
-        out = self._self_attention(qkv)
-        out += skip
+        out = self._self_attention(qkv, _residual=skip)      # `out += skip` (transformer.py:39) in the GEMM epilogue
         if not self._norm_first:
             out = self._dropout1(out)
             out = self._norm1(out)
@@ -58,8 +57,7 @@ class TransformerEncoder(layer.Layer):
         if self._norm_first:
             out = normalizations.dropout_layernorm_forward(self._dropout2, self._norm2, out)
         out = self._dense1(out)
-        out = self._dense2(out)
-        out += skip
+        out = self._dense2(out, _residual=skip)               # `out += skip` (transformer.py:53,155)
         if not self._norm_first:
             out = self._dropout2(out)
             out = self._norm2(out)
@@ -87,8 +85,7 @@ class TransformerEncoder(layer.Layer):
             dy = self._norm1.backward(dy, optimizer_)
             dy = self._dropout1.backward(dy)
         dskip = dy
-        dy = self._self_attention.backward(dy, optimizer_)
-        dy = _sum3(dy)
+        dy, _ = self._self_attention.backward(dy, optimizer_, _sum_inputs=True)   # np.sum(dy, axis=0) (:85,196)
         if self._norm_first:
             dy = normalizations.dropout_layernorm_backward(self._dropout1, self._norm1, dy, dskip, optimizer_)
         else:
@@ -129,8 +126,7 @@ class TransformerDecoder(layer.Layer):
         skip = q
         if self._norm_first:
             q = normalizations.dropout_layernorm_forward(self._dropout1, self._norm1, q)
-        out = self._self_attention(q)
-        out += skip
+        out = self._self_attention(q, _residual=skip)        # `out += skip` (transformer.py:129) in the GEMM epilogue
         if not self._norm_first:
             out = self._dropout1(out)
             out = self._norm1(out)
@@ -139,8 +135,7 @@ class TransformerDecoder(layer.Layer):
 
         if self._norm_first:
             out = normalizations.dropout_layernorm_forward(self._dropout2, self._norm2, out)
-        out = self._cross_attention(out, kv)
-        out += skip
+        out = self._cross_attention(out, kv, _residual=skip)  # `out += skip` (transformer.py:143)
         if not self._norm_first:
             out = self._dropout2(out)
             out = self._norm2(out)
@@ -151,8 +146,7 @@ class TransformerDecoder(layer.Layer):
         if self._norm_first:
             out = normalizations.dropout_layernorm_forward(self._dropout3, self._norm3, out)
         out = self._dense1(out)
-        out = self._dense2(out)
-        out += skip
+        out = self._dense2(out, _residual=skip)               # `out += skip` (transformer.py:53,155)
         if not self._norm_first:
             out = self._dropout3(out)
             out = self._norm3(out)
@@ -180,9 +174,7 @@ class TransformerDecoder(layer.Layer):
             dy = self._norm2.backward(dy, optimizer_)
             dy = self._dropout2.backward(dy)
         dskip = dy
-        dy = self._cross_attention.backward(dy, optimizer_)
-        dkv = dy[1] + dy[2]          # np.sum(dy[1:3], axis=0) (transformer.py:184)
-        dy = dy[0]
+        dy, dkv = self._cross_attention.backward(dy, optimizer_, _sum_inputs=True)   # dkv = dkey + dvalue (:184)
         if self._norm_first:
             dy = normalizations.dropout_layernorm_backward(self._dropout2, self._norm2, dy, dskip, optimizer_)
         else:
@@ -191,8 +183,7 @@ class TransformerDecoder(layer.Layer):
             dy = self._norm1.backward(dy, optimizer_)
             dy = self._dropout1.backward(dy)
         dskip = dy
-        dy = self._self_attention.backward(dy, optimizer_)
-        dy = _sum3(dy)
+        dy, _ = self._self_attention.backward(dy, optimizer_, _sum_inputs=True)   # np.sum(dy, axis=0) (:85,196)
         if self._norm_first:
             dy = normalizations.dropout_layernorm_backward(self._dropout1, self._norm1, dy, dskip, optimizer_)
         else:

@@ -31,7 +31,13 @@ class GemmDesc(Structure):
         ('a_bs1', c_int64), ('a_bs2', c_int64), ('b_bs1', c_int64), ('b_bs2', c_int64),
         ('c_bs1', c_int64), ('c_bs2', c_int64),
         ('alpha', c_float), ('flags', c_int32), ('precision', c_int32),
+        ('residual', c_void_p), ('ldr', c_int64),
     ]
+
+
+class MhaStrides(Structure):
+    """npm_mha_strides (include/npm_b200.h): floats between consecutive tokens, 0 = dense."""
+    _fields_ = [('q', c_int64), ('k', c_int64), ('v', c_int64), ('dq', c_int64), ('dk', c_int64), ('dv', c_int64)]
 
 
 class TensorEntry(Structure):
@@ -53,6 +59,7 @@ SIGNATURES = {
     'npm_device_info': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'npm_gemm': (c_int, [POINTER(GemmDesc), P]),
     'npm_linear_fwd': (c_int, [P, P, P, P, I64, I64, I64, I, I, P]),
+    'npm_linear_fwd_residual': (c_int, [P, P, P, P, P, I64, I64, I64, I, P]),
     'npm_linear_bwd_dx': (c_int, [P, P, P, I64, I64, I64, I, P]),
     'npm_linear_bwd_dw_db': (c_int, [P, P, P, P, I64, I64, I64, I, P, P]),
     'npm_colsum_workspace': (c_size_t, [I64, I64]),
@@ -81,6 +88,8 @@ SIGNATURES = {
     'npm_mha_core_bwd_scratch_bytes': (c_size_t, [I64] * 6),
     'npm_mha_core_fwd': (c_int, [P, P, P, P, P] + [I64] * 6 + [P]),
     'npm_mha_core_bwd': (c_int, [P] * 10 + [I64] * 6 + [P]),
+    'npm_mha_core_fwd_strided': (c_int, [P, P, P, P, P] + [I64] * 6 + [P, P]),
+    'npm_mha_core_bwd_strided': (c_int, [P] * 10 + [I64] * 6 + [P, P]),
     'npm_mha_core_scores': (c_int, [P, P, P, P] + [I64] * 6 + [P]),
     'npm_conv2d_workspace': (c_size_t, [I64, I64, I64, I64, I64, I]),
     'npm_conv2d_fwd': (c_int, [P, P, P, P, I64, I64, I64, I64, I64, I, I, P, P]),

@@ -39,6 +39,11 @@ class Optimizer(metaclass=abc.ABCMeta):
         """Device buffer a layer should write the gradient of `obj.attribute` into."""
         return device.empty(shape)
 
+    def grad_buffer_pack(self, obj: object, attributes, shape):
+        """One `[len(attributes), *shape]` buffer whose leading-axis slices are the gradients of
+        `obj.<attribute>` (parameters a layer keeps adjacent so one GEMM produces all their gradients)."""
+        return device.empty((len(attributes),) + tuple(int(s) for s in shape))
+
     def _enter(self):
         pass
 
@@ -83,6 +88,7 @@ class _FusedOptimizer(Optimizer):
         self._pending = []        # (identifier, variable, gradient)
         self._depth = 0
         self._grads = {}          # identifier -> persistent grad buffer
+        self._grad_packs = {}     # (id(obj), attributes, shape) -> [n, *shape] buffer whose slices are in _grads
         self._arena = _Arena()
         self._tables = {}         # key -> (device table, n_chunks, keepalive)
         self.grad_sync = None     # callable(optimizer) run before a flush applies (data parallel)
@@ -96,6 +102,17 @@ class _FusedOptimizer(Optimizer):
             buf = self._arena.alloc(shape)
             self._grads[identifier] = buf
         return buf
+
+    def grad_buffer_pack(self, obj, attributes, shape):
+        shape = tuple(int(s) for s in shape)
+        key = (id(obj), tuple(attributes), shape)
+        pack = self._grad_packs.get(key)
+        if pack is None:
+            pack = self._arena.alloc((len(attributes),) + shape)
+            self._grad_packs[key] = pack
+            for i, attribute in enumerate(attributes):
+                self._grads[f'{id(obj)}.{attribute}'] = pack[i]
+        return pack
 
     def _enter(self):
         self._depth += 1

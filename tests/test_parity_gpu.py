@@ -103,6 +103,30 @@ def test_linear_vs_oracle_shapes(m, k, n):
     close(g['_b'], odb, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('prec', ['3xtf32', 'tf32', 'fp32'])
+@pytest.mark.parametrize('m,k,n', [(256, 128, 128), (513, 100, 36), (1024, 1024, 1024), (1, 8, 4), (300, 64, 520)])
+def test_linear_residual_epilogue(prec, m, k, n):
+    """`out = dense2(out); out += skip` (transformer.py:52-53) with the add run in the GEMM epilogue."""
+    import npm_b200
+    from layers import Linear
+    from oracle import np_oracle as O
+    npm_b200.set_precision(prec)
+    rng = np.random.default_rng(m + 3 * n)
+    x = rng.standard_normal((m, k), dtype=np.float32)
+    skip = rng.standard_normal((m, n), dtype=np.float32)
+    w = (rng.standard_normal((k, n)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    layer = Linear(n)
+    layer(x)
+    bind(layer, {'_w': w, '_b': b})
+    from npm_b200 import device
+    skip_d = device.asdevice(skip)
+    want = O.linear_fwd(x, w, b) + skip
+    tol = dict(rtol=2e-3, atol=5e-3) if prec == 'tf32' else TC   # one-pass TF32: 10-bit operand mantissas
+    close(layer(x, _residual=skip_d), want, **tol)
+    close(skip_d, skip, rtol=0, atol=0)           # the skip branch is read, never written
+
+
 # ------------------------------------------------------------------ activations / norm / dropout
 def test_activations_golden():
     from layers import ReLU, Softmax
@@ -246,6 +270,69 @@ def test_mha_golden(tag):
         assert got[k].shape == g['g.' + k].shape
         close(got[k], g['g.' + k])
     assert copy.deepcopy(layer) is not layer                # attentions_test.py:72 deep-copies layers
+
+
+@pytest.mark.parametrize('prec', ['3xtf32', 'tf32'])
+@pytest.mark.parametrize('mode', ['qkv', 'kv', 'separate'])
+@pytest.mark.parametrize('dims', [(2, 40, 56, 4, 64), (1, 130, 130, 2, 64), (2, 9, 17, 3, 8)])
+def test_mha_packed_projection_modes(prec, mode, dims):
+    """Self-attention runs q|k|v as one packed projection GEMM, key-is-value cross-attention k|v; three distinct
+    inputs take three GEMMs.  All must equal the reference algorithm (attentions.py:67-199), through the public
+    3-tuple API and through the summed form the transformer blocks use (transformer.py:85,184-185,196)."""
+    import npm_b200
+    from layers import MultiHeadAttention
+    from oracle import np_oracle as O
+    npm_b200.set_precision(prec)
+    b, sq, skv, h, d = dims
+    if mode == 'qkv':
+        skv = sq
+    rng = np.random.default_rng(sq * 31 + d)
+    dm = h * d
+    query = rng.standard_normal((b, sq, dm), dtype=np.float32)
+    key = rng.standard_normal((b, skv, dm), dtype=np.float32)
+    value = rng.standard_normal((b, skv, dm), dtype=np.float32)
+    args = {'qkv': (query,), 'kv': (query, key), 'separate': (query, key, value)}[mode]
+    dy = rng.standard_normal((b, sq, dm), dtype=np.float32)
+    layer = MultiHeadAttention(h)
+    layer(*args)
+    params = {k: (np.asarray(getattr(layer, k)) * (1.0 / np.sqrt(dm) if k.startswith('_w') else 0.1)).astype(np.float32)
+              for k in O.MHA_PARAMS}
+    bind(layer, params)
+    tol = dict(rtol=2e-3, atol=2e-2) if prec == 'tf32' else TC
+    want, cache = O.mha_fwd(params, *args)
+    close(layer(*args), want, **tol)
+    assert layer._mode == mode
+    (dq_, dk_, dv_), grads = O.mha_bwd(params, cache, dy)
+    gtol = dict(rtol=2e-3, atol=2e-2 * np.sqrt(b * sq)) if prec == 'tf32' else dict(rtol=1e-3, atol=1e-4 * np.sqrt(b * sq))
+    for summed in (False, True):
+        rec = Recorder()
+        clone = copy.deepcopy(layer)                        # the copy re-packs its parameters on first use
+        close(clone(*args), want, **tol)
+        if summed:
+            if mode == 'separate':
+                continue
+            got = clone.backward(dy, rec, _sum_inputs=True)
+            if mode == 'qkv':
+                assert got[1] is None
+                close(got[0], dq_ + dk_ + dv_, **tol)
+            else:
+                close(got[0], dq_, **tol)
+                close(got[1], dk_ + dv_, **tol)
+        else:
+            got = clone(dy, backprop=True, optimizer_=rec)
+            close(got[0], dq_, **tol); close(got[1], dk_, **tol); close(got[2], dv_, **tol)
+        gg = grads_of(clone, rec, O.MHA_PARAMS)
+        for k in O.MHA_PARAMS:
+            assert gg[k].shape == grads[k].shape
+            close(gg[k], grads[k], **gtol)
+    # a real optimizer step through the packed gradient arena updates the three slices in place
+    import optimizer
+    opt = optimizer.SGDOptimizer(0.1)
+    alias = layer._wk
+    layer(*args)
+    layer(dy, backprop=True, optimizer_=opt)
+    close(alias, params['_wk'] - 0.1 * grads['_wk'], **gtol)
+    close(layer._bv, params['_bv'] - 0.1 * grads['_bv'], **gtol)
 
 
 def test_mha_mask_raises():
