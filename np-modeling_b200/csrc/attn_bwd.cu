@@ -16,7 +16,10 @@
 // swizzle ("R" image, K-major operand); contracted over its rows it is landed with 32-byte swizzle
 // atoms ("T" image, MN-major operand) — tf32 operands cannot be transposed at 16-byte granularity.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -46,6 +49,7 @@ struct BwdArgs {
     float* dk;                // [B, Skv, H, 64]  token stride lddk
     float* dv;                // [B, Skv, H, 64]  token stride lddv
     int64_t lddq, lddk, lddv;
+    long long* dbg;           // tools only: per-CTA cycle counters of the dK/dV MMA issuer's waits (NPM_ATTN_DEBUG_TIMES)
     int debug_skip;           // tools only: 1 = exp warps do no work, 2 = dS warps do no work, 3 = both (timing experiments)
 };
 
@@ -201,10 +205,21 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
         if (lane == 0) {
             constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
             constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
+            long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            long long* const dbg = args.dbg;
+            auto twait = [&](int slot, int which, uint32_t parity) {
+                if (dbg) {
+                    const long long t0 = clock64();
+                    ptx::mbar_wait(bar(which), parity);
+                    acc[slot] += clock64() - t0;
+                } else {
+                    ptx::mbar_wait(bar(which), parity);
+                }
+            };
             auto issue_st = [&](uint32_t g) {        // S^T(g) = K Q^T
                 const int it = g / n_q, i = g - it * n_q;
-                if (i == 0) ptx::mbar_wait(bar(K_FULL), it & 1);
-                ptx::mbar_wait(bar(QR_FULL), g & 1);
+                if (i == 0) twait(0, K_FULL, it & 1);
+                twait(1, QR_FULL, g & 1);
                 ptx::tc_fence_after();
                 mma_rr(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s);
                 ptx::umma_commit(bar(QR_EMPTY));
@@ -213,32 +228,38 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             };
             auto issue_dpt = [&](uint32_t g) {       // dP^T(g) = V dO^T
                 const int it = g / n_q, i = g - it * n_q;
-                if (i == 0) ptx::mbar_wait(bar(V_FULL), it & 1);
-                ptx::mbar_wait(bar(DOR_FULL), g & 1);
+                if (i == 0) twait(2, V_FULL, it & 1);
+                twait(3, DOR_FULL, g & 1);
                 ptx::tc_fence_after();
                 mma_rr(tm_dpt, vr_addr, dor_addr, idesc_s);
                 ptx::umma_commit(bar(DOR_EMPTY));
                 ptx::umma_commit(bar(DPT_FULL));
                 if (i == n_q - 1) ptx::umma_commit(bar(V_EMPTY));
             };
+            const long long t_begin = dbg ? clock64() : 0;
             if (G > 0) { issue_st(0); issue_dpt(0); }
             if (G > 1) issue_st(1);
             for (uint32_t g = 0; g < G; ++g) {
                 const int i = g % n_q;
-                ptx::mbar_wait(bar(P_READY0 + (g & 1u)), (g >> 1) & 1);
-                ptx::mbar_wait(bar(DOT_FULL), g & 1);
+                twait(4, P_READY0 + (g & 1u), (g >> 1) & 1);
+                twait(5, DOT_FULL, g & 1);
                 ptx::tc_fence_after();
                 mma_ts(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, i != 0);    // dV += P^T dO
                 ptx::umma_commit(bar(DOT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DV_DONE));
-                ptx::mbar_wait(bar(DS_READY), g & 1);
-                ptx::mbar_wait(bar(QT_FULL), g & 1);
+                twait(6, DS_READY, g & 1);
+                twait(7, QT_FULL, g & 1);
                 ptx::tc_fence_after();
                 mma_ts(tm_dk, tm_dpt, qt_addr, idesc_ts, i != 0);                          // dK += dS^T Q
                 ptx::umma_commit(bar(QT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DK_DONE));
                 if (g + 1 < G) issue_dpt(g + 1);
                 if (g + 2 < G) issue_st(g + 2);
+            }
+            if (dbg) {
+                acc[8] = clock64() - t_begin;
+                acc[9] = G;
+                for (int k = 0; k < 12; ++k) dbg[blockIdx.x * 12 + k] = acc[k];
             }
         }
     } else if (warp >= 4) {
@@ -631,6 +652,12 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
     a.lse = lse; a.dsum = dsum; a.dq = dq; a.dk = dk; a.dv = dv;
     a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
     a.debug_skip = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
+    a.dbg = nullptr;
+    const bool dbg_times = getenv("NPM_ATTN_DEBUG_TIMES") != nullptr;       // tools only: synchronises and prints
+    if (dbg_times) {
+        cudaMalloc(&a.dbg, sizeof(long long) * 12 * num_sms());
+        cudaMemset(a.dbg, 0, sizeof(long long) * 12 * num_sms());
+    }
 
     static bool configured = false;
     if (!configured) {
@@ -657,6 +684,21 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         attn_bwd_dkdv_kernel<<<grid, kThreads, kKvSmem, stream>>>(tQr, tQt, tKr, tVr, tDOr, tDOt, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dkdv_kernel"))) return rc;
+        if (dbg_times) {
+            cudaStreamSynchronize(stream);
+            std::vector<long long> h(12 * (size_t)grid);
+            cudaMemcpy(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+            static const char* names[10] = {"K_FULL", "QR_FULL", "V_FULL", "DOR_FULL", "P_READY", "DOT_FULL", "DS_READY",
+                                            "QT_FULL", "total", "blocks"};
+            double sum[12] = {0};
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 12; ++k) sum[k] += (double)h[12 * c + k];
+            const double blocks = sum[9] > 0 ? sum[9] : 1;
+            fprintf(stderr, "[attn_bwd_dkdv issuer, cycles per q block, mean over %d CTAs]", grid);
+            for (int k = 0; k < 9; ++k) fprintf(stderr, " %s=%.0f", names[k], sum[k] / blocks);
+            fprintf(stderr, "\n");
+            cudaFree(a.dbg);
+            a.dbg = nullptr;
+        }
     }
     {
         const int64_t items = B * H * a.n_q;

@@ -19,6 +19,11 @@
 //                                lo*hi + hi*lo + hi*hi, recovering ~fp32 accuracy.
 // Operands may be K-major or MN-major ("transposed"): the UMMA descriptors take the
 // 128B-swizzled tiles exactly as TMA lands them, so no transposes are ever materialised.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -40,6 +45,9 @@ struct GemmTcArgs {
     int64_t ldr;
     int relu, accum;
     uint64_t desc_a, desc_b;   // UMMA shared-memory descriptor templates (start address = 0)
+    int dbg_mode;              // tools only: 1 = no TMA loads / no full-barrier waits (pure MMA issue rate)
+    int a_chunked, b_chunked;  // pair kernel: MN-major operand described as a 5-D {32, K, MN/32, nb1, nb2} tensor, one box per stage
+    long long* dbg;            // tools only (NPM_GEMM_DEBUG_TIMES): per-CTA wait-cycle counters of the pair kernel's roles
 };
 
 template <int BLOCK_N, int NPASS>
@@ -418,7 +426,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int n0 = (r / args.tiles_m) * BLOCK_N + (int)rank * Cfg::kHalfN;
                 const int z1 = z % args.nb1, z2 = z / args.nb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (args.dbg_mode == 1) break;
+                    if (args.dbg) {
+                        const long long t0 = clock64();
+                        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                        args.dbg[blockIdx.x * 8 + 0] += clock64() - t0;
+                    } else {
+                        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    }
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
                     const uint32_t sB = sA + Cfg::kABytes;
                     const uint32_t fb = ptx::mapa(full_bar(stage), 0);       // the leader's barrier
@@ -426,6 +441,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int k0 = kb * kBlockK;
                     if (!A_MN) {
                         ptx::tma_load_4d_2sm(sA, &tmA, fb, k0, m0, z1, z2);
+                    } else if (args.a_chunked) {
+                        // one 16 KB box {32 m, 32 k, 4 chunks}: the TMA unit's cost is ~46 clk per box + bytes / 70 B/clk
+                        // (tools/micro/tma_bw.cu), so four 4 KB boxes cost 1.5x the time of one 16 KB box
+                        ptx::tma_load_5d_2sm(sA, &tmA, fb, 0, k0, m0 / 32, z1, z2);
                     } else {
 #pragma unroll
                         for (int c = 0; c < kBlockM / 32; ++c)
@@ -433,6 +452,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (!B_MN) {
                         ptx::tma_load_4d_2sm(sB, &tmB, fb, k0, n0, z1, z2);
+                    } else if (args.b_chunked) {
+                        ptx::tma_load_5d_2sm(sB, &tmB, fb, 0, k0, n0 / 32, z1, z2);
                     } else {
 #pragma unroll
                         for (int c = 0; c < Cfg::kHalfN / 32; ++c)
@@ -451,14 +472,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
+            long long w_full = 0, w_tempty = 0, n_ksteps = 0;
+            const long long t_begin = args.dbg ? clock64() : 0;
             for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
                 const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
                 const int kb1 = min(num_kb, kb0 + args.kb_per_split);
-                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                if (args.dbg) {
+                    const long long t0 = clock64();
+                    ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    w_tempty += clock64() - t0;
+                } else {
+                    ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                }
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(full_bar(stage), phase);
+                    if (args.dbg_mode == 1) {
+                        ++n_ksteps;
+                    } else if (args.dbg) {
+                        const long long t0 = clock64();
+                        ptx::mbar_wait(full_bar(stage), phase);
+                        w_full += clock64() - t0;
+                        ++n_ksteps;
+                    } else {
+                        ptx::mbar_wait(full_bar(stage), phase);
+                    }
                     ptx::tc_fence_after();
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
                     const uint32_t sB = sA + Cfg::kABytes;
@@ -475,6 +513,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
+            if (args.dbg) {
+                args.dbg[blockIdx.x * 8 + 1] = w_full;
+                args.dbg[blockIdx.x * 8 + 2] = w_tempty;
+                args.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin;
+                args.dbg[blockIdx.x * 8 + 4] = n_ksteps;
+            }
         }
     } else if (warp < 4) {
         // ============================== epilogue (both CTAs) ==============================
@@ -490,6 +534,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int m0 = (r % args.tiles_m) * (2 * kBlockM) + (int)rank * kBlockM;
             const int n0 = (r / args.tiles_m) * BLOCK_N;
             const int z1 = z % args.nb1, z2 = z / args.nb1;
+            if (args.dbg && warp == 0 && lane == 0) {
+                const long long t0 = clock64();
+                ptx::mbar_wait(tfull_bar(acc), acc_phase);
+                args.dbg[blockIdx.x * 8 + 5] += clock64() - t0;
+                args.dbg[blockIdx.x * 8 + 6] -= clock64();
+            }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const bool rows_live = (m0 + warp * 32) < args.M;
@@ -549,6 +599,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 ++nstore;
             }
+            if (args.dbg && warp == 0 && lane == 0) args.dbg[blockIdx.x * 8 + 6] += clock64();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -642,6 +693,32 @@ int make_tensor_map_4d_box(CUtensorMap* tm, const float* base, const uint64_t di
     return NPM_OK;
 }
 
+// MN-major operand [K rows, MN contiguous] (leading dimension ld) as a 5-D tensor {32, K, MN/32, nb1, nb2}: one TMA box
+// {32, box_k, chunks} lands `chunks` consecutive 4 KB swizzle-atom slabs — the same shared-memory image as `chunks`
+// separate {32, box_k} boxes, in one TMA instruction.  Needs MN % 32 == 0.
+int make_tensor_map_mn_chunked(CUtensorMap* tm, const float* base, uint64_t MN, uint64_t K, uint64_t nb1, uint64_t nb2,
+                               uint64_t ld, uint64_t s2, uint64_t s3, uint32_t box_k, uint32_t chunks, bool round_tf32) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return NPM_ERR_CUDA;
+    }
+    cuuint64_t dims[5]    = {32, K, MN / 32, nb1, nb2};
+    cuuint64_t strides[4] = {ld * 4, 32 * 4, s2 * 4, s3 * 4};
+    cuuint32_t box[5]     = {32, box_k, chunks, 1, 1};
+    cuuint32_t estr[5]    = {1, 1, 1, 1, 1};
+    CUresult rc = fn(tm, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                     const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (chunked MN-major) failed (%d): MN=%llu K=%llu ld=%llu", (int)rc,
+                  (unsigned long long)MN, (unsigned long long)K, (unsigned long long)ld);
+        return NPM_ERR_CUDA;
+    }
+    return NPM_OK;
+}
+
 namespace {
 
 template <int BN, bool AMN, bool BMN, int NP>
@@ -697,9 +774,31 @@ int launch_one2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, c, args);
+    GemmTcArgs largs = args;
+    const bool dbg_times = getenv("NPM_GEMM_DEBUG_TIMES") != nullptr;      // tools only: synchronises and prints
+    if (dbg_times) {
+        cudaMalloc(&largs.dbg, sizeof(long long) * 8 * grid);
+        cudaMemset(largs.dbg, 0, sizeof(long long) * 8 * grid);
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, c, largs);
     count_launch();
     if (e != cudaSuccess) { set_error("gemm_tc2_kernel launch: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+    if (dbg_times) {
+        cudaStreamSynchronize(stream);
+        std::vector<long long> h(8 * (size_t)grid);
+        cudaMemcpy(h.data(), largs.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        double prod_empty = 0, w_full = 0, w_tempty = 0, total = 0, ks = 0, e_wait = 0, e_busy = 0;
+        int leaders = 0;
+        for (int cta = 0; cta < grid; ++cta) {
+            prod_empty += (double)h[8 * cta]; e_wait += (double)h[8 * cta + 5]; e_busy += (double)h[8 * cta + 6];
+            if ((cta & 1) == 0) { w_full += (double)h[8 * cta + 1]; w_tempty += (double)h[8 * cta + 2]; total += (double)h[8 * cta + 3]; ks += (double)h[8 * cta + 4]; ++leaders; }
+        }
+        fprintf(stderr, "[gemm_tc2 M=%d N=%d K=%d] issuer: %.0f clk total, %.0f k-steps per leader -> %.0f clk/k-step; waits per k-step: "
+                "full %.0f, tmem-empty %.0f | producer empty-wait %.0f clk/k-step | epilogue warp0: tfull-wait %.0f, busy %.0f clk per CTA\n",
+                args.M, args.N, args.K, total / leaders, ks / leaders, total / ks, w_full / ks, w_tempty / ks, prod_empty / (2 * ks),
+                e_wait / grid, e_busy / grid);
+        cudaFree(largs.dbg);
+    }
     return check_launch("gemm_tc2_kernel");
 }
 
@@ -804,6 +903,9 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     CUtensorMap tmA, tmB, tmC;
     int rc;
     const uint64_t M = d.m, N = d.n, K = d.k;
+    static const bool chunk_off = env_flag("NPM_GEMM_NO_CHUNKED_MN", false);
+    const bool a_chunked = pair && a_mn && !chunk_off && (d.m % 32 == 0);
+    const bool b_chunked = pair && b_mn && !chunk_off && (d.n % 32 == 0);
     auto bs = [](int nb, int64_t s, uint64_t natural) -> uint64_t { return nb > 1 ? (uint64_t)s : natural; };
     if (!a_mn) {
         const uint64_t ld = d.a_rs;
@@ -812,7 +914,8 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     } else {
         const uint64_t ld = d.a_cs;
         const uint64_t s2 = bs(nb1, d.a_bs1, ld * K), s3 = bs(nb2, d.a_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
+        if (a_chunked) rc = make_tensor_map_mn_chunked(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, kBlockK, kBlockM / 32, round_ab);
+        else           rc = make_tensor_map_4d(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
     }
     if (rc) return rc;
     if (!b_mn) {
@@ -822,7 +925,8 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     } else {
         const uint64_t ld = d.b_rs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * K), s3 = bs(nb2, d.b_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
+        if (b_chunked) rc = make_tensor_map_mn_chunked(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, kBlockK, bn / 2 / 32, round_ab);
+        else           rc = make_tensor_map_4d(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
     }
     if (rc) return rc;
     {
@@ -841,6 +945,10 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     args.bias = d.bias;
     args.residual = d.residual;
     args.ldr = d.ldr;
+    args.dbg = nullptr;
+    args.dbg_mode = getenv("NPM_GEMM_DEBUG_MODE") ? atoi(getenv("NPM_GEMM_DEBUG_MODE")) : 0;
+    args.a_chunked = a_chunked ? 1 : 0;
+    args.b_chunked = b_chunked ? 1 : 0;
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
     args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
     // Shared-memory descriptors.

@@ -1,2 +1,4 @@
-set -x
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+for i in 1 2; do
+NPM_GEMM_NO_CHUNKED_MN=1 python bench.py --steps 5 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('nochunk', d['ms_per_step'], d['clocks']['sm_mhz'], d['roofline']['achieved'])"
+python bench.py --steps 5 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('chunked', d['ms_per_step'], d['clocks']['sm_mhz'], d['roofline']['achieved'])"
+done
