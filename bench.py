@@ -33,7 +33,7 @@ FLOP_PER_TOKEN_LAYER = lambda d, s, f: 3 * (16 * d * d + 8 * s * d + 4 * d * f) 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('NPM_BENCH_PRECISION', 'tf32'), choices=['tf32', '3xtf32'])
@@ -147,6 +147,8 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.rows = []
+        self.all_rows = []
+        self.t_mark = 0.0
         self.proc = None
 
     def start(self):
@@ -155,7 +157,7 @@ class ClockSampler:
                 ['nvidia-smi', '-i', str(self.index),
                  '--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
                  'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '100'],
+                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -163,13 +165,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.all_rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this (and before stop) are reported."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        t_end = time.perf_counter()
         time.sleep(0.15)
         self.proc.terminate()
+        # nvidia-smi prints a sample ~every 50 ms, each describing the interval before it
+        self.rows = [r for (t, r) in self.all_rows if self.t_mark + 0.02 <= t <= t_end + 0.06]
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -261,13 +270,14 @@ def run_b200(args):
         stack, trainer = build(precision)
         init_weights(stack)
         adam = opt_mod.AdamOptimizer(learning_rate=1e-4)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()            # nvidia-smi needs a few hundred ms to come up: start it before the warm-up
         for _ in range(warmup):
             trainer.train((q_d, kv_d), t_d, 1, adam)
         torch.cuda.synchronize()
         npm_b200.reset_launch_count()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
+        sampler.mark()
         ms = timed(trainer, adam, (q_d, kv_d), t_d, steps, read_loss=False)
         clocks = sampler.stop() if rank == 0 else None
         launches = npm_b200.launch_count()

@@ -102,6 +102,10 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool l
 }
 
 // =============================================================================== dK, dV
+// Measured design notes (NPM_ATTN_DEBUG_SKIP / NPM_ATTN_DEBUG_TIMES): with the MMAs and the elementwise work both
+// skipped this kernel still takes ~3700 clk per 128-row q block — it is bound by the 128 KB of tile loads per block
+// (Q and dO, each as an R and a T image) at ~35 B/clk/SM with 128 KB in flight.  A variant with 64-row q blocks and
+// every stream double buffered (same bytes in flight) measured 204 us against 152 us for this one at B8 H16 S1024.
 // smem: K_R, V_R (resident per item) | Q_R, dO_R, Q_T, dO_T (one q block each) | L/D staging | barriers
 constexpr int kKvSmem = 6 * kTileBytes + 2 * 2 * kBlk * 4 + 1024 + 256;
 
@@ -158,7 +162,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
         // K_R is released by the LAST S^T of an item (issued two blocks early) and V_R by its last
         // dP^T, so the next item's K / V land while the current item is still finishing; V is queued
         // behind Q_R(0) because S^T(0) of the next item is issued before V_R is free.
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             uint32_t g = 0;
             int it = 0;
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
@@ -185,7 +189,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
         }
     } else if (warp == 1) {
         // ============ producer: dO_T, Q_T per q block ============
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             uint32_t g = 0;
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
                 const int bh = item / args.n_kv;
@@ -202,7 +206,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
         }
     } else if (warp == 2) {
         // ============ MMA issuer ============
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
             constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
             long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -418,7 +422,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
 
     if (warp == 0) {
         // ============ producer: Q_R + dO_R per item; K_R, V_R per kv block ============
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             uint32_t g = 0;
             int it = 0;
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
@@ -442,7 +446,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
         }
     } else if (warp == 1) {
         // ============ producer: K_T per kv block ============
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             uint32_t g = 0;
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
                 const int bh = item / args.n_q;
@@ -456,7 +460,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
         }
     } else if (warp == 2) {
         // ============ MMA issuer ============
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
             constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
             auto issue_s = [&](uint32_t g) {         // S(g) = Q K^T

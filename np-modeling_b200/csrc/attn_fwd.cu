@@ -108,7 +108,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     if (warp == 0) {
         // ===================== Q + K producer =====================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             uint32_t gk = 0;
             int it = 0;
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
@@ -131,7 +131,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else if (warp == 1) {
         // ======================= V producer =======================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             uint32_t gv = 0;
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
                 const int bh = item / args.q_tiles;
@@ -147,7 +147,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else if (warp == 2) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBM, kBN, false, false);
             constexpr uint32_t idesc_pv = ptx::umma_idesc_tf32(kBM, kD, false, true);
             const uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);

@@ -139,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 4) {
         // ============================ TMA producer ============================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
@@ -199,7 +199,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < nkb; ++kb) {
                 ptx::mbar_wait(full_bar(stage), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                __syncwarp();
+                if (ptx::elect_one()) {
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
                     const uint32_t sB = sA + Cfg::kABytes;
 #pragma unroll
@@ -267,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     if (MODE == WGRAD) ptx::tma_reduce_add_4d(&tmC, stg_addr + buf * 4096, nc, c1, c2, c3);
                     else               ptx::tma_store_4d(&tmC, stg_addr + buf * 4096, nc, c1, c2, c3);
                     ptx::tma_commit_group();

@@ -128,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 4) {
         // ============================ TMA producer ============================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
@@ -182,7 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(NPASS == 3 ? xf_bar(stage) : full_bar(stage), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                __syncwarp();
+                if (ptx::elect_one()) {
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
                     const uint32_t sB = sA + Cfg::kABytes;
 #pragma unroll
@@ -276,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     if (args.accum || args.splits > 1)
                         ptx::tma_reduce_add_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
                     else
@@ -413,7 +414,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     if (warp == 4) {
         // ============================ TMA producer (both CTAs) ============================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
@@ -465,7 +466,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp == 5) {
         // ============================= MMA issuer (leader CTA) =============================
-        if (rank == 0 && lane == 0) {
+        if (rank == 0 && ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * kBlockM, BLOCK_N, A_MN, B_MN);
             const uint64_t descA = args.desc_a, descB = args.desc_b;
             constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;
@@ -590,7 +591,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     if (args.accum || args.splits > 1)
                         ptx::tma_reduce_add_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
                     else
@@ -688,6 +689,31 @@ int make_tensor_map_4d_box(CUtensorMap* tm, const float* base, const uint64_t di
                   (int)rc, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
                   (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
                   (unsigned long long)strides[2], box[0], box[1], box[2], box[3], (const void*)base);
+        return NPM_ERR_CUDA;
+    }
+    return NPM_OK;
+}
+
+// General fp32 tensor map of rank 3..5 (dims[0] contiguous; strides of dims 1.. in ELEMENTS; any box).
+int make_tensor_map_nd(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                       const uint32_t* box, bool round_tf32, bool atom32b) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return NPM_ERR_CUDA;
+    }
+    cuuint64_t d[5], st[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i] * 4;
+    CUresult rc = fn(tm, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                     const_cast<float*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (rank %d) failed (%d): dims0..2=(%llu,%llu,%llu) box0..2=(%u,%u,%u) base=%p", rank,
+                  (int)rc, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0],
+                  box[1], box[2], (const void*)base);
         return NPM_ERR_CUDA;
     }
     return NPM_OK;

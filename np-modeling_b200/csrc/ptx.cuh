@@ -12,6 +12,20 @@ namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// True in exactly one lane of a fully converged warp.  Guarding the single-thread tcgen05 / TMA issue code with this
+// (instead of `lane == 0`) lets ptxas prove the region is executed by one thread: with `lane == 0` it wraps every
+// tcgen05.mma / commit in an ELECT + R2UR + BRA.U.ANY "waterfall" loop (~15 extra instructions, ~70 clk per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t lane_id() {
     uint32_t l;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));

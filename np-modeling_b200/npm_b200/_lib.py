@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libnpm_b200.so')
+LIB_PATH = os.environ.get('NPM_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'libnpm_b200.so')   # env override: tools only
 
 NPM_OK = 0
 PREC_TF32, PREC_3XTF32, PREC_FP32 = 0, 1, 2

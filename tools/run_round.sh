@@ -1,4 +1,3 @@
-for i in 1 2; do
-NPM_GEMM_NO_CHUNKED_MN=1 python bench.py --steps 5 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('nochunk', d['ms_per_step'], d['clocks']['sm_mhz'], d['roofline']['achieved'])"
-python bench.py --steps 5 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('chunked', d['ms_per_step'], d['clocks']['sm_mhz'], d['roofline']['achieved'])"
-done
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_elect.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_elect.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['clocks'], d['roofline']['achieved'], d['roofline']['frac'], d['e2e']['value'], d['alt'])"
+python tools/conv_bench.py 2>&1 | tail -8
