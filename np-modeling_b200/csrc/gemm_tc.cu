@@ -339,11 +339,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // releases the ring slot / publishes the accumulator in both CTAs; both CTAs run their own
 // producer and their own epilogue (TMEM lanes = their 128 rows).
 // ===========================================================================================
-template <int BLOCK_N>
+template <int BLOCK_N, int KS>
 struct Tc2Cfg {
     static constexpr int kHalfN      = BLOCK_N / 2;
-    static constexpr int kABytes     = kBlockM * kBlockK * 4;           // 16 KB
-    static constexpr int kBBytes     = kHalfN * kBlockK * 4;
+    static constexpr int kABytes     = kBlockM * KS * 4;                // 16 KB per 32 k
+    static constexpr int kBBytes     = kHalfN * KS * 4;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kEpiBytes   = 4 * 2 * 4096;
     static constexpr int kBarBytes   = 512;
@@ -355,11 +355,14 @@ struct Tc2Cfg {
     static constexpr int kThreads    = 192;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// KS = fp32 elements of K per ring stage: 32, or 64 with each operand landed by ONE 32 KB TMA box (K-major: {32 k, rows,
+// 2 k-chunks} of a {32, rows, K/32} view; MN-major: {32 mn, 64 k, chunks}) — the TMA unit costs ~46 clk per box on top
+// of bytes / 70 B/clk (tools/micro/tma_bw.cu), and with fp32 operands the ring is what limits the main loop.
+template <int BLOCK_N, bool A_MN, bool B_MN, int KS>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const GemmTcArgs args) {
-    using Cfg = Tc2Cfg<BLOCK_N>;
+    using Cfg = Tc2Cfg<BLOCK_N, KS>;
     constexpr int S = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -382,7 +385,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t rank = ptx::cluster_ctarank();          // 0 = pair leader
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
-    const int num_kb = (args.K + kBlockK - 1) / kBlockK;
+    const int num_kb = (args.K + KS - 1) / KS;
 
     if (warp == 4 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -439,9 +442,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t sB = sA + Cfg::kABytes;
                     const uint32_t fb = ptx::mapa(full_bar(stage), 0);       // the leader's barrier
                     if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-                    const int k0 = kb * kBlockK;
+                    const int k0 = kb * KS;
                     if (!A_MN) {
-                        ptx::tma_load_4d_2sm(sA, &tmA, fb, k0, m0, z1, z2);
+                        if (KS == 32) ptx::tma_load_4d_2sm(sA, &tmA, fb, k0, m0, z1, z2);
+                        else          ptx::tma_load_5d_2sm(sA, &tmA, fb, 0, m0, k0 / 32, z1, z2);
                     } else if (args.a_chunked) {
                         // one 16 KB box {32 m, 32 k, 4 chunks}: the TMA unit's cost is ~46 clk per box + bytes / 70 B/clk
                         // (tools/micro/tma_bw.cu), so four 4 KB boxes cost 1.5x the time of one 16 KB box
@@ -452,7 +456,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             ptx::tma_load_4d_2sm(sA + c * 4096, &tmA, fb, m0 + c * 32, k0, z1, z2);
                     }
                     if (!B_MN) {
-                        ptx::tma_load_4d_2sm(sB, &tmB, fb, k0, n0, z1, z2);
+                        if (KS == 32) ptx::tma_load_4d_2sm(sB, &tmB, fb, k0, n0, z1, z2);
+                        else          ptx::tma_load_5d_2sm(sB, &tmB, fb, 0, n0, k0 / 32, z1, z2);
                     } else if (args.b_chunked) {
                         ptx::tma_load_5d_2sm(sB, &tmB, fb, 0, k0, n0 / 32, z1, z2);
                     } else {
@@ -469,8 +474,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (rank == 0 && ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(2 * kBlockM, BLOCK_N, A_MN, B_MN);
             const uint64_t descA = args.desc_a, descB = args.desc_b;
-            constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;
-            constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
+            // K-major: 32 B per K8 step inside a 128-byte row, the next 32-k slab after 4 steps; MN-major: 8 k-rows of 128 B
+            auto a_off = [](int kk) -> uint32_t { return A_MN ? uint32_t(kk) * 1024u : uint32_t(kk >> 2) * (kBlockM * 128u) + uint32_t(kk & 3) * 32u; };
+            auto b_off = [](int kk) -> uint32_t { return B_MN ? uint32_t(kk) * 1024u : uint32_t(kk >> 2) * (Cfg::kHalfN * 128u) + uint32_t(kk & 3) * 32u; };
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             long long w_full = 0, w_tempty = 0, n_ksteps = 0;
@@ -502,9 +508,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
                     const uint32_t sB = sA + Cfg::kABytes;
 #pragma unroll
-                    for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
-                        const uint64_t da = ptx::umma_desc(descA, sA + kk * a_kstep);
-                        const uint64_t db = ptx::umma_desc(descB, sB + kk * b_kstep);
+                    for (int kk = 0; kk < KS / kUmmaK; ++kk) {
+                        const uint64_t da = ptx::umma_desc(descA, sA + a_off(kk));
+                        const uint64_t db = ptx::umma_desc(descB, sB + b_off(kk));
                         ptx::umma_tf32_2sm(d_tmem, da, db, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
                     }
                     ptx::umma_commit_2sm(empty_bar(stage), 3);                    // slot reusable in both CTAs
@@ -719,6 +725,16 @@ int make_tensor_map_nd(CUtensorMap* tm, const float* base, int rank, const uint6
     return NPM_OK;
 }
 
+// K-major operand [rows, K contiguous] (leading dimension ld) as a 5-D tensor {32, rows, K/32, nb1, nb2}: one box
+// {32, box_rows, 2} lands two consecutive 32-k slabs (each the usual 128B-swizzled K-major image).  Needs K % 32 == 0.
+int make_tensor_map_k_chunked(CUtensorMap* tm, const float* base, uint64_t K, uint64_t rows, uint64_t nb1, uint64_t nb2,
+                              uint64_t ld, uint64_t s2, uint64_t s3, uint32_t box_rows, bool round_tf32) {
+    const uint64_t dims[5] = {32, rows, K / 32, nb1, nb2};
+    const uint64_t strides[4] = {ld, 32, s2, s3};
+    const uint32_t box[5] = {32, box_rows, 2, 1, 1};
+    return make_tensor_map_nd(tm, base, 5, dims, strides, box, round_tf32, false);
+}
+
 // MN-major operand [K rows, MN contiguous] (leading dimension ld) as a 5-D tensor {32, K, MN/32, nb1, nb2}: one TMA box
 // {32, box_k, chunks} lands `chunks` consecutive 4 KB swizzle-atom slabs — the same shared-memory image as `chunks`
 // separate {32, box_k} boxes, in one TMA instruction.  Needs MN % 32 == 0.
@@ -776,11 +792,11 @@ int launch_major(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap& b,
 }
 
 
-template <int BN, bool AMN, bool BMN>
+template <int BN, bool AMN, bool BMN, int KS>
 int launch_one2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmTcArgs& args,
                 int grid, cudaStream_t stream) {
-    using Cfg = Tc2Cfg<BN>;
-    auto kern = gemm_tc2_kernel<BN, AMN, BMN>;
+    using Cfg = Tc2Cfg<BN, KS>;
+    auto kern = gemm_tc2_kernel<BN, AMN, BMN, KS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -828,13 +844,13 @@ int launch_one2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
     return check_launch("gemm_tc2_kernel");
 }
 
-template <int BN>
+template <int BN, int KS>
 int launch_major2(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                   const GemmTcArgs& args, int grid, cudaStream_t s) {
-    if (!amn && !bmn) return launch_one2<BN, false, false>(a, b, c, args, grid, s);
-    if (!amn && bmn) return launch_one2<BN, false, true>(a, b, c, args, grid, s);
-    if (amn && !bmn) return launch_one2<BN, true, false>(a, b, c, args, grid, s);
-    return launch_one2<BN, true, true>(a, b, c, args, grid, s);
+    if (!amn && !bmn) return launch_one2<BN, false, false, KS>(a, b, c, args, grid, s);
+    if (!amn && bmn) return launch_one2<BN, false, true, KS>(a, b, c, args, grid, s);
+    if (amn && !bmn) return launch_one2<BN, true, false, KS>(a, b, c, args, grid, s);
+    return launch_one2<BN, true, true, KS>(a, b, c, args, grid, s);
 }
 
 inline bool mult4(int64_t v) { return (v & 3) == 0; }
@@ -910,8 +926,18 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
         }
     }
     const int bn = best_bn;
-    const int kb_per_split = (num_kb_total + best_splits - 1) / best_splits;
-    const int splits = (num_kb_total + kb_per_split - 1) / kb_per_split;
+    static const bool chunk_off = env_flag("NPM_GEMM_NO_CHUNKED_MN", false);
+    const bool a_chunked = pair && a_mn && !chunk_off && (d.m % 32 == 0);
+    const bool b_chunked = pair && b_mn && !chunk_off && (d.n % 32 == 0);
+    // 64-wide K stages (one 32 KB box per operand) when every operand has a chunked view.  Opt-in (NPM_GEMM_KS64=1):
+    // measured equal or slightly slower than six 32-wide stages (FFN shapes 671/616 vs 678/639 TF) — three coarse
+    // stages pipeline worse, which costs what the saved per-box overhead gains.
+    static const bool ks64_on = env_flag("NPM_GEMM_KS64", false);
+    const bool ks64 = pair && ks64_on && (a_mn ? a_chunked : d.k % 32 == 0) && (b_mn ? b_chunked : d.k % 32 == 0) && d.k >= 128;
+    const uint32_t ks = ks64 ? 64 : kBlockK;
+    const int num_kb_stage = (int)((d.k + ks - 1) / ks);        // ring stages along K
+    const int kb_per_split = (num_kb_stage + best_splits - 1) / best_splits;
+    const int splits = (num_kb_stage + kb_per_split - 1) / kb_per_split;
     const int64_t tiles_n = (d.n + bn - 1) / bn;
     const int64_t items_per_split = tiles_m * tiles_n * nb1 * nb2;
     const int64_t total = items_per_split * splits;
@@ -929,29 +955,28 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     CUtensorMap tmA, tmB, tmC;
     int rc;
     const uint64_t M = d.m, N = d.n, K = d.k;
-    static const bool chunk_off = env_flag("NPM_GEMM_NO_CHUNKED_MN", false);
-    const bool a_chunked = pair && a_mn && !chunk_off && (d.m % 32 == 0);
-    const bool b_chunked = pair && b_mn && !chunk_off && (d.n % 32 == 0);
     auto bs = [](int nb, int64_t s, uint64_t natural) -> uint64_t { return nb > 1 ? (uint64_t)s : natural; };
     if (!a_mn) {
         const uint64_t ld = d.a_rs;
         const uint64_t s2 = bs(nb1, d.a_bs1, ld * M), s3 = bs(nb2, d.a_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockK, kBlockM, round_ab, k_atom32);
+        if (ks64) rc = make_tensor_map_k_chunked(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockM, round_ab);
+        else      rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kBlockK, kBlockM, round_ab, k_atom32);
     } else {
         const uint64_t ld = d.a_cs;
         const uint64_t s2 = bs(nb1, d.a_bs1, ld * K), s3 = bs(nb2, d.a_bs2, s2 * nb1);
-        if (a_chunked) rc = make_tensor_map_mn_chunked(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, kBlockK, kBlockM / 32, round_ab);
+        if (a_chunked) rc = make_tensor_map_mn_chunked(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, ks, kBlockM / 32, round_ab);
         else           rc = make_tensor_map_4d(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
     }
     if (rc) return rc;
     if (!b_mn) {
         const uint64_t ld = d.b_cs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * N), s3 = bs(nb2, d.b_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, pair ? bn / 2 : bn, round_ab, k_atom32);
+        if (ks64) rc = make_tensor_map_k_chunked(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, bn / 2, round_ab);
+        else      rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kBlockK, pair ? bn / 2 : bn, round_ab, k_atom32);
     } else {
         const uint64_t ld = d.b_rs;
         const uint64_t s2 = bs(nb1, d.b_bs1, ld * K), s3 = bs(nb2, d.b_bs2, s2 * nb1);
-        if (b_chunked) rc = make_tensor_map_mn_chunked(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, kBlockK, bn / 2 / 32, round_ab);
+        if (b_chunked) rc = make_tensor_map_mn_chunked(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, ks, bn / 2 / 32, round_ab);
         else           rc = make_tensor_map_4d(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, 32, kBlockK, round_ab, true);
     }
     if (rc) return rc;
@@ -985,7 +1010,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     //                    each {32 mn, 32 k} box as 32 K-rows of 128 B; UMMA layout
     //                    SWIZZLE_128B_BASE32B, 32-element MN chunks 4096 B apart (LBO), 4-row K groups
     //                    512 B apart (SBO).
-    static const uint32_t mn_lbo = getenv("NPM_MN_LBO") ? (uint32_t)atoi(getenv("NPM_MN_LBO")) : 4096u;
+    const uint32_t mn_lbo = getenv("NPM_MN_LBO") ? (uint32_t)atoi(getenv("NPM_MN_LBO")) : ks * 128u;   // one {32 mn, ks k} chunk
     static const uint32_t mn_sbo = getenv("NPM_MN_SBO") ? (uint32_t)atoi(getenv("NPM_MN_SBO")) : 512u;
     const uint64_t desc_k  = k_atom32 ? ptx::umma_desc_base(1, 16, 1024) : ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
     const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, mn_lbo, mn_sbo);
@@ -993,8 +1018,12 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     args.desc_b = b_mn ? desc_mn : desc_k;
     if (pair) {
         const int grid2 = 2 * (int)(total < units ? total : units);
-        if (bn == 256) return launch_major2<256>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
-        return launch_major2<128>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
+        if (ks64) {
+            if (bn == 256) return launch_major2<256, 64>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
+            return launch_major2<128, 64>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
+        }
+        if (bn == 256) return launch_major2<256, 32>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
+        return launch_major2<128, 32>(a_mn, b_mn, tmA, tmB, tmC, args, grid2, stream);
     }
     const int grid = (int)(total < sms ? total : sms);
 
