@@ -70,3 +70,66 @@ def dropout_range(n: int, base: int, rank: int, world_size: int):
     Returns (offset for this rank, next base)."""
     n4 = (n + 3) // 4 * 4
     return base + rank * n4, base + world_size * n4
+
+
+class BucketTracker:
+    """Which gradient buckets (arena blocks) are complete during a backward pass.
+
+    The optimizer's gradient arena is filled in first-use = backward order, so bucket b holds the
+    gradients of a contiguous run of layers; once every gradient that lives in b has been handed to
+    `Optimizer.update` in this pass, b can be all-reduced while the rest of backward still runs
+    (SURVEY.md §8e).  Pure host logic: `mark(identifier)` returns the bucket that just became
+    complete, or None."""
+
+    def __init__(self, bucket_of):
+        self.bucket_of = dict(bucket_of)                  # identifier -> bucket index
+        self.expected = {}
+        for b in self.bucket_of.values():
+            self.expected[b] = self.expected.get(b, 0) + 1
+        self.begin_step()
+
+    def begin_step(self):
+        self.seen = set()
+        self.count = {b: 0 for b in self.expected}
+
+    def mark(self, identifier):
+        b = self.bucket_of.get(identifier)
+        if b is None or identifier in self.seen:
+            return None
+        self.seen.add(identifier)
+        self.count[b] += 1
+        return b if self.count[b] == self.expected[b] else None
+
+
+class AsyncBucketReducer:
+    """SUM all-reduce of buckets as they complete, off the compute stream.
+
+    CUDA tensors: the collective is enqueued on a side stream that first waits for the compute stream's
+    work so far (the kernels that wrote the bucket); `finish()` makes the compute stream wait for the side
+    stream.  CPU tensors (gloo, tests): asynchronous work handles, waited in `finish()`."""
+
+    def __init__(self):
+        self._side = None
+        self._handles = []
+        self.reduced = set()
+
+    def reduce(self, index, tensor):
+        if world()[1] > 1:
+            if tensor.is_cuda:
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+            else:
+                self._handles.append(dist.all_reduce(tensor, op=dist.ReduceOp.SUM, async_op=True))
+        self.reduced.add(index)
+
+    def finish(self):
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        done, self.reduced = self.reduced, set()
+        return done

@@ -64,6 +64,8 @@ class _Arena:
     def __init__(self):
         self.blocks = []   # [tensor, used]
         self.total = 0
+        self.last_block = -1
+        self.version = 0   # bumped by every allocation (a bucket schedule is valid for one version)
 
     def alloc(self, shape):
         n = int(np.prod(shape)) if len(shape) else 1
@@ -75,6 +77,8 @@ class _Arena:
         view = blk[0][blk[1]:blk[1] + n].view(*shape)
         blk[1] += need
         self.total += need
+        self.last_block = len(self.blocks) - 1
+        self.version += 1
         return device.DeviceArray(view)
 
     def used_views(self):
@@ -93,6 +97,10 @@ class _FusedOptimizer(Optimizer):
         self._tables = {}         # key -> (device table, n_chunks, keepalive)
         self.grad_sync = None     # callable(optimizer) run before a flush applies (data parallel)
         self.grad_scale = 1.0     # multiplies every gradient at apply time
+        self.bucket_ready = None  # callable(optimizer, block index): every gradient of an arena block has been produced
+        self._grad_block = {}     # identifier -> arena block index
+        self._tracker = None      # npm_b200.dist.BucketTracker, rebuilt when the arena grows
+        self._tracker_version = -1
 
     def grad_buffer(self, obj, attribute, shape):
         identifier = f'{id(obj)}.{attribute}'
@@ -101,6 +109,7 @@ class _FusedOptimizer(Optimizer):
         if buf is None or buf.shape != shape:
             buf = self._arena.alloc(shape)
             self._grads[identifier] = buf
+            self._grad_block[identifier] = self._arena.last_block
         return buf
 
     def grad_buffer_pack(self, obj, attributes, shape):
@@ -112,6 +121,7 @@ class _FusedOptimizer(Optimizer):
             self._grad_packs[key] = pack
             for i, attribute in enumerate(attributes):
                 self._grads[f'{id(obj)}.{attribute}'] = pack[i]
+                self._grad_block[f'{id(obj)}.{attribute}'] = self._arena.last_block
         return pack
 
     def _enter(self):
@@ -129,9 +139,23 @@ class _FusedOptimizer(Optimizer):
         if any(p[0] == identifier for p in self._pending):
             self.flush()   # same parameter twice in one backward: keep the reference's sequential semantics
         self._pending.append((identifier, variable, gradient))
+        if self.bucket_ready is not None and self._depth > 0:
+            self._mark_bucket(identifier, gradient)
         if self._depth == 0:
             self.flush()
         return variable
+
+    def _mark_bucket(self, identifier, gradient):
+        """Data parallel: tell `bucket_ready` when the last gradient of an arena block arrives.  Only once the arena
+        layout is stable (no allocation since the previous flush) and only for gradients that live in the arena."""
+        if self._tracker is None or self._tracker_version != self._arena.version:
+            return
+        own = self._grads.get(identifier)
+        if own is None or own.ptr != gradient.ptr:
+            return
+        done = self._tracker.mark(identifier)
+        if done is not None:
+            self.bucket_ready(self, done)
 
     def _table(self, entries, moments):
         key = tuple((v.ptr, g.ptr, v.size) for (_, v, g) in entries)
@@ -162,6 +186,12 @@ class _FusedOptimizer(Optimizer):
             return
         if self.grad_sync is not None:
             self.grad_sync(self)
+        if self.bucket_ready is not None:
+            if self._tracker_version != self._arena.version:
+                from npm_b200.dist import BucketTracker
+                self._tracker = BucketTracker(self._grad_block)
+                self._tracker_version = self._arena.version
+            self._tracker.begin_step()
         pending, self._pending = self._pending, []
         self._apply(pending)
 

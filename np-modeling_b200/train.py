@@ -8,12 +8,14 @@ arrays and are copied host→device every step; the loss is read back every step
 Data parallel (one process per GPU, `torch.distributed` initialised with NCCL — or gloo for the
 CPU tests of this logic): rank r trains on rows [r*B/n, (r+1)*B/n) of `inputs`/`targets`.  Parameters
 are broadcast from rank 0 after the lazy initialisation of step 0; gradients, which the optimizer keeps
-in a flat arena, are all-reduced (SUM) block by block right before the fused update and scaled by
-1/n when the loss is a mean over the local shard (MSELoss) or by 1 when it is a sum
-(CrossEntropyLoss) — so the update equals the single-process one on the full batch
+in a flat arena filled in backward order, are all-reduced (SUM) block by block — each block on a side
+stream as soon as the backward pass has produced its last gradient, so the exchange overlaps the rest of
+backward; what is left is reduced right before the fused update — and scaled by 1/n when the loss is a
+mean over the local shard (MSELoss) or by 1 when it is a sum (CrossEntropyLoss) — so the update equals the single-process one on the full batch
 (SURVEY.md §8e).  The printed loss is the global one.
 """
 import logging
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -112,14 +114,23 @@ class Trainer:
             return
         optimizer_.grad_scale = npm_dist.grad_scale(getattr(self._loss, 'dp_mean', True), world)
 
+        reducer = npm_dist.AsyncBucketReducer()
+
+        def bucket_ready(opt, b):
+            # every gradient of arena block b exists: all-reduce it on the side stream while backward continues
+            blk = opt._arena.blocks[b]
+            reducer.reduce(b, blk[0][:blk[1]])
+
         def sync(opt):
-            npm_dist.allreduce_sum(opt._arena.used_views())
+            done = reducer.finish()
+            npm_dist.allreduce_sum([blk[0][:blk[1]] for b, blk in enumerate(opt._arena.blocks) if blk[1] > 0 and b not in done])
             # gradients that did not come from the arena (user-supplied buffers)
             arena_ptrs = [(b[0].data_ptr(), b[0].data_ptr() + b[0].numel() * 4) for b in opt._arena.blocks]
             npm_dist.allreduce_sum([g.t for _, _, g in opt._pending
                                     if not any(lo <= g.ptr < hi for lo, hi in arena_ptrs)])
 
         optimizer_.grad_sync = sync
+        optimizer_.bucket_ready = None if os.environ.get('NPM_DP_NO_OVERLAP') else bucket_ready
 
     def _global_loss(self, l):
         rank, world = _world()

@@ -86,6 +86,26 @@ def _worker(rank, world, port, out):
         whole = philox.dropout_mask(n_local * world, 0.75, seed, base)
         assert np.array_equal(mine, whole[rank * n_local:(rank + 1) * n_local])
         assert nxt == base + world * n_local
+        # bucketed, overlapped all-reduce: buckets are reduced as their last gradient arrives, the rest at the end;
+        # the result equals one all-reduce of everything
+        bucket_of = {'l2.w': 0, 'l2.b': 0, 'l1.w': 1, 'l1.b': 1, 'l0.w': 2}
+        tracker = D.BucketTracker(bucket_of)
+        blocks = [torch.full((4,), float(rank + 1 + b)) for b in range(3)]
+        reducer = D.AsyncBucketReducer()
+        fired = []
+        for ident in ('l2.w', 'l2.b', 'l2.b', 'l1.w', 'unknown', 'l1.b'):       # l0.w never arrives in this pass
+            b = tracker.mark(ident)
+            if b is not None:
+                fired.append(b)
+                reducer.reduce(b, blocks[b])
+        assert fired == [0, 1]
+        done = reducer.finish()
+        assert done == {0, 1}
+        D.allreduce_sum([blk for b, blk in enumerate(blocks) if b not in done])
+        for b in range(3):
+            assert torch.equal(blocks[b], torch.full((4,), float(sum(r + 1 + b for r in range(world)))))
+        tracker.begin_step()
+        assert tracker.mark('l0.w') == 2 and tracker.mark('l0.w') is None
         out.put((rank, res))
     finally:
         dist.destroy_process_group()
