@@ -105,7 +105,11 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool l
 // Measured design notes (NPM_ATTN_DEBUG_SKIP / NPM_ATTN_DEBUG_TIMES): with the MMAs and the elementwise work both
 // skipped this kernel still takes ~3700 clk per 128-row q block — it is bound by the 128 KB of tile loads per block
 // (Q and dO, each as an R and a T image) at ~35 B/clk/SM with 128 KB in flight.  A variant with 64-row q blocks and
-// every stream double buffered (same bytes in flight) measured 204 us against 152 us for this one at B8 H16 S1024.
+// every stream double buffered (same bytes in flight) measured 204 us against 152 us for this one at B8 H16 S1024, and a
+// CTA-pair variant (cta_group::2, M = 256: each CTA loads only half of every streamed tile and the TS products run at
+// 32 instead of 45 clk per K8 step, tools/micro/mma_rate.cu) 168 us: what bounds a q block is the dependency chain
+// dP^T MMA -> dS warps -> dK MMA -> next dP^T MMA through the single dP^T buffer (TMEM is full: 2 x S^T, dP^T, dV, dK =
+// 512 columns), not the loads, and the pair's cross-CTA mbarrier hops lengthen exactly that chain.
 // smem: K_R, V_R (resident per item) | Q_R, dO_R, Q_T, dO_T (one q block each) | L/D staging | barriers
 constexpr int kKvSmem = 6 * kTileBytes + 2 * 2 * kBlk * 4 + 1024 + 256;
 

@@ -52,7 +52,63 @@ template <int MODE> void run(const char* name, int grid) {
     printf("%-44s grid %3d: %7.1f cycles / MMA   (%s)\n", name, grid, (double)h[0] / (iters * 16), cudaGetErrorString(e));
     cudaFree(d);
 }
+// cta_group::2 rates: MODE 0: SS M256 N128 K8 (B = 64 rows per CTA); 1: TS M256 N64 K8 (A from TMEM, B = one 32-wide MN slab per CTA)
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) rate2_kernel(long long* out, int iters) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint32_t slot;
+    __shared__ uint64_t barmem;
+    const uint32_t bar = ptx::smem_u32(&barmem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    if (warp == 0) { if (lane == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); } __syncwarp(); ptx::tmem_alloc_2sm(ptx::smem_u32(&slot), 512); ptx::tmem_relinquish_2sm(); }
+    ptx::tc_fence_before(); ptx::cluster_sync(); ptx::tc_fence_after();
+    const uint32_t tm = slot;
+    if (warp == 1 && rank == 0 && ptx::elect_one()) {
+        const uint64_t dk = ptx::umma_desc_base(2, 16, 1024), dmn = ptx::umma_desc_base(1, 16384, 512);
+        constexpr int N = MODE == 0 ? 128 : 64;
+        const uint32_t idesc = ptx::umma_idesc_tf32(256, N, false, MODE == 1);
+        long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                if (MODE == 1)
+                    ptx::umma_tf32_ts_2sm(tm + 256, tm + (kk & 15) * 8, ptx::umma_desc(dmn, base + 65536 + kk * 1024), idesc, 1u);
+                else
+                    ptx::umma_tf32_2sm(tm + 256, ptx::umma_desc(dk, base + (kk & 3) * 32 + (kk >> 2) * 16384),
+                                       ptx::umma_desc(dk, base + 65536 + (kk & 3) * 32 + (kk >> 2) * 8192), idesc, 1u);
+            }
+        }
+        ptx::umma_commit_2sm(bar, 1);
+        ptx::mbar_wait(bar, 0);
+        long long t1 = clock64();
+        out[blockIdx.x] = t1 - t0;
+    }
+    ptx::tc_fence_before(); ptx::cluster_sync();
+    if (warp == 0) ptx::tmem_dealloc_2sm(tm, 512);
+}
+template <int MODE> void run2(const char* name, int grid) {
+    long long* d; cudaMalloc(&d, sizeof(long long) * grid);
+    const int smem = 200 * 1024, iters = 200;
+    auto kern = rate2_kernel<MODE>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 2; ++rep) { cudaLaunchKernelEx(&cfg, kern, d, iters); e = cudaDeviceSynchronize(); }
+    long long h[148]; cudaMemcpy(h, d, sizeof(long long) * (grid < 148 ? grid : 148), cudaMemcpyDeviceToHost);
+    printf("%-44s grid %3d: %7.1f cycles / MMA   (%s)\n", name, grid, (double)h[0] / (iters * 16), cudaGetErrorString(e));
+    cudaFree(d);
+}
 int main() {
+    for (int grid : {2, 148}) {
+        run2<0>("2SM SS M256 N128 K8", grid);
+        run2<1>("2SM TS M256 N64  K8 (A from TMEM)", grid);
+    }
     for (int grid : {1, 148}) {
         run<0>("SS  M128 N128 K8 (A,B K-major from smem)", grid);
         run<2>("SS  M128 N256 K8", grid);

@@ -1,3 +1,5 @@
-python -m pytest tests/test_dp_gpu.py -m gpu -q -x 2>&1 | tail -15
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 10 --warmup 3 --no-alt --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('overlap on ', d['n_gpus'], d['value'], d['ms_per_step'])"
-NPM_DP_NO_OVERLAP=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 10 --warmup 3 --no-alt --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('overlap off', d['n_gpus'], d['value'], d['ms_per_step'])"
+timeout 120 python tools/attn_probe.py 2 4 256 384 --bwd 2>&1 | grep -E "err|rror"
+timeout 120 python tools/attn_probe.py 1 3 200 77 --bwd 2>&1 | grep -E "err|rror"
+timeout 120 python tools/attn_probe.py 1 2 130 300 --bwd 2>&1 | grep -E "err|rror"
+timeout 120 python tools/attn_probe.py 8 16 1024 1024 --bwd --time 2>&1 | grep -E "fwd|bwd|err"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:attn_ -c 4 python tools/attn_probe.py 8 16 1024 1024 --bwd 2>&1 | grep -E "attn_|gpu__time" | sed 's/(.*//'
