@@ -178,6 +178,19 @@ int npm_dropout_layernorm_bwd(const float* dz, const float* x,
                               float keep_prob, void* workspace,
                               npm_stream_t stream);
 
+/* Same, and dx_colsum[cols] = column sums of the dx written (NULL: not computed).
+ * dx is the gradient of the residual stream, so its column sum is the bias
+ * gradient of the projection / second FFN layer that wrote that stream
+ * (attentions.py:129 `dbo`, mlp.py:34 `db`): taken from registers here instead of
+ * re-reading dx in a npm_colsum launch. */
+int npm_dropout_layernorm_bwd_colsum(const float* dz, const float* x,
+                                     const float* gamma, const float* mean,
+                                     const float* rstd, const uint32_t* maskbits,
+                                     const float* dskip, float* dx, float* dgamma,
+                                     float* dbeta, float* dx_colsum, int64_t rows,
+                                     int64_t cols, float keep_prob, void* workspace,
+                                     npm_stream_t stream);
+
 /* ---- DropOut (layers/normalizations.py:9-30) ------------------------------ */
 /* Element i is kept iff philox4x32_10(counter=(offset+i)/4, key=seed)[(offset+i)%4]
  * < floor(keep_prob * 2^32); kept values are scaled by 1/keep_prob.  If

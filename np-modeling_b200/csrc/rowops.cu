@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_generic(const float
 // dgamma/dbeta in registers; warps of a CTA are combined through shared memory and each CTA
 // writes one partial row pair to the workspace [grid][2][cols]; colsum-style second stage
 // finishes the reduction (no atomics → deterministic).
-template <int NV, bool DROP = false>
+// XSUM: also accumulate the column sums of the dx this kernel writes (third partial row): dx is the gradient of the
+// residual stream, whose column sum is the bias gradient of the projection / FFN layer that produced that stream
+// (attentions.py:129, mlp.py:34) — summed here from registers instead of re-reading dx in a colsum launch.
+template <int NV, bool DROP = false, bool XSUM = false>
 __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -225,18 +228,20 @@ __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd_kernel(const flo
                                                                     int64_t rows, int cols, DropArgs drop = DropArgs{},
                                                                     const float* __restrict__ dskip = nullptr,
                                                                     const uint32_t* __restrict__ maskbits = nullptr) {
-    extern __shared__ float sred[];   // [kWarpsPerCta][2][cols_padded]
+    extern __shared__ float sred[];   // [kWarpsPerCta][NP][cols_padded], NP = 2 (+1 with XSUM)
+    constexpr int NP = XSUM ? 3 : 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // dgamma / dbeta of this warp's rows accumulate in the warp's own shared-memory slice and gamma is
     // re-read through L1 for every row: with only the two row images in registers two CTAs fit an SM,
     // and 16 warps of loads in flight are what a latency-bound row kernel needs to approach HBM speed.
     constexpr int cpad = NV * 128;
-    float* my = sred + (size_t)warp * 2 * cpad;
+    float* my = sred + (size_t)warp * NP * cpad;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 4;
         *reinterpret_cast<float4*>(my + c) = make_float4(0, 0, 0, 0);
         *reinterpret_cast<float4*>(my + cpad + c) = make_float4(0, 0, 0, 0);
+        if (XSUM) *reinterpret_cast<float4*>(my + 2 * cpad + c) = make_float4(0, 0, 0, 0);
     }
     const float inv_c = 1.0f / (float)cols;
     for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < rows; row += (int64_t)gridDim.x * kWarpsPerCta) {
@@ -304,16 +309,27 @@ __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd_kernel(const flo
                 }
             }
         }
+        if (XSUM) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = (i * 32 + lane) * 4;
+                if (c < cols) {
+                    float4 a = *reinterpret_cast<float4*>(my + 2 * cpad + c);
+                    a.x += rz.v[i].x; a.y += rz.v[i].y; a.z += rz.v[i].z; a.w += rz.v[i].w;
+                    *reinterpret_cast<float4*>(my + 2 * cpad + c) = a;
+                }
+            }
+        }
         rz.store(dx + row * cols, cols, lane);
     }
     // CTA reduce of the parameter-gradient partials
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * cpad; c += kRowThreads) {
+    for (int c = threadIdx.x; c < NP * cpad; c += kRowThreads) {
         float acc = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerCta; ++w) acc += sred[(size_t)w * 2 * cpad + c];
+        for (int w = 0; w < kWarpsPerCta; ++w) acc += sred[(size_t)w * NP * cpad + c];
         const int which = c / cpad, col = c - which * cpad;
-        if (col < cols) partial[((size_t)blockIdx.x * 2 + which) * cols + col] = acc;
+        if (col < cols) partial[((size_t)blockIdx.x * NP + which) * cols + col] = acc;
     }
 }
 
@@ -364,11 +380,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_param_generic(const float* 
 // blockIdx.y = 1 (LayerNorm: dbeta) reads the partials `cols` further on and writes out2.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                               int64_t cols, int nslabs, int64_t slab_stride,
-                                                              float* __restrict__ out2 = nullptr) {
+                                                              float* __restrict__ out2 = nullptr,
+                                                              float* __restrict__ out3 = nullptr) {
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * 32 + tx;
     if (blockIdx.y == 1) { partial += cols; out = out2; }
+    if (blockIdx.y == 2) { partial += 2 * cols; out = out3; }
     float acc = 0.0f;
     if (c < cols)
         for (int s = ty; s < nslabs; s += 8) acc += partial[(size_t)s * slab_stride + c];
@@ -643,7 +661,7 @@ static bool ln_fast(int64_t cols) { return (cols & 3) == 0 && cols <= 1024; }
 size_t npm_layernorm_bwd_workspace(int64_t rows, int64_t cols) {
     if (rows <= 0 || cols <= 0) return 0;
     const int64_t slabs = ln_fast(cols) ? ln_bwd_grid(rows) : ln_generic_slabs(rows);
-    return (size_t)slabs * 2 * (size_t)cols * sizeof(float);
+    return (size_t)slabs * 3 * (size_t)cols * sizeof(float);    // 3 partial rows per slab: dgamma, dbeta, column sums of dx
 }
 
 int npm_layernorm_bwd(const float* dz, const float* x, const float* gamma, const float* mean, const float* rstd,
@@ -747,6 +765,14 @@ int npm_dropout_layernorm_fwd(const float* x, const float* gamma, const float* b
 int npm_dropout_layernorm_bwd(const float* dz, const float* x, const float* gamma, const float* mean, const float* rstd,
                               const uint32_t* maskbits, const float* dskip, float* dx, float* dgamma, float* dbeta,
                               int64_t rows, int64_t cols, float keep_prob, void* workspace, npm_stream_t stream) {
+    return npm_dropout_layernorm_bwd_colsum(dz, x, gamma, mean, rstd, maskbits, dskip, dx, dgamma, dbeta, nullptr, rows, cols,
+                                            keep_prob, workspace, stream);
+}
+
+int npm_dropout_layernorm_bwd_colsum(const float* dz, const float* x, const float* gamma, const float* mean,
+                                     const float* rstd, const uint32_t* maskbits, const float* dskip, float* dx,
+                                     float* dgamma, float* dbeta, float* dx_colsum, int64_t rows, int64_t cols,
+                                     float keep_prob, void* workspace, npm_stream_t stream) {
     NPM_REQUIRE(maskbits != nullptr, "dropout_layernorm_bwd: maskbits is NULL");
     const uint64_t seed = 0, offset = 0;      // the mask comes from the forward pass
     if (rows <= 0 || cols <= 0) return NPM_OK;
@@ -761,8 +787,24 @@ int npm_dropout_layernorm_bwd(const float* dz, const float* x, const float* gamm
     float* partial = reinterpret_cast<float*>(workspace);
     const int slabs = ln_bwd_grid(rows);
     const int nv = nv_for(cols);
-    const size_t smem = (size_t)kWarpsPerCta * 2 * nv * 128 * sizeof(float);
+    const bool xsum = dx_colsum != nullptr;
+    const int np = xsum ? 3 : 2;
+    const size_t smem = (size_t)kWarpsPerCta * np * nv * 128 * sizeof(float);
     const DropArgs d = make_drop(keep_prob, seed, offset);
+    if (xsum && nv == 8) {
+        static bool configured3 = false;
+        if (!configured3) {
+            cudaFuncSetAttribute(layernorm_bwd_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured3 = true;
+        }
+        layernorm_bwd_kernel<8, true, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
+    } else if (xsum && nv == 4) {
+        layernorm_bwd_kernel<4, true, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
+    } else if (xsum && nv == 2) {
+        layernorm_bwd_kernel<2, true, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
+    } else if (xsum) {
+        layernorm_bwd_kernel<1, true, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
+    } else
     switch (nv) {
         case 1: layernorm_bwd_kernel<1, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits); break;
         case 2: layernorm_bwd_kernel<2, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits); break;
@@ -780,7 +822,7 @@ int npm_dropout_layernorm_bwd(const float* dz, const float* x, const float* gamm
     int rc = check_launch("dropout_layernorm_bwd");
     if (rc) return rc;
     const unsigned g2 = (unsigned)((cols + 31) / 32);
-    reduce_partials_kernel<<<dim3(g2, 2), 256, 0, s>>>(partial, dgamma, cols, slabs, 2 * cols, dbeta);
+    reduce_partials_kernel<<<dim3(g2, np), 256, 0, s>>>(partial, dgamma, cols, slabs, (int64_t)np * cols, dbeta, dx_colsum);
     count_launch();
     return check_launch("dropout_layernorm_bwd_reduce");
 }

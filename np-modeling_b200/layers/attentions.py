@@ -185,6 +185,11 @@ class MultiHeadAttention(layer.StatefulLayer):
             """dw [n, k] (output-major) = dy^T x, db [n] = column sums of dy, for y = x @ W^T + b."""
             m, k = x2d.shape
             n = dy2d.shape[1]
+            if dy2d.colsum is not None:
+                # the kernel that produced dy (fused LayerNorm backward) already summed its columns (attentions.py:129)
+                db.copy_from(dy2d.colsum)
+                C.npm_linear_bwd_dw_db(x2d.ptr, dy2d.ptr, dw.ptr, None, m, k, n, 1, None, s)
+                return
             ws = device.workspace(C.npm_colsum_workspace(m, n))
             C.npm_linear_bwd_dw_db(x2d.ptr, dy2d.ptr, dw.ptr, db.ptr, m, k, n, 1, ws.data_ptr(), s)
 

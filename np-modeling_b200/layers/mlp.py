@@ -47,7 +47,11 @@ class Linear(layer.StatefulLayer):
         n = w.shape[1]
         s = device.stream()
         dw = optimizer_.grad_buffer(self, '_w', (k, n))
-        if _db is None:
+        if _db is None and dy.colsum is not None:
+            # the kernel that produced dy (fused LayerNorm backward) already summed its columns: mlp.py:34 for free
+            db = optimizer_.grad_buffer(self, '_b', (n,)).copy_from(dy.colsum)
+            C.npm_linear_bwd_dw_db(x.ptr, dy.ptr, dw.ptr, None, m, k, n, 0, None, s)
+        elif _db is None:
             db = optimizer_.grad_buffer(self, '_b', (n,))
             ws = device.workspace(C.npm_colsum_workspace(m, n))
             C.npm_linear_bwd_dw_db(x.ptr, dy.ptr, dw.ptr, db.ptr, m, k, n, 0, ws.data_ptr(), s)

@@ -1,6 +1,8 @@
 """DropOut / LayerNormalization — drop-in for layers/normalizations.py."""
 import itertools
 
+import os
+
 import numpy as np
 import torch
 
@@ -162,6 +164,9 @@ def dropout_layernorm_forward(drop: DropOut, norm: LayerNormalization, x):
     return out
 
 
+_NO_COLSUM_RIDE = bool(os.environ.get('NPM_NO_COLSUM_RIDE'))      # A/B switch for tools
+
+
 def dropout_layernorm_backward(drop: DropOut, norm: LayerNormalization, dz, dskip, optimizer_):
     """dropout.backward(norm.backward(dz)) + dskip"""
     dz = device.asdevice(dz)
@@ -179,9 +184,14 @@ def dropout_layernorm_backward(drop: DropOut, norm: LayerNormalization, dz, dski
     dgamma = optimizer_.grad_buffer(norm, '_gamma', (cols,))
     dbeta = optimizer_.grad_buffer(norm, '_beta', (cols,))
     ws = device.workspace(C.npm_layernorm_bwd_workspace(rows, cols))
-    C.npm_dropout_layernorm_bwd(dz.ptr, x.ptr, gamma.ptr, norm._mean.ptr, norm._rstd.ptr, norm._maskbits.data_ptr(),
-                                dskip.ptr, dx.ptr, dgamma.ptr, dbeta.ptr, rows, cols, keep_prob, ws.data_ptr(),
-                                device.stream())
+    # dx is the gradient of the residual stream: its column sums are the bias gradient of whichever layer wrote the
+    # stream (the previous sublayer's output projection / second FFN layer), so they ride along with dx
+    if not _NO_COLSUM_RIDE:
+        dx.colsum = device.empty((cols,))
+    C.npm_dropout_layernorm_bwd_colsum(dz.ptr, x.ptr, gamma.ptr, norm._mean.ptr, norm._rstd.ptr,
+                                       norm._maskbits.data_ptr(), dskip.ptr, dx.ptr, dgamma.ptr, dbeta.ptr,
+                                       dx.colsum.ptr if dx.colsum is not None else None,
+                                       rows, cols, keep_prob, ws.data_ptr(), device.stream())
     optimizer_.update(norm, '_gamma', dgamma)
     optimizer_.update(norm, '_beta', dbeta)
     return dx

@@ -77,6 +77,7 @@ SIGNATURES = {
     'npm_dropout_layernorm_mask_bytes': (c_size_t, [I64, I64]),
     'npm_dropout_layernorm_fwd': (c_int, [P, P, P, P, P, P, P, I64, I64, F, F, U64, U64, P]),
     'npm_dropout_layernorm_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, I64, I64, F, P, P]),
+    'npm_dropout_layernorm_bwd_colsum': (c_int, [P, P, P, P, P, P, P, P, P, P, P, I64, I64, F, P, P]),
     'npm_dropout_fwd': (c_int, [P, P, I64, F, U64, U64, P, P]),
     'npm_dropout_bwd': (c_int, [P, P, I64, F, U64, U64, P, P]),
     'npm_dropout_mask': (c_int, [P, I64, F, U64, U64, P]),

@@ -28,12 +28,16 @@ def _device():
 
 
 class DeviceArray:
-    __slots__ = ('t',)
+    # `colsum`: optional DeviceArray [shape[-1]] holding the sums over all leading axes, attached by a kernel that had
+    # the values in registers anyway (the fused LayerNorm backward); consumers that need exactly that reduction — the
+    # bias gradient `np.sum(dy, axis=0)` of mlp.py:34 / attentions.py:129 — use it instead of re-reading the array.
+    __slots__ = ('t', 'colsum')
     __array_priority__ = 1000
 
-    def __init__(self, t: torch.Tensor):
+    def __init__(self, t: torch.Tensor, colsum=None):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'DeviceArray wraps contiguous fp32 CUDA'
         self.t = t
+        self.colsum = colsum
 
     # ---- ndarray-like surface -------------------------------------------------
     @property
@@ -72,7 +76,9 @@ class DeviceArray:
     def reshape(self, *shape):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
-        return DeviceArray(self.t.view(*shape))
+        v = self.t.view(*shape)
+        keep = self.colsum is not None and v.dim() >= 1 and self.t.dim() >= 1 and v.shape[-1] == self.t.shape[-1]
+        return DeviceArray(v, self.colsum if keep else None)
 
     def copy(self):
         return DeviceArray(self.t.clone())
@@ -90,6 +96,7 @@ class DeviceArray:
         other = asdevice(other)
         assert other.shape == self.shape, f'{other.shape} vs {self.shape}'
         C.npm_add_inplace(self.ptr, other.ptr, self.size, stream())
+        self.colsum = None
         return self
 
     def __add__(self, other):
@@ -112,6 +119,7 @@ class DeviceArray:
         else:
             host = np.ascontiguousarray(np.asarray(src), dtype=np.float32).reshape(self.shape)
             self.t.copy_(torch.from_numpy(host), non_blocking=False)
+        self.colsum = None
         return self
 
 

@@ -1,5 +1,4 @@
-timeout 120 python tools/attn_probe.py 2 4 256 384 --bwd 2>&1 | grep -E "err|rror"
-timeout 120 python tools/attn_probe.py 1 3 200 77 --bwd 2>&1 | grep -E "err|rror"
-timeout 120 python tools/attn_probe.py 1 2 130 300 --bwd 2>&1 | grep -E "err|rror"
-timeout 120 python tools/attn_probe.py 8 16 1024 1024 --bwd --time 2>&1 | grep -E "fwd|bwd|err"
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:attn_ -c 4 python tools/attn_probe.py 8 16 1024 1024 --bwd 2>&1 | grep -E "attn_|gpu__time" | sed 's/(.*//'
+for i in 1 2; do
+NPM_NO_COLSUM_RIDE=1 python bench.py --steps 10 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('off', d['ms_per_step'], d['value'], d['clocks']['sm_mhz'], d['gpu_launches'])"
+python bench.py --steps 10 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('on ', d['ms_per_step'], d['value'], d['clocks']['sm_mhz'], d['gpu_launches'])"
+done
