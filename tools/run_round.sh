@@ -1,1 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus 8 --steps 10 --warmup 3 --no-alt --no-cpu > gpurun_out/bench_8gpu.log 2>&1; echo rc=$?; tail -1 gpurun_out/bench_8gpu.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=8', d['value'], d['ms_per_step'], d['e2e'], d['clocks'])"
+python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -3
+python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_default.log | cut -c1-600
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-700
