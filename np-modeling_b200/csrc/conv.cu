@@ -167,6 +167,94 @@ int check_conv(int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int k
 }
 
 }  // namespace
+
+// dgrad for a layer with very few INPUT channels (the image layer: Cin = 3): the GEMM's N dimension is Cin, so the
+// 64-wide tile above wastes 95 % of its work.  Here one warp owns an output pixel: each lane takes two of every 64 dy
+// channels, multiplies them with the (flipped) filters held in shared memory for all CIN outputs and the warp reduces
+// the CIN sums with shuffles; taps in the halo are skipped warp-uniformly.            conv.py:110-153
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_dgrad_smallc_kernel(const float* __restrict__ dy, const float* __restrict__ f,
+                                                               float* __restrict__ dx, int N, int H, int W, int Cout,
+                                                               int ks, int64_t pixels) {
+    extern __shared__ float sf[];                 // [taps][CIN][Cout], tap already flipped
+    const int taps = ks * ks, pad = ks / 2;
+    for (int e = threadIdx.x; e < taps * CIN * Cout; e += blockDim.x) {
+        const int o = e % Cout, c = (e / Cout) % CIN, tap = e / (Cout * CIN);
+        sf[e] = __ldg(f + ((int64_t)(taps - 1 - tap) * CIN + c) * Cout + o);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int npix = (int)pixels;                 // the launcher guarantees pixels < 2^31: 32-bit index arithmetic
+    for (int p = blockIdx.x * 8 + warp; p < npix; p += gridDim.x * 8) {
+        const int w = p % W;
+        const int r = p / W;
+        const int h = r % H;
+        const int n = r / H;
+        float acc[CIN];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) acc[c] = 0.0f;
+        if (Cout == 64 && ks == 3) {
+            // the image layer of cfg2: all nine taps' loads are issued before the FMAs (halo taps read pixel p, weight 0)
+            float2 v[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+                const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+                const float2 t = __ldg(reinterpret_cast<const float2*>(dy + ((size_t)(n * H + (ok ? hh : h)) * W + (ok ? ww : w)) * 64 + lane * 2));
+                v[tap] = ok ? t : make_float2(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) {
+                    const float2 g = *reinterpret_cast<const float2*>(sf + (tap * CIN + c) * 64 + lane * 2);
+                    acc[c] = fmaf(v[tap].x, g.x, fmaf(v[tap].y, g.y, acc[c]));
+                }
+        } else {
+            for (int tap = 0; tap < taps; ++tap) {
+                const int hh = h + tap / ks - pad, ww = w + tap % ks - pad;
+                if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+                const float* row = dy + ((size_t)(n * H + hh) * W + ww) * Cout;
+                const float* ft = sf + tap * CIN * Cout;
+                for (int o = lane * 2; o < Cout; o += 64) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(row + o));
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) {
+                        const float2 g = *reinterpret_cast<const float2*>(ft + c * Cout + o);
+                        acc[c] = fmaf(v.x, g.x, fmaf(v.y, g.y, acc[c]));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) dx[(size_t)p * CIN + c] = acc[c];
+        }
+    }
+}
+
+template <int CIN>
+int launch_dgrad_smallc(const float* dy, const float* f, float* dx, int64_t N, int64_t H, int64_t W, int64_t Cout, int ks,
+                        cudaStream_t s) {
+    const size_t smem = (size_t)ks * ks * CIN * Cout * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_dgrad_smallc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv_dgrad_smallc smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+        configured = smem;
+    }
+    const int64_t pixels = N * H * W;
+    int64_t grid = (pixels + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (grid > cap) grid = cap;
+    conv_dgrad_smallc_kernel<CIN><<<(unsigned)grid, 256, smem, s>>>(dy, f, dx, (int)N, (int)H, (int)W, (int)Cout, ks, pixels);
+    count_launch();
+    return check_launch("conv_dgrad_smallc_kernel");
+}
 }  // namespace npm
 
 using namespace npm;
@@ -205,6 +293,16 @@ int npm_conv2d_bwd_dx(const float* dy, const float* f, float* dx, int64_t N, int
     NPM_REQUIRE(dy && f && dx, "conv2d_bwd_dx: NULL pointer");
     if (use_tc(dy, f, dx, N, H, W, Cin, Cout, ksize))
         return conv_tc_fprop_dgrad(true, dy, f, nullptr, dx, N, H, W, Cin, Cout, ksize, 0, (cudaStream_t)stream);
+    if (Cin <= 4 && Cout % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0 && N * H * W < (1ll << 31) &&
+        (size_t)ksize * ksize * Cin * Cout * sizeof(float) <= 160 * 1024) {
+        cudaStream_t s = (cudaStream_t)stream;
+        switch (Cin) {
+            case 1: return launch_dgrad_smallc<1>(dy, f, dx, N, H, W, Cout, ksize, s);
+            case 2: return launch_dgrad_smallc<2>(dy, f, dx, N, H, W, Cout, ksize, s);
+            case 3: return launch_dgrad_smallc<3>(dy, f, dx, N, H, W, Cout, ksize, s);
+            default: return launch_dgrad_smallc<4>(dy, f, dx, N, H, W, Cout, ksize, s);
+        }
+    }
     ConvArgs a{};
     a.act = dy; a.other = f; a.out = dx; a.bias = nullptr;
     a.N = (int)N; a.H = (int)H; a.W = (int)W; a.Ca = (int)Cout; a.Co = (int)Cin;

@@ -441,7 +441,8 @@ def test_conv_golden(tag):
     close(got['_w'], g['g._w']); close(got['_b'], g['g._b'])
 
 
-@pytest.mark.parametrize('shape', [(4, 32, 32, 3, 64, 3), (2, 32, 32, 64, 128, 3), (3, 9, 7, 16, 20, 5), (2, 16, 16, 32, 32, 1)])
+@pytest.mark.parametrize('shape', [(4, 32, 32, 3, 64, 3), (2, 32, 32, 64, 128, 3), (3, 9, 7, 16, 20, 5), (2, 16, 16, 32, 32, 1),
+                                   (2, 8, 8, 3, 20, 5), (2, 5, 6, 1, 128, 3), (2, 6, 5, 4, 64, 1), (1, 7, 9, 2, 192, 3)])
 def test_conv_vs_oracle(shape):
     from layers import Conv2D
     from oracle import np_oracle as O

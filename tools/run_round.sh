@@ -1,3 +1,3 @@
-python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -3
-python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_default.log | cut -c1-600
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-700
+python -m pytest tests -m gpu -q -x -k "conv" 2>&1 | tail -3
+python tools/conv_bench.py 2>&1 | grep "32,32,3"
+python tools/config_bench.py tf32 2>&1 | tail -4
