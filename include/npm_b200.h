@@ -243,6 +243,10 @@ int npm_mha_core_bwd(const float* q, const float* k, const float* v,
 typedef struct npm_mha_strides {
     int64_t q, k, v;          /* inputs                                         */
     int64_t dq, dk, dv;       /* gradients written by the backward              */
+    int64_t causal;           /* != 0: key position t > query position s is masked (needs Sq == Skv).
+                               * BEYOND the reference, whose mask argument is unusable (`if mask:` on an
+                               * ndarray raises, attentions.py:84; backward NotImplementedError :152-153);
+                               * SURVEY.md §8 f1.  The fused kernels skip the blocks above the diagonal. */
 } npm_mha_strides;
 int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v,
                              float* o, void* saved, int64_t B, int64_t H,

@@ -53,13 +53,23 @@ size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
 // attn_fwd.cu / attn_bwd.cu
 bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv);
 int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, cudaStream_t stream);
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, cudaStream_t stream);
 size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq);
 int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, cudaStream_t stream);
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal,
+                    cudaStream_t stream);
 int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
+
+// scores[bh, s, t] = -inf for t > s (before the row softmax): the materialised-scores path of the causal mask
+__global__ void __launch_bounds__(256) causal_mask_kernel(float* __restrict__ p, int64_t rows, int64_t Sq, int64_t Skv) {
+    const int64_t n = rows * Skv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = i % Skv, s = (i / Skv) % Sq;
+        if (t > s) p[i] = -INFINITY;
+    }
+}
 
 static int require_sm100() {
     static int ok = -1;
@@ -235,7 +245,9 @@ int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v, flo
     const int64_t ldq = ld && ld->q ? ld->q : H * dk, ldk = ld && ld->k ? ld->k : H * dk,
                   ldv = ld && ld->v ? ld->v : H * dv;
     NPM_REQUIRE(ldq >= H * dk && ldk >= H * dk && ldv >= H * dv, "mha_core_fwd: token strides must be >= H*d");
-    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, s);
+    const int causal = ld && ld->causal ? 1 : 0;
+    NPM_REQUIRE(!causal || Sq == Skv, "mha_core_fwd: the causal mask needs Sq == Skv");
+    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, causal, s);
     // S[b,h] = (1/sqrt(dk)) q[b,:,h,:] k[b,:,h,:]^T
     npm_gemm_desc d = blank_desc();
     d.a = q; d.b = k; d.c = P;
@@ -250,6 +262,11 @@ int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v, flo
     d.alpha = (float)(1.0 / sqrt((double)dk));
     int rc = gemm_dispatch(d, s);
     if (rc) return rc;
+    if (causal) {
+        causal_mask_kernel<<<bw_grid((size_t)(B * H * Sq * Skv), 256), 256, 0, s>>>(P, B * H * Sq, Sq, Skv);
+        count_launch();
+        if ((rc = check_launch("causal_mask_kernel"))) return rc;
+    }
     rc = npm_softmax_fwd(P, P, B * H * Sq, Skv, stream);
     if (rc) return rc;
     // o[b,:,h,:] = P[b,h] v[b,:,h,:]
@@ -286,7 +303,8 @@ int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v, con
                 "mha_core_bwd: token strides must be >= H*d");
     if (attn_fused(B, H, Sq, Skv, dk, dv))
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
-                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, lddq, lddk, lddv, s);
+                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, lddq, lddk, lddv,
+                               ld && ld->causal ? 1 : 0, s);
     const float* P = reinterpret_cast<const float*>(saved);
     float* dP = reinterpret_cast<float*>(scratch);
     int rc;

@@ -26,6 +26,7 @@
 
 namespace npm {
 
+int gcd_int(int a, int b);
 int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                        uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, bool round_tf32,
                        bool atom32b);
@@ -49,6 +50,7 @@ struct BwdArgs {
     float* dk;                // [B, Skv, H, 64]  token stride lddk
     float* dv;                // [B, Skv, H, 64]  token stride lddv
     int64_t lddq, lddk, lddv;
+    int causal;               // kv position t > q position s is masked (Sq == Skv): blocks above the diagonal are skipped
     long long* dbg;           // tools only: per-CTA cycle counters of the dK/dV MMA issuer's waits (NPM_ATTN_DEBUG_TIMES)
     int debug_skip;           // tools only: 1 = exp warps do no work, 2 = dS warps do no work, 3 = both (timing experiments)
 };
@@ -113,6 +115,7 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool l
 // smem: K_R, V_R (resident per item) | Q_R, dO_R, Q_T, dO_T (one q block each) | L/D staging | barriers
 constexpr int kKvSmem = 6 * kTileBytes + 2 * 2 * kBlk * 4 + 1024 + 256;
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmQt,
                      const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmVr,
@@ -158,8 +161,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
     const uint32_t tm_dpt = tmem_base + 256, tm_dv = tmem_base + 384, tm_dk = tmem_base + 448;
 
     const int n_q = args.n_q;
-    const int my_items = (args.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t G = (uint32_t)my_items * (uint32_t)n_q;     // q blocks this CTA walks, over all its items
+    // first q block of an item (b, h, kv tile nt): 0, or nt under the causal mask (q blocks above the diagonal see none
+    // of this kv tile)
+    auto first_q = [&](int item) -> int { return CAUSAL ? item % args.n_kv : 0; };
+    uint32_t G = 0;                                            // q blocks this CTA walks, over all its items
+    for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) G += (uint32_t)(n_q - first_q(item));
 
     if (warp == 0) {
         // ============ producer: K_R, V_R per item; Q_R, dO_R per q block ============
@@ -176,11 +182,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 ptx::mbar_wait(bar(K_EMPTY), (it & 1) ^ 1u);
                 ptx::mbar_arrive_expect_tx(bar(K_FULL), kTileBytes);
                 load_tile(kr_addr, &tmKr, bar(K_FULL), nt * kBlk, h, b);
-                for (int i = 0; i < n_q; ++i, ++g) {
+                const int i0 = first_q(item);
+                for (int i = i0; i < n_q; ++i, ++g) {
                     ptx::mbar_wait(bar(QR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(QR_FULL), kTileBytes);
                     load_tile(qr_addr, &tmQr, bar(QR_FULL), i * kBlk, h, b);
-                    if (i == 0) {
+                    if (i == i0) {
                         ptx::mbar_wait(bar(V_EMPTY), (it & 1) ^ 1u);
                         ptx::mbar_arrive_expect_tx(bar(V_FULL), kTileBytes);
                         load_tile(vr_addr, &tmVr, bar(V_FULL), nt * kBlk, h, b);
@@ -198,7 +205,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
                 const int bh = item / args.n_kv;
                 const int h = bh % args.H, b = bh / args.H;
-                for (int i = 0; i < n_q; ++i, ++g) {
+                for (int i = first_q(item); i < n_q; ++i, ++g) {
                     ptx::mbar_wait(bar(DOT_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(DOT_FULL), kTileBytes);
                     load_tile(dot_addr, &tmDOt, bar(DOT_FULL), i * kBlk, h, b);
@@ -224,9 +231,27 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     ptx::mbar_wait(bar(which), parity);
                 }
             };
+            // (item, q block) sequence of this CTA; S^T runs two blocks and dP^T one block ahead of dV / dK: three cursors
+            struct Cur { int item, it, i, i0; };
+            auto cur_init = [&](Cur& c) {
+                c.item = blockIdx.x; c.it = 0;
+                c.i0 = c.item < args.total_items ? first_q(c.item) : 0;
+                c.i = c.i0;
+            };
+            auto cur_next = [&](Cur& c) {
+                if (++c.i == n_q) {
+                    c.item += gridDim.x; ++c.it;
+                    c.i0 = c.item < args.total_items ? first_q(c.item) : 0;
+                    c.i = c.i0;
+                }
+            };
+            Cur c_st, c_dpt, c_main;
+            cur_init(c_st); cur_init(c_dpt); cur_init(c_main);
             auto issue_st = [&](uint32_t g) {        // S^T(g) = K Q^T
-                const int it = g / n_q, i = g - it * n_q;
-                if (i == 0) twait(0, K_FULL, it & 1);
+                const int it = c_st.it, i = c_st.i;
+                const bool first = i == c_st.i0;
+                cur_next(c_st);
+                if (first) twait(0, K_FULL, it & 1);
                 twait(1, QR_FULL, g & 1);
                 ptx::tc_fence_after();
                 mma_rr(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s);
@@ -235,8 +260,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 if (i == n_q - 1) ptx::umma_commit(bar(K_EMPTY));
             };
             auto issue_dpt = [&](uint32_t g) {       // dP^T(g) = V dO^T
-                const int it = g / n_q, i = g - it * n_q;
-                if (i == 0) twait(2, V_FULL, it & 1);
+                const int it = c_dpt.it, i = c_dpt.i;
+                const bool first = i == c_dpt.i0;
+                cur_next(c_dpt);
+                if (first) twait(2, V_FULL, it & 1);
                 twait(3, DOR_FULL, g & 1);
                 ptx::tc_fence_after();
                 mma_rr(tm_dpt, vr_addr, dor_addr, idesc_s);
@@ -248,17 +275,19 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             if (G > 0) { issue_st(0); issue_dpt(0); }
             if (G > 1) issue_st(1);
             for (uint32_t g = 0; g < G; ++g) {
-                const int i = g % n_q;
+                const int i = c_main.i;
+                const bool first = i == c_main.i0;
+                cur_next(c_main);
                 twait(4, P_READY0 + (g & 1u), (g >> 1) & 1);
                 twait(5, DOT_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_ts(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, i != 0);    // dV += P^T dO
+                mma_ts(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, !first);    // dV += P^T dO
                 ptx::umma_commit(bar(DOT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DV_DONE));
                 twait(6, DS_READY, g & 1);
                 twait(7, QT_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_ts(tm_dk, tm_dpt, qt_addr, idesc_ts, i != 0);                          // dK += dS^T Q
+                mma_ts(tm_dk, tm_dpt, qt_addr, idesc_ts, !first);                          // dK += dS^T Q
                 ptx::umma_commit(bar(QT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DK_DONE));
                 if (g + 1 < G) issue_dpt(g + 1);
@@ -290,18 +319,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
         };
         uint32_t g = 0;
         int it = 0;
-        float next = (int)blockIdx.x < args.total_items ? fetch(blockIdx.x, 0) : 0.0f;
+        float next = (int)blockIdx.x < args.total_items ? fetch(blockIdx.x, first_q(blockIdx.x)) : 0.0f;
         for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
             const int nt = item % args.n_kv;
             const int bh = item / args.n_kv;
             const int h = bh % args.H, b = bh / args.H;
-            for (int i = 0; i < n_q; ++i, ++g) {
+            for (int i = first_q(item); i < n_q; ++i, ++g) {
                 const uint32_t buf = g & 1u;
                 // stage this block's L (or D) — fetched one block ago — and prefetch the next block's
                 stage[buf * kBlk + tid] = next;
                 {
                     int ni = i + 1, nitem = item;
-                    if (ni == n_q) { ni = 0; nitem = item + gridDim.x; }
+                    if (ni == n_q) { nitem = item + gridDim.x; ni = nitem < args.total_items ? first_q(nitem) : 0; }
                     if (nitem < args.total_items) next = fetch(nitem, ni);
                 }
                 bar_sync_128(bar_id);
@@ -324,6 +353,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                             p[k + 1] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 1], c, -l4.y))));
                             p[k + 2] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 2], c, -l4.z))));
                             p[k + 3] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 3], c, -l4.w))));
+                        }
+                        if (CAUSAL && i == nt) {            // diagonal block: q position (column) before kv position (lane)
+#pragma unroll
+                            for (int k = 0; k < 64; ++k)
+                                if (hf * 64 + k < tid) p[k] = 0.0f;
                         }
                         ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
                         ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
@@ -379,6 +413,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
 // smem: Q_R, dO_R (double buffered across items) | K_R, V_R, K_T (one kv block each) | barriers
 constexpr int kDqSmem = 7 * kTileBytes + 1024 + 256;
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmDOr,
                    const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmKt,
@@ -421,8 +456,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
     const uint32_t tm_dp = tmem_base + 256, tm_dq = tmem_base + 384;
 
     const int n_kv = args.n_kv;
-    const int my_items = (args.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t G = (uint32_t)my_items * (uint32_t)n_kv;
+    // kv blocks of an item (b, h, q tile mt): all, or 0..mt under the causal mask
+    auto blocks_of = [&](int item) -> int { return CAUSAL ? (item % args.n_q) + 1 : n_kv; };
+    uint32_t G = 0;
+    for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) G += (uint32_t)blocks_of(item);
 
     if (warp == 0) {
         // ============ producer: Q_R + dO_R per item; K_R, V_R per kv block ============
@@ -438,7 +475,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 ptx::mbar_arrive_expect_tx(bar(QDO_FULL0 + qb), 2 * kTileBytes);
                 load_tile(qr_addr + qb * kTileBytes, &tmQr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
                 load_tile(dor_addr + qb * kTileBytes, &tmDOr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
-                for (int j = 0; j < n_kv; ++j, ++g) {
+                const int nb = blocks_of(item);
+                for (int j = 0; j < nb; ++j, ++g) {
                     ptx::mbar_wait(bar(KR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(KR_FULL), kTileBytes);
                     load_tile(kr_addr, &tmKr, bar(KR_FULL), j * kBlk, h, b);
@@ -455,7 +493,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
                 const int bh = item / args.n_q;
                 const int h = bh % args.H, b = bh / args.H;
-                for (int j = 0; j < n_kv; ++j, ++g) {
+                const int nb = blocks_of(item);
+                for (int j = 0; j < nb; ++j, ++g) {
                     ptx::mbar_wait(bar(KT_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(KT_FULL), kTileBytes);
                     load_tile(kt_addr, &tmKt, bar(KT_FULL), j * kBlk, h, b);
@@ -467,8 +506,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
         if (ptx::elect_one()) {
             constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
             constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
+            struct Cur { int item, it, j, cnt; };
+            auto cur_init = [&](Cur& c) {
+                c.item = blockIdx.x; c.it = 0; c.j = 0;
+                c.cnt = c.item < args.total_items ? blocks_of(c.item) : 0;
+            };
+            auto cur_next = [&](Cur& c) {
+                if (++c.j == c.cnt) {
+                    c.j = 0; c.item += gridDim.x; ++c.it;
+                    c.cnt = c.item < args.total_items ? blocks_of(c.item) : 0;
+                }
+            };
+            Cur c_s, c_dp, c_main;
+            cur_init(c_s); cur_init(c_dp); cur_init(c_main);
             auto issue_s = [&](uint32_t g) {         // S(g) = Q K^T
-                const int it = g / n_kv, j = g - it * n_kv;
+                const int it = c_s.it, j = c_s.j;
+                cur_next(c_s);
                 if (j == 0) ptx::mbar_wait(bar(QDO_FULL0 + (it & 1)), (it >> 1) & 1);
                 ptx::mbar_wait(bar(KR_FULL), g & 1);
                 ptx::tc_fence_after();
@@ -477,24 +530,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 ptx::umma_commit(bar(S_FULL0 + (g & 1u)));
             };
             auto issue_dp = [&](uint32_t g) {        // dP(g) = dO V^T
-                const int it = g / n_kv, j = g - it * n_kv;
+                const int it = c_dp.it, j = c_dp.j;
+                const bool last = j == c_dp.cnt - 1;
+                cur_next(c_dp);
                 ptx::mbar_wait(bar(VR_FULL), g & 1);
                 ptx::tc_fence_after();
                 mma_rr(tm_dp, dor_addr + (it & 1) * kTileBytes, vr_addr, idesc_s);
                 ptx::umma_commit(bar(VR_EMPTY));
                 ptx::umma_commit(bar(DP_FULL));
-                if (j == n_kv - 1) ptx::umma_commit(bar(QDO_EMPTY0 + (it & 1)));
+                if (last) ptx::umma_commit(bar(QDO_EMPTY0 + (it & 1)));
             };
             if (G > 0) { issue_s(0); issue_dp(0); }
             if (G > 1) issue_s(1);
             for (uint32_t g = 0; g < G; ++g) {
-                const int j = g % n_kv;
+                const int j = c_main.j;
+                const bool last = j == c_main.cnt - 1;
+                cur_next(c_main);
                 ptx::mbar_wait(bar(DS_READY), g & 1);
                 ptx::mbar_wait(bar(KT_FULL), g & 1);
                 ptx::tc_fence_after();
                 mma_ts(tm_dq, tm_dp, kt_addr, idesc_ts, j != 0);                           // dQ += dS K
                 ptx::umma_commit(bar(KT_EMPTY));
-                if (j == n_kv - 1) ptx::umma_commit(bar(ACC_DONE));
+                if (last) ptx::umma_commit(bar(ACC_DONE));
                 if (g + 1 < G) issue_dp(g + 1);
                 if (g + 2 < G) issue_s(g + 2);
             }
@@ -522,7 +579,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
             const int h = bh % args.H, b = bh / args.H;
             const float mine = next;                              // L (exp warps) or D (dS warps) of this thread's q row
             if (item + (int)gridDim.x < args.total_items) next = fetch(item + gridDim.x);
-            for (int j = 0; j < n_kv; ++j, ++g) {
+            const int nb = blocks_of(item);
+            for (int j = 0; j < nb; ++j, ++g) {
                 const uint32_t buf = g & 1u;
                 const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
                 if (exp_group) {
@@ -538,7 +596,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < 64; ++k) {
                             const float e = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -mine))));
-                            p[k] = (hf * 64 + k < kv_left) ? e : 0.0f;       // zero-filled K rows past Skv
+                            const bool masked = CAUSAL && j == mt && hf * 64 + k > tid;          // kv position after q position
+                            p[k] = (hf * 64 + k < kv_left && !masked) ? e : 0.0f;   // zero-filled K rows past Skv
                         }
                         ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
                         ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
@@ -634,7 +693,9 @@ int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_
 
 int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, cudaStream_t stream) {
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal,
+                    cudaStream_t stream) {
+    NPM_REQUIRE(!causal || Sq == Skv, "mha_core_bwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(o != nullptr, "mha_core_bwd: the fused path needs the forward output o");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
                 aligned16(dk) && aligned16(dv), "mha_core_bwd: pointers must be 16-byte aligned");
@@ -659,6 +720,7 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
     a.scale = (float)(1.0 / sqrt((double)kD));
     a.lse = lse; a.dsum = dsum; a.dq = dq; a.dk = dk; a.dv = dv;
     a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
+    a.causal = causal ? 1 : 0;
     a.debug_skip = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
     a.dbg = nullptr;
     const bool dbg_times = getenv("NPM_ATTN_DEBUG_TIMES") != nullptr;       // tools only: synchronises and prints
@@ -669,9 +731,13 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
 
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem);
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+            e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
         if (e != cudaSuccess) { set_error("attn_bwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
         configured = true;
     }
@@ -688,8 +754,10 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         const int64_t items = B * H * a.n_kv;
         NPM_REQUIRE(items < (1ll << 30), "mha_core_bwd: too many tiles");
         a.total_items = (int)items;
-        const int grid = (int)(items < num_sms() ? items : num_sms());
-        attn_bwd_dkdv_kernel<<<grid, kThreads, kKvSmem, stream>>>(tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        int grid = (int)(items < num_sms() ? items : num_sms());
+        if (causal) while (grid > 1 && gcd_int(grid, a.n_kv) != 1) --grid;     // see attn_fwd_launch
+        if (causal) attn_bwd_dkdv_kernel<true><<<grid, kThreads, kKvSmem, stream>>>(tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        else        attn_bwd_dkdv_kernel<false><<<grid, kThreads, kKvSmem, stream>>>(tQr, tQt, tKr, tVr, tDOr, tDOt, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dkdv_kernel"))) return rc;
         if (dbg_times) {
@@ -712,8 +780,10 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         const int64_t items = B * H * a.n_q;
         NPM_REQUIRE(items < (1ll << 30), "mha_core_bwd: too many tiles");
         a.total_items = (int)items;
-        const int grid = (int)(items < num_sms() ? items : num_sms());
-        attn_bwd_dq_kernel<<<grid, kThreads, kDqSmem, stream>>>(tQr, tDOr, tKr, tKt, tVr, a);
+        int grid = (int)(items < num_sms() ? items : num_sms());
+        if (causal) while (grid > 1 && gcd_int(grid, a.n_q) != 1) --grid;
+        if (causal) attn_bwd_dq_kernel<true><<<grid, kThreads, kDqSmem, stream>>>(tQr, tDOr, tKr, tKt, tVr, a);
+        else        attn_bwd_dq_kernel<false><<<grid, kThreads, kDqSmem, stream>>>(tQr, tDOr, tKr, tKt, tVr, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
     }

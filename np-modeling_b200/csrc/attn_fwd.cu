@@ -42,6 +42,8 @@ constexpr float kRescaleThreshold = 8.0f;    // log2 units
 struct FwdArgs {
     int B, H, Sq, Skv;
     int q_tiles, n_kv, total_items;
+    int causal;              // scores of kv position t > query position s are masked (Sq == Skv): kv blocks past the
+                             // diagonal are never visited, the diagonal block is masked element-wise
     float c;                 // log2(e) / sqrt(dk)
     float* o;                // [B, Sq, H, 64]
     float* lse;              // [B, H, Sq]  log2-domain: m + log2(sum)
@@ -52,6 +54,7 @@ struct FwdArgs {
 // issues on the XU pipe, which the ex2 of the softmax already saturates.)
 __device__ __forceinline__ uint32_t rna_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
@@ -105,6 +108,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tmem_o = tmem_base + 256;          // S/P buffers at columns [0,128) and [128,256)
 
     const int n_kv = args.n_kv;
+    // kv blocks item (b, h, q tile mt) walks: all of them, or 0..mt under the causal mask (kBM == kBN, Sq == Skv)
+    auto blocks_of = [&](int item) -> int { return CAUSAL ? (item % args.q_tiles) + 1 : n_kv; };
 
     if (warp == 0) {
         // ===================== Q + K producer =====================
@@ -120,7 +125,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 ptx::mbar_arrive_expect_tx(q_full(qb), kTileBytes);
                 ptx::tma_load_4d(q_addr + qb * kTileBytes, &tmQ, q_full(qb), 0, mt * kBM, h, b);
                 ptx::tma_load_4d(q_addr + qb * kTileBytes + kChunkBytes, &tmQ, q_full(qb), 32, mt * kBM, h, b);
-                for (int j = 0; j < n_kv; ++j, ++gk) {
+                const int nb = blocks_of(item);
+                for (int j = 0; j < nb; ++j, ++gk) {
                     const int st = gk % kKS;
                     ptx::mbar_wait(k_empty(st), ((gk / kKS) & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(k_full(st), kTileBytes);
@@ -136,7 +142,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
                 const int bh = item / args.q_tiles;
                 const int h = bh % args.H, b = bh / args.H;
-                for (int j = 0; j < n_kv; ++j, ++gv) {
+                const int nb = blocks_of(item);
+                for (int j = 0; j < nb; ++j, ++gv) {
                     const int st = gv % kVS;
                     ptx::mbar_wait(v_empty(st), ((gv / kVS) & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(v_full(st), kTileBytes);
@@ -152,12 +159,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             constexpr uint32_t idesc_pv = ptx::umma_idesc_tf32(kBM, kD, false, true);
             const uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
             const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, kChunkBytes, 512);
-            const int my_items = (args.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            const uint32_t total_blocks = (uint32_t)my_items * (uint32_t)n_kv;
+            // (item, kv block) sequence of this CTA; the S products run one block ahead of the PV products, so two cursors
+            struct Cur { int item, it, j, cnt; };
+            auto cur_init = [&](Cur& c) {
+                c.item = blockIdx.x; c.it = 0; c.j = 0;
+                c.cnt = c.item < args.total_items ? blocks_of(c.item) : 0;
+            };
+            auto cur_next = [&](Cur& c) {
+                if (++c.j == c.cnt) {
+                    c.j = 0; c.item += gridDim.x; ++c.it;
+                    c.cnt = c.item < args.total_items ? blocks_of(c.item) : 0;
+                }
+            };
+            uint32_t total_blocks = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) total_blocks += (uint32_t)blocks_of(item);
 
-            // S(gs): the score block of global index gs (item gs / n_kv, kv block gs % n_kv)
-            auto issue_s = [&](uint32_t gs) {
-                const int it = gs / n_kv, j = gs - it * n_kv;
+            // S(gs): the score block of sequence index gs = cursor cs
+            auto issue_s = [&](uint32_t gs, const Cur& cs) {
+                const int it = cs.it, j = cs.j;
                 const int qb = it & 1;
                 if (j == 0) ptx::mbar_wait(q_full(qb), (it >> 1) & 1);
                 const int st = gs % kKS;
@@ -175,13 +194,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     }
                 ptx::umma_commit(k_empty(st));
                 ptx::umma_commit(s_full(gs & 1u));
-                if (j == n_kv - 1) ptx::umma_commit(q_empty(qb));
+                if (j == cs.cnt - 1) ptx::umma_commit(q_empty(qb));
             };
 
-            if (total_blocks > 0) issue_s(0);
+            Cur cs, cm;
+            cur_init(cs);
+            cur_init(cm);
+            if (total_blocks > 0) { issue_s(0, cs); cur_next(cs); }
             for (uint32_t g = 0; g < total_blocks; ++g) {
-                if (g + 1 < total_blocks) issue_s(g + 1);
-                const int j = g % n_kv;
+                if (g + 1 < total_blocks) { issue_s(g + 1, cs); cur_next(cs); }
+                const int j = cm.j;
+                cur_next(cm);
                 const int st = g % kVS;
                 ptx::mbar_wait(p_ready(g & 1u), (g >> 1) & 1);
                 ptx::mbar_wait(v_full(st), (g / kVS) & 1);
@@ -209,7 +232,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int bh = item / args.q_tiles;
             const int h = bh % args.H, b = bh / args.H;
             float m_ref = -INFINITY, l = 0.0f;
-            for (int j = 0; j < n_kv; ++j, ++g) {
+            const int nb = blocks_of(item);
+            for (int j = 0; j < nb; ++j, ++g) {
                 const uint32_t buf = g & 1u;
                 ptx::mbar_wait(s_full(buf), (g >> 1) & 1);
                 ptx::tc_fence_after();
@@ -224,6 +248,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < kBN; ++k)
                         if (k >= kv_left) s[k] = -INFINITY;
+                }
+                if (CAUSAL && j == mt) {                // the diagonal block: kv position k > query position row
+#pragma unroll
+                    for (int k = 0; k < kBN; ++k)
+                        if (k > row) s[k] = -INFINITY;
                 }
                 float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
@@ -305,13 +334,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace
 
+int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
 bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
     return dk == kD && dv == kD && B > 0 && H > 0 && Sq > 0 && Skv > 0 && B < 65536 && H < 65536 &&
            Sq < (1ll << 30) && Skv < (1ll << 30);
 }
 
 int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, cudaStream_t stream) {
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, cudaStream_t stream) {
+    NPM_REQUIRE(!causal || Sq == Skv, "mha_core_fwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "mha_core_fwd: pointers must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
     int rc;
@@ -329,16 +361,23 @@ int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, fl
     const int64_t items = B * H * a.q_tiles;
     NPM_REQUIRE(items < (1ll << 30), "mha_core_fwd: too many tiles");
     a.total_items = (int)items;
+    a.causal = causal ? 1 : 0;
     a.c = (float)(1.4426950408889634 / sqrt((double)kD));
     a.o = o; a.lse = lse;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { set_error("attn_fwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
         configured = true;
     }
-    const int grid = (int)(items < num_sms() ? items : num_sms());
-    attn_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
+    int grid = (int)(items < num_sms() ? items : num_sms());
+    // causal: the work of an item grows with its tile index, and CTA c takes items c, c + grid, ...: a grid size
+    // coprime with the tile count makes every CTA cycle through all tile indices (148 and 8 share the factor 4)
+    if (causal) while (grid > 1 && gcd_int(grid, a.q_tiles) != 1) --grid;
+    if (causal) attn_fwd_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
+    else        attn_fwd_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
     count_launch();
     return check_launch("attn_fwd_kernel");
 }

@@ -13,9 +13,9 @@ from npm_b200 import device
 
 class DecoderStack(layer.Layer):
     def __init__(self, num_layers: int, num_heads: int, hidden_units: int, norm_first: bool,
-                 drop_rate: float = 0.0, *args, **kwargs):
+                 drop_rate: float = 0.0, *args, causal: bool = False, **kwargs):
         super().__init__(*args, **kwargs)
-        self._layers = [transformer.TransformerDecoder(num_heads, hidden_units, norm_first, drop_rate)
+        self._layers = [transformer.TransformerDecoder(num_heads, hidden_units, norm_first, drop_rate, causal=causal)
                         for _ in range(num_layers)]
 
     def forward(self, q, kv):

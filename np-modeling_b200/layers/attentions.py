@@ -23,9 +23,13 @@ def _add3(parts):
 
 
 class MultiHeadAttention(layer.StatefulLayer):
-    def __init__(self, num_heads: int, *args, **kwargs):
+    def __init__(self, num_heads: int, *args, causal: bool = False, **kwargs):
+        """`causal=True` (keyword-only, BEYOND the reference — SURVEY.md §8 f1): key position t > query position s is
+        masked, forward and backward; needs seq_len_q == seq_len_kv.  The reference's own `mask=` argument cannot be
+        used (attentions.py:84 raises for arrays, :152-153 has no backward) and keeps raising here."""
         super().__init__(*args, **kwargs)
         self._num_heads = num_heads
+        self._causal = bool(causal)
         self._softmax = activations.Softmax()
 
     def initialize(self, query, key=None, value=None, *args, **kwargs) -> None:
@@ -152,7 +156,8 @@ class MultiHeadAttention(layer.StatefulLayer):
 
         self._saved = device.workspace(C.npm_mha_core_saved_bytes(batch, h, sq, skv, dk, dv))
         values = device.empty((batch, sq, h, dv))          # [B, Sq, H, dv] (reference keeps [B,H,Sq,dv])
-        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2])
+        assert not self._causal or sq == skv, 'causal attention needs seq_len_q == seq_len_kv'
+        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], causal=int(self._causal))
         qp, kp, vp = self._qkv_ptrs
         C.npm_mha_core_fwd_strided(qp, kp, vp, values.ptr, self._saved.data_ptr(), batch, h, sq, skv, dk, dv,
                                    ctypes.byref(ld), device.stream())
@@ -232,7 +237,8 @@ class MultiHeadAttention(layer.StatefulLayer):
             dv2 = device.empty((batch * skv, h * dv))
             dptrs, dld, dbufs = (dq2.ptr, dk2.ptr, dv2.ptr), (hd, hd, h * dv), (dq2, dk2, dv2)
         scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes(batch, h, sq, skv, dk, dv))
-        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], dq=dld[0], dk=dld[1], dv=dld[2])
+        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], dq=dld[0], dk=dld[1], dv=dld[2],
+                        causal=int(self._causal))
         qp, kp, vp = self._qkv_ptrs
         C.npm_mha_core_bwd_strided(qp, kp, vp, self._values.ptr, dvalues.ptr, self._saved.data_ptr(), dptrs[0],
                                    dptrs[1], dptrs[2], scratch.data_ptr(), batch, h, sq, skv, dk, dv,
@@ -296,6 +302,9 @@ class MultiHeadAttention(layer.StatefulLayer):
         out = device.empty((b, h, sq, self._seq_len_kv))
         C.npm_mha_core_scores(q.ptr, k.ptr, self._saved.data_ptr(), out.ptr, b, h, sq, self._seq_len_kv,
                               self._key_dim, self._value_dim, device.stream())
+        if getattr(self, '_causal', False):     # debug view only: the recomputed probabilities ignore the mask
+            import torch
+            out.t.masked_fill_(torch.triu(torch.ones(sq, sq, dtype=torch.bool, device=out.t.device), 1), 0.0)
         return out
 
     def _block(self, i, seq):

@@ -24,9 +24,11 @@ class TransformerEncoder(layer.Layer):
                  norm_first: bool,
                  drop_rate: float = 0.0,
                  *args,
+                 causal: bool = False,
                  **kwargs):
+        # causal (keyword-only, beyond the reference — SURVEY.md §8 f1): causal mask in the self-attention
         super().__init__(*args, **kwargs)
-        self._self_attention = attentions.MultiHeadAttention(num_heads)
+        self._self_attention = attentions.MultiHeadAttention(num_heads, causal=causal)
         self._dense1 = mlp.Dense(units=hidden_units)
         self._norm1 = normalizations.LayerNormalization()
         self._norm2 = normalizations.LayerNormalization()
@@ -101,9 +103,12 @@ class TransformerDecoder(layer.Layer):
                  norm_first: bool,
                  drop_rate: float = 0.0,
                  *args,
+                 causal: bool = False,
                  **kwargs):
+        # causal (keyword-only, beyond the reference — SURVEY.md §8 f1): causal mask in the SELF-attention (the
+        # GPT-style decoder of north_star); the cross-attention over `kv` stays unmasked
         super().__init__(*args, **kwargs)
-        self._self_attention = attentions.MultiHeadAttention(num_heads)
+        self._self_attention = attentions.MultiHeadAttention(num_heads, causal=causal)
         self._cross_attention = attentions.MultiHeadAttention(num_heads)
         self._dense1 = mlp.Dense(units=hidden_units)
         self._norm1 = normalizations.LayerNormalization()

@@ -37,7 +37,8 @@ class GemmDesc(Structure):
 
 class MhaStrides(Structure):
     """npm_mha_strides (include/npm_b200.h): floats between consecutive tokens, 0 = dense."""
-    _fields_ = [('q', c_int64), ('k', c_int64), ('v', c_int64), ('dq', c_int64), ('dk', c_int64), ('dv', c_int64)]
+    _fields_ = [('q', c_int64), ('k', c_int64), ('v', c_int64), ('dq', c_int64), ('dk', c_int64), ('dv', c_int64),
+                ('causal', c_int64)]
 
 
 class TensorEntry(Structure):

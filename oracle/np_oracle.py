@@ -117,8 +117,11 @@ def layernorm_bwd(x, gamma, dz, eps=1e-3):
 MHA_PARAMS = ('_wq', '_wk', '_wv', '_wo', '_bq', '_bk', '_bv', '_bo')
 
 
-def mha_fwd(p, query, key=None, value=None):
-    """MultiHeadAttention.forward, unmasked.  p: dict with _wq,_wk [H,dk,D], _wv [H,dv,D],
+def mha_fwd(p, query, key=None, value=None, causal=False):
+    """MultiHeadAttention.forward, unmasked (the reference's only usable mode).  `causal=True` is the extension of
+    SURVEY.md §8 f1 — scores of key position t > query position s are set to -inf before the softmax, which is what the
+    reference's `np.where(mask, scores, -np.inf)` (attentions.py:106-107) would do with a lower-triangular mask if its
+    `if mask:` test accepted arrays; pinned against torch's scaled_dot_product_attention(is_causal=True) in tests.  p: dict with _wq,_wk [H,dk,D], _wv [H,dv,D],
     _wo [D,H,dv], _bq,_bk [H,dk], _bv [H,dv], _bo [D].  Returns (out, cache).
     layers/attentions.py:67-120"""
     query = _f(query)
@@ -130,6 +133,9 @@ def mha_fwd(p, query, key=None, value=None):
     k = _es('btd,hkd->bthk', key, wk) + _f(p['_bk'])            # :94-96
     v = _es('btd,hcd->bthc', value, wv) + _f(p['_bv'])          # :98-100
     s = _es('bshk,bthk->bhst', q, k) / np.sqrt(dk)              # :103-104
+    if causal:
+        assert s.shape[-1] == s.shape[-2], 'causal mask needs Sq == Skv'
+        s = np.where(np.tril(np.ones(s.shape[-2:], dtype=bool)), s, -np.inf)   # :106-107 with a lower-triangular mask
     prob = softmax_fwd(s)                                             # :108
     vals = _es('bhst,bthc->bhsc', prob, v)                      # :112
     out = _es('bhsc,dhc->bsd', vals, wo) + _f(p['_bo'])         # :116-117
@@ -196,7 +202,7 @@ def _drop(x, mask, keep):
     return x if mask is None else dropout_apply(x, mask, keep)
 
 
-def encoder_fwd(p, x, norm_first, masks=(None, None), keep_prob=1.0, eps=1e-3):
+def encoder_fwd(p, x, norm_first, masks=(None, None), keep_prob=1.0, eps=1e-3, causal=False):
     """TransformerEncoder.forward.  p keys: '_self_attention._wq', '_norm1._gamma', '_dense1._w',
     '_dense2._w', ... ; masks: dropout masks for (_dropout1, _dropout2) or None.
     layers/transformer.py:29-62"""
@@ -208,7 +214,7 @@ def encoder_fwd(p, x, norm_first, masks=(None, None), keep_prob=1.0, eps=1e-3):
     if norm_first:
         c['ln1_in'] = _drop(h, masks[0], keep_prob)                    # :35-37 Dropout THEN LayerNorm
         h = _ln_fwd(p, '_norm1', c['ln1_in'], eps)
-    out, c['att'] = mha_fwd(_sub(p, '_self_attention.'), h)           # :38
+    out, c['att'] = mha_fwd(_sub(p, '_self_attention.'), h, causal=causal)           # :38
     out = out + skip                                                  # :39
     if not norm_first:
         c['ln1_in'] = _drop(out, masks[0], keep_prob)                  # :40-42
@@ -252,7 +258,7 @@ def encoder_bwd(p, c, dy, norm_first, masks=(None, None), keep_prob=1.0, eps=1e-
     return dy + dskip, g                                                             # :92
 
 
-def decoder_fwd(p, q, kv, norm_first, masks=(None, None, None), keep_prob=1.0, eps=1e-3):
+def decoder_fwd(p, q, kv, norm_first, masks=(None, None, None), keep_prob=1.0, eps=1e-3, causal=False):
     """TransformerDecoder.forward (unmasked self-attention, cross-attention on kv).
     layers/transformer.py:119-160"""
     q, kv = _f(q), _f(kv)
@@ -263,7 +269,7 @@ def decoder_fwd(p, q, kv, norm_first, masks=(None, None, None), keep_prob=1.0, e
     if norm_first:
         c['ln1_in'] = _drop(h, masks[0], keep_prob)                    # :125-127
         h = _ln_fwd(p, '_norm1', c['ln1_in'], eps)
-    out, c['self'] = mha_fwd(_sub(p, '_self_attention.'), h)          # :128
+    out, c['self'] = mha_fwd(_sub(p, '_self_attention.'), h, causal=causal)          # :128 (causal: §8 f1 extension)
     out = out + skip
     if not norm_first:
         c['ln1_in'] = _drop(out, masks[0], keep_prob)                  # :130-132

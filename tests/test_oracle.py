@@ -178,3 +178,35 @@ def test_trainer_mlp_losses():
     close(losses, g['losses'], rtol=1e-4, atol=1e-5)
     for k, v in sub(g, 'p1.').items():
         close(p[k], v, rtol=1e-4, atol=1e-5)
+
+
+def test_causal_extension_matches_torch_sdpa():
+    """SURVEY.md §8 f1 is beyond the reference (its mask argument is unusable), so the oracle's `causal=True` is pinned
+    against an independent implementation: torch scaled_dot_product_attention(is_causal=True) and its autograd, fp64."""
+    import torch
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(5)
+    b, s_, h, d = 2, 9, 3, 4
+    dm = h * d
+    p = {'_wq': rng.standard_normal((h, d, dm)) * 0.3, '_wk': rng.standard_normal((h, d, dm)) * 0.3,
+         '_wv': rng.standard_normal((h, d, dm)) * 0.3, '_wo': rng.standard_normal((dm, h, d)) * 0.3,
+         '_bq': rng.standard_normal((h, d)) * 0.1, '_bk': rng.standard_normal((h, d)) * 0.1,
+         '_bv': rng.standard_normal((h, d)) * 0.1, '_bo': rng.standard_normal(dm) * 0.1}
+    x = rng.standard_normal((b, s_, dm))
+    dy = rng.standard_normal((b, s_, dm))
+    out, cache = O.mha_fwd(p, x, causal=True)
+    (dq, dk, dv), g = O.mha_bwd(p, cache, dy)
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
+    tx = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    q = torch.einsum('bsd,hkd->bhsk', tx, tp['_wq']) + tp['_bq'][None, :, None, :]
+    k = torch.einsum('bsd,hkd->bhsk', tx, tp['_wk']) + tp['_bk'][None, :, None, :]
+    v = torch.einsum('bsd,hkd->bhsk', tx, tp['_wv']) + tp['_bv'][None, :, None, :]
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)
+    tout = torch.einsum('bhsc,dhc->bsd', o, tp['_wo']) + tp['_bo']
+    tout.backward(torch.tensor(dy))
+    np.testing.assert_allclose(out, tout.detach().numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(dq + dk + dv, tx.grad.numpy(), rtol=1e-9, atol=1e-11)
+    for name in O.MHA_PARAMS:
+        np.testing.assert_allclose(g[name], tp[name].grad.numpy(), rtol=1e-9, atol=1e-11, err_msg=name)
+    # the first query row only sees the first key: its output is v[0] projected
+    assert np.allclose(cache['prob'][:, :, 0, 1:], 0.0) and np.allclose(cache['prob'][:, :, 0, 0], 1.0)

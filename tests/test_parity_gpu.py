@@ -335,6 +335,78 @@ def test_mha_packed_projection_modes(prec, mode, dims):
     close(layer._bv, params['_bv'] - 0.1 * grads['_bv'], **gtol)
 
 
+@pytest.mark.parametrize('prec', ['3xtf32', 'tf32'])
+@pytest.mark.parametrize('dims', [(2, 40, 4, 64), (1, 130, 2, 64), (2, 384, 3, 64), (2, 9, 3, 8)])
+def test_mha_causal_extension(prec, dims):
+    """causal=True (beyond the reference): fused kernels (head dim 64, tf32) and the materialised path
+    against the oracle, whose causal variant is pinned against torch in tests/test_oracle.py."""
+    import npm_b200
+    from layers import MultiHeadAttention
+    from oracle import np_oracle as O
+    npm_b200.set_precision(prec)
+    b, sq, h, d = dims
+    rng = np.random.default_rng(sq * 7 + d)
+    dm = h * d
+    x = rng.standard_normal((b, sq, dm), dtype=np.float32)
+    dy = rng.standard_normal((b, sq, dm), dtype=np.float32)
+    layer = MultiHeadAttention(h, causal=True)
+    layer(x)
+    params = {k: (np.asarray(getattr(layer, k)) * (1.0 / np.sqrt(dm) if k.startswith('_w') else 0.1)).astype(np.float32)
+              for k in O.MHA_PARAMS}
+    bind(layer, params)
+    tol = dict(rtol=2e-3, atol=2e-2) if prec == 'tf32' else TC
+    want, cache = O.mha_fwd(params, x, causal=True)
+    close(layer(x), want, **tol)
+    close(layer._attention_scores, cache['prob'], rtol=2e-3, atol=1e-3 if prec == 'tf32' else 1e-5)
+    (dq_, dk_, dv_), grads = O.mha_bwd(params, cache, dy)
+    rec = Recorder()
+    got = layer(dy, backprop=True, optimizer_=rec)
+    close(got[0], dq_, **tol); close(got[1], dk_, **tol); close(got[2], dv_, **tol)
+    gtol = dict(rtol=2e-3, atol=2e-2 * np.sqrt(b * sq)) if prec == 'tf32' else dict(rtol=1e-3, atol=1e-4 * np.sqrt(b * sq))
+    gg = grads_of(layer, rec, O.MHA_PARAMS)
+    for k in O.MHA_PARAMS:
+        close(gg[k], grads[k], **gtol)
+    # unmasked and causal layers differ (the mask is really applied)
+    plain = MultiHeadAttention(h)
+    plain(x)
+    bind(plain, params)
+    assert np.abs(np.asarray(plain(x)) - want).max() > 1e-3
+
+
+def test_decoder_causal_self_attention():
+    import npm_b200
+    from layers import TransformerDecoder
+    from oracle import np_oracle as O
+    from train import iter_parameters
+    npm_b200.set_precision('3xtf32')
+    rng = np.random.default_rng(11)
+    b, s_, d, h, f = 2, 48, 128, 2, 256
+    q = rng.standard_normal((b, s_, d)).astype(np.float32)
+    kv = rng.standard_normal((b, 40, d)).astype(np.float32)
+    layer = TransformerDecoder(h, f, True, 0.0, causal=True)
+    layer(q, kv)
+    params = {}
+    for owner, name in iter_parameters(layer):
+        v = np.asarray(getattr(owner, name))
+        if name.startswith('_w'):
+            v = (v * 0.1).astype(np.float32)
+            setattr(owner, name, v)
+    def path_of(owner, name):
+        for attr, val in vars(layer).items():
+            if val is owner:
+                return f'{attr}.{name}'
+            for attr2, val2 in (vars(val).items() if hasattr(val, '__dict__') else []):
+                if val2 is owner:
+                    return f'{attr}.{attr2}.{name}'
+        raise KeyError(name)
+    for owner, name in iter_parameters(layer):
+        params[path_of(owner, name)] = np.asarray(getattr(owner, name))
+    want, _ = O.decoder_fwd(params, q, kv, True, causal=True)
+    close(layer(q, kv), want)
+    plain, _ = O.decoder_fwd(params, q, kv, True)
+    assert np.abs(plain - want).max() > 1e-3
+
+
 def test_mha_mask_raises():
     from layers import MultiHeadAttention
     layer = MultiHeadAttention(2)

@@ -77,6 +77,18 @@ def run(B, H, Sq, Skv, bwd=False, timing=False, seed=0):
                                           B, H, Sq, Skv, D, D, st))
         fl = 4.0 * B * H * Sq * Skv * D
         print(f'  fwd {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s', flush=True)
+        if '--causal' in sys.argv and Sq == Skv:
+            import ctypes
+            from npm_b200._lib import MhaStrides
+            ld = MhaStrides(causal=1)
+            msc = t(lambda: C.npm_mha_core_fwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), saved.data_ptr(),
+                                                       B, H, Sq, Skv, D, D, ctypes.byref(ld), st))
+            print(f'  causal fwd {msc:.3f} ms  ({ms / msc:.2f}x the unmasked launch)', flush=True)
+            if bwd:
+                msb = t(lambda: C.npm_mha_core_bwd_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(),
+                                                           saved.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                                           scratch.data_ptr(), B, H, Sq, Skv, D, D, ctypes.byref(ld), st))
+                print(f'  causal bwd {msb:.3f} ms', flush=True)
         if bwd:
             ms = t(lambda: C.npm_mha_core_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(),
                                               saved.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
