@@ -185,6 +185,50 @@ class Trainer:
                 # mid-step; the text is the reference's (train.py:32)
                 print('Loss: ', self.last_loss)
 
+    # ---- checkpoint / resume (the reference has none) -------------------------
+    def save_checkpoint(self, path: str, optimizer_: Optional[optimizer.Optimizer] = None) -> None:
+        """Parameters (in `iter_parameters` order), the Adam state (step count and both moments per parameter) and the
+        dropout stream position → one .npz.  Rank 0 writes; parameters are replicated under data parallel."""
+        from layers import normalizations
+        torch.cuda.synchronize()
+        out = {}
+        params = list(iter_parameters(list(self._layers)))
+        for i, (owner, name) in enumerate(params):
+            out[f'p{i}'] = np.asarray(owner._p(name))
+            if isinstance(optimizer_, optimizer.AdamOptimizer):
+                ident = f'{id(owner)}.{name}'
+                if ident in optimizer_._momentums:
+                    out[f'm{i}'] = np.asarray(optimizer_._momentums[ident])
+                    out[f'v{i}'] = np.asarray(optimizer_._velocities[ident])
+                    out[f't{i}'] = np.int64(optimizer_._steps.get(ident, 1))
+        out['n_params'] = np.int64(len(params))
+        out['dropout'] = np.array([normalizations._philox['seed'], normalizations._philox['offset']], dtype=np.uint64)
+        if _world()[0] == 0:
+            np.savez(path, **out)
+
+    def load_checkpoint(self, path: str, optimizer_: Optional[optimizer.Optimizer] = None, example_inputs=None) -> None:
+        """Restore what `save_checkpoint` wrote.  Parameters are created lazily by the first forward
+        (layers/layer.py:33-35), so pass `example_inputs` (one batch) unless the layers have already been called."""
+        from layers import normalizations
+        if example_inputs is not None:
+            self._forward(self._to_device('inputs', self._shard(example_inputs)))
+        with np.load(path if str(path).endswith('.npz') else str(path) + '.npz') as z:
+            params = list(iter_parameters(list(self._layers)))
+            assert int(z['n_params']) == len(params), f"checkpoint has {int(z['n_params'])} parameters, the model {len(params)}"
+            for i, (owner, name) in enumerate(params):
+                p = owner._p(name)
+                assert p.shape == z[f'p{i}'].shape, f'{name}: {p.shape} vs {z[f"p{i}"].shape}'
+                p.copy_from(z[f'p{i}'])                       # in place: aliases and packed blocks stay valid
+                if isinstance(optimizer_, optimizer.AdamOptimizer) and f'm{i}' in z.files:
+                    ident = f'{id(owner)}.{name}'
+                    m, v = optimizer_._moments(ident, p)
+                    m.copy_from(z[f'm{i}'])
+                    v.copy_from(z[f'v{i}'])
+                    optimizer_._steps[ident] = int(z[f't{i}'])
+            seed, offset = (int(x) for x in z['dropout'])
+            normalizations.set_dropout_seed(seed, offset)
+        self._synced = True      # every rank loaded the same values
+
     def eval(self, inputs, targets) -> None:
         inputs, targets = self._shard(inputs), self._shard(targets)
         y = self._to_device('inputs', inputs)

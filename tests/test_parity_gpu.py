@@ -714,3 +714,47 @@ def test_fused_dropout_layernorm_equals_the_two_layers(shape):
     for u, v in zip(a[:4], b[:4]):
         np.testing.assert_allclose(u, v, rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(v).max())))
     assert abs(a[4].mean() - 0.75) < 0.05
+
+
+def test_checkpoint_resume_is_bit_exact(tmp_path):
+    """parameters + Adam state + dropout stream position round-trip through Trainer.save_checkpoint /
+    load_checkpoint; training resumed from the file continues exactly like the uninterrupted run."""
+    import npm_b200
+    import loss
+    import optimizer
+    from layers.adapters import EncoderStack
+    from layers.normalizations import set_dropout_seed
+    from train import Trainer, iter_parameters
+    npm_b200.set_precision('3xtf32')
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 24, 64)).astype(np.float32)
+    t = rng.standard_normal((2, 24, 64)).astype(np.float32)
+
+    def fresh():
+        np.random.seed(5)
+        stack = EncoderStack(2, 2, 96, True, 0.1)
+        tr = Trainer([stack], loss.MSELoss(), verbose=False)
+        tr._forward(x)
+        for owner, name in iter_parameters([stack]):
+            if name.startswith('_w'):
+                setattr(owner, name, (np.asarray(getattr(owner, name)) * 0.1).astype(np.float32))
+        return stack, tr
+
+    set_dropout_seed(99)
+    stack_a, tr_a = fresh()
+    adam_a = optimizer.AdamOptimizer(learning_rate=1e-2)
+    tr_a.train(x, t, 2, adam_a)
+    tr_a.save_checkpoint(str(tmp_path / 'ck'), adam_a)
+    tr_a.train(x, t, 2, adam_a)
+    want = [np.asarray(getattr(o, n)) for o, n in iter_parameters([stack_a])]
+
+    set_dropout_seed(1)                                   # a different stream position: the checkpoint must restore it
+    stack_b, tr_b = fresh()
+    adam_b = optimizer.AdamOptimizer(learning_rate=1e-2)
+    tr_b.load_checkpoint(str(tmp_path / 'ck'), adam_b)
+    tr_b.train(x, t, 2, adam_b)
+    got = [np.asarray(getattr(o, n)) for o, n in iter_parameters([stack_b])]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    assert abs(float(tr_a.last_loss) - float(tr_b.last_loss)) == 0.0
