@@ -71,6 +71,11 @@ __global__ void __launch_bounds__(256) causal_mask_kernel(float* __restrict__ p,
     }
 }
 
+bool pdl_enabled() {
+    static const bool on = !(getenv("NPM_NO_PDL") && getenv("NPM_NO_PDL")[0] != '0');
+    return on;
+}
+
 static int require_sm100() {
     static int ok = -1;
     if (ok < 0) {

@@ -121,6 +121,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                      const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmVr,
                      const __grid_constant__ CUtensorMap tmDOr, const __grid_constant__ CUtensorMap tmDOt,
                      const BwdArgs args) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
     const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -158,6 +159,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();               // only shared memory / TMEM set-up above
     const uint32_t tm_dpt = tmem_base + 256, tm_dv = tmem_base + 384, tm_dk = tmem_base + 448;
 
     const int n_q = args.n_q;
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmDOr,
                    const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmKt,
                    const __grid_constant__ CUtensorMap tmVr, const BwdArgs args) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
     const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -453,6 +456,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();               // only shared memory / TMEM set-up above
     const uint32_t tm_dp = tmem_base + 256, tm_dq = tmem_base + 384;
 
     const int n_kv = args.n_kv;
@@ -648,6 +652,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
 // dQ kernel as much as or more than this launch (0.267 / 0.279 ms vs 0.265 ms for the whole backward at B8 H16 S1024).
 __global__ void __launch_bounds__(256) attn_dsum_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
                                                         float* __restrict__ dsum, int B, int H, int Sq) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t rows = (int64_t)B * Sq * H;
     const int sub = threadIdx.x & 15;
     const int64_t step = ((int64_t)gridDim.x * blockDim.x) >> 4;
@@ -748,7 +754,7 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         int grid = (int)((rows * 16 + 255) / 256);
         const int cap = num_sms() * 8;
         if (grid > cap) grid = cap;
-        attn_dsum_kernel<<<grid, 256, 0, stream>>>(d_o, o, dsum, (int)B, (int)H, (int)Sq);
+        launch_pdl(attn_dsum_kernel, dim3(grid), dim3(256), 0, stream, 1, d_o, o, dsum, (int)B, (int)H, (int)Sq);
         count_launch();
         if ((rc = check_launch("attn_dsum_kernel"))) return rc;
     }
@@ -758,8 +764,8 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         a.total_items = (int)items;
         int grid = (int)(items < num_sms() ? items : num_sms());
         if (causal) while (grid > 1 && gcd_int(grid, a.n_kv) != 1) --grid;     // see attn_fwd_launch
-        if (causal) attn_bwd_dkdv_kernel<true><<<grid, kThreads, kKvSmem, stream>>>(tQr, tQt, tKr, tVr, tDOr, tDOt, a);
-        else        attn_bwd_dkdv_kernel<false><<<grid, kThreads, kKvSmem, stream>>>(tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        if (causal) launch_pdl(attn_bwd_dkdv_kernel<true>, dim3(grid), dim3(kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        else        launch_pdl(attn_bwd_dkdv_kernel<false>, dim3(grid), dim3(kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dkdv_kernel"))) return rc;
         if (dbg_times) {
@@ -784,8 +790,8 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         a.total_items = (int)items;
         int grid = (int)(items < num_sms() ? items : num_sms());
         if (causal) while (grid > 1 && gcd_int(grid, a.n_q) != 1) --grid;
-        if (causal) attn_bwd_dq_kernel<true><<<grid, kThreads, kDqSmem, stream>>>(tQr, tDOr, tKr, tKt, tVr, a);
-        else        attn_bwd_dq_kernel<false><<<grid, kThreads, kDqSmem, stream>>>(tQr, tDOr, tKr, tKt, tVr, a);
+        if (causal) launch_pdl(attn_bwd_dq_kernel<true>, dim3(grid), dim3(kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
+        else        launch_pdl(attn_bwd_dq_kernel<false>, dim3(grid), dim3(kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
     }

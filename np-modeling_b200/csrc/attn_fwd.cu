@@ -58,6 +58,7 @@ template <bool CAUSAL>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
     const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -105,6 +106,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();               // only shared memory / TMEM set-up above
     const uint32_t tmem_o = tmem_base + 256;          // S/P buffers at columns [0,128) and [128,256)
 
     const int n_kv = args.n_kv;
@@ -376,8 +378,9 @@ int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, fl
     // causal: the work of an item grows with its tile index, and CTA c takes items c, c + grid, ...: a grid size
     // coprime with the tile count makes every CTA cycle through all tile indices (148 and 8 share the factor 4)
     if (causal) while (grid > 1 && gcd_int(grid, a.q_tiles) != 1) --grid;
-    if (causal) attn_fwd_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
-    else        attn_fwd_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
+    cudaError_t le = causal ? launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a)
+                            : launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a);
+    if (le != cudaSuccess) { set_error("attn_fwd_kernel launch: %s", cudaGetErrorString(le)); return NPM_ERR_CUDA; }
     count_launch();
     return check_launch("attn_fwd_kernel");
 }

@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/npm_b200.h"
 
 namespace npm {
@@ -29,6 +31,43 @@ void count_launch(int n = 1);              // npm_launch_count() bookkeeping
             return NPM_ERR_INVALID;                                         \
         }                                                                   \
     } while (0)
+
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch.  ~1000 dependent kernels per training step leave the GPU idle ~2 us at every boundary
+// (launch latency + the next kernel's prologue).  A kernel launched through launch_pdl() may start while its
+// predecessor in the stream is still running: every such kernel calls pdl_trigger() first (its own successor may be
+// scheduled) and pdl_wait() before it touches ANY global memory — only barrier / TMEM / tensor-map set-up may precede
+// the wait.  pdl_wait() returns once all prerequisite grids have completed and their writes are visible, so stream
+// order semantics are unchanged.  Without the launch attribute both instructions are no-ops.  NPM_NO_PDL=1 disables.
+// ---------------------------------------------------------------------------
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... Params, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = (unsigned)n;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------------------
 // Small device helpers

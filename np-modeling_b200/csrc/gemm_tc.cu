@@ -364,6 +364,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmC, const GemmTcArgs args) {
     using Cfg = Tc2Cfg<BLOCK_N, KS>;
     constexpr int S = Cfg::kStages;
+    pdl_trigger();            // the next kernel in the stream may be scheduled; it waits for this grid before reading
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
@@ -412,6 +413,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();               // everything above touched only this CTA's shared memory / TMEM: now wait for the predecessor
 
     const int tiles_mn = args.tiles_m * args.tiles_n;      // tiles_m counts 256-row tiles here
 
@@ -806,23 +808,13 @@ int launch_one2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
         }
         configured = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     GemmTcArgs largs = args;
     const bool dbg_times = getenv("NPM_GEMM_DEBUG_TIMES") != nullptr;      // tools only: synchronises and prints
     if (dbg_times) {
         cudaMalloc(&largs.dbg, sizeof(long long) * 8 * grid);
         cudaMemset(largs.dbg, 0, sizeof(long long) * 8 * grid);
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, c, largs);
+    cudaError_t e = launch_pdl(kern, dim3((unsigned)grid, 1, 1), dim3(Cfg::kThreads, 1, 1), Cfg::kSmemBytes, stream, 2, a, b, c, largs);
     count_launch();
     if (e != cudaSuccess) { set_error("gemm_tc2_kernel launch: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
     if (dbg_times) {

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(kThreads) ce_fwd_kernel(const float* __restric
 }
 __global__ void __launch_bounds__(kThreads) mse_bwd_kernel(const float* __restrict__ y, const float* __restrict__ t,
                                                            float* __restrict__ dy, int64_t n, float nf) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         dy[i] = __fdiv_rn(2.0f * (y[i] - t[i]), nf);
@@ -72,6 +74,8 @@ template <bool kAdam>
 __global__ void __launch_bounds__(kThreads) opt_multi_kernel(const npm_tensor_entry* __restrict__ tab, int n_tensors,
                                                              int64_t n_chunks, float lr, float b1, float b2, float eps,
                                                              float bc1, float bc2, float gscale) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const int ti = find_tensor(tab, n_tensors, chunk);
         const npm_tensor_entry e = tab[ti];
@@ -145,7 +149,7 @@ int npm_ce_fwd(const float* y, const float* t, float* loss_out, int64_t n, npm_s
 }
 int npm_mse_bwd(const float* y, const float* t, float* dy, int64_t n, npm_stream_t stream) {
     NPM_REQUIRE(n > 0, "mse_bwd: empty input");
-    mse_bwd_kernel<<<bw_grid(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(y, t, dy, n, (float)n);
+    launch_pdl(mse_bwd_kernel, dim3(bw_grid(n, kThreads)), dim3(kThreads), 0, (cudaStream_t)stream, 1, y, t, dy, n, (float)n);
     count_launch();
     return check_launch("mse_bwd_kernel");
 }
@@ -176,8 +180,8 @@ int npm_adam_multi(const npm_tensor_entry* table_dev, int32_t n_tensors, int64_t
     const float bc2 = (float)(1.0 - pow((double)beta2, (double)t));
     const int64_t cap = (int64_t)num_sms() * 8;
     const int grid = (int)(n_chunks < cap ? n_chunks : cap);
-    opt_multi_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(table_dev, n_tensors, n_chunks, lr, beta1,
-                                                                        beta2, epsilon, bc1, bc2, grad_scale);
+    launch_pdl(opt_multi_kernel<true>, dim3(grid), dim3(kThreads), 0, (cudaStream_t)stream, 1, table_dev, n_tensors, n_chunks, lr,
+               beta1, beta2, epsilon, bc1, bc2, grad_scale);
     count_launch();
     return check_launch("adam_multi_kernel");
 }

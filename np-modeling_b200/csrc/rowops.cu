@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float*
                                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                     int64_t rows, int cols, float eps, DropArgs drop = DropArgs{},
                                                                     uint32_t* __restrict__ maskbits = nullptr) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd_kernel(const flo
                                                                     int64_t rows, int cols, DropArgs drop = DropArgs{},
                                                                     const float* __restrict__ dskip = nullptr,
                                                                     const uint32_t* __restrict__ maskbits = nullptr) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sred[];   // [kWarpsPerCta][NP][cols_padded], NP = 2 (+1 with XSUM)
     constexpr int NP = XSUM ? 3 : 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -382,6 +386,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
                                                               int64_t cols, int nslabs, int64_t slab_stride,
                                                               float* __restrict__ out2 = nullptr,
                                                               float* __restrict__ out3 = nullptr) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * 32 + tx;
@@ -413,6 +419,8 @@ __global__ void __launch_bounds__(kRowThreads) colsum_kernel(const float* __rest
                                                             float* __restrict__ out, int64_t rows, int64_t cols,
                                                             int64_t rows_per_slab, unsigned ticket_base,
                                                             const float* __restrict__ relu_y, float* __restrict__ masked) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 sm[kWarpsPerCta][32];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -533,8 +541,8 @@ int colsum_relu_launch(const float* x, float* out, int64_t rows, int64_t cols, v
     const bool vec = (cols & 3) == 0 && aligned16(x) && aligned16(partial) && aligned16(out) &&
                      (relu_y == nullptr || (aligned16(relu_y) && aligned16(masked)));
     if (vec && col_ctas <= kTicketCols) {
-        colsum_kernel<<<dim3((unsigned)col_ctas, slabs), kRowThreads, 0, s>>>(x, partial, out, rows, cols, rps,
-                                                                            next_ticket_base(col_ctas), relu_y, masked);
+        launch_pdl(colsum_kernel, dim3((unsigned)col_ctas, slabs), dim3(kRowThreads), 0, s, 1, x, partial, out, rows, cols, rps,
+                   next_ticket_base(col_ctas), relu_y, masked);
         count_launch();
         return check_launch("colsum_kernel");
     }
@@ -756,7 +764,7 @@ int npm_dropout_layernorm_fwd(const float* x, const float* gamma, const float* b
         case 1: layernorm_fwd_kernel<1, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
         case 2: layernorm_fwd_kernel<2, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
         case 4: layernorm_fwd_kernel<4, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
-        default: layernorm_fwd_kernel<8, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
+        default: launch_pdl(layernorm_fwd_kernel<8, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
     }
     count_launch();
     return check_launch("dropout_layernorm_fwd");
@@ -797,7 +805,7 @@ int npm_dropout_layernorm_bwd_colsum(const float* dz, const float* x, const floa
             cudaFuncSetAttribute(layernorm_bwd_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured3 = true;
         }
-        layernorm_bwd_kernel<8, true, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
+        launch_pdl(layernorm_bwd_kernel<8, true, true>, dim3(slabs), dim3(kRowThreads), smem, s, 1, dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
     } else if (xsum && nv == 4) {
         layernorm_bwd_kernel<4, true, true><<<slabs, kRowThreads, smem, s>>>(dz, x, gamma, mean, rstd, dx, partial, rows, (int)cols, d, dskip, maskbits);
     } else if (xsum && nv == 2) {
@@ -822,7 +830,7 @@ int npm_dropout_layernorm_bwd_colsum(const float* dz, const float* x, const floa
     int rc = check_launch("dropout_layernorm_bwd");
     if (rc) return rc;
     const unsigned g2 = (unsigned)((cols + 31) / 32);
-    reduce_partials_kernel<<<dim3(g2, np), 256, 0, s>>>(partial, dgamma, cols, slabs, (int64_t)np * cols, dbeta, dx_colsum);
+    launch_pdl(reduce_partials_kernel, dim3(g2, np), dim3(256), 0, s, 1, (const float*)partial, dgamma, cols, slabs, (int64_t)np * cols, dbeta, dx_colsum);
     count_launch();
     return check_launch("dropout_layernorm_bwd_reduce");
 }

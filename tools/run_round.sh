@@ -1,7 +1,5 @@
-timeout 120 python tools/attn_probe.py 2 4 256 384 --bwd 2>&1 | grep -E "err|rror"
-timeout 120 python tools/attn_probe.py 1 3 200 77 --bwd 2>&1 | grep -E "err|rror"
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
 for i in 1 2; do
-NPM_B200_LIB=$PWD/tools/tmp/libnpm_prev.so timeout 120 python tools/attn_probe.py 8 16 1024 1024 --bwd --time 2>&1 | grep -E "fwd|bwd " | tr '\n' ' '; echo " <- before"
-timeout 120 python tools/attn_probe.py 8 16 1024 1024 --bwd --time 2>&1 | grep -E "fwd|bwd " | tr '\n' ' '; echo " <- now"
+NPM_NO_PDL=1 python bench.py --steps 10 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('nopdl', d['ms_per_step'], d['value'], d['clocks']['sm_mhz'], d['final_loss'])"
+python bench.py --steps 10 --warmup 3 --no-cpu --no-alt 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('pdl  ', d['ms_per_step'], d['value'], d['clocks']['sm_mhz'], d['final_loss'])"
 done
-timeout 600 python -m pytest tests -m gpu -q -x -k "causal or mha or decoder or attention or encoder" 2>&1 | tail -3
