@@ -757,4 +757,5 @@ def test_checkpoint_resume_is_bit_exact(tmp_path):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         np.testing.assert_array_equal(a, b)
-    assert abs(float(tr_a.last_loss) - float(tr_b.last_loss)) == 0.0
+    # the loss itself is a sum of per-CTA partials combined with atomics: equal up to the summation order
+    assert abs(float(tr_a.last_loss) - float(tr_b.last_loss)) <= 1e-6 * abs(float(tr_a.last_loss))
