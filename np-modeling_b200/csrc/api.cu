@@ -224,9 +224,10 @@ int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db, 
 }
 
 // ---------------------------------------------------------- attention core
-// Round-1 implementation: the batched products run on the tcgen05 GEMM with the scores
-// materialised ([B,H,Sq,Skv], as the reference does at attentions.py:103-111); `saved` holds the
-// probabilities P.  A fused online-softmax kernel can replace this behind the same ABI.
+// Two implementations behind one ABI.  TF32 mode with dk = dv = 64: the fused online-softmax kernels of attn_fwd.cu /
+// attn_bwd.cu (`saved` = one log-sum-exp per row).  Otherwise (3xTF32 / fp32 modes, other head dims): the batched
+// products run on the GEMM with the scores materialised ([B,H,Sq,Skv], as the reference does at attentions.py:103-111)
+// and `saved` holds the probabilities P.
 size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
     if (attn_fused(B, H, Sq, Skv, dk, dv)) return (size_t)B * H * Sq * sizeof(float);   // log-sum-exp per row
     return (size_t)B * H * Sq * Skv * sizeof(float);                                      // P
