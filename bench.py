@@ -199,7 +199,7 @@ def run_b200(args):
     from layers import adapters
     from layers.normalizations import set_dropout_seed
     from npm_b200 import device
-    from npm_b200._lib import C, GemmDesc
+    from npm_b200._lib import C
     from train import Trainer, iter_parameters
 
     rank = int(os.environ.get('RANK', '0'))

@@ -8,7 +8,6 @@ gradients are single tcgen05 GEMMs on the arrays as stored; the attention core r
 `npm_mha_core_fwd/bwd`.
 """
 import ctypes
-from typing import Optional
 
 import optimizer
 from layers import activations, layer

@@ -1,6 +1,4 @@
 """DropOut / LayerNormalization — drop-in for layers/normalizations.py."""
-import itertools
-
 import os
 
 import numpy as np

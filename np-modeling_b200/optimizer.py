@@ -13,7 +13,6 @@ backward), so deferring is result-identical.  Gradients live in a flat arena so 
 data-parallel training all-reduces a few large contiguous blocks (see train.py).
 """
 import abc
-import ctypes
 import dataclasses
 
 import numpy as np

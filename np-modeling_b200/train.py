@@ -20,7 +20,6 @@ from typing import Optional, Sequence
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
 import loss
 import optimizer

@@ -2,7 +2,6 @@
 cfg5 is bench.py's workload.  usage: python tools/config_bench.py [tf32|3xtf32]"""
 import os
 import sys
-import time
 
 import numpy as np
 import torch

@@ -1,6 +1,5 @@
 """tools/cublas_probe.py — run cuBLAS TF32 GEMMs at the cfg5 shapes (for an ncu capture of the library's kernel choice:
 tile, cluster, shared memory), next to this repo's GEMM.  Diagnostic only; nothing in the product path calls cuBLAS."""
-import sys
 import torch
 torch.backends.cuda.matmul.allow_tf32 = True
 shapes = [(8192, 4096, 1024), (8192, 1024, 4096), (8192, 1024, 1024), (1024, 4096, 8192)]
