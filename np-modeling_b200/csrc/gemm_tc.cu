@@ -45,6 +45,8 @@ struct GemmTcArgs {
     int64_t ldr;
     int relu, accum;
     uint64_t desc_a, desc_b;   // UMMA shared-memory descriptor templates (start address = 0)
+    int band_m;                // pair kernel: tiles are walked in bands of band_m row tiles (n fastest inside a band) so that the
+                               // tiles running concurrently share A AND B panels instead of all hammering one B panel; 0 = m fastest
     int dbg_mode;              // tools only: 1 = no TMA loads / no full-barrier waits (pure MMA issue rate)
     int a_chunked, b_chunked;  // pair kernel: MN-major operand described as a 5-D {32, K, MN/32, nb1, nb2} tensor, one box per stage
     long long* dbg;            // tools only (NPM_GEMM_DEBUG_TIMES): per-CTA wait-cycle counters of the pair kernel's roles
@@ -339,6 +341,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // releases the ring slot / publishes the accumulator in both CTAs; both CTAs run their own
 // producer and their own epilogue (TMEM lanes = their 128 rows).
 // ===========================================================================================
+// r-th tile of a z slice -> (row tile, column tile)
+__device__ __forceinline__ void tile_coords(int r, int tiles_m, int tiles_n, int band, int& tm, int& tn) {
+    if (band <= 1) { tm = r % tiles_m; tn = r / tiles_m; return; }
+    const int per_band = band * tiles_n;
+    const int b = r / per_band, idx = r - b * per_band;
+    const int width = min(band, tiles_m - b * band);        // the last band may be narrower
+    tm = b * band + idx % width;
+    tn = idx / width;
+}
+
 template <int BLOCK_N, int KS>
 struct Tc2Cfg {
     static constexpr int kHalfN      = BLOCK_N / 2;
@@ -428,8 +440,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int r  = t2 - z * tiles_mn;
                 const int kb0 = sp * args.kb_per_split;
                 const int kb1 = min(num_kb, kb0 + args.kb_per_split);
-                const int m0 = (r % args.tiles_m) * (2 * kBlockM) + (int)rank * kBlockM;
-                const int n0 = (r / args.tiles_m) * BLOCK_N + (int)rank * Cfg::kHalfN;
+                int tm, tn;
+                tile_coords(r, args.tiles_m, args.tiles_n, args.band_m, tm, tn);
+                const int m0 = tm * (2 * kBlockM) + (int)rank * kBlockM;
+                const int n0 = tn * BLOCK_N + (int)rank * Cfg::kHalfN;
                 const int z1 = z % args.nb1, z2 = z / args.nb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (args.dbg_mode == 1) break;
@@ -540,8 +554,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int sp = tile / args.items_per_split, t2 = tile - sp * args.items_per_split;
             const int z  = t2 / tiles_mn;
             const int r  = t2 - z * tiles_mn;
-            const int m0 = (r % args.tiles_m) * (2 * kBlockM) + (int)rank * kBlockM;
-            const int n0 = (r / args.tiles_m) * BLOCK_N;
+            int tm, tn;
+            tile_coords(r, args.tiles_m, args.tiles_n, args.band_m, tm, tn);
+            const int m0 = tm * (2 * kBlockM) + (int)rank * kBlockM;
+            const int n0 = tn * BLOCK_N;
             const int z1 = z % args.nb1, z2 = z / args.nb1;
             if (args.dbg && warp == 0 && lane == 0) {
                 const long long t0 = clock64();
@@ -989,6 +1005,10 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     args.residual = d.residual;
     args.ldr = d.ldr;
     args.dbg = nullptr;
+    {
+        static const int band_env = getenv("NPM_GEMM_BAND") ? atoi(getenv("NPM_GEMM_BAND")) : 8;
+        args.band_m = (pair && tiles_m > band_env && tiles_n > 1) ? band_env : 0;
+    }
     args.dbg_mode = getenv("NPM_GEMM_DEBUG_MODE") ? atoi(getenv("NPM_GEMM_DEBUG_MODE")) : 0;
     args.a_chunked = a_chunked ? 1 : 0;
     args.b_chunked = b_chunked ? 1 : 0;

@@ -1,2 +1,2 @@
-NPM_DP_NO_OVERLAP=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29713 bench.py --gpus 8 --steps 10 --warmup 3 --no-alt --no-cpu 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=8 no-overlap', d['value'], d['ms_per_step'])"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29714 bench.py --gpus 8 --steps 10 --warmup 3 --no-alt --no-cpu 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=8 overlap   ', d['value'], d['ms_per_step'])"
+for b in 0 8 4; do echo "band=$b"; NPM_GEMM_BAND=$b python tools/gemm_bench.py 2>&1 | sed -n 4,11p | cut -c1-150; done
+python tools/gemm_probe.py km:tf32:4096x2048x512; python tools/gemm_probe.py mm:tf32:3072x1024x512; python tools/gemm_probe.py kk:tf32:2304x768x256
