@@ -1,2 +1,6 @@
-for b in 0 8 4; do echo "band=$b"; NPM_GEMM_BAND=$b python tools/gemm_bench.py 2>&1 | sed -n 4,11p | cut -c1-150; done
-python tools/gemm_probe.py km:tf32:4096x2048x512; python tools/gemm_probe.py mm:tf32:3072x1024x512; python tools/gemm_probe.py kk:tf32:2304x768x256
+#!/bin/bash
+# What the round-end driver does, in one gpurun call:  gpurun --timeout 900 -- 'bash tools/run_round.sh'
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -2
+python bench.py > gpurun_out/bench_final.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_final.log | cut -c1-400
