@@ -326,10 +326,10 @@ def run_b200(args):
     tf, gemm_ms = gemm_roofline(args.precision)
     tf32_peak = pk['bf16'] / 2.0          # kind::tf32 runs at half the bf16 rate; burst figure: kernel timed alone
     flop_per_token = L * FLOP_PER_TOKEN_LAYER(D, S, F)
-    # DRAM traffic of this launch from the committed ncu --set full capture (profiles/r01_ncu_gemm_tc2_ffn_v2.txt):
-    # 70.0 MB read + 95.5 MB written per launch, against 184.5 MB algorithmic (A + B once, C once; part of C is
+    # DRAM traffic of this launch from the committed ncu --set full capture (profiles/r01_ncu_gemm_tc2_ffn_v3.txt):
+    # 60.8 MB read + 86.0 MB written per launch, against 184.5 MB algorithmic (A + B once, C once; part of C is
     # still in the 126 MB L2 when the kernel ends) — no re-reads.
-    traffic = 165.5e6 if (B * S, D, F) == (8192, 1024, 4096) else None
+    traffic = 146.7e6 if (B * S, D, F) == (8192, 1024, 4096) else None
     roofline = dict(bound='tensor', achieved=tf, peak=tf32_peak, unit='TFLOP/s', frac=tf / tf32_peak, traffic=traffic,
                     kernel=f'gemm_tc2_kernel (CTA-pair tcgen05, {args.precision}) linear_fwd M={B * S} K={D} N={F}',
                     launch_ms=gemm_ms, l2='flushed between launches (256 MiB write)',
