@@ -275,7 +275,45 @@ def case_trainer():
     save('trainer_mlp', x=x, t=t, losses=np.array(losses), **with_prefix('p0.', p0), **with_prefix('p1.', p1))
 
 
+def _train_case(name, layers, x, t, steps, lr, w_scale):
+    """The reference's own Trainer + AdamOptimizer for a few steps: losses printed per step and every parameter
+    before / after (end-to-end pin of forward, backward, in-layer updates and Adam state on composite layers)."""
+    trainer = ref_train.Trainer(layers, ref_loss.MSELoss())
+    with contextlib.redirect_stdout(io.StringIO()):
+        trainer.eval(x, t)                      # lazy initialisation
+    for layer in layers:
+        _rescale(layer, w_scale)
+    p0 = {}
+    for i, layer in enumerate(layers):
+        p0.update({f'{i}.{k}': getattr(o, a).copy() for k, (o, a) in named_params(layer).items()})
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        trainer.train(x, t, steps, ref_optimizer.AdamOptimizer(learning_rate=lr))
+    losses = [float(line.split()[-1]) for line in buf.getvalue().splitlines() if line.startswith('Loss')]
+    p1 = {}
+    for i, layer in enumerate(layers):
+        p1.update({f'{i}.{k}': getattr(o, a).copy() for k, (o, a) in named_params(layer).items()})
+    save(name, x=x, t=t, losses=np.array(losses), **with_prefix('p0.', p0), **with_prefix('p1.', p1))
+
+
+def case_trainer_conv():
+    np.random.seed(9)
+    x, t = rand(2, 6, 6, 3), rand(2, 6, 6, 6)
+    _train_case('trainer_conv', [Conv2D(4, 3), Conv2D(6, 3)], x, t, 3, 1e-2, 0.3)
+
+
+def case_trainer_encoder():
+    np.random.seed(10)
+    x, t = rand(2, 8, 16), rand(2, 8, 16)
+    layers = [TransformerEncoder(2, 32, True, 0.0), TransformerEncoder(2, 32, False, 0.0)]
+    _train_case('trainer_encoder', layers, x, t, 3, 1e-2, 0.25)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'trainers':      # only the end-to-end Trainer fixtures added later
+        case_trainer_conv()
+        case_trainer_encoder()
+        sys.exit(0)
     for fn in (case_dense, case_activations, case_layernorm, case_dropout, case_mha, case_transformer, case_conv,
-               case_loss, case_optimizer, case_trainer):
+               case_loss, case_optimizer, case_trainer, case_trainer_conv, case_trainer_encoder):
         fn()

@@ -180,6 +180,50 @@ def test_trainer_mlp_losses():
         close(p[k], v, rtol=1e-4, atol=1e-5)
 
 
+def _adam_all(p, grads, state, t, lr):
+    for k in grads:
+        p[k], m, v = O.adam_step(p[k], grads[k], *state.setdefault(k, (np.zeros_like(p[k]), np.zeros_like(p[k]))), t, lr)
+        state[k] = (m, v)
+
+
+def test_trainer_conv_adam_steps():
+    """The reference's Trainer on [Conv2D(4,3), Conv2D(6,3)] + MSELoss + AdamOptimizer, 3 steps, end to end."""
+    g = load_golden('trainer_conv')
+    p = {k: v.astype(np.float64) for k, v in sub(g, 'p0.').items()}
+    state, losses = {}, []
+    for step in range(3):
+        y0, z0 = O.conv_layer_fwd(g['x'], p['0._w'], p['0._b'])
+        y1, z1 = O.conv_layer_fwd(y0, p['1._w'], p['1._b'])
+        losses.append(O.mse_fwd(y1, g['t']))
+        dy = O.mse_bwd(y1, g['t'])
+        d0, dw1, db1 = O.conv_layer_bwd(y0, p['1._w'], z1, dy)
+        _, dw0, db0 = O.conv_layer_bwd(g['x'], p['0._w'], z0, d0)
+        _adam_all(p, {'1._w': dw1, '1._b': db1, '0._w': dw0, '0._b': db0}, state, step + 1, 1e-2)
+    close(losses, g['losses'], rtol=1e-5, atol=1e-6)
+    for k, v in sub(g, 'p1.').items():
+        close(p[k], v, rtol=1e-4, atol=1e-5)
+
+
+def test_trainer_encoder_adam_steps():
+    """The reference's Trainer on [TransformerEncoder(pre-norm), TransformerEncoder(post-norm)] + MSELoss + Adam."""
+    g = load_golden('trainer_encoder')
+    p = [{k: v.astype(np.float64) for k, v in sub(g, f'p0.{i}.').items()} for i in range(2)]
+    state, losses = [{}, {}], []
+    for step in range(3):
+        h0, c0 = O.encoder_fwd(p[0], g['x'], True)
+        h1, c1 = O.encoder_fwd(p[1], h0, False)
+        losses.append(O.mse_fwd(h1, g['t']))
+        dy = O.mse_bwd(h1, g['t'])
+        d1, g1 = O.encoder_bwd(p[1], c1, dy, False)
+        _, g0 = O.encoder_bwd(p[0], c0, d1, True)
+        _adam_all(p[1], g1, state[1], step + 1, 1e-2)
+        _adam_all(p[0], g0, state[0], step + 1, 1e-2)
+    close(losses, g['losses'], rtol=1e-5, atol=1e-6)
+    for i in range(2):
+        for k, v in sub(g, f'p1.{i}.').items():
+            close(p[i][k], v, rtol=1e-4, atol=2e-5)
+
+
 def test_causal_extension_matches_torch_sdpa():
     """SURVEY.md §8 f1 is beyond the reference (its mask argument is unusable), so the oracle's `causal=True` is pinned
     against an independent implementation: torch scaled_dot_product_attention(is_causal=True) and its autograd, fp64."""

@@ -624,6 +624,43 @@ def test_trainer_mlp_golden(capsys):
             close(param_values(layer, [k])[k], v, rtol=1e-3, atol=1e-4)
 
 
+def _trainer_golden(name, make_layers, steps=3, lr=1e-2, ptol=None, ltol=None):
+    import loss
+    import optimizer
+    from train import Trainer
+    g = load_golden(name)
+    layers = make_layers()
+    trainer = Trainer(layers, loss.MSELoss(), verbose=False)
+    trainer.eval(g['x'], g['t'])                                   # lazy initialisation, as the generator did
+    for i, layer in enumerate(layers):
+        bind(layer, sub(g, f'p0.{i}.'))
+    losses = []
+    adam = optimizer.AdamOptimizer(learning_rate=lr)
+    for _ in range(steps):
+        trainer.train(g['x'], g['t'], 1, adam)
+        losses.append(float(trainer.last_loss))
+    close(losses, g['losses'], **(ltol or dict(rtol=1e-3, atol=1e-4)))
+    for i, layer in enumerate(layers):
+        for k, v in sub(g, f'p1.{i}.').items():
+            close(param_values(layer, [k])[k], v, **(ptol or dict(rtol=1e-3, atol=2e-4)))
+
+
+def test_trainer_conv_golden():
+    """The reference's Trainer + AdamOptimizer on two Conv2D layers, 3 steps (tests/golden/trainer_conv.npz): losses and
+    every parameter after training."""
+    from layers import Conv2D
+    _trainer_golden('trainer_conv', lambda: [Conv2D(4, 3), Conv2D(6, 3)])
+
+
+def test_trainer_encoder_golden():
+    """The reference's Trainer + AdamOptimizer on a pre-norm and a post-norm TransformerEncoder, 3 steps."""
+    from layers import TransformerEncoder
+    # Adam normalises the update to ~lr per element whatever the gradient's size, so a gradient element that is tiny
+    # relative to the 3xTF32 error can move by a sizeable fraction of lr = 1e-2: compare parameters to 1e-3 absolute
+    _trainer_golden('trainer_encoder', lambda: [TransformerEncoder(2, 32, True, 0.0), TransformerEncoder(2, 32, False, 0.0)],
+                    ptol=dict(rtol=1e-3, atol=1e-3))
+
+
 # ------------------------------------------------------------------ fused bandwidth kernels
 def test_dense_fused_relu_keeps_reference_gradient_at_zero():
     """Dense's default ReLU runs in the GEMM epilogue (pre-activation never written).  The reference's
