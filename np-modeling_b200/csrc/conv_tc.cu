@@ -251,9 +251,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 if (MODE == FPROP && args.bias != nullptr) {
+                    const float* bp = args.bias + nc;       // 128-bit broadcast loads (see gemm_tc.cu)
+                    if (nc + 32 <= args.Nn && ((reinterpret_cast<uintptr_t>(bp) & 15u) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nc + j < args.Nn) f[j] += __ldg(args.bias + nc + j);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nc + j < args.Nn) f[j] += __ldg(bp + j);
+                    }
                 }
                 if (MODE == FPROP && args.relu) {
 #pragma unroll

@@ -242,9 +242,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
                 if (args.bias != nullptr && sp == 0) {
+                    // 8 x 128-bit broadcast loads: 32 scalar loads per chunk made this epilogue longer than the main
+                    // loop of a K = 1024 tile (FFN up-projection 730 -> 590 TF with a bias)
+                    const float* bp = args.bias + nc;
+                    if (nc + 32 <= args.N && ((reinterpret_cast<uintptr_t>(bp) & 15u) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nc + j < args.N) f[j] += __ldg(args.bias + nc + j);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nc + j < args.N) f[j] += __ldg(bp + j);
+                    }
                 }
                 if (args.residual != nullptr && sp == 0) {
                     const int64_t row_g = (int64_t)m0 + warp * 32 + lane;
@@ -579,9 +590,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
                 if (args.bias != nullptr && sp == 0) {
+                    // 8 x 128-bit broadcast loads: 32 scalar loads per chunk made this epilogue longer than the main
+                    // loop of a K = 1024 tile (FFN up-projection 730 -> 590 TF with a bias)
+                    const float* bp = args.bias + nc;
+                    if (nc + 32 <= args.N && ((reinterpret_cast<uintptr_t>(bp) & 15u) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nc + j < args.N) f[j] += __ldg(args.bias + nc + j);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nc + j < args.N) f[j] += __ldg(bp + j);
+                    }
                 }
                 if (args.residual != nullptr && sp == 0) {
                     const int64_t row_g = (int64_t)m0 + warp * 32 + lane;

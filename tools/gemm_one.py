@@ -11,12 +11,13 @@ from npm_b200._lib import C, GemmDesc  # noqa: E402
 
 mj = sys.argv[1]
 M, N, K = (int(v) for v in sys.argv[2:5])
-reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+reps = int(sys.argv[5]) if len(sys.argv) > 5 and sys.argv[5].isdigit() else 3
 a = torch.randn(M, K, device='cuda') if mj[0] == 'k' else torch.randn(K, M, device='cuda')
 b = torch.randn(N, K, device='cuda') if mj[1] == 'k' else torch.randn(K, N, device='cuda')
 c = torch.empty(M, N, device='cuda')
 d = GemmDesc()
-d.a, d.b, d.c, d.bias = a.data_ptr(), b.data_ptr(), c.data_ptr(), None
+bias = torch.zeros(N, device='cuda') if '--bias' in sys.argv else None
+d.a, d.b, d.c, d.bias = a.data_ptr(), b.data_ptr(), c.data_ptr(), (bias.data_ptr() if bias is not None else None)
 d.m, d.n, d.k = M, N, K
 d.a_rs, d.a_cs = (K, 1) if mj[0] == 'k' else (1, M)
 d.b_rs, d.b_cs = (1, K) if mj[1] == 'k' else (N, 1)
