@@ -38,6 +38,12 @@ extern "C" {
 #define NPM_PREC_TF32   0   /* one tcgen05 kind::tf32 pass                      */
 #define NPM_PREC_3XTF32 1   /* hi/lo split, three passes, ~fp32 accuracy        */
 #define NPM_PREC_FP32   2   /* CUDA-core fp32 FMA (exact-order SIMT kernel)     */
+#define NPM_PREC_BF16X3 3   /* fp32 operands split into bf16 hi + mid on the way into shared memory,
+                             * three tcgen05 kind::f16 products (mid*hi + hi*mid + hi*hi), fp32
+                             * accumulate: ~2^-17 relative per product, 1.5x the time of one TF32 pass.
+                             * Meets rtol 1e-3 / atol 1e-4; the mode bench.py reports.            */
+#define NPM_PREC_BF16   4   /* bf16 hi*hi only (bf16 compute on fp32 storage, fp32 accumulate):
+                             * SURVEY.md §8 f3; stated tolerance 2e-2 of each tensor's magnitude  */
 
 typedef void* npm_stream_t; /* cudaStream_t */
 

@@ -49,6 +49,8 @@ int num_sms() {
 bool gemm_tc_supported(const npm_gemm_desc& d);
 int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream);
 int gemm_simt_launch(const npm_gemm_desc& d, cudaStream_t stream);
+bool gemm_bx_supported(const npm_gemm_desc& d);
+int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream);
 size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
 // attn_fwd.cu / attn_bwd.cu
 bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv);
@@ -105,6 +107,13 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     int rc = require_sm100();
     if (rc) return rc;
     int prec = d.precision >= 0 ? d.precision : g_precision.load();
+    if (prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16) {
+        // split-bf16 CTA-pair kernel; problems it does not take (a single row tile, ragged 16-byte chunks) run the
+        // TF32 kernels at the same or better accuracy class (3xTF32 for bf16x3, one TF32 pass for bf16)
+        static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
+        if (!bx_off && gemm_bx_supported(d)) return gemm_bx_launch(d, prec == NPM_PREC_BF16X3 ? 3 : 1, stream);
+        prec = prec == NPM_PREC_BF16X3 ? NPM_PREC_3XTF32 : NPM_PREC_TF32;
+    }
     if (prec != NPM_PREC_FP32 && gemm_tc_supported(d)) return gemm_tc_launch(d, prec, stream);
     return gemm_simt_launch(d, stream);
 }
@@ -137,7 +146,7 @@ int npm_version(void) { return 100; }
 uint64_t npm_launch_count(void) { return g_launches.load(); }
 void npm_reset_launch_count(void) { g_launches.store(0); }
 int npm_set_precision(int precision) {
-    if (precision < NPM_PREC_TF32 || precision > NPM_PREC_FP32) return g_precision.load();
+    if (precision < NPM_PREC_TF32 || precision > NPM_PREC_BF16) return g_precision.load();
     return g_precision.exchange(precision);
 }
 int npm_get_precision(void) { return g_precision.load(); }

@@ -1,0 +1,651 @@
+// gemm_bx.cu — split-bf16 GEMM on tcgen05 (kind::f16) for fp32 operands: the "bf16x3" contraction mode.
+//
+//   C[z][m,n] (=|+=) alpha * sum_k A[z][m,k] * B[z][k,n] (+ bias[n]) (+ residual) (ReLU)       (fp32 in HBM, fp32 out)
+//
+// Every fp32 operand element x is split on the way into shared memory into two bf16 numbers
+//   hi = bf16_rn(x),  mid = bf16_rn(x - hi)          (x - hi - mid is below 2^-17 |x|)
+// and the tensor cores run the three products  mid*hi + hi*mid + hi*hi  with fp32 accumulation in TMEM.  The dropped
+// terms (mid*mid and the two residuals) are <= 3 * 2^-18 of |a||b| per product, i.e. ~50x below a single TF32 pass
+// (2^-11), which is what north_star's rtol 1e-3 / atol 1e-4 needs — at 1.5x the tensor time of one TF32 pass instead
+// of the 3x of 3xTF32 (kind::f16 runs K = 16 per instruction where kind::tf32 runs K = 8).  NTERMS = 1 keeps only
+// hi*hi: plain bf16 compute on fp32 storage.
+//
+// The reference contractions this serves are the same as gemm_tc.cu: Linear fwd/dX/dW (layers/mlp.py:21-40), the
+// MultiHeadAttention projections and their gradients (layers/attentions.py:88-100,116,129-135,169-184).
+//
+// Structure = the CTA-pair kernel of gemm_tc.cu (cta_group::2, 256 x BLOCK_N tile per pair, two TMEM accumulator
+// buffers, four epilogue warps per CTA) with a different producer: TMA cannot convert, and a split pass through
+// shared memory would cost 64 KB of LSU traffic per 32 KB stage on top of the MMA's own operand reads, so eight
+// producer warps per CTA load the fp32 operands straight from global memory into registers (LDG.128, two K stages in
+// flight per thread), split them there and store the bf16 images in the canonical UMMA layouts:
+//   K-major operand  [rows, 32 k]: one 128-byte row per operand row = [hi k0..31 | mid k0..31], 128B swizzle;
+//                                  an MMA K16 slice is a 32-byte column of that row (hi: 0,32; mid: 64,96)
+//   MN-major operand [32 k, rows]: hi image then mid image, each rows/64 slabs of 32 k-rows x 128 B (64 mn), 128B swizzle;
+//                                  an MMA K16 slice is 16 k-rows = 2048 B of a slab
+// Shared-memory traffic per stage: 32 KB of STS + the MMA operand reads; HBM/L2 traffic = the fp32 operands, once.
+//
+// Who fences: generic-proxy stores must be ordered before the tensor core's async-proxy reads by a
+// fence.proxy.async, which nvcc lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC — and a MEMBAR in a thread that has global
+// loads in flight waits for them, i.e. it serialises the register prefetch (first version of this kernel: 2900 clk per
+// stage = one full load latency, 200 TF).  So the producers only store and arrive (release.cta, no MEMBAR) on their
+// CTA's full barrier; the proxy fence is executed by a thread with nothing in flight that has acquired that barrier —
+// the MMA issuer in the leader CTA, two relay lanes in the peer CTA, which then arrive (release.cluster) on the
+// leader's peer barrier.  The fence is on the causality path between the stores and the MMA, which is what the PTX
+// memory model asks of a proxy fence.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace npm {
+
+int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                       uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, bool round_tf32, bool atom32b);
+
+namespace {
+
+constexpr int kBM = 128;        // rows of A per CTA (256 per pair)
+constexpr int kKS = 32;         // fp32 elements of K per ring stage
+constexpr int kProducerWarps = 8;
+constexpr int kFirstProducerWarp = 5;
+constexpr int kFencerWarpB = kFirstProducerWarp + kProducerWarps;       // 13: second proxy-fence relay of the peer CTA
+constexpr int kThreadsBx = 32 * (kFencerWarpB + 1);                      // 448: 4 epilogue, 1 issuer / relay, 8 producers, 1 relay
+constexpr int kPrefetch = 2;    // K stages each producer thread keeps in flight in registers
+
+struct GemmBxArgs {
+    const float* a; const float* b;
+    int64_t a_ld, b_ld;                        // elements between consecutive rows of the stored operand
+    int64_t a_bs1, a_bs2, b_bs1, b_bs2;
+    int M, N, K;
+    int tiles_m, tiles_n, nb1, total_tiles;
+    int splits, kb_per_split, items_per_split;
+    int band_m;
+    float alpha;
+    const float* bias;
+    const float* residual;
+    int64_t ldr;
+    int relu, accum;
+    long long* dbg;            // tools only (NPM_GEMM_DEBUG_TIMES): 16 wait-cycle counters per CTA
+};
+
+template <int BLOCK_N>
+struct BxCfg {
+    static constexpr int kHalfN      = BLOCK_N / 2;
+    static constexpr int kABytes     = kBM * 128;                      // 16 KB: hi + mid of a 128 x 32 tile
+    static constexpr int kBBytes     = kHalfN * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kEpiBytes   = 4 * 2 * 4096;
+    static constexpr int kBarBytes   = 512;
+    static constexpr int kBudget     = 232448 - 1024;
+    static constexpr int kStagesRaw  = (kBudget - kEpiBytes - kBarBytes) / kStageBytes;
+    static constexpr int kStages     = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSmemBytes  = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+    static constexpr int kTmemCols   = 2 * BLOCK_N;
+};
+
+__device__ __forceinline__ void tile_coords_bx(int r, int tiles_m, int tiles_n, int band, int& tm, int& tn) {
+    if (band <= 1) { tm = r % tiles_m; tn = r / tiles_m; return; }
+    const int per_band = band * tiles_n;
+    const int b = r / per_band, idx = r - b * per_band;
+    const int width = min(band, tiles_m - b * band);
+    tm = b * band + idx % width;
+    tn = idx / width;
+}
+
+// {lo16 = bf16_rn(lo), hi16 = bf16_rn(hi)}
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+// One operand of one CTA: R rows (A: 128 rows of M, B: BLOCK_N/2 rows of N) x 32 k per stage.
+// Each producer thread owns NLD 16-byte fp32 chunks of the stage, fixed for the whole kernel.
+template <int R, bool MN, int NTERMS>
+struct OperandLoader {
+    static constexpr int NLD = R / 32;              // LDG.128 per thread per stage (256 producer threads)
+    // K-major : a warp instruction covers 4 rows x 128 B (8 lanes per row); rows of one instruction are
+    //           {r, r+4} per half-warp so the two 64-byte halves written per row never share a bank group
+    // MN-major: a warp instruction covers 128 consecutive mn of one k-row (R = 128) or of two k-rows (R = 64)
+    int   row[NLD];          // K-major: operand row in the tile;  MN-major: k-row in the stage
+    int   col;               // K-major: first k of the chunk (4c);  MN-major: first mn of the chunk
+    uint32_t soff[NLD];      // byte offset of the hi 8-byte store inside the operand's stage image
+
+    __device__ __forceinline__ void init(int pw, int lane) {
+        if (!MN) {
+            const int c = lane & 7, q = lane >> 3;
+            col = 4 * c;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int g = i >> 1, j = i & 1;
+                const int r = pw * (R / 8) + g * 8 + (q & 1) * 4 + (q >> 1) + 2 * j;
+                row[i] = r;
+                soff[i] = uint32_t(r) * 128u + (uint32_t((c >> 1) ^ (r & 7)) << 4) + uint32_t(c & 1) * 8u;
+            }
+        } else {
+            constexpr int LPR = R / 4;                 // lanes per k-row
+            constexpr int RPI = 32 / LPR;              // k-rows per warp instruction
+            const int mnl = (lane % LPR) * 4;
+            col = mnl;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int kk = (pw * NLD + i) * RPI + lane / LPR;
+                row[i] = kk;
+                soff[i] = uint32_t(mnl >> 6) * 4096u + uint32_t(kk) * 128u +
+                          (uint32_t(((mnl & 63) >> 3) ^ (kk & 7)) << 4) + uint32_t((mnl >> 2) & 1) * 8u;
+            }
+        }
+    }
+    // base: first element of this CTA's tile rows at k = 0 (K-major: &X[r0, 0]; MN-major: &X[0, r0]); r0 / rows_total
+    // bound the rows, k0 / K the contraction index.  Out-of-range chunks are zero.
+    __device__ __forceinline__ void load(float4 (&v)[NLD], const float* base, int64_t ld, int r0, int rows_total,
+                                         int k0, int K) const {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            bool ok;
+            const float* p;
+            if (!MN) {
+                ok = (r0 + row[i] < rows_total) && (k0 + col < K);
+                p = base + (int64_t)row[i] * ld + (k0 + col);
+            } else {
+                ok = (k0 + row[i] < K) && (r0 + col < rows_total);
+                p = base + (int64_t)(k0 + row[i]) * ld + col;
+            }
+            v[i] = ok ? ldg_f4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __device__ __forceinline__ void store(const float4 (&v)[NLD], uint32_t image) const {
+        constexpr uint32_t mid_delta = MN ? uint32_t(R / 64) * 4096u : 64u;   // MN-major: the mid image follows the hi image
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const uint32_t h01 = bf16x2_rn(v[i].x, v[i].y), h23 = bf16x2_rn(v[i].z, v[i].w);
+            const uint32_t a = image + soff[i];
+            sts_v2(a, h01, h23);
+            if (NTERMS == 3) {
+                const float rx = v[i].x - __uint_as_float(h01 << 16), ry = v[i].y - __uint_as_float(h01 & 0xffff0000u);
+                const float rz = v[i].z - __uint_as_float(h23 << 16), rw = v[i].w - __uint_as_float(h23 & 0xffff0000u);
+                sts_v2(MN ? a + mid_delta : (a ^ 64u), bf16x2_rn(rx, ry), bf16x2_rn(rz, rw));
+            }
+        }
+    }
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int NTERMS>
+__global__ void __launch_bounds__(kThreadsBx, 1)
+gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
+    using Cfg = BxCfg<BLOCK_N>;
+    constexpr int S = Cfg::kStages;
+    pdl_trigger();
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+
+    const uint32_t stage_addr = base_addr;
+    const uint32_t epi_addr   = base_addr + S * Cfg::kStageBytes;
+    const uint32_t bar_addr   = epi_addr + Cfg::kEpiBytes;
+    auto full_bar   = [&](int s) { return bar_addr + 8u * s; };                 // this CTA's producers have stored stage s
+    auto empty_bar  = [&](int s) { return bar_addr + 8u * (S + s); };
+    auto peer_bar   = [&](int s) { return bar_addr + 8u * (2 * S + s); };       // leader only: the peer's stage s is stored and fenced
+    auto tfull_bar  = [&](int a) { return bar_addr + 8u * (3 * S + a); };
+    auto tempty_bar = [&](int a) { return bar_addr + 8u * (3 * S + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
+        base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + 8 * (3 * S + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();          // 0 = pair leader
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_kb = (args.K + kKS - 1) / kKS;
+
+    if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmC);
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s) {
+                ptx::mbar_init(full_bar(s), kProducerWarps);       // one arrive per producer warp of this CTA
+                ptx::mbar_init(empty_bar(s), 1);                   // one multicast commit
+                ptx::mbar_init(peer_bar(s), 1);                    // one remote arrive of the peer's relay
+            }
+            for (int a = 0; a < 2; ++a) {
+                ptx::mbar_init(tfull_bar(a), 1);
+                ptx::mbar_init(tempty_bar(a), 8);
+            }
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc_2sm(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    const int tiles_mn = args.tiles_m * args.tiles_n;      // tiles_m counts 256-row tiles
+
+    if (warp >= kFirstProducerWarp && warp < kFencerWarpB) {
+        // ===================== producers: global fp32 -> registers -> split bf16 -> shared =====================
+        const int pw = warp - kFirstProducerWarp;
+        OperandLoader<kBM, A_MN, NTERMS> la;
+        OperandLoader<Cfg::kHalfN, B_MN, NTERMS> lb;
+        la.init(pw, lane);
+        lb.init(pw, lane);
+
+        struct Cur { int tile, kb, kb1, m0, n0; const float* a; const float* b; };
+        auto cur_setup = [&](Cur& c) {
+            if (c.tile >= args.total_tiles) return;
+            const int sp = c.tile / args.items_per_split, t2 = c.tile - sp * args.items_per_split;
+            const int z  = t2 / tiles_mn;
+            const int r  = t2 - z * tiles_mn;
+            c.kb  = sp * args.kb_per_split;
+            c.kb1 = min(num_kb, c.kb + args.kb_per_split);
+            int tm, tn;
+            tile_coords_bx(r, args.tiles_m, args.tiles_n, args.band_m, tm, tn);
+            c.m0 = tm * (2 * kBM) + (int)rank * kBM;
+            c.n0 = tn * BLOCK_N + (int)rank * Cfg::kHalfN;
+            const int z1 = z % args.nb1, z2 = z / args.nb1;
+            const float* az = args.a + (int64_t)z1 * args.a_bs1 + (int64_t)z2 * args.a_bs2;
+            const float* bz = args.b + (int64_t)z1 * args.b_bs1 + (int64_t)z2 * args.b_bs2;
+            c.a = A_MN ? az + c.m0 : az + (int64_t)c.m0 * args.a_ld;
+            c.b = B_MN ? bz + c.n0 : bz + (int64_t)c.n0 * args.b_ld;
+        };
+        auto cur_next = [&](Cur& c) {
+            if (++c.kb >= c.kb1) { c.tile += num_clusters; cur_setup(c); }
+        };
+        Cur lc, sc;
+        lc.tile = cluster_id; cur_setup(lc);
+        sc = lc;
+
+        float4 va[kPrefetch][OperandLoader<kBM, A_MN, NTERMS>::NLD];
+        float4 vb[kPrefetch][OperandLoader<Cfg::kHalfN, B_MN, NTERMS>::NLD];
+        auto issue = [&](int d) {
+            la.load(va[d], lc.a, args.a_ld, lc.m0, args.M, lc.kb * kKS, args.K);
+            lb.load(vb[d], lc.b, args.b_ld, lc.n0, args.N, lc.kb * kKS, args.K);
+            cur_next(lc);
+        };
+#pragma unroll
+        for (int d = 0; d < kPrefetch; ++d)
+            if (lc.tile < args.total_tiles) issue(d);
+
+        int stage = 0;
+        uint32_t phase = 0;
+        while (sc.tile < args.total_tiles) {
+#pragma unroll
+            for (int d = 0; d < kPrefetch; ++d) {
+                if (sc.tile >= args.total_tiles) break;
+                const bool dbg = args.dbg != nullptr && pw == 0 && lane == 0;
+                long long t0 = 0, t1 = 0, t2 = 0;
+                if (dbg) t0 = clock64();
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (dbg) t1 = clock64();
+                const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                la.store(va[d], sA);
+                lb.store(vb[d], sA + Cfg::kABytes);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(full_bar(stage));       // release.cta; the proxy fence is the consumer's (see top)
+                if (dbg) t2 = clock64();
+                cur_next(sc);
+                if (lc.tile < args.total_tiles) issue(d);
+                if (dbg) {
+                    args.dbg[blockIdx.x * 16 + 0] += t1 - t0;            // wait for a free slot
+                    args.dbg[blockIdx.x * 16 + 1] += t2 - t1;            // wait for the loads + split + store
+                    args.dbg[blockIdx.x * 16 + 2] += clock64() - t2;     // address arithmetic + load issue
+                    args.dbg[blockIdx.x * 16 + 3] += 1;
+                }
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (rank == 1 && (warp == 4 || warp == kFencerWarpB)) {
+        // ============ peer CTA: proxy-fence relays (stages alternate between the two lanes) ============
+        if (ptx::elect_one()) {
+            int total_it = 0;
+            for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+                const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
+                total_it += min(num_kb, kb0 + args.kb_per_split) - kb0;
+            }
+            const uint32_t peer_remote = ptx::mapa(peer_bar(0), 0);
+            for (int it = (warp == 4 ? 0 : 1); it < total_it; it += 2) {
+                const int stage = it % S;
+                const bool dbg = args.dbg != nullptr && warp == 4;
+                long long t0 = 0, t1 = 0, t2 = 0;
+                if (dbg) t0 = clock64();
+                ptx::mbar_wait(full_bar(stage), uint32_t(it / S) & 1u);
+                if (dbg) t1 = clock64();
+                ptx::fence_proxy_async_smem();
+                if (dbg) t2 = clock64();
+                ptx::mbar_arrive_cluster(peer_remote + 8u * stage);
+                if (dbg) {
+                    args.dbg[blockIdx.x * 16 + 4] += t1 - t0;            // relay: wait for the producers
+                    args.dbg[blockIdx.x * 16 + 5] += t2 - t1;            // relay: proxy fence
+                    args.dbg[blockIdx.x * 16 + 6] += clock64() - t2;     // relay: release.cluster arrive
+                    args.dbg[blockIdx.x * 16 + 7] += 1;
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ============================= MMA issuer (leader CTA) =============================
+        if (rank == 0 && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kBM, BLOCK_N, A_MN, B_MN);
+            constexpr uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
+            constexpr uint64_t desc_mn = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 4096, 1024);   // LBO: next 64-mn slab, SBO: next 8 k-rows
+            constexpr uint64_t descA = A_MN ? desc_mn : desc_k, descB = B_MN ? desc_mn : desc_k;
+            // byte offset of K16 slice s of the hi (t = 0) / mid (t = 1) image
+            auto a_off = [](int t, int s) -> uint32_t { return A_MN ? uint32_t(t) * (kBM / 64) * 4096u + uint32_t(s) * 2048u : uint32_t(t) * 64u + uint32_t(s) * 32u; };
+            auto b_off = [](int t, int s) -> uint32_t { return B_MN ? uint32_t(t) * (Cfg::kHalfN / 64) * 4096u + uint32_t(s) * 2048u : uint32_t(t) * 64u + uint32_t(s) * 32u; };
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+                const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
+                const int kb1 = min(num_kb, kb0 + args.kb_per_split);
+                {
+                    const long long t0 = args.dbg ? clock64() : 0;
+                    ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    if (args.dbg) args.dbg[blockIdx.x * 16 + 12] += clock64() - t0;   // issuer: wait for a free accumulator
+                }
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    long long t0 = 0, t1 = 0, t2 = 0;
+                    if (args.dbg) t0 = clock64();
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    if (args.dbg) t1 = clock64();
+                    ptx::mbar_wait_cluster(peer_bar(stage), phase);
+                    if (args.dbg) t2 = clock64();
+                    ptx::fence_proxy_async_smem();
+                    ptx::tc_fence_after();
+                    if (args.dbg) {
+                        args.dbg[blockIdx.x * 16 + 8] += t1 - t0;            // issuer: wait for own producers
+                        args.dbg[blockIdx.x * 16 + 9] += t2 - t1;            // issuer: wait for the peer
+                        args.dbg[blockIdx.x * 16 + 10] += clock64() - t2;    // issuer: proxy fence
+                        args.dbg[blockIdx.x * 16 + 11] += 1;
+                    }
+                    const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                    const uint32_t sB = sA + Cfg::kABytes;
+                    uint32_t accum = (kb != kb0) ? 1u : 0u;
+                    if (NTERMS == 3) {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {          // mid * hi
+                            ptx::umma_f16_2sm(d_tmem, ptx::umma_desc(descA, sA + a_off(1, s)), ptx::umma_desc(descB, sB + b_off(0, s)), idesc, accum);
+                            accum = 1u;
+                        }
+#pragma unroll
+                        for (int s = 0; s < 2; ++s)            // hi * mid
+                            ptx::umma_f16_2sm(d_tmem, ptx::umma_desc(descA, sA + a_off(0, s)), ptx::umma_desc(descB, sB + b_off(1, s)), idesc, 1u);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {              // hi * hi
+                        ptx::umma_f16_2sm(d_tmem, ptx::umma_desc(descA, sA + a_off(0, s)), ptx::umma_desc(descB, sB + b_off(0, s)), idesc, accum);
+                        accum = 1u;
+                    }
+                    ptx::umma_commit_2sm(empty_bar(stage), 3);
+                    if (kb == kb1 - 1) ptx::umma_commit_2sm(tfull_bar(acc), 3);
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp < 4) {
+        // ============================== epilogue (both CTAs; same as gemm_tc2_kernel) ==============================
+        uint8_t* stg_base = base_ptr + S * Cfg::kStageBytes + warp * 2 * 4096;
+        const uint32_t stg_addr = epi_addr + warp * 2 * 4096;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t nstore = 0;
+        for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+            const int sp = tile / args.items_per_split, t2 = tile - sp * args.items_per_split;
+            const int z  = t2 / tiles_mn;
+            const int r  = t2 - z * tiles_mn;
+            int tm, tn;
+            tile_coords_bx(r, args.tiles_m, args.tiles_n, args.band_m, tm, tn);
+            const int m0 = tm * (2 * kBM) + (int)rank * kBM;
+            const int n0 = tn * BLOCK_N;
+            const int z1 = z % args.nb1, z2 = z / args.nb1;
+            ptx::mbar_wait(tfull_bar(acc), acc_phase);
+            ptx::tc_fence_after();
+            const bool rows_live = (m0 + warp * 32) < args.M;
+#pragma unroll 1
+            for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+                const int nc = n0 + chunk * 32;
+                if (nc >= args.N || !rows_live) break;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(tmem_base + (uint32_t(warp * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+                ptx::tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
+                if (args.bias != nullptr && sp == 0) {
+                    const float* bp = args.bias + nc;
+                    if (nc + 32 <= args.N && ((reinterpret_cast<uintptr_t>(bp) & 15u) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+                            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nc + j < args.N) f[j] += __ldg(bp + j);
+                    }
+                }
+                if (args.residual != nullptr && sp == 0) {
+                    const int64_t row_g = (int64_t)m0 + warp * 32 + lane;
+                    if (row_g < args.M) {
+                        const float* rrow = args.residual + row_g * args.ldr + nc;
+                        if (nc + 32 <= args.N && ((reinterpret_cast<uintptr_t>(rrow) & 15u) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+                                f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nc + j < args.N) f[j] += __ldg(rrow + j);
+                        }
+                    }
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)      // sign bit set <=> pre-activation < 0 (a genuine -0.0 is >= 0, activations.py:19: store +0.0)
+                        f[j] = f[j] < 0.0f ? -0.0f : __uint_as_float(__float_as_uint(f[j]) & 0x7fffffffu);
+                }
+                const uint32_t buf = nstore & 1u;
+                if (lane == 0) ptx::tma_wait_group_read<1>();
+                __syncwarp();
+                uint8_t* row = stg_base + buf * 4096 + lane * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = o;
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (ptx::elect_one()) {
+                    if (args.accum || args.splits > 1)
+                        ptx::tma_reduce_add_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
+                    else
+                        ptx::tma_store_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, z1, z2);
+                    ptx::tma_commit_group();
+                }
+                ++nstore;
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+                else           ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(acc), 0));
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (lane == 0) ptx::tma_wait_group<0>();
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 4) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+}
+
+template <int BN, bool AMN, bool BMN, int NT>
+int launch_bx(const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream_t stream) {
+    using Cfg = BxCfg<BN>;
+    auto kern = gemm_bx_kernel<BN, AMN, BMN, NT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(gemm_bx, smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+            return NPM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    GemmBxArgs largs = args;
+    static const bool dbg_times = getenv("NPM_GEMM_DEBUG_TIMES") != nullptr;      // tools only: synchronises and prints
+    if (dbg_times) {
+        cudaMalloc(&largs.dbg, sizeof(long long) * 16 * grid);
+        cudaMemset(largs.dbg, 0, sizeof(long long) * 16 * grid);
+    }
+    cudaError_t e = launch_pdl(kern, dim3((unsigned)grid, 1, 1), dim3(kThreadsBx, 1, 1), Cfg::kSmemBytes, stream, 2, c, largs);
+    count_launch();
+    if (e != cudaSuccess) { set_error("gemm_bx_kernel launch: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+    if (dbg_times) {
+        cudaStreamSynchronize(stream);
+        std::vector<long long> h(16 * (size_t)grid);
+        cudaMemcpy(h.data(), largs.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        double s[16] = {0};
+        for (int cta = 0; cta < grid; ++cta)
+            for (int i = 0; i < 16; ++i) s[i] += (double)h[16 * cta + i];
+        fprintf(stderr, "[gemm_bx M=%d N=%d K=%d nt=%d] per stage: producer(w0) slot-wait %.0f, loads+split+store %.0f, issue %.0f | relay wait %.0f, "
+                "fence %.0f, arrive %.0f | issuer own-wait %.0f, peer-wait %.0f, fence %.0f, acc-wait/stage %.0f\n",
+                args.M, args.N, args.K, NT, s[0] / s[3], s[1] / s[3], s[2] / s[3], s[4] / s[7], s[5] / s[7], s[6] / s[7],
+                s[8] / s[11], s[9] / s[11], s[10] / s[11], s[12] / s[11]);
+        cudaFree(largs.dbg);
+    }
+    return check_launch("gemm_bx_kernel");
+}
+
+template <int BN, int NT>
+int launch_bx_major(bool amn, bool bmn, const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream_t s) {
+    if (!amn && !bmn) return launch_bx<BN, false, false, NT>(c, args, grid, s);
+    if (!amn && bmn) return launch_bx<BN, false, true, NT>(c, args, grid, s);
+    if (amn && !bmn) return launch_bx<BN, true, false, NT>(c, args, grid, s);
+    return launch_bx<BN, true, true, NT>(c, args, grid, s);
+}
+
+inline bool mult4(int64_t v) { return (v & 3) == 0; }
+
+}  // namespace
+
+// The split-bf16 kernel takes problems with at least two row tiles whose operands can be read in 16-byte chunks that
+// never straddle an edge; everything else in these modes runs the 3xTF32 kernel (at least as accurate).
+bool gemm_bx_supported(const npm_gemm_desc& d) {
+    if (d.m <= kBM || d.n <= 0 || d.k <= 0) return false;
+    if (!aligned16(d.a) || !aligned16(d.b) || !aligned16(d.c)) return false;
+    if (!(d.a_cs == 1 || d.a_rs == 1) || !(d.b_cs == 1 || d.b_rs == 1)) return false;
+    const bool a_mn = !(d.a_cs == 1), b_mn = !(d.b_rs == 1);
+    const int64_t a_ld = a_mn ? d.a_cs : d.a_rs, b_ld = b_mn ? d.b_rs : d.b_cs;
+    if (!mult4(a_ld) || !mult4(b_ld) || !mult4(d.ldc) || a_ld <= 0 || b_ld <= 0 || d.ldc < d.n) return false;
+    if (!mult4(d.k)) return false;
+    if (a_mn && !mult4(d.m)) return false;
+    if (b_mn && !mult4(d.n)) return false;
+    if (d.nb1 > 1 && !(mult4(d.a_bs1) && mult4(d.b_bs1) && mult4(d.c_bs1))) return false;
+    if (d.nb2 > 1 && !(mult4(d.a_bs2) && mult4(d.b_bs2) && mult4(d.c_bs2))) return false;
+    if (d.m > (1ll << 31) - 512 || d.n > (1ll << 31) - 512 || d.k > (1ll << 31) - 512) return false;
+    return true;
+}
+
+int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
+    const int nb1 = d.nb1 > 0 ? d.nb1 : 1, nb2 = d.nb2 > 0 ? d.nb2 : 1;
+    const bool a_mn = !(d.a_cs == 1), b_mn = !(d.b_rs == 1);
+    const int units = num_sms() / 2;
+    const int64_t tiles_m = (d.m + 2 * kBM - 1) / (2 * kBM);
+    const int num_kb_total = (int)((d.k + kKS - 1) / kKS);
+    const bool c_dense = (d.ldc == d.n) && (nb1 == 1 || d.c_bs1 == d.m * d.n) && (nb2 == 1 || d.c_bs2 == d.m * d.n * nb1);
+    static const bool no_splitk = getenv("NPM_GEMM_NO_SPLITK") != nullptr;
+    static const int forced_bn = getenv("NPM_GEMM_BLOCK_N_DYN") ? atoi(getenv("NPM_GEMM_BLOCK_N_DYN")) : 0;
+    const bool may_split = c_dense && !(d.flags & (NPM_GEMM_RELU | NPM_GEMM_ACCUM)) && !no_splitk;
+    int best_bn = 128, best_splits = 1;
+    {
+        // cycles per K stage of one pair: 2 * nterms MMAs of N x K16 at N/2 clk each (tensor floor)
+        double best_cost = 1e300;
+        const int cands[2] = {256, 128};
+        for (int i = 0; i < 2; ++i) {
+            const int bn = cands[i];
+            if (forced_bn && bn != forced_bn) continue;
+            const double kstep = (nterms == 3 ? 3.0 : 1.0) * bn + (bn == 128 ? 120.0 : 0.0);
+            const int64_t tn = (d.n + bn - 1) / bn;
+            const int64_t tiles = tiles_m * tn * nb1 * nb2;
+            for (int sp = 1; sp <= (may_split ? 16 : 1); sp *= 2) {
+                const int kbs = (num_kb_total + sp - 1) / sp;
+                if (sp > 1 && kbs < 16) break;
+                const int64_t waves = (tiles * sp + units - 1) / units;
+                double cost = double(waves) * (kbs * kstep + 1500.0 + 8.0 * bn);
+                if (sp > 1) cost = cost * 1.08 + 3000.0;
+                if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_splits = sp; }
+            }
+        }
+    }
+    const int bn = best_bn;
+    const int kb_per_split = (num_kb_total + best_splits - 1) / best_splits;
+    const int splits = (num_kb_total + kb_per_split - 1) / kb_per_split;
+    const int64_t tiles_n = (d.n + bn - 1) / bn;
+    const int64_t items_per_split = tiles_m * tiles_n * nb1 * nb2;
+    const int64_t total = items_per_split * splits;
+    if (total > (1ll << 30)) { set_error("gemm: too many tiles"); return NPM_ERR_INVALID; }
+    if (splits > 1) {
+        cudaError_t e = cudaMemsetAsync(d.c, 0, sizeof(float) * (size_t)d.m * d.n * nb1 * nb2, stream);
+        if (e != cudaSuccess) { set_error("gemm split-K memset: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+    }
+    CUtensorMap tmC;
+    auto bs = [](int nb, int64_t s, uint64_t natural) -> uint64_t { return nb > 1 ? (uint64_t)s : natural; };
+    {
+        const uint64_t ld = d.ldc;
+        const uint64_t s2 = bs(nb1, d.c_bs1, ld * d.m), s3 = bs(nb2, d.c_bs2, s2 * nb1);
+        int rc = make_tensor_map_4d(&tmC, d.c, d.n, d.m, nb1, nb2, ld, s2, s3, 32, 32, false, false);
+        if (rc) return rc;
+    }
+    GemmBxArgs args;
+    args.a = d.a; args.b = d.b;
+    args.a_ld = a_mn ? d.a_cs : d.a_rs;
+    args.b_ld = b_mn ? d.b_rs : d.b_cs;
+    args.a_bs1 = nb1 > 1 ? d.a_bs1 : 0; args.a_bs2 = nb2 > 1 ? d.a_bs2 : 0;
+    args.b_bs1 = nb1 > 1 ? d.b_bs1 : 0; args.b_bs2 = nb2 > 1 ? d.b_bs2 : 0;
+    args.M = (int)d.m; args.N = (int)d.n; args.K = (int)d.k;
+    args.tiles_m = (int)tiles_m; args.tiles_n = (int)tiles_n; args.nb1 = nb1;
+    args.total_tiles = (int)total;
+    args.splits = splits; args.kb_per_split = kb_per_split; args.items_per_split = (int)items_per_split;
+    static const int band_env = getenv("NPM_GEMM_BAND") ? atoi(getenv("NPM_GEMM_BAND")) : 8;
+    args.band_m = (tiles_m > band_env && tiles_n > 1) ? band_env : 0;
+    args.alpha = d.alpha;
+    args.bias = d.bias;
+    args.residual = d.residual;
+    args.ldr = d.ldr;
+    args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
+    args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
+    args.dbg = nullptr;
+    const int grid = 2 * (int)(total < units ? total : units);
+    if (nterms == 3) {
+        if (bn == 256) return launch_bx_major<256, 3>(a_mn, b_mn, tmC, args, grid, stream);
+        return launch_bx_major<128, 3>(a_mn, b_mn, tmC, args, grid, stream);
+    }
+    if (bn == 256) return launch_bx_major<256, 1>(a_mn, b_mn, tmC, args, grid, stream);
+    return launch_bx_major<128, 1>(a_mn, b_mn, tmC, args, grid, stream);
+}
+
+}  // namespace npm

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs p) {
             float v = acc[i][j] * p.alpha;
             if (p.bias) v += __ldg(p.bias + gn);
             if (p.residual) v += __ldg(p.residual + gm * p.ldr + gn);
-            if (p.relu) v = v < 0.0f ? -0.0f : v;
+            if (p.relu) v = v < 0.0f ? -0.0f : fabsf(v);     // sign bit set <=> pre-activation < 0 (a genuine -0.0 is >= 0)
             float* dst = C + gm * p.ldc + gn;
             *dst = p.accum ? (*dst + v) : v;
         }

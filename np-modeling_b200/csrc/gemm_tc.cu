@@ -276,7 +276,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (args.relu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? -0.0f : f[j];   // -0.0 keeps "x < 0" for ReLU.backward
+                    for (int j = 0; j < 32; ++j)      // sign bit set <=> pre-activation < 0 (a genuine -0.0 is >= 0, activations.py:19: store +0.0)
+                        f[j] = f[j] < 0.0f ? -0.0f : __uint_as_float(__float_as_uint(f[j]) & 0x7fffffffu);
                 }
                 const uint32_t buf = nstore & 1u;
                 // the store that last read this buffer (two stores ago) must have drained
@@ -624,7 +625,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (args.relu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? -0.0f : f[j];   // -0.0 keeps "x < 0" for ReLU.backward
+                    for (int j = 0; j < 32; ++j)      // sign bit set <=> pre-activation < 0 (a genuine -0.0 is >= 0, activations.py:19: store +0.0)
+                        f[j] = f[j] < 0.0f ? -0.0f : __uint_as_float(__float_as_uint(f[j]) & 0x7fffffffu);
                 }
                 const uint32_t buf = nstore & 1u;
                 if (lane == 0) ptx::tma_wait_group_read<1>();

@@ -87,7 +87,7 @@ class Dense(layer.StatefulLayer):
         self._linear = Linear(units=units)
         self._activation = activation or activations.ReLU()
 
-    def initialize(self, x) -> None:
+    def initialize(self, x, **kwargs) -> None:
         self._linear.initialize(x)
         self._linear._initialized = True
         self._activation.initialize()
@@ -98,10 +98,13 @@ class Dense(layer.StatefulLayer):
         # written); anything else (e.g. Softmax, a user subclass) runs as its own layer.
         return type(self._activation) is activations.ReLU
 
-    def forward(self, x):
+    def forward(self, x, _alias_ok: bool = False):
+        """`_alias_ok=True` (the transformer blocks, which never write into this output) returns the buffer the
+        backward pass reads its ReLU mask from; any other caller gets its own copy, so that the reference's idiom
+        `out = layer(x); out += skip` (in-place on a layer output) cannot destroy the mask."""
         if self._fused_relu():
             self._y = self._linear.forward(x, _relu=True)
-            return self._y
+            return self._y if _alias_ok else self._y.copy()
         y = self._linear.forward(x)
         return self._activation.forward(y)
 

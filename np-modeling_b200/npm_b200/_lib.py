@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('NPM_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'libnpm_b200.so')   # env override: tools only
 
 NPM_OK = 0
-PREC_TF32, PREC_3XTF32, PREC_FP32 = 0, 1, 2
+PREC_TF32, PREC_3XTF32, PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2, 3, 4
 GEMM_RELU, GEMM_ACCUM = 1, 2
 OPT_CHUNK = 8192
 

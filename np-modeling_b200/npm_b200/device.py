@@ -31,13 +31,29 @@ class DeviceArray:
     # `colsum`: optional DeviceArray [shape[-1]] holding the sums over all leading axes, attached by a kernel that had
     # the values in registers anyway (the fused LayerNorm backward); consumers that need exactly that reduction — the
     # bias gradient `np.sum(dy, axis=0)` of mlp.py:34 / attentions.py:129 — use it instead of re-reading the array.
-    __slots__ = ('t', 'colsum')
+    # The attachment lives in a cell shared by every reshape() alias / leading-axis view of the same storage, so an
+    # in-place write through ANY of them invalidates it for all of them.
+    __slots__ = ('t', '_cs')
     __array_priority__ = 1000
 
-    def __init__(self, t: torch.Tensor, colsum=None):
+    def __init__(self, t: torch.Tensor, colsum=None, _cell=None):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'DeviceArray wraps contiguous fp32 CUDA'
         self.t = t
-        self.colsum = colsum
+        self._cs = _cell if _cell is not None else [None, 0]     # [colsum DeviceArray, numel of the array it sums]
+        if colsum is not None:
+            self.colsum = colsum
+
+    @property
+    def colsum(self):
+        cs, numel = self._cs
+        if cs is None or numel != self.t.numel() or self.t.dim() < 1 or cs.size != self.t.shape[-1]:
+            return None
+        return cs
+
+    @colsum.setter
+    def colsum(self, value):
+        self._cs[0] = value
+        self._cs[1] = self.t.numel() if value is not None else 0
 
     # ---- ndarray-like surface -------------------------------------------------
     @property
@@ -76,9 +92,7 @@ class DeviceArray:
     def reshape(self, *shape):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
-        v = self.t.view(*shape)
-        keep = self.colsum is not None and v.dim() >= 1 and self.t.dim() >= 1 and v.shape[-1] == self.t.shape[-1]
-        return DeviceArray(v, self.colsum if keep else None)
+        return DeviceArray(self.t.view(*shape), _cell=self._cs)
 
     def copy(self):
         return DeviceArray(self.t.clone())
@@ -90,7 +104,7 @@ class DeviceArray:
         v = self.t[idx]
         if not v.is_contiguous():
             raise IndexError('DeviceArray only supports contiguous (leading-axis) views')
-        return DeviceArray(v)
+        return DeviceArray(v, _cell=self._cs)     # a write through the view invalidates the parent's column sums
 
     def __iadd__(self, other):
         other = asdevice(other)
@@ -105,6 +119,42 @@ class DeviceArray:
         out = empty(self.shape)
         C.npm_add3(self.ptr, other.ptr, None, out.ptr, self.size, stream())
         return out
+
+    # The rest of the arithmetic a user-defined Optimizer written in the reference's style needs
+    # (`variable -= lr * gradient`, optimizer.py:32): each is one or two of this library's elementwise kernels.
+    def _scaled(self, s: float):
+        out = self.copy()
+        C.npm_scale(out.ptr, float(s), out.size, stream())
+        return out
+
+    def __mul__(self, other):
+        if isinstance(other, (int, float, np.floating, np.integer)):
+            return self._scaled(float(other))
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        if isinstance(other, (int, float, np.floating, np.integer)):
+            return self._scaled(1.0 / float(other))
+        return NotImplemented
+
+    def __neg__(self):
+        return self._scaled(-1.0)
+
+    def __sub__(self, other):
+        return self + (-asdevice(other))
+
+    def __isub__(self, other):
+        self += -asdevice(other)
+        return self
+
+    def __imul__(self, other):
+        if not isinstance(other, (int, float, np.floating, np.integer)):
+            return NotImplemented
+        C.npm_scale(self.ptr, float(other), self.size, stream())
+        self.colsum = None
+        return self
 
     def item(self):
         return float(self.t.item())

@@ -103,6 +103,10 @@ class _FusedOptimizer(Optimizer):
 
     def grad_buffer(self, obj, attribute, shape):
         identifier = f'{id(obj)}.{attribute}'
+        if any(p[0] == identifier for p in self._pending):
+            # the same parameter a second time inside one bracket (a layer applied twice): its queued update still
+            # points at this persistent buffer, so apply it before the buffer is handed out to be overwritten
+            self.flush()
         buf = self._grads.get(identifier)
         shape = tuple(int(s) for s in shape)
         if buf is None or buf.shape != shape:
@@ -114,6 +118,8 @@ class _FusedOptimizer(Optimizer):
     def grad_buffer_pack(self, obj, attributes, shape):
         shape = tuple(int(s) for s in shape)
         key = (id(obj), tuple(attributes), shape)
+        if any(p[0] in {f'{id(obj)}.{a}' for a in attributes} for p in self._pending):
+            self.flush()
         pack = self._grad_packs.get(key)
         if pack is None:
             pack = self._arena.alloc((len(attributes),) + shape)

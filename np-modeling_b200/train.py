@@ -92,12 +92,26 @@ class Trainer:
         a = np.asarray(a)
         if not torch.cuda.is_available():
             raise RuntimeError('np-modeling_b200 needs a CUDA device; there is no CPU fallback')
-        pin = self._pinned.get(key)
-        if pin is None or tuple(pin.shape) != a.shape:
-            pin = torch.empty(a.shape, dtype=torch.float32).pin_memory()
-            self._pinned[key] = pin
+        # Two pinned staging buffers per input, used alternately, each guarded by the event of its last H2D copy: the
+        # copy is asynchronous and queued behind ~1000 kernels while the host runs ahead, so rewriting a staging buffer
+        # whose copy has not executed yet would upload the NEXT batch's bytes for the current step
+        # (`for xb, yb in data: trainer.train(xb, yb, 1, opt)`).
+        slot = self._pinned.get(key)
+        if slot is None or tuple(slot['bufs'][0].shape) != a.shape:
+            slot = {'bufs': [torch.empty(a.shape, dtype=torch.float32).pin_memory() for _ in range(2)],
+                    'events': [None, None], 'next': 0}
+            self._pinned[key] = slot
+        i = slot['next']
+        slot['next'] = i ^ 1
+        if slot['events'][i] is not None:
+            slot['events'][i].synchronize()
+        pin = slot['bufs'][i]
         pin.numpy()[...] = a
-        return device.from_pinned(pin)
+        out = device.from_pinned(pin)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        slot['events'][i] = ev
+        return out
 
     # ---- data-parallel plumbing -----------------------------------------------------------
     def _broadcast_parameters(self):
