@@ -36,7 +36,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('NPM_BENCH_PRECISION', 'tf32'), choices=['tf32', '3xtf32'])
+    ap.add_argument('--precision', default=os.environ.get('NPM_BENCH_PRECISION', 'tf32'), choices=['bf16x3', 'tf32', '3xtf32', 'bf16'])
     ap.add_argument('--layers', type=int, default=24)
     ap.add_argument('--d-model', type=int, default=1024)
     ap.add_argument('--heads', type=int, default=16)

@@ -228,6 +228,19 @@ int npm_fill(float* x, float v, int64_t n, npm_stream_t stream);
  * (TF32 mode with dk = dv = 64: the fused tcgen05 kernels, `saved` = one
  * log-sum-exp per row; otherwise the probabilities P).  The size queries, fwd
  * and bwd of one attention call must run under the same precision mode. */
+/* Implementation the CURRENT precision mode selects for this shape: 0 = batched
+ * GEMMs + row softmax with the scores materialised (`saved` = P), 1 = fused TF32
+ * kernels (`saved` = log-sum-exp), 2 = fused split-bf16 kernels (`saved` =
+ * log-sum-exp + the bf16 hi/mid planes of q, k, v).  Callers that keep state
+ * from forward to backward record it and pass 1 + path in npm_mha_strides.path;
+ * the *_for size queries take it explicitly. */
+int    npm_mha_core_path(int64_t B, int64_t H, int64_t Sq, int64_t Skv,
+                         int64_t dk, int64_t dv);
+size_t npm_mha_core_saved_bytes_for(int path, int64_t B, int64_t H, int64_t Sq,
+                                    int64_t Skv, int64_t dk, int64_t dv);
+size_t npm_mha_core_bwd_scratch_bytes_for(int path, int64_t B, int64_t H,
+                                          int64_t Sq, int64_t Skv, int64_t dk,
+                                          int64_t dv);
 size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv,
                                 int64_t dk, int64_t dv);
 size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq,
@@ -253,6 +266,10 @@ typedef struct npm_mha_strides {
                                * BEYOND the reference, whose mask argument is unusable (`if mask:` on an
                                * ndarray raises, attentions.py:84; backward NotImplementedError :152-153);
                                * SURVEY.md §8 f1.  The fused kernels skip the blocks above the diagonal. */
+    int64_t path;             /* 0: the implementation the current precision mode selects; otherwise
+                               * 1 + the value npm_mha_core_path() returned when the forward ran — pins
+                               * forward, backward and the layout of `saved` to one implementation even if
+                               * the precision mode changes in between.                              */
 } npm_mha_strides;
 int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v,
                              float* o, void* saved, int64_t B, int64_t H,

@@ -54,12 +54,13 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream);
 size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
 // attn_fwd.cu / attn_bwd.cu
 bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv);
-int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, cudaStream_t stream);
-size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq);
-int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
+int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float* lse, int64_t B, int64_t H,
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, bool bx, cudaStream_t stream);
+size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, bool bx);
+int attn_split_launch(const float* x, int64_t ld, void* planes, int64_t rows, int64_t HD, cudaStream_t stream);
+int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal,
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal, bool bx,
                     cudaStream_t stream);
 int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
@@ -118,12 +119,35 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     return gemm_simt_launch(d, stream);
 }
 
-// The fused attention kernels serve head dim 64 in TF32 mode (the throughput mode); the 3xTF32 /
-// fp32 modes and other head dims run the batched-GEMM + softmax chain below.  fwd, bwd and the size
-// queries must be called under the same precision mode.
-static bool attn_fused(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
-    const bool off = getenv("NPM_ATTN_UNFUSED") != nullptr;     // A/B switch for tools/ and tests
-    return !off && g_precision.load() == NPM_PREC_TF32 && attn_fused_supported(B, H, Sq, Skv, dk, dv);
+// Which implementation serves an attention-core call (the value npm_mha_core_path() reports and npm_mha_strides.path
+// pins): head dim 64 runs the fused online-softmax kernels — in TF32 mode with tf32 operands (1), in the split-bf16
+// modes with pre-split bf16 operands (2); the 3xTF32 / fp32 modes and other head dims run the batched GEMM + softmax
+// chain with the scores materialised (0).
+enum { ATTN_MATERIALISED = 0, ATTN_FUSED_TF32 = 1, ATTN_FUSED_BX = 2 };
+static int attn_path_now(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    static const bool off = getenv("NPM_ATTN_UNFUSED") != nullptr;     // A/B switch for tools/ and tests
+    if (off || !attn_fused_supported(B, H, Sq, Skv, dk, dv)) return ATTN_MATERIALISED;
+    const int prec = g_precision.load();
+    if (prec == NPM_PREC_TF32) return ATTN_FUSED_TF32;
+    if (prec == NPM_PREC_BF16X3) return ATTN_FUSED_BX;
+    return ATTN_MATERIALISED;
+}
+// the path a call runs: the one pinned in the strides struct (1 + path), else the current mode's
+static int attn_path_of(const npm_mha_strides* ld, int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    if (ld && ld->path > 0) return (int)ld->path - 1;
+    return attn_path_now(B, H, Sq, Skv, dk, dv);
+}
+static size_t pad256(size_t n) { return (n + 255) & ~(size_t)255; }
+// split-bf16 path: `saved` = log-sum-exp | q planes | k planes | v planes (each [2][B,S,H,64] bf16)
+struct BxSaved { float* lse; uint8_t* q; uint8_t* k; uint8_t* v; };
+static BxSaved bx_saved(void* saved, int64_t B, int64_t H, int64_t Sq, int64_t Skv) {
+    BxSaved r;
+    uint8_t* p = reinterpret_cast<uint8_t*>(saved);
+    r.lse = reinterpret_cast<float*>(p);
+    r.q = p + pad256((size_t)B * H * Sq * sizeof(float));
+    r.k = r.q + (size_t)B * Sq * H * 64 * 4;
+    r.v = r.k + (size_t)B * Skv * H * 64 * 4;
+    return r;
 }
 
 static npm_gemm_desc blank_desc() {
@@ -237,13 +261,23 @@ int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db, 
 // attn_bwd.cu (`saved` = one log-sum-exp per row).  Otherwise (3xTF32 / fp32 modes, other head dims): the batched
 // products run on the GEMM with the scores materialised ([B,H,Sq,Skv], as the reference does at attentions.py:103-111)
 // and `saved` holds the probabilities P.
-size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
-    if (attn_fused(B, H, Sq, Skv, dk, dv)) return (size_t)B * H * Sq * sizeof(float);   // log-sum-exp per row
+int npm_mha_core_path(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    return attn_path_now(B, H, Sq, Skv, dk, dv);
+}
+size_t npm_mha_core_saved_bytes_for(int path, int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    if (path == ATTN_FUSED_TF32) return (size_t)B * H * Sq * sizeof(float);             // log-sum-exp per row
+    if (path == ATTN_FUSED_BX) return pad256((size_t)B * H * Sq * sizeof(float)) + (size_t)B * (Sq + 2 * Skv) * H * 64 * 4;
     return (size_t)B * H * Sq * Skv * sizeof(float);                                      // P
 }
-size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
-    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_bwd_scratch_bytes(B, H, Sq);      // D = rowsum(dO o O)
+size_t npm_mha_core_bwd_scratch_bytes_for(int path, int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    if (path != ATTN_MATERIALISED) return attn_bwd_scratch_bytes(B, H, Sq, path == ATTN_FUSED_BX);   // D (+ dO planes)
     return (size_t)B * H * Sq * Skv * sizeof(float);   // dP / dS
+}
+size_t npm_mha_core_saved_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    return npm_mha_core_saved_bytes_for(attn_path_now(B, H, Sq, Skv, dk, dv), B, H, Sq, Skv, dk, dv);
+}
+size_t npm_mha_core_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv) {
+    return npm_mha_core_bwd_scratch_bytes_for(attn_path_now(B, H, Sq, Skv, dk, dv), B, H, Sq, Skv, dk, dv);
 }
 
 int npm_mha_core_fwd(const float* q, const float* k, const float* v, float* o, void* saved, int64_t B, int64_t H,
@@ -262,7 +296,17 @@ int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v, flo
     NPM_REQUIRE(ldq >= H * dk && ldk >= H * dk && ldv >= H * dv, "mha_core_fwd: token strides must be >= H*d");
     const int causal = ld && ld->causal ? 1 : 0;
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_fwd: the causal mask needs Sq == Skv");
-    if (attn_fused(B, H, Sq, Skv, dk, dv)) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, causal, s);
+    const int path = attn_path_of(ld, B, H, Sq, Skv, dk, dv);
+    NPM_REQUIRE(path == ATTN_MATERIALISED || attn_fused_supported(B, H, Sq, Skv, dk, dv), "mha_core_fwd: the pinned path does not serve this shape");
+    if (path == ATTN_FUSED_TF32) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, causal, false, s);
+    if (path == ATTN_FUSED_BX) {
+        const BxSaved sv = bx_saved(saved, B, H, Sq, Skv);
+        int rc;
+        if ((rc = attn_split_launch(q, ldq, sv.q, B * Sq, H * dk, s))) return rc;
+        if ((rc = attn_split_launch(k, ldk, sv.k, B * Skv, H * dk, s))) return rc;
+        if ((rc = attn_split_launch(v, ldv, sv.v, B * Skv, H * dv, s))) return rc;
+        return attn_fwd_launch(sv.q, sv.k, sv.v, o, sv.lse, B, H, Sq, Skv, 0, 0, 0, causal, true, s);
+    }
     // S[b,h] = (1/sqrt(dk)) q[b,:,h,:] k[b,:,h,:]^T
     npm_gemm_desc d = blank_desc();
     d.a = q; d.b = k; d.c = P;
@@ -316,10 +360,17 @@ int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v, con
                   lddk = ld && ld->dk ? ld->dk : H * dk, lddv = ld && ld->dv ? ld->dv : H * dv;
     NPM_REQUIRE(ldq >= H * dk && ldk >= H * dk && ldv >= H * dv && lddq >= H * dk && lddk >= H * dk && lddv >= H * dv,
                 "mha_core_bwd: token strides must be >= H*d");
-    if (attn_fused(B, H, Sq, Skv, dk, dv))
+    const int path = attn_path_of(ld, B, H, Sq, Skv, dk, dv);
+    NPM_REQUIRE(path == ATTN_MATERIALISED || attn_fused_supported(B, H, Sq, Skv, dk, dv), "mha_core_bwd: the pinned path does not serve this shape");
+    if (path == ATTN_FUSED_TF32)
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
                                reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, lddq, lddk, lddv,
-                               ld && ld->causal ? 1 : 0, s);
+                               ld && ld->causal ? 1 : 0, false, s);
+    if (path == ATTN_FUSED_BX) {
+        const BxSaved sv = bx_saved(const_cast<void*>(saved), B, H, Sq, Skv);
+        return attn_bwd_launch(sv.q, sv.k, sv.v, o, d_o, sv.lse, dq, dk_out, dv_out, reinterpret_cast<float*>(scratch), B, H,
+                               Sq, Skv, 0, 0, 0, lddq, lddk, lddv, ld && ld->causal ? 1 : 0, true, s);
+    }
     const float* P = reinterpret_cast<const float*>(saved);
     float* dP = reinterpret_cast<float*>(scratch);
     int rc;
@@ -384,8 +435,8 @@ int npm_mha_core_scores(const float* q, const float* k, const void* saved, float
                         int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, npm_stream_t stream) {
     NPM_REQUIRE(saved && p_out, "mha_core_scores: NULL pointer");
     cudaStream_t s = (cudaStream_t)stream;
-    if (attn_fused(B, H, Sq, Skv, dk, dv)) {
-        // recompute P = exp(q k^T / sqrt(dk) - lse) from the saved log-sum-exp
+    if (attn_path_now(B, H, Sq, Skv, dk, dv) != ATTN_MATERIALISED) {
+        // recompute P = exp(q k^T / sqrt(dk) - lse) from the saved log-sum-exp (first thing in `saved` on both fused paths)
         NPM_REQUIRE(q && k, "mha_core_scores: q and k are needed to recompute the probabilities");
         npm_gemm_desc d = blank_desc();
         d.a = q; d.b = k; d.c = p_out;

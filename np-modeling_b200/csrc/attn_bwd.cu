@@ -15,6 +15,11 @@
 // A [rows, 64] fp32 tile that is contracted over its 64 columns is landed with the plain 128-byte
 // swizzle ("R" image, K-major operand); contracted over its rows it is landed with 32-byte swizzle
 // atoms ("T" image, MN-major operand) — tf32 operands cannot be transposed at 16-byte granularity.
+//
+// BX = true: the split-bf16 ("bf16x3") variant of both kernels, as in attn_fwd.cu: q / k / v / dO arrive as bf16 hi + mid
+// planes (attn_split_kernel below), every product runs mid*hi + hi*mid + hi*hi with kind::f16, P / dS go back to TMEM as
+// packed bf16 pairs (per 64-column half: 32 columns hi, 32 columns mid).  A bf16 [128, 64] tile with the 128-byte
+// swizzle serves as the "R" and as the "T" image at once; the T loads below then land the same bytes again.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -30,6 +35,8 @@ int gcd_int(int a, int b);
 int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                        uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, bool round_tf32,
                        bool atom32b);
+int make_tensor_map_bf16_planes(CUtensorMap* tm, const void* base, uint64_t S, uint64_t H, uint64_t B, uint64_t ld,
+                                uint64_t plane_elems, uint32_t box_rows);
 
 namespace {
 
@@ -65,14 +72,30 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) { return __float_as_uint(x
 __device__ __forceinline__ void bar_sync_128(int id) {
     asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
-// both 16 KB boxes of a [128 rows, 64] tile
+// both 16 KB boxes of a [128 rows, 64] tile: fp32 = d 0..31 and d 32..63; split bf16 = hi plane and mid plane
+template <bool BX>
 __device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int row0, int h, int b) {
-    ptx::tma_load_4d(dst, tm, bar, 0, row0, h, b);
-    ptx::tma_load_4d(dst + kChunkBytes, tm, bar, 32, row0, h, b);
+    if (BX) {
+        ptx::tma_load_5d(dst, tm, bar, 0, row0, h, b, 0);
+        ptx::tma_load_5d(dst + kChunkBytes, tm, bar, 0, row0, h, b, 1);
+    } else {
+        ptx::tma_load_4d(dst, tm, bar, 0, row0, h, b);
+        ptx::tma_load_4d(dst + kChunkBytes, tm, bar, 32, row0, h, b);
+    }
 }
 // D[tmem] (=|+=) A[smem, K-major R image] * B[smem, K-major R image]^T over the 64-wide head dim
+template <bool BX>
 __device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc) {
     const uint64_t desc_k = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
+    if (BX) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)            // mid*hi, hi*mid, hi*hi (the mid image follows the hi image)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_f16(d_tmem, ptx::umma_desc(desc_k, a_addr + (t == 0 ? kChunkBytes : 0) + kk * 32),
+                              ptx::umma_desc(desc_k, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 32), idesc, (t | kk) != 0 ? 1u : 0u);
+        return;
+    }
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -81,12 +104,36 @@ __device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_
                            ptx::umma_desc(desc_k, b_addr + kb * kChunkBytes + kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
 }
 // D[tmem, 128 x 64] (=|+=) A[tmem, 128 lanes x 128 cols] * B[smem T image: 128 rows (k) x 64 (n)]
+template <bool BX>
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+    if (BX) {
+        // A: per 64-k half [32 columns hi | 32 columns mid], two bf16 per column; a K16 step = 8 columns of A and 16
+        // rows (2048 B) of the B image (plain 128-byte swizzle, N = 64 = one 128-byte chunk, 8-row groups 1024 B apart)
+        const uint64_t desc_mn = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, kChunkBytes, 1024);
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int kk = 0; kk < kBlk / 16; ++kk)
+                ptx::umma_f16_ts(d_tmem, a_tmem + (kk >> 2) * 64 + (t == 0 ? 32 : 0) + (kk & 3) * 8,
+                                 ptx::umma_desc(desc_mn, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 2048), idesc,
+                                 (accumulate || (t | kk) != 0) ? 1u : 0u);
+        return;
+    }
     const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, kChunkBytes, 512);
 #pragma unroll
     for (int kk = 0; kk < kBlk / 8; ++kk)
         ptx::umma_tf32_ts(d_tmem, a_tmem + kk * 8, ptx::umma_desc(desc_mn, b_addr + kk * 1024), idesc,
                           (accumulate || kk != 0) ? 1u : 0u);
+}
+// p0, p1 (consecutive k) -> packed bf16 hi pair and mid pair; and back
+__device__ __forceinline__ void split_pack(float p0, float p1, uint32_t& hi, uint32_t& mid) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
+    const float r0 = p0 - __uint_as_float(hi << 16), r1 = p1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ float unpack_lo(uint32_t hi, uint32_t mid) { return __uint_as_float(hi << 16) + __uint_as_float(mid << 16); }
+__device__ __forceinline__ float unpack_hi(uint32_t hi, uint32_t mid) {
+    return __uint_as_float(hi & 0xffff0000u) + __uint_as_float(mid & 0xffff0000u);
 }
 // one accumulator row (64 fp32 in TMEM) → 256 contiguous bytes of global memory
 __device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool live) {
@@ -115,7 +162,7 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool l
 // smem: K_R, V_R (resident per item) | Q_R, dO_R, Q_T, dO_T (one q block each) | L/D staging | barriers
 constexpr int kKvSmem = 6 * kTileBytes + 2 * 2 * kBlk * 4 + 1024 + 256;
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool BX>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmQt,
                      const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmVr,
@@ -183,20 +230,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 const int h = bh % args.H, b = bh / args.H;
                 ptx::mbar_wait(bar(K_EMPTY), (it & 1) ^ 1u);
                 ptx::mbar_arrive_expect_tx(bar(K_FULL), kTileBytes);
-                load_tile(kr_addr, &tmKr, bar(K_FULL), nt * kBlk, h, b);
+                load_tile<BX>(kr_addr, &tmKr, bar(K_FULL), nt * kBlk, h, b);
                 const int i0 = first_q(item);
                 for (int i = i0; i < n_q; ++i, ++g) {
                     ptx::mbar_wait(bar(QR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(QR_FULL), kTileBytes);
-                    load_tile(qr_addr, &tmQr, bar(QR_FULL), i * kBlk, h, b);
+                    load_tile<BX>(qr_addr, &tmQr, bar(QR_FULL), i * kBlk, h, b);
                     if (i == i0) {
                         ptx::mbar_wait(bar(V_EMPTY), (it & 1) ^ 1u);
                         ptx::mbar_arrive_expect_tx(bar(V_FULL), kTileBytes);
-                        load_tile(vr_addr, &tmVr, bar(V_FULL), nt * kBlk, h, b);
+                        load_tile<BX>(vr_addr, &tmVr, bar(V_FULL), nt * kBlk, h, b);
                     }
                     ptx::mbar_wait(bar(DOR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(DOR_FULL), kTileBytes);
-                    load_tile(dor_addr, &tmDOr, bar(DOR_FULL), i * kBlk, h, b);
+                    load_tile<BX>(dor_addr, &tmDOr, bar(DOR_FULL), i * kBlk, h, b);
                 }
             }
         }
@@ -210,18 +257,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 for (int i = first_q(item); i < n_q; ++i, ++g) {
                     ptx::mbar_wait(bar(DOT_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(DOT_FULL), kTileBytes);
-                    load_tile(dot_addr, &tmDOt, bar(DOT_FULL), i * kBlk, h, b);
+                    load_tile<BX>(dot_addr, &tmDOt, bar(DOT_FULL), i * kBlk, h, b);
                     ptx::mbar_wait(bar(QT_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(QT_FULL), kTileBytes);
-                    load_tile(qt_addr, &tmQt, bar(QT_FULL), i * kBlk, h, b);
+                    load_tile<BX>(qt_addr, &tmQt, bar(QT_FULL), i * kBlk, h, b);
                 }
             }
         }
     } else if (warp == 2) {
         // ============ MMA issuer ============
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
-            constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
+            constexpr uint32_t idesc_s  = BX ? ptx::umma_idesc_bf16(kBlk, kBlk, false, false) : ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
+            constexpr uint32_t idesc_ts = BX ? ptx::umma_idesc_bf16(kBlk, kD, false, true) : ptx::umma_idesc_tf32(kBlk, kD, false, true);
             long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             long long* const dbg = args.dbg;
             auto twait = [&](int slot, int which, uint32_t parity) {
@@ -256,7 +303,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 if (first) twait(0, K_FULL, it & 1);
                 twait(1, QR_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_rr(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s);
+                mma_rr<BX>(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s);
                 ptx::umma_commit(bar(QR_EMPTY));
                 ptx::umma_commit(bar(ST_FULL0 + (g & 1u)));
                 if (i == n_q - 1) ptx::umma_commit(bar(K_EMPTY));
@@ -268,7 +315,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 if (first) twait(2, V_FULL, it & 1);
                 twait(3, DOR_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_rr(tm_dpt, vr_addr, dor_addr, idesc_s);
+                mma_rr<BX>(tm_dpt, vr_addr, dor_addr, idesc_s);
                 ptx::umma_commit(bar(DOR_EMPTY));
                 ptx::umma_commit(bar(DPT_FULL));
                 if (i == n_q - 1) ptx::umma_commit(bar(V_EMPTY));
@@ -283,13 +330,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 twait(4, P_READY0 + (g & 1u), (g >> 1) & 1);
                 twait(5, DOT_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_ts(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, !first);    // dV += P^T dO
+                mma_ts<BX>(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, !first);    // dV += P^T dO
                 ptx::umma_commit(bar(DOT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DV_DONE));
                 twait(6, DS_READY, g & 1);
                 twait(7, QT_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_ts(tm_dk, tm_dpt, qt_addr, idesc_ts, !first);                          // dK += dS^T Q
+                mma_ts<BX>(tm_dk, tm_dpt, qt_addr, idesc_ts, !first);                          // dK += dS^T Q
                 ptx::umma_commit(bar(QT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DK_DONE));
                 if (g + 1 < G) issue_dpt(g + 1);
@@ -351,18 +398,30 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
 #pragma unroll
                         for (int k = 0; k < 64; k += 4) {
                             const float4 l4 = V4[(hf * 64 + k) >> 2];
-                            p[k]     = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -l4.x))));
-                            p[k + 1] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 1], c, -l4.y))));
-                            p[k + 2] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 2], c, -l4.z))));
-                            p[k + 3] = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k + 3], c, -l4.w))));
+                            p[k]     = ptx::ex2(fmaf(p[k], c, -l4.x));
+                            p[k + 1] = ptx::ex2(fmaf(p[k + 1], c, -l4.y));
+                            p[k + 2] = ptx::ex2(fmaf(p[k + 2], c, -l4.z));
+                            p[k + 3] = ptx::ex2(fmaf(p[k + 3], c, -l4.w));
+                            if (!BX) {
+                                p[k] = __uint_as_float(rna_tf32(p[k])); p[k + 1] = __uint_as_float(rna_tf32(p[k + 1]));
+                                p[k + 2] = __uint_as_float(rna_tf32(p[k + 2])); p[k + 3] = __uint_as_float(rna_tf32(p[k + 3]));
+                            }
                         }
                         if (CAUSAL && i == nt) {            // diagonal block: q position (column) before kv position (lane)
 #pragma unroll
                             for (int k = 0; k < 64; ++k)
                                 if (hf * 64 + k < tid) p[k] = 0.0f;
                         }
-                        ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
-                        ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                        if (BX) {
+                            uint32_t hi[32], mid[32];
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) split_pack(p[2 * k], p[2 * k + 1], hi[k], mid[k]);
+                            ptx::tmem_st_32x32(s_tmem + hf * 64, hi);
+                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, mid);
+                        } else {
+                            ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                        }
                     }
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before();
@@ -372,6 +431,29 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     ptx::mbar_wait(bar(DPT_FULL), g & 1);
                     ptx::tc_fence_after();
                     const uint32_t p_tmem = tmem_base + lane_off + buf * kBlk;
+                    if (BX) {
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t ph[32], pm[32], dp[64];
+                            ptx::tmem_ld_32x32(p_tmem + hf * 64, ph);
+                            ptx::tmem_ld_32x32(p_tmem + hf * 64 + 32, pm);
+                            ptx::tmem_ld_32x32(tm_dpt + lane_off + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+                            ptx::tmem_ld_32x32(tm_dpt + lane_off + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 32; k += 2) {          // pairs (2k, 2k+1), (2k+2, 2k+3) = one float4 of D
+                                const float4 d4 = V4[(hf * 64 + 2 * k) >> 2];
+                                const float s0 = unpack_lo(ph[k], pm[k]) * ((__uint_as_float(dp[2 * k]) - d4.x) * scale);
+                                const float s1 = unpack_hi(ph[k], pm[k]) * ((__uint_as_float(dp[2 * k + 1]) - d4.y) * scale);
+                                const float s2 = unpack_lo(ph[k + 1], pm[k + 1]) * ((__uint_as_float(dp[2 * k + 2]) - d4.z) * scale);
+                                const float s3 = unpack_hi(ph[k + 1], pm[k + 1]) * ((__uint_as_float(dp[2 * k + 3]) - d4.w) * scale);
+                                split_pack(s0, s1, ph[k], pm[k]);
+                                split_pack(s2, s3, ph[k + 1], pm[k + 1]);
+                            }
+                            ptx::tmem_st_32x32(tm_dpt + lane_off + hf * 64, ph);
+                            ptx::tmem_st_32x32(tm_dpt + lane_off + hf * 64 + 32, pm);
+                        }
+                    } else
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         if (args.debug_skip & 2) break;
@@ -415,7 +497,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
 // smem: Q_R, dO_R (double buffered across items) | K_R, V_R, K_T (one kv block each) | barriers
 constexpr int kDqSmem = 7 * kTileBytes + 1024 + 256;
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool BX>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmDOr,
                    const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmKt,
@@ -477,16 +559,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 const int qb = it & 1;
                 ptx::mbar_wait(bar(QDO_EMPTY0 + qb), ((it >> 1) & 1) ^ 1u);
                 ptx::mbar_arrive_expect_tx(bar(QDO_FULL0 + qb), 2 * kTileBytes);
-                load_tile(qr_addr + qb * kTileBytes, &tmQr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
-                load_tile(dor_addr + qb * kTileBytes, &tmDOr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
+                load_tile<BX>(qr_addr + qb * kTileBytes, &tmQr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
+                load_tile<BX>(dor_addr + qb * kTileBytes, &tmDOr, bar(QDO_FULL0 + qb), mt * kBlk, h, b);
                 const int nb = blocks_of(item);
                 for (int j = 0; j < nb; ++j, ++g) {
                     ptx::mbar_wait(bar(KR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(KR_FULL), kTileBytes);
-                    load_tile(kr_addr, &tmKr, bar(KR_FULL), j * kBlk, h, b);
+                    load_tile<BX>(kr_addr, &tmKr, bar(KR_FULL), j * kBlk, h, b);
                     ptx::mbar_wait(bar(VR_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(VR_FULL), kTileBytes);
-                    load_tile(vr_addr, &tmVr, bar(VR_FULL), j * kBlk, h, b);
+                    load_tile<BX>(vr_addr, &tmVr, bar(VR_FULL), j * kBlk, h, b);
                 }
             }
         }
@@ -501,15 +583,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 for (int j = 0; j < nb; ++j, ++g) {
                     ptx::mbar_wait(bar(KT_EMPTY), (g & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(bar(KT_FULL), kTileBytes);
-                    load_tile(kt_addr, &tmKt, bar(KT_FULL), j * kBlk, h, b);
+                    load_tile<BX>(kt_addr, &tmKt, bar(KT_FULL), j * kBlk, h, b);
                 }
             }
         }
     } else if (warp == 2) {
         // ============ MMA issuer ============
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
-            constexpr uint32_t idesc_ts = ptx::umma_idesc_tf32(kBlk, kD, false, true);
+            constexpr uint32_t idesc_s  = BX ? ptx::umma_idesc_bf16(kBlk, kBlk, false, false) : ptx::umma_idesc_tf32(kBlk, kBlk, false, false);
+            constexpr uint32_t idesc_ts = BX ? ptx::umma_idesc_bf16(kBlk, kD, false, true) : ptx::umma_idesc_tf32(kBlk, kD, false, true);
             struct Cur { int item, it, j, cnt; };
             auto cur_init = [&](Cur& c) {
                 c.item = blockIdx.x; c.it = 0; c.j = 0;
@@ -529,7 +611,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 if (j == 0) ptx::mbar_wait(bar(QDO_FULL0 + (it & 1)), (it >> 1) & 1);
                 ptx::mbar_wait(bar(KR_FULL), g & 1);
                 ptx::tc_fence_after();
-                mma_rr(tmem_base + (g & 1u) * kBlk, qr_addr + (it & 1) * kTileBytes, kr_addr, idesc_s);
+                mma_rr<BX>(tmem_base + (g & 1u) * kBlk, qr_addr + (it & 1) * kTileBytes, kr_addr, idesc_s);
                 ptx::umma_commit(bar(KR_EMPTY));
                 ptx::umma_commit(bar(S_FULL0 + (g & 1u)));
             };
@@ -539,7 +621,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 cur_next(c_dp);
                 ptx::mbar_wait(bar(VR_FULL), g & 1);
                 ptx::tc_fence_after();
-                mma_rr(tm_dp, dor_addr + (it & 1) * kTileBytes, vr_addr, idesc_s);
+                mma_rr<BX>(tm_dp, dor_addr + (it & 1) * kTileBytes, vr_addr, idesc_s);
                 ptx::umma_commit(bar(VR_EMPTY));
                 ptx::umma_commit(bar(DP_FULL));
                 if (last) ptx::umma_commit(bar(QDO_EMPTY0 + (it & 1)));
@@ -553,7 +635,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 ptx::mbar_wait(bar(DS_READY), g & 1);
                 ptx::mbar_wait(bar(KT_FULL), g & 1);
                 ptx::tc_fence_after();
-                mma_ts(tm_dq, tm_dp, kt_addr, idesc_ts, j != 0);                           // dQ += dS K
+                mma_ts<BX>(tm_dq, tm_dp, kt_addr, idesc_ts, j != 0);                           // dQ += dS K
                 ptx::umma_commit(bar(KT_EMPTY));
                 if (last) ptx::umma_commit(bar(ACC_DONE));
                 if (g + 1 < G) issue_dp(g + 1);
@@ -599,12 +681,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int k = 0; k < 64; ++k) {
-                            const float e = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -mine))));
+                            const float e0 = ptx::ex2(fmaf(p[k], c, -mine));
+                            const float e = BX ? e0 : __uint_as_float(rna_tf32(e0));
                             const bool masked = CAUSAL && j == mt && hf * 64 + k > tid;          // kv position after q position
                             p[k] = (hf * 64 + k < kv_left && !masked) ? e : 0.0f;   // zero-filled K rows past Skv
                         }
-                        ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
-                        ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                        if (BX) {
+                            uint32_t hi[32], mid[32];
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) split_pack(p[2 * k], p[2 * k + 1], hi[k], mid[k]);
+                            ptx::tmem_st_32x32(s_tmem + hf * 64, hi);
+                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, mid);
+                        } else {
+                            ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
+                        }
                     }
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before();
@@ -614,6 +705,25 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                     ptx::mbar_wait(bar(DP_FULL), g & 1);
                     ptx::tc_fence_after();
                     const float dscale = mine * scale;
+                    if (BX) {
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t ph[32], pm[32], dp[64];
+                            ptx::tmem_ld_32x32(s_tmem + hf * 64, ph);
+                            ptx::tmem_ld_32x32(s_tmem + hf * 64 + 32, pm);
+                            ptx::tmem_ld_32x32(tm_dp + lane_off + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
+                            ptx::tmem_ld_32x32(tm_dp + lane_off + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const float s0 = unpack_lo(ph[k], pm[k]) * fmaf(__uint_as_float(dp[2 * k]), scale, -dscale);
+                                const float s1 = unpack_hi(ph[k], pm[k]) * fmaf(__uint_as_float(dp[2 * k + 1]), scale, -dscale);
+                                split_pack(s0, s1, ph[k], pm[k]);
+                            }
+                            ptx::tmem_st_32x32(tm_dp + lane_off + hf * 64, ph);
+                            ptx::tmem_st_32x32(tm_dp + lane_off + hf * 64 + 32, pm);
+                        }
+                    } else
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t pp[32], dp[32];
@@ -650,8 +760,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
 // D[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]: 16 lanes x float4 per (b,s,h) row.  A separate 18 us launch: computing D
 // inside the dQ kernel (by its dS warps at item start, or by its exp warps one item ahead) was measured and costs the
 // dQ kernel as much as or more than this launch (0.267 / 0.279 ms vs 0.265 ms for the whole backward at B8 H16 S1024).
+// `planes` != nullptr (split-bf16 mode): dO is also written as bf16 hi / mid planes ([2][B,Sq,H,64]) for the backward
+// kernels, and D uses the exact fp32 dO (hi + mid carries 16 bits, there is no common-mode rounding to cancel).
 __global__ void __launch_bounds__(256) attn_dsum_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
-                                                        float* __restrict__ dsum, int B, int H, int Sq) {
+                                                        float* __restrict__ dsum, uint2* __restrict__ planes, int B, int H, int Sq) {
     pdl_trigger();
     pdl_wait();
     const int64_t rows = (int64_t)B * Sq * H;
@@ -665,10 +777,19 @@ __global__ void __launch_bounds__(256) attn_dsum_kernel(const float* __restrict_
         if (ok) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(d_o + r * kD) + sub);
             const float4 bb = __ldg(reinterpret_cast<const float4*>(o + r * kD) + sub);
-            // dO rounded exactly as the tensor core will see it: D then equals sum_t P dP for the dP the
-            // MMA computes, so the common-mode part of its TF32 error cancels in dS = P o (dP - D)
-            v = __uint_as_float(cvt_tf32(a.x)) * bb.x + __uint_as_float(cvt_tf32(a.y)) * bb.y +
-                __uint_as_float(cvt_tf32(a.z)) * bb.z + __uint_as_float(cvt_tf32(a.w)) * bb.w;
+            if (planes != nullptr) {
+                uint2 hi, mid;
+                split_pack(a.x, a.y, hi.x, mid.x);
+                split_pack(a.z, a.w, hi.y, mid.y);
+                planes[r * (kD / 4) + sub] = hi;
+                planes[(rows + r) * (kD / 4) + sub] = mid;
+                v = a.x * bb.x + a.y * bb.y + a.z * bb.z + a.w * bb.w;
+            } else {
+                // dO rounded exactly as the tensor core will see it: D then equals sum_t P dP for the dP the
+                // MMA computes, so the common-mode part of its TF32 error cancels in dS = P o (dP - D)
+                v = __uint_as_float(cvt_tf32(a.x)) * bb.x + __uint_as_float(cvt_tf32(a.y)) * bb.y +
+                    __uint_as_float(cvt_tf32(a.z)) * bb.z + __uint_as_float(cvt_tf32(a.w)) * bb.w;
+            }
         }
 #pragma unroll
         for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -678,6 +799,25 @@ __global__ void __launch_bounds__(256) attn_dsum_kernel(const float* __restrict_
             const int s = (int)(bs % Sq), b = (int)(bs / Sq);
             dsum[((size_t)b * H + h) * Sq + s] = v;
         }
+    }
+}
+
+// x [rows, HD] fp32 with row stride ld (a column block of a packed projection output) -> bf16 hi plane [rows, HD]
+// followed by the mid plane [rows, HD]: hi = bf16_rn(x), mid = bf16_rn(x - hi).  8 B/elem, HBM bound.
+__global__ void __launch_bounds__(256) attn_split_kernel(const float* __restrict__ x, int64_t ld, uint2* __restrict__ planes,
+                                                         int64_t rows, int hd4) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t n = rows * hd4;                        // float4 chunks
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / hd4;
+        const int c = (int)(i - r * hd4);
+        const float4 a = ld_stream(reinterpret_cast<const float4*>(x + r * ld) + c);
+        uint2 hi, mid;
+        split_pack(a.x, a.y, hi.x, mid.x);
+        split_pack(a.z, a.w, hi.y, mid.y);
+        planes[i] = hi;
+        planes[n + i] = mid;
     }
 }
 
@@ -691,7 +831,20 @@ __global__ void __launch_bounds__(256) attn_scores_from_lse_kernel(float* __rest
 
 }  // namespace
 
-size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq) { return (size_t)B * H * Sq * sizeof(float); }
+// D [B,H,Sq]; split-bf16 mode: + the dO planes [2][B,Sq,H,64] bf16
+size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, bool bx) {
+    const size_t d = ((size_t)B * H * Sq * sizeof(float) + 255) & ~(size_t)255;
+    return bx ? d + (size_t)B * Sq * H * kD * 4 : d;
+}
+
+// split-bf16 planes of a [rows, HD] fp32 matrix (row stride ld): attn_split_kernel
+int attn_split_launch(const float* x, int64_t ld, void* planes, int64_t rows, int64_t HD, cudaStream_t stream) {
+    NPM_REQUIRE(aligned16(x) && aligned16(planes) && ld % 4 == 0 && HD % 4 == 0, "attention split: operands must be 16-byte aligned");
+    const int64_t n = rows * (HD / 4);
+    launch_pdl(attn_split_kernel, dim3(bw_grid((size_t)n, 256)), dim3(256), 0, stream, 1, x, ld, reinterpret_cast<uint2*>(planes), rows, (int)(HD / 4));
+    count_launch();
+    return check_launch("attn_split_kernel");
+}
 
 int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream) {
     attn_scores_from_lse_kernel<<<bw_grid((size_t)(rows * cols), 256), 256, 0, stream>>>(p, lse, rows, cols);
@@ -699,9 +852,11 @@ int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_
     return check_launch("attn_scores_from_lse_kernel");
 }
 
-int attn_bwd_launch(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
+// bx = false: q / k / v fp32 with token strides.  bx = true: q / k / v are the split-bf16 planes the forward pass
+// saved ([2][B,S,H,64]); dO is split into `scratch` behind D by the dsum kernel.
+int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal,
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal, bool bx,
                     cudaStream_t stream) {
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_bwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(o != nullptr, "mha_core_bwd: the fused path needs the forward output o");
@@ -710,15 +865,30 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
     const uint64_t HD = (uint64_t)H * kD;
     CUtensorMap tQr, tQt, tKr, tKt, tVr, tDOr, tDOt;
     int rc;
-    for (int64_t ld : {ldq, ldk, ldv, lddq, lddk, lddv})
+    for (int64_t ld : {lddq, lddk, lddv})
         NPM_REQUIRE(ld >= (int64_t)HD && ld % 4 == 0, "mha_core_bwd: token strides must be >= H*d and multiples of 4 floats");
-    if ((rc = make_tensor_map_4d(&tQr, q, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBlk, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tQt, q, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBlk, true, true))) return rc;
-    if ((rc = make_tensor_map_4d(&tKr, k, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBlk, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tKt, k, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBlk, true, true))) return rc;
-    if ((rc = make_tensor_map_4d(&tVr, v, kD, Skv, H, B, ldv, kD, Skv * ldv, 32, kBlk, true, false))) return rc;
+    uint2* do_planes = nullptr;
+    if (bx) {
+        do_planes = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dsum) + (((size_t)B * H * Sq * sizeof(float) + 255) & ~(size_t)255));
+        if ((rc = make_tensor_map_bf16_planes(&tQr, q, Sq, H, B, HD, (uint64_t)B * Sq * HD, kBlk))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tKr, k, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBlk))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tVr, v, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBlk))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tDOr, do_planes, Sq, H, B, HD, (uint64_t)B * Sq * HD, kBlk))) return rc;
+        tQt = tQr; tKt = tKr; tDOt = tDOr;          // one bf16 image serves as the R and the T operand
+    } else {
+    for (int64_t ld : {ldq, ldk, ldv})
+        NPM_REQUIRE(ld >= (int64_t)HD && ld % 4 == 0, "mha_core_bwd: token strides must be >= H*d and multiples of 4 floats");
+    const float* qf = reinterpret_cast<const float*>(q);
+    const float* kf = reinterpret_cast<const float*>(k);
+    const float* vf = reinterpret_cast<const float*>(v);
+    if ((rc = make_tensor_map_4d(&tQr, qf, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tQt, qf, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBlk, true, true))) return rc;
+    if ((rc = make_tensor_map_4d(&tKr, kf, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBlk, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tKt, kf, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBlk, true, true))) return rc;
+    if ((rc = make_tensor_map_4d(&tVr, vf, kD, Skv, H, B, ldv, kD, Skv * ldv, 32, kBlk, true, false))) return rc;
     if ((rc = make_tensor_map_4d(&tDOr, d_o, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, false))) return rc;
     if ((rc = make_tensor_map_4d(&tDOt, d_o, kD, Sq, H, B, HD, kD, Sq * HD, 32, kBlk, true, true))) return rc;
+    }
 
     BwdArgs a;
     a.B = (int)B; a.H = (int)H; a.Sq = (int)Sq; a.Skv = (int)Skv;
@@ -739,13 +909,12 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
 
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+        cudaError_t e = cudaSuccess;
+        auto set = [&](auto kern, int bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
+        set(attn_bwd_dkdv_kernel<false, false>, kKvSmem); set(attn_bwd_dkdv_kernel<true, false>, kKvSmem);
+        set(attn_bwd_dkdv_kernel<false, true>, kKvSmem);  set(attn_bwd_dkdv_kernel<true, true>, kKvSmem);
+        set(attn_bwd_dq_kernel<false, false>, kDqSmem);   set(attn_bwd_dq_kernel<true, false>, kDqSmem);
+        set(attn_bwd_dq_kernel<false, true>, kDqSmem);    set(attn_bwd_dq_kernel<true, true>, kDqSmem);
         if (e != cudaSuccess) { set_error("attn_bwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
         configured = true;
     }
@@ -754,7 +923,7 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         int grid = (int)((rows * 16 + 255) / 256);
         const int cap = num_sms() * 8;
         if (grid > cap) grid = cap;
-        launch_pdl(attn_dsum_kernel, dim3(grid), dim3(256), 0, stream, 1, d_o, o, dsum, (int)B, (int)H, (int)Sq);
+        launch_pdl(attn_dsum_kernel, dim3(grid), dim3(256), 0, stream, 1, d_o, o, dsum, do_planes, (int)B, (int)H, (int)Sq);
         count_launch();
         if ((rc = check_launch("attn_dsum_kernel"))) return rc;
     }
@@ -764,8 +933,9 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         a.total_items = (int)items;
         int grid = (int)(items < num_sms() ? items : num_sms());
         if (causal) while (grid > 1 && gcd_int(grid, a.n_kv) != 1) --grid;     // see attn_fwd_launch
-        if (causal) launch_pdl(attn_bwd_dkdv_kernel<true>, dim3(grid), dim3(kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
-        else        launch_pdl(attn_bwd_dkdv_kernel<false>, dim3(grid), dim3(kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        auto kern = causal ? (bx ? attn_bwd_dkdv_kernel<true, true> : attn_bwd_dkdv_kernel<true, false>)
+                           : (bx ? attn_bwd_dkdv_kernel<false, true> : attn_bwd_dkdv_kernel<false, false>);
+        launch_pdl(kern, dim3(grid), dim3(kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dkdv_kernel"))) return rc;
         if (dbg_times) {
@@ -790,8 +960,9 @@ int attn_bwd_launch(const float* q, const float* k, const float* v, const float*
         a.total_items = (int)items;
         int grid = (int)(items < num_sms() ? items : num_sms());
         if (causal) while (grid > 1 && gcd_int(grid, a.n_q) != 1) --grid;
-        if (causal) launch_pdl(attn_bwd_dq_kernel<true>, dim3(grid), dim3(kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
-        else        launch_pdl(attn_bwd_dq_kernel<false>, dim3(grid), dim3(kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
+        auto kern = causal ? (bx ? attn_bwd_dq_kernel<true, true> : attn_bwd_dq_kernel<true, false>)
+                           : (bx ? attn_bwd_dq_kernel<false, true> : attn_bwd_dq_kernel<false, false>);
+        launch_pdl(kern, dim3(grid), dim3(kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
     }

@@ -16,6 +16,12 @@
 //                          maximum is only raised when it grew by more than 2^8 (the O accumulator
 //                          is then rescaled in TMEM), so the rescale is off the critical path.
 // S/P is double buffered in TMEM so that S(j+1) is computed while the softmax of block j runs.
+//
+// BX = true is the split-bf16 ("bf16x3") variant of the same kernel: q / k / v arrive pre-split as bf16 hi + mid planes
+// ([2][B,S,H,64], written by attn_split_kernel in attn_bwd.cu), a tile is its hi image (16 KB) followed by its mid image,
+// every product runs as mid*hi + hi*mid + hi*hi with kind::f16 (K = 16), and P goes back to TMEM as packed bf16
+// pairs, per 64-column half [32 columns hi | 32 columns mid].  In bf16 a [rows, 64] tile with the 128-byte swizzle is
+// at once a K-major operand over its 64 columns and an MN-major operand over its rows, so V needs no second layout.
 #include <math.h>
 
 #include "common.cuh"
@@ -26,6 +32,8 @@ namespace npm {
 int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                        uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, bool round_tf32,
                        bool atom32b);
+int make_tensor_map_bf16_planes(CUtensorMap* tm, const void* base, uint64_t S, uint64_t H, uint64_t B, uint64_t ld,
+                                uint64_t plane_elems, uint32_t box_rows);
 
 namespace {
 
@@ -54,7 +62,14 @@ struct FwdArgs {
 // issues on the XU pipe, which the ex2 of the softmax already saturates.)
 __device__ __forceinline__ uint32_t rna_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
 
-template <bool CAUSAL>
+// p0, p1 (consecutive k) -> packed bf16 hi pair and mid pair
+__device__ __forceinline__ void split_pack(float p0, float p1, uint32_t& hi, uint32_t& mid) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
+    const float r0 = p0 - __uint_as_float(hi << 16), r1 = p1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
+}
+
+template <bool CAUSAL, bool BX>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
@@ -125,15 +140,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int qb = it & 1;
                 ptx::mbar_wait(q_empty(qb), ((it >> 1) & 1) ^ 1u);
                 ptx::mbar_arrive_expect_tx(q_full(qb), kTileBytes);
-                ptx::tma_load_4d(q_addr + qb * kTileBytes, &tmQ, q_full(qb), 0, mt * kBM, h, b);
-                ptx::tma_load_4d(q_addr + qb * kTileBytes + kChunkBytes, &tmQ, q_full(qb), 32, mt * kBM, h, b);
+                if (BX) {
+                    ptx::tma_load_5d(q_addr + qb * kTileBytes, &tmQ, q_full(qb), 0, mt * kBM, h, b, 0);
+                    ptx::tma_load_5d(q_addr + qb * kTileBytes + kChunkBytes, &tmQ, q_full(qb), 0, mt * kBM, h, b, 1);
+                } else {
+                    ptx::tma_load_4d(q_addr + qb * kTileBytes, &tmQ, q_full(qb), 0, mt * kBM, h, b);
+                    ptx::tma_load_4d(q_addr + qb * kTileBytes + kChunkBytes, &tmQ, q_full(qb), 32, mt * kBM, h, b);
+                }
                 const int nb = blocks_of(item);
                 for (int j = 0; j < nb; ++j, ++gk) {
                     const int st = gk % kKS;
                     ptx::mbar_wait(k_empty(st), ((gk / kKS) & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(k_full(st), kTileBytes);
-                    ptx::tma_load_4d(k_addr + st * kTileBytes, &tmK, k_full(st), 0, j * kBN, h, b);
-                    ptx::tma_load_4d(k_addr + st * kTileBytes + kChunkBytes, &tmK, k_full(st), 32, j * kBN, h, b);
+                    if (BX) {
+                        ptx::tma_load_5d(k_addr + st * kTileBytes, &tmK, k_full(st), 0, j * kBN, h, b, 0);
+                        ptx::tma_load_5d(k_addr + st * kTileBytes + kChunkBytes, &tmK, k_full(st), 0, j * kBN, h, b, 1);
+                    } else {
+                        ptx::tma_load_4d(k_addr + st * kTileBytes, &tmK, k_full(st), 0, j * kBN, h, b);
+                        ptx::tma_load_4d(k_addr + st * kTileBytes + kChunkBytes, &tmK, k_full(st), 32, j * kBN, h, b);
+                    }
                 }
             }
         }
@@ -149,18 +174,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const int st = gv % kVS;
                     ptx::mbar_wait(v_empty(st), ((gv / kVS) & 1) ^ 1u);
                     ptx::mbar_arrive_expect_tx(v_full(st), kTileBytes);
-                    ptx::tma_load_4d(v_addr + st * kTileBytes, &tmV, v_full(st), 0, j * kBN, h, b);
-                    ptx::tma_load_4d(v_addr + st * kTileBytes + kChunkBytes, &tmV, v_full(st), 32, j * kBN, h, b);
+                    if (BX) {
+                        ptx::tma_load_5d(v_addr + st * kTileBytes, &tmV, v_full(st), 0, j * kBN, h, b, 0);
+                        ptx::tma_load_5d(v_addr + st * kTileBytes + kChunkBytes, &tmV, v_full(st), 0, j * kBN, h, b, 1);
+                    } else {
+                        ptx::tma_load_4d(v_addr + st * kTileBytes, &tmV, v_full(st), 0, j * kBN, h, b);
+                        ptx::tma_load_4d(v_addr + st * kTileBytes + kChunkBytes, &tmV, v_full(st), 32, j * kBN, h, b);
+                    }
                 }
             }
         }
     } else if (warp == 2) {
         // ======================= MMA issuer =======================
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc_s  = ptx::umma_idesc_tf32(kBM, kBN, false, false);
-            constexpr uint32_t idesc_pv = ptx::umma_idesc_tf32(kBM, kD, false, true);
+            constexpr uint32_t idesc_s  = BX ? ptx::umma_idesc_bf16(kBM, kBN, false, false) : ptx::umma_idesc_tf32(kBM, kBN, false, false);
+            constexpr uint32_t idesc_pv = BX ? ptx::umma_idesc_bf16(kBM, kD, false, true) : ptx::umma_idesc_tf32(kBM, kD, false, true);
             const uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
-            const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, kChunkBytes, 512);
+            // MN-major B operand.  tf32: 32-byte swizzle atoms, 32-element chunks 16 KB apart, 4-row K groups.  bf16: the
+            // plain 128-byte swizzle, N = 64 is one 128-byte chunk (LBO unused), 8-row K groups 1024 B apart.
+            const uint64_t desc_mn = BX ? ptx::umma_desc_base(2 /*SWIZZLE_128B*/, kChunkBytes, 1024)
+                                        : ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, kChunkBytes, 512);
             // (item, kv block) sequence of this CTA; the S products run one block ahead of the PV products, so two cursors
             struct Cur { int item, it, j, cnt; };
             auto cur_init = [&](Cur& c) {
@@ -186,14 +219,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (gs & 1u) * kBN;
                 const uint32_t qa = q_addr + qb * kTileBytes, ka = k_addr + st * kTileBytes;
+                if (BX) {
+                    // (A image, B image): mid*hi, hi*mid, hi*hi; the mid image of a tile follows its hi image
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+                    for (int t = 0; t < 3; ++t)
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t da = ptx::umma_desc(desc_k, qa + kb * kChunkBytes + kk * 32);
-                        const uint64_t db = ptx::umma_desc(desc_k, ka + kb * kChunkBytes + kk * 32);
-                        ptx::umma_tf32(d_tmem, da, db, idesc_s, (kb | kk) != 0 ? 1u : 0u);
-                    }
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t da = ptx::umma_desc(desc_k, qa + (t == 0 ? kChunkBytes : 0) + kk * 32);
+                            const uint64_t db = ptx::umma_desc(desc_k, ka + (t == 1 ? kChunkBytes : 0) + kk * 32);
+                            ptx::umma_f16(d_tmem, da, db, idesc_s, (t | kk) != 0 ? 1u : 0u);
+                        }
+                } else {
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t da = ptx::umma_desc(desc_k, qa + kb * kChunkBytes + kk * 32);
+                            const uint64_t db = ptx::umma_desc(desc_k, ka + kb * kChunkBytes + kk * 32);
+                            ptx::umma_tf32(d_tmem, da, db, idesc_s, (kb | kk) != 0 ? 1u : 0u);
+                        }
+                }
                 ptx::umma_commit(k_empty(st));
                 ptx::umma_commit(s_full(gs & 1u));
                 if (j == cs.cnt - 1) ptx::umma_commit(q_empty(qb));
@@ -213,10 +258,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 ptx::tc_fence_after();
                 const uint32_t p_tmem = tmem_base + (g & 1u) * kBN;
                 const uint32_t va = v_addr + st * kTileBytes;
+                if (BX) {
+                    // P in TMEM: per 64-k half [32 columns hi | 32 columns mid], two bf16 per column; a K16 step is 8 columns
+                    // of P and 16 rows (2048 B) of the V image
 #pragma unroll
-                for (int kk = 0; kk < kBN / 8; ++kk) {
-                    const uint64_t db = ptx::umma_desc(desc_mn, va + kk * 1024);
-                    ptx::umma_tf32_ts(tmem_o, p_tmem + kk * 8, db, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                    for (int t = 0; t < 3; ++t)
+#pragma unroll
+                        for (int kk = 0; kk < kBN / 16; ++kk) {
+                            const uint32_t pa = p_tmem + (kk >> 2) * 64 + (t == 0 ? 32 : 0) + (kk & 3) * 8;
+                            const uint64_t db = ptx::umma_desc(desc_mn, va + (t == 1 ? kChunkBytes : 0) + kk * 2048);
+                            ptx::umma_f16_ts(tmem_o, pa, db, idesc_pv, (j | t | kk) != 0 ? 1u : 0u);
+                        }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < kBN / 8; ++kk) {
+                        const uint64_t db = ptx::umma_desc(desc_mn, va + kk * 1024);
+                        ptx::umma_tf32_ts(tmem_o, p_tmem + kk * 8, db, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+                    }
                 }
                 ptx::umma_commit(v_empty(st));
                 ptx::umma_commit(o_done);
@@ -297,13 +355,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const float p2 = ptx::ex2(fmaf(s[k + 2], c, -m_ref));
                     const float p3 = ptx::ex2(fmaf(s[k + 3], c, -m_ref));
                     l0 += p0; l1 += p1; l2 += p2; l3 += p3;       // rounding to nearest is zero-mean: sum the exact p
-                    s[k] = __uint_as_float(rna_tf32(p0)); s[k + 1] = __uint_as_float(rna_tf32(p1));
-                    s[k + 2] = __uint_as_float(rna_tf32(p2)); s[k + 3] = __uint_as_float(rna_tf32(p3));
+                    if (BX) {
+                        s[k] = p0; s[k + 1] = p1; s[k + 2] = p2; s[k + 3] = p3;
+                    } else {
+                        s[k] = __uint_as_float(rna_tf32(p0)); s[k + 1] = __uint_as_float(rna_tf32(p1));
+                        s[k + 2] = __uint_as_float(rna_tf32(p2)); s[k + 3] = __uint_as_float(rna_tf32(p3));
+                    }
                 }
                 l += (l0 + l1) + (l2 + l3);
+                if (BX) {
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                    ptx::tmem_st_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]));
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t hi[32], mid[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) split_pack(s[hf * 64 + 2 * i], s[hf * 64 + 2 * i + 1], hi[i], mid[i]);
+                        ptx::tmem_st_32x32(s_tmem + hf * 64, hi);
+                        ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, mid);
+                    }
+                } else {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                        ptx::tmem_st_32x32(s_tmem + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]));
+                }
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(p_ready(buf));
@@ -343,19 +416,30 @@ bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t
            Sq < (1ll << 30) && Skv < (1ll << 30);
 }
 
-int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, cudaStream_t stream) {
+// bx = false: q / k / v are fp32 (token strides ld*).  bx = true: q / k / v point at split-bf16 planes [2][B,S,H,64]
+// (dense; hi plane, then mid plane) and ld* are ignored.
+int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float* lse, int64_t B, int64_t H,
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, bool bx, cudaStream_t stream) {
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_fwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "mha_core_fwd: pointers must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
     int rc;
     const uint64_t HD = (uint64_t)H * kD;
+    if (bx) {
+        if ((rc = make_tensor_map_bf16_planes(&tmQ, q, Sq, H, B, HD, (uint64_t)B * Sq * HD, kBM))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tmK, k, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBN))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tmV, v, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBN))) return rc;
+    } else {
     NPM_REQUIRE(ldq >= (int64_t)HD && ldk >= (int64_t)HD && ldv >= (int64_t)HD && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0,
                 "mha_core_fwd: token strides must be >= H*d and multiples of 4 floats");
     // token stride ld*: q / k / v may be column blocks of one packed [tokens, 3*H*d] projection output
-    if ((rc = make_tensor_map_4d(&tmQ, q, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBM, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tmK, k, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBN, true, false))) return rc;
-    if ((rc = make_tensor_map_4d(&tmV, v, kD, Skv, H, B, ldv, kD, Skv * ldv, 32, kBN, true, true))) return rc;
+    const float* qf = reinterpret_cast<const float*>(q);
+    const float* kf = reinterpret_cast<const float*>(k);
+    const float* vf = reinterpret_cast<const float*>(v);
+    if ((rc = make_tensor_map_4d(&tmQ, qf, kD, Sq, H, B, ldq, kD, Sq * ldq, 32, kBM, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tmK, kf, kD, Skv, H, B, ldk, kD, Skv * ldk, 32, kBN, true, false))) return rc;
+    if ((rc = make_tensor_map_4d(&tmV, vf, kD, Skv, H, B, ldv, kD, Skv * ldv, 32, kBN, true, true))) return rc;
+    }
     FwdArgs a;
     a.B = (int)B; a.H = (int)H; a.Sq = (int)Sq; a.Skv = (int)Skv;
     a.q_tiles = (int)((Sq + kBM - 1) / kBM);
@@ -368,9 +452,13 @@ int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, fl
     a.o = o; a.lse = lse;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+            e = cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) { set_error("attn_fwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
         configured = true;
     }
@@ -378,8 +466,9 @@ int attn_fwd_launch(const float* q, const float* k, const float* v, float* o, fl
     // causal: the work of an item grows with its tile index, and CTA c takes items c, c + grid, ...: a grid size
     // coprime with the tile count makes every CTA cycle through all tile indices (148 and 8 share the factor 4)
     if (causal) while (grid > 1 && gcd_int(grid, a.q_tiles) != 1) --grid;
-    cudaError_t le = causal ? launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a)
-                            : launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a);
+    auto kern = causal ? (bx ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
+                       : (bx ? attn_fwd_kernel<false, true> : attn_fwd_kernel<false, false>);
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a);
     if (le != cudaSuccess) { set_error("attn_fwd_kernel launch: %s", cudaGetErrorString(le)); return NPM_ERR_CUDA; }
     count_launch();
     return check_launch("attn_fwd_kernel");

@@ -2,7 +2,7 @@
 //
 //   C[z][m,n] (=|+=) alpha * sum_k A[z][m,k] * B[z][k,n] (+ bias[n]) (+ residual) (ReLU)       (fp32 in HBM, fp32 out)
 //
-// Every fp32 operand element x is split on the way into shared memory into two bf16 numbers
+// Every fp32 operand element x is split inside shared memory into two bf16 numbers
 //   hi = bf16_rn(x),  mid = bf16_rn(x - hi)          (x - hi - mid is below 2^-17 |x|)
 // and the tensor cores run the three products  mid*hi + hi*mid + hi*hi  with fp32 accumulation in TMEM.  The dropped
 // terms (mid*mid and the two residuals) are <= 3 * 2^-18 of |a||b| per product, i.e. ~50x below a single TF32 pass
@@ -14,24 +14,21 @@
 // MultiHeadAttention projections and their gradients (layers/attentions.py:88-100,116,129-135,169-184).
 //
 // Structure = the CTA-pair kernel of gemm_tc.cu (cta_group::2, 256 x BLOCK_N tile per pair, two TMEM accumulator
-// buffers, four epilogue warps per CTA) with a different producer: TMA cannot convert, and a split pass through
-// shared memory would cost 64 KB of LSU traffic per 32 KB stage on top of the MMA's own operand reads, so eight
-// producer warps per CTA load the fp32 operands straight from global memory into registers (LDG.128, two K stages in
-// flight per thread), split them there and store the bf16 images in the canonical UMMA layouts:
-//   K-major operand  [rows, 32 k]: one 128-byte row per operand row = [hi k0..31 | mid k0..31], 128B swizzle;
-//                                  an MMA K16 slice is a 32-byte column of that row (hi: 0,32; mid: 64,96)
-//   MN-major operand [32 k, rows]: hi image then mid image, each rows/64 slabs of 32 k-rows x 128 B (64 mn), 128B swizzle;
-//                                  an MMA K16 slice is 16 k-rows = 2048 B of a slab
-// Shared-memory traffic per stage: 32 KB of STS + the MMA operand reads; HBM/L2 traffic = the fp32 operands, once.
-//
-// Who fences: generic-proxy stores must be ordered before the tensor core's async-proxy reads by a
-// fence.proxy.async, which nvcc lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC — and a MEMBAR in a thread that has global
-// loads in flight waits for them, i.e. it serialises the register prefetch (first version of this kernel: 2900 clk per
-// stage = one full load latency, 200 TF).  So the producers only store and arrive (release.cta, no MEMBAR) on their
-// CTA's full barrier; the proxy fence is executed by a thread with nothing in flight that has acquired that barrier —
-// the MMA issuer in the leader CTA, two relay lanes in the peer CTA, which then arrive (release.cluster) on the
-// leader's peer barrier.  The fence is on the causality path between the stores and the MMA, which is what the PTX
-// memory model asks of a proxy fence.
+// buffers, four epilogue warps per CTA) with a conversion step between TMA and the tensor core:
+//   warp 4      TMA producer : lands this CTA's fp32 operand tiles (128-byte swizzle) in a ring stage
+//   warps 5-12  converters   : LDS the stage into registers (256 threads x 8 float4 = the whole stage), barrier, and
+//                              store the bf16 hi / mid images IN PLACE in the canonical UMMA layouts:
+//     K-major operand  [rows, 32 k]: one 128-byte row per operand row = [hi k0..31 | mid k0..31], 128B swizzle;
+//                                    an MMA K16 slice is a 32-byte column of that row (hi: 0,32; mid: 64,96)
+//     MN-major operand [32 k, rows]: hi image then mid image, each rows/64 slabs of 32 k-rows x 128 B (64 mn), 128B
+//                                    swizzle; an MMA K16 slice is 16 k-rows = 2048 B of a slab
+//                              then fence.proxy.async and arrive on the pair leader's barrier
+//   warp 13     MMA issuer (leader CTA)
+// Why not convert on the way in from global memory (the first version of this kernel: LDG.128 into registers, two
+// stages in flight per thread, split, STS)?  Measured (NPM_GEMM_DEBUG_TIMES): the LSU path accepts ~18 B/clk/SM of
+// loads under load — issuing the 8 LDG.128 of a stage stalled 1800 clk — against the 42 B/clk/SM this kernel needs
+// and the 55-64 B/clk/SM TMA sustains; 320-350 TF.  (Before that: fence.proxy.async lowers to MEMBAR.ALL.CTA +
+// FENCE.VIEW.ASYNC, and a MEMBAR in a thread with global loads in flight waits for them: 200 TF.)
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -44,21 +41,21 @@ namespace npm {
 
 int make_tensor_map_4d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                        uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, bool round_tf32, bool atom32b);
+int make_tensor_map_nd(CUtensorMap* tm, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                       const uint32_t* box, bool round_tf32, bool atom32b);
 
 namespace {
 
 constexpr int kBM = 128;        // rows of A per CTA (256 per pair)
 constexpr int kKS = 32;         // fp32 elements of K per ring stage
-constexpr int kProducerWarps = 8;
-constexpr int kFirstProducerWarp = 5;
-constexpr int kFencerWarpB = kFirstProducerWarp + kProducerWarps;       // 13: second proxy-fence relay of the peer CTA
-constexpr int kThreadsBx = 32 * (kFencerWarpB + 1);                      // 448: 4 epilogue, 1 issuer / relay, 8 producers, 1 relay
-constexpr int kPrefetch = 2;    // K stages each producer thread keeps in flight in registers
+constexpr int kConvWarps = 8;
+constexpr int kTmaWarp = 4;
+constexpr int kFirstConvWarp = 5;
+constexpr int kMmaWarp = kFirstConvWarp + kConvWarps;                    // 13
+constexpr int kThreadsBx = 32 * (kMmaWarp + 1);                          // 448: 4 epilogue, TMA, 8 converters, MMA issuer
 
 struct GemmBxArgs {
-    const float* a; const float* b;
-    int64_t a_ld, b_ld;                        // elements between consecutive rows of the stored operand
-    int64_t a_bs1, a_bs2, b_bs1, b_bs2;
+    int a_chunked, b_chunked;                  // MN-major operand described as a 5-D {32, K, MN/32, nb1, nb2} tensor: one box per stage
     int M, N, K;
     int tiles_m, tiles_n, nb1, total_tiles;
     int splits, kb_per_split, items_per_split;
@@ -101,77 +98,65 @@ __device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-__device__ __forceinline__ float4 ldg_f4(const float* p) {
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
     return r;
 }
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void bar_sync_conv() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kConvWarps) : "memory"); }
+// plain (release.cta) arrive on a barrier of another CTA of the cluster — the form CUTLASS's ClusterBarrier uses.  The
+// release.cluster form lowers to MEMBAR.ALL.GPU (~2000 clk measured); nothing the leader reads depends on it: the data
+// this signals sits in THIS CTA's shared memory, already proxy-fenced, and is read by THIS SM's tensor core.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 
-// One operand of one CTA: R rows (A: 128 rows of M, B: BLOCK_N/2 rows of N) x 32 k per stage.
-// Each producer thread owns NLD 16-byte fp32 chunks of the stage, fixed for the whole kernel.
+// One operand of one CTA: R rows (A: 128 rows of M, B: BLOCK_N/2 rows of N) x 32 k per stage, 16 KB (R = 128) as
+// fp32 and as bf16 hi + mid.  Each of the 256 converter threads owns NLD 16-byte fp32 chunks of the stage.
 template <int R, bool MN, int NTERMS>
-struct OperandLoader {
-    static constexpr int NLD = R / 32;              // LDG.128 per thread per stage (256 producer threads)
-    // K-major : a warp instruction covers 4 rows x 128 B (8 lanes per row); rows of one instruction are
-    //           {r, r+4} per half-warp so the two 64-byte halves written per row never share a bank group
-    // MN-major: a warp instruction covers 128 consecutive mn of one k-row (R = 128) or of two k-rows (R = 64)
-    int   row[NLD];          // K-major: operand row in the tile;  MN-major: k-row in the stage
-    int   col;               // K-major: first k of the chunk (4c);  MN-major: first mn of the chunk
-    uint32_t soff[NLD];      // byte offset of the hi 8-byte store inside the operand's stage image
+struct OperandConverter {
+    static constexpr int NLD = R / 32;
+    // K-major : TMA box {32 k, R rows}: row r = 128 B, 16-byte chunk c at position c ^ (r & 7).  A warp instruction
+    //           covers 4 rows (8 lanes per row); the rows of one half-warp are {r, r+4} so that the two 64-byte hi
+    //           halves it writes never share a bank group.
+    // MN-major: TMA boxes {32 mn, 32 k}: 4 KB per 32-mn chunk, k-row kk = 128 B, chunk j at j ^ (kk & 7).  A warp
+    //           instruction covers 4 k-rows of one chunk, again {kk, kk+4} per half-warp.
+    uint32_t src[NLD];       // byte offset of the fp32 chunk in the staged image
+    uint32_t dst[NLD];       // byte offset of the 8-byte hi store in the bf16 image
 
     __device__ __forceinline__ void init(int pw, int lane) {
-        if (!MN) {
-            const int c = lane & 7, q = lane >> 3;
-            col = 4 * c;
-#pragma unroll
-            for (int i = 0; i < NLD; ++i) {
-                const int g = i >> 1, j = i & 1;
-                const int r = pw * (R / 8) + g * 8 + (q & 1) * 4 + (q >> 1) + 2 * j;
-                row[i] = r;
-                soff[i] = uint32_t(r) * 128u + (uint32_t((c >> 1) ^ (r & 7)) << 4) + uint32_t(c & 1) * 8u;
-            }
-        } else {
-            constexpr int LPR = R / 4;                 // lanes per k-row
-            constexpr int RPI = 32 / LPR;              // k-rows per warp instruction
-            const int mnl = (lane % LPR) * 4;
-            col = mnl;
-#pragma unroll
-            for (int i = 0; i < NLD; ++i) {
-                const int kk = (pw * NLD + i) * RPI + lane / LPR;
-                row[i] = kk;
-                soff[i] = uint32_t(mnl >> 6) * 4096u + uint32_t(kk) * 128u +
-                          (uint32_t(((mnl & 63) >> 3) ^ (kk & 7)) << 4) + uint32_t((mnl >> 2) & 1) * 8u;
-            }
-        }
-    }
-    // base: first element of this CTA's tile rows at k = 0 (K-major: &X[r0, 0]; MN-major: &X[0, r0]); r0 / rows_total
-    // bound the rows, k0 / K the contraction index.  Out-of-range chunks are zero.
-    __device__ __forceinline__ void load(float4 (&v)[NLD], const float* base, int64_t ld, int r0, int rows_total,
-                                         int k0, int K) const {
+        const int c = lane & 7, q = lane >> 3;
 #pragma unroll
         for (int i = 0; i < NLD; ++i) {
-            bool ok;
-            const float* p;
             if (!MN) {
-                ok = (r0 + row[i] < rows_total) && (k0 + col < K);
-                p = base + (int64_t)row[i] * ld + (k0 + col);
+                const int g = i >> 1, j = i & 1;
+                const int r = pw * (R / 8) + g * 8 + (q & 1) * 4 + (q >> 1) + 2 * j;
+                src[i] = uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+                dst[i] = uint32_t(r) * 128u + (uint32_t((c >> 1) ^ (r & 7)) << 4) + uint32_t(c & 1) * 8u;
             } else {
-                ok = (k0 + row[i] < K) && (r0 + col < rows_total);
-                p = base + (int64_t)(k0 + row[i]) * ld + col;
+                const int t = pw * NLD + i;                       // warp instruction index: chunk t / 8, row group t % 8
+                const int ch = t >> 3, g8 = t & 7;
+                const int kk = (g8 >> 1) * 8 + (q & 1) * 4 + (q >> 1) + 2 * (g8 & 1);
+                const int mn = ch * 32 + 4 * c;
+                src[i] = uint32_t(ch) * 4096u + uint32_t(kk) * 128u + (uint32_t(c ^ (kk & 7)) << 4);
+                dst[i] = uint32_t(mn >> 6) * 4096u + uint32_t(kk) * 128u + (uint32_t(((mn & 63) >> 3) ^ (kk & 7)) << 4) +
+                         uint32_t((mn >> 2) & 1) * 8u;
             }
-            v[i] = ok ? ldg_f4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
+    __device__ __forceinline__ void load(float4 (&v)[NLD], uint32_t image) const {
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) v[i] = lds_f4(image + src[i]);
+    }
     __device__ __forceinline__ void store(const float4 (&v)[NLD], uint32_t image) const {
-        constexpr uint32_t mid_delta = MN ? uint32_t(R / 64) * 4096u : 64u;   // MN-major: the mid image follows the hi image
+        constexpr uint32_t mid_delta = uint32_t(R / 64) * 4096u;   // MN-major: the mid image follows the hi image
 #pragma unroll
         for (int i = 0; i < NLD; ++i) {
             const uint32_t h01 = bf16x2_rn(v[i].x, v[i].y), h23 = bf16x2_rn(v[i].z, v[i].w);
-            const uint32_t a = image + soff[i];
+            const uint32_t a = image + dst[i];
             sts_v2(a, h01, h23);
             if (NTERMS == 3) {
                 const float rx = v[i].x - __uint_as_float(h01 << 16), ry = v[i].y - __uint_as_float(h01 & 0xffff0000u);
@@ -184,7 +169,8 @@ struct OperandLoader {
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int NTERMS>
 __global__ void __launch_bounds__(kThreadsBx, 1)
-gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
+gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
     using Cfg = BxCfg<BLOCK_N>;
     constexpr int S = Cfg::kStages;
     pdl_trigger();
@@ -197,9 +183,9 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
     const uint32_t stage_addr = base_addr;
     const uint32_t epi_addr   = base_addr + S * Cfg::kStageBytes;
     const uint32_t bar_addr   = epi_addr + Cfg::kEpiBytes;
-    auto full_bar   = [&](int s) { return bar_addr + 8u * s; };                 // this CTA's producers have stored stage s
-    auto empty_bar  = [&](int s) { return bar_addr + 8u * (S + s); };
-    auto peer_bar   = [&](int s) { return bar_addr + 8u * (2 * S + s); };       // leader only: the peer's stage s is stored and fenced
+    auto tma_bar    = [&](int s) { return bar_addr + 8u * s; };                 // this CTA's fp32 tiles of stage s have landed
+    auto empty_bar  = [&](int s) { return bar_addr + 8u * (S + s); };           // the MMAs that read stage s have completed
+    auto full_bar   = [&](int s) { return bar_addr + 8u * (2 * S + s); };       // leader: both CTAs converted stage s
     auto tfull_bar  = [&](int a) { return bar_addr + 8u * (3 * S + a); };
     auto tempty_bar = [&](int a) { return bar_addr + 8u * (3 * S + 2 + a); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
@@ -212,13 +198,17 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
     const int num_clusters = gridDim.x >> 1;
     const int num_kb = (args.K + kKS - 1) / kKS;
 
-    if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmC);
-    if (warp == 4) {
+    if (warp == kTmaWarp && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&tmC);
+    }
+    if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int s = 0; s < S; ++s) {
-                ptx::mbar_init(full_bar(s), kProducerWarps);       // one arrive per producer warp of this CTA
+                ptx::mbar_init(tma_bar(s), 1);                     // this CTA's arrive.expect_tx
                 ptx::mbar_init(empty_bar(s), 1);                   // one multicast commit
-                ptx::mbar_init(peer_bar(s), 1);                    // one remote arrive of the peer's relay
+                ptx::mbar_init(full_bar(s), 2 * kConvWarps);       // one arrive per converter warp of each CTA
             }
             for (int a = 0; a < 2; ++a) {
                 ptx::mbar_init(tfull_bar(a), 1);
@@ -238,106 +228,95 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
 
     const int tiles_mn = args.tiles_m * args.tiles_n;      // tiles_m counts 256-row tiles
 
-    if (warp >= kFirstProducerWarp && warp < kFencerWarpB) {
-        // ===================== producers: global fp32 -> registers -> split bf16 -> shared =====================
-        const int pw = warp - kFirstProducerWarp;
-        OperandLoader<kBM, A_MN, NTERMS> la;
-        OperandLoader<Cfg::kHalfN, B_MN, NTERMS> lb;
-        la.init(pw, lane);
-        lb.init(pw, lane);
-
-        struct Cur { int tile, kb, kb1, m0, n0; const float* a; const float* b; };
-        auto cur_setup = [&](Cur& c) {
-            if (c.tile >= args.total_tiles) return;
-            const int sp = c.tile / args.items_per_split, t2 = c.tile - sp * args.items_per_split;
-            const int z  = t2 / tiles_mn;
-            const int r  = t2 - z * tiles_mn;
-            c.kb  = sp * args.kb_per_split;
-            c.kb1 = min(num_kb, c.kb + args.kb_per_split);
-            int tm, tn;
-            tile_coords_bx(r, args.tiles_m, args.tiles_n, args.band_m, tm, tn);
-            c.m0 = tm * (2 * kBM) + (int)rank * kBM;
-            c.n0 = tn * BLOCK_N + (int)rank * Cfg::kHalfN;
-            const int z1 = z % args.nb1, z2 = z / args.nb1;
-            const float* az = args.a + (int64_t)z1 * args.a_bs1 + (int64_t)z2 * args.a_bs2;
-            const float* bz = args.b + (int64_t)z1 * args.b_bs1 + (int64_t)z2 * args.b_bs2;
-            c.a = A_MN ? az + c.m0 : az + (int64_t)c.m0 * args.a_ld;
-            c.b = B_MN ? bz + c.n0 : bz + (int64_t)c.n0 * args.b_ld;
-        };
-        auto cur_next = [&](Cur& c) {
-            if (++c.kb >= c.kb1) { c.tile += num_clusters; cur_setup(c); }
-        };
-        Cur lc, sc;
-        lc.tile = cluster_id; cur_setup(lc);
-        sc = lc;
-
-        float4 va[kPrefetch][OperandLoader<kBM, A_MN, NTERMS>::NLD];
-        float4 vb[kPrefetch][OperandLoader<Cfg::kHalfN, B_MN, NTERMS>::NLD];
-        auto issue = [&](int d) {
-            la.load(va[d], lc.a, args.a_ld, lc.m0, args.M, lc.kb * kKS, args.K);
-            lb.load(vb[d], lc.b, args.b_ld, lc.n0, args.N, lc.kb * kKS, args.K);
-            cur_next(lc);
-        };
+    if (warp == kTmaWarp) {
+        // ============================ TMA producer (both CTAs): fp32 tiles ============================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+                const int sp = tile / args.items_per_split, t2 = tile - sp * args.items_per_split;
+                const int z  = t2 / tiles_mn;
+                const int r  = t2 - z * tiles_mn;
+                const int kb0 = sp * args.kb_per_split;
+                const int kb1 = min(num_kb, kb0 + args.kb_per_split);
+                int tm, tn;
+                tile_coords_bx(r, args.tiles_m, args.tiles_n, args.band_m, tm, tn);
+                const int m0 = tm * (2 * kBM) + (int)rank * kBM;
+                const int n0 = tn * BLOCK_N + (int)rank * Cfg::kHalfN;
+                const int z1 = z % args.nb1, z2 = z / args.nb1;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                    const uint32_t sB = sA + Cfg::kABytes;
+                    const uint32_t fb = tma_bar(stage);
+                    ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                    const int k0 = kb * kKS;
+                    if (!A_MN) {
+                        ptx::tma_load_4d(sA, &tmA, fb, k0, m0, z1, z2);
+                    } else if (args.a_chunked) {
+                        ptx::tma_load_5d(sA, &tmA, fb, 0, k0, m0 / 32, z1, z2);
+                    } else {
 #pragma unroll
-        for (int d = 0; d < kPrefetch; ++d)
-            if (lc.tile < args.total_tiles) issue(d);
-
+                        for (int c = 0; c < kBM / 32; ++c) ptx::tma_load_4d(sA + c * 4096, &tmA, fb, m0 + c * 32, k0, z1, z2);
+                    }
+                    if (!B_MN) {
+                        ptx::tma_load_4d(sB, &tmB, fb, k0, n0, z1, z2);
+                    } else if (args.b_chunked) {
+                        ptx::tma_load_5d(sB, &tmB, fb, 0, k0, n0 / 32, z1, z2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < Cfg::kHalfN / 32; ++c) ptx::tma_load_4d(sB + c * 4096, &tmB, fb, n0 + c * 32, k0, z1, z2);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= kFirstConvWarp && warp < kMmaWarp) {
+        // ===================== converters: fp32 stage -> registers -> bf16 hi / mid images in place =====================
+        const int pw = warp - kFirstConvWarp;
+        OperandConverter<kBM, A_MN, NTERMS> ca;
+        OperandConverter<Cfg::kHalfN, B_MN, NTERMS> cb;
+        ca.init(pw, lane);
+        cb.init(pw, lane);
+        const uint32_t full_leader = ptx::mapa(full_bar(0), 0);
+        int total_it = 0;
+        for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+            const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
+            total_it += min(num_kb, kb0 + args.kb_per_split) - kb0;
+        }
         int stage = 0;
         uint32_t phase = 0;
-        while (sc.tile < args.total_tiles) {
-#pragma unroll
-            for (int d = 0; d < kPrefetch; ++d) {
-                if (sc.tile >= args.total_tiles) break;
-                const bool dbg = args.dbg != nullptr && pw == 0 && lane == 0;
-                long long t0 = 0, t1 = 0, t2 = 0;
-                if (dbg) t0 = clock64();
-                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                if (dbg) t1 = clock64();
-                const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
-                la.store(va[d], sA);
-                lb.store(vb[d], sA + Cfg::kABytes);
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(full_bar(stage));       // release.cta; the proxy fence is the consumer's (see top)
-                if (dbg) t2 = clock64();
-                cur_next(sc);
-                if (lc.tile < args.total_tiles) issue(d);
-                if (dbg) {
-                    args.dbg[blockIdx.x * 16 + 0] += t1 - t0;            // wait for a free slot
-                    args.dbg[blockIdx.x * 16 + 1] += t2 - t1;            // wait for the loads + split + store
-                    args.dbg[blockIdx.x * 16 + 2] += clock64() - t2;     // address arithmetic + load issue
-                    args.dbg[blockIdx.x * 16 + 3] += 1;
-                }
-                if (++stage == S) { stage = 0; phase ^= 1u; }
+        for (int it = 0; it < total_it; ++it) {
+            const bool dbg = args.dbg != nullptr && pw == 0 && lane == 0;
+            long long t0 = 0, t1 = 0, t2 = 0;
+            if (dbg) t0 = clock64();
+            ptx::mbar_wait(tma_bar(stage), phase);
+            if (dbg) t1 = clock64();
+            const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+            float4 va[OperandConverter<kBM, A_MN, NTERMS>::NLD];
+            float4 vb[OperandConverter<Cfg::kHalfN, B_MN, NTERMS>::NLD];
+            ca.load(va, sA);
+            cb.load(vb, sA + Cfg::kABytes);
+            bar_sync_conv();                                 // every fp32 chunk of the stage is in registers: overwrite it
+            if (dbg) t2 = clock64();
+            ca.store(va, sA);
+            cb.store(vb, sA + Cfg::kABytes);
+            ptx::fence_proxy_async_smem();                   // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) ptx::mbar_arrive(full_bar(stage));
+                else           mbar_arrive_remote(full_leader + 8u * stage);
             }
+            if (dbg) {
+                const long long t3 = clock64();
+                args.dbg[blockIdx.x * 16 + 0] += t1 - t0;            // wait for the TMA tiles
+                args.dbg[blockIdx.x * 16 + 1] += t2 - t1;            // LDS + barrier
+                args.dbg[blockIdx.x * 16 + 2] += t3 - t2;            // split + STS + fence + arrive
+                args.dbg[blockIdx.x * 16 + 3] += 1;
+            }
+            if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-    } else if (rank == 1 && (warp == 4 || warp == kFencerWarpB)) {
-        // ============ peer CTA: proxy-fence relays (stages alternate between the two lanes) ============
-        if (ptx::elect_one()) {
-            int total_it = 0;
-            for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
-                const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
-                total_it += min(num_kb, kb0 + args.kb_per_split) - kb0;
-            }
-            const uint32_t peer_remote = ptx::mapa(peer_bar(0), 0);
-            for (int it = (warp == 4 ? 0 : 1); it < total_it; it += 2) {
-                const int stage = it % S;
-                const bool dbg = args.dbg != nullptr && warp == 4;
-                long long t0 = 0, t1 = 0, t2 = 0;
-                if (dbg) t0 = clock64();
-                ptx::mbar_wait(full_bar(stage), uint32_t(it / S) & 1u);
-                if (dbg) t1 = clock64();
-                ptx::fence_proxy_async_smem();
-                if (dbg) t2 = clock64();
-                ptx::mbar_arrive_cluster(peer_remote + 8u * stage);
-                if (dbg) {
-                    args.dbg[blockIdx.x * 16 + 4] += t1 - t0;            // relay: wait for the producers
-                    args.dbg[blockIdx.x * 16 + 5] += t2 - t1;            // relay: proxy fence
-                    args.dbg[blockIdx.x * 16 + 6] += clock64() - t2;     // relay: release.cluster arrive
-                    args.dbg[blockIdx.x * 16 + 7] += 1;
-                }
-            }
-        }
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
         // ============================= MMA issuer (leader CTA) =============================
         if (rank == 0 && ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kBM, BLOCK_N, A_MN, B_MN);
@@ -360,18 +339,11 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    long long t0 = 0, t1 = 0, t2 = 0;
-                    if (args.dbg) t0 = clock64();
-                    ptx::mbar_wait(full_bar(stage), phase);
-                    if (args.dbg) t1 = clock64();
-                    ptx::mbar_wait_cluster(peer_bar(stage), phase);
-                    if (args.dbg) t2 = clock64();
-                    ptx::fence_proxy_async_smem();
+                    const long long t0 = args.dbg ? clock64() : 0;
+                    ptx::mbar_wait_cluster(full_bar(stage), phase);     // arrivals come from both CTAs of the pair
                     ptx::tc_fence_after();
                     if (args.dbg) {
-                        args.dbg[blockIdx.x * 16 + 8] += t1 - t0;            // issuer: wait for own producers
-                        args.dbg[blockIdx.x * 16 + 9] += t2 - t1;            // issuer: wait for the peer
-                        args.dbg[blockIdx.x * 16 + 10] += clock64() - t2;    // issuer: proxy fence
+                        args.dbg[blockIdx.x * 16 + 8] += clock64() - t0;     // issuer: wait for a converted stage
                         args.dbg[blockIdx.x * 16 + 11] += 1;
                     }
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
@@ -489,7 +461,7 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
             __syncwarp();
             if (lane == 0) {
                 if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
-                else           ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(acc), 0));
+                else           mbar_arrive_remote(ptx::mapa(tempty_bar(acc), 0));
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
@@ -499,11 +471,11 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
 
     ptx::tc_fence_before();
     ptx::cluster_sync();
-    if (warp == 4) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    if (warp == kMmaWarp) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
 }
 
 template <int BN, bool AMN, bool BMN, int NT>
-int launch_bx(const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream_t stream) {
+int launch_bx(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream_t stream) {
     using Cfg = BxCfg<BN>;
     auto kern = gemm_bx_kernel<BN, AMN, BMN, NT>;
     static bool configured = false;
@@ -521,7 +493,7 @@ int launch_bx(const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream
         cudaMalloc(&largs.dbg, sizeof(long long) * 16 * grid);
         cudaMemset(largs.dbg, 0, sizeof(long long) * 16 * grid);
     }
-    cudaError_t e = launch_pdl(kern, dim3((unsigned)grid, 1, 1), dim3(kThreadsBx, 1, 1), Cfg::kSmemBytes, stream, 2, c, largs);
+    cudaError_t e = launch_pdl(kern, dim3((unsigned)grid, 1, 1), dim3(kThreadsBx, 1, 1), Cfg::kSmemBytes, stream, 2, a, b, c, largs);
     count_launch();
     if (e != cudaSuccess) { set_error("gemm_bx_kernel launch: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
     if (dbg_times) {
@@ -531,44 +503,29 @@ int launch_bx(const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream
         double s[16] = {0};
         for (int cta = 0; cta < grid; ++cta)
             for (int i = 0; i < 16; ++i) s[i] += (double)h[16 * cta + i];
-        fprintf(stderr, "[gemm_bx M=%d N=%d K=%d nt=%d] per stage: producer(w0) slot-wait %.0f, loads+split+store %.0f, issue %.0f | relay wait %.0f, "
-                "fence %.0f, arrive %.0f | issuer own-wait %.0f, peer-wait %.0f, fence %.0f, acc-wait/stage %.0f\n",
-                args.M, args.N, args.K, NT, s[0] / s[3], s[1] / s[3], s[2] / s[3], s[4] / s[7], s[5] / s[7], s[6] / s[7],
-                s[8] / s[11], s[9] / s[11], s[10] / s[11], s[12] / s[11]);
+        fprintf(stderr, "[gemm_bx M=%d N=%d K=%d nt=%d] cycles per stage: converter(w0) tma-wait %.0f, LDS+barrier %.0f, split+STS+fence+arrive %.0f | "
+                "issuer stage-wait %.0f, acc-wait %.0f\n",
+                args.M, args.N, args.K, NT, s[0] / s[3], s[1] / s[3], s[2] / s[3], s[8] / s[11], s[12] / s[11]);
         cudaFree(largs.dbg);
     }
     return check_launch("gemm_bx_kernel");
 }
 
 template <int BN, int NT>
-int launch_bx_major(bool amn, bool bmn, const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream_t s) {
-    if (!amn && !bmn) return launch_bx<BN, false, false, NT>(c, args, grid, s);
-    if (!amn && bmn) return launch_bx<BN, false, true, NT>(c, args, grid, s);
-    if (amn && !bmn) return launch_bx<BN, true, false, NT>(c, args, grid, s);
-    return launch_bx<BN, true, true, NT>(c, args, grid, s);
+int launch_bx_major(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args, int grid,
+                    cudaStream_t s) {
+    if (!amn && !bmn) return launch_bx<BN, false, false, NT>(a, b, c, args, grid, s);
+    if (!amn && bmn) return launch_bx<BN, false, true, NT>(a, b, c, args, grid, s);
+    if (amn && !bmn) return launch_bx<BN, true, false, NT>(a, b, c, args, grid, s);
+    return launch_bx<BN, true, true, NT>(a, b, c, args, grid, s);
 }
-
-inline bool mult4(int64_t v) { return (v & 3) == 0; }
 
 }  // namespace
 
-// The split-bf16 kernel takes problems with at least two row tiles whose operands can be read in 16-byte chunks that
-// never straddle an edge; everything else in these modes runs the 3xTF32 kernel (at least as accurate).
-bool gemm_bx_supported(const npm_gemm_desc& d) {
-    if (d.m <= kBM || d.n <= 0 || d.k <= 0) return false;
-    if (!aligned16(d.a) || !aligned16(d.b) || !aligned16(d.c)) return false;
-    if (!(d.a_cs == 1 || d.a_rs == 1) || !(d.b_cs == 1 || d.b_rs == 1)) return false;
-    const bool a_mn = !(d.a_cs == 1), b_mn = !(d.b_rs == 1);
-    const int64_t a_ld = a_mn ? d.a_cs : d.a_rs, b_ld = b_mn ? d.b_rs : d.b_cs;
-    if (!mult4(a_ld) || !mult4(b_ld) || !mult4(d.ldc) || a_ld <= 0 || b_ld <= 0 || d.ldc < d.n) return false;
-    if (!mult4(d.k)) return false;
-    if (a_mn && !mult4(d.m)) return false;
-    if (b_mn && !mult4(d.n)) return false;
-    if (d.nb1 > 1 && !(mult4(d.a_bs1) && mult4(d.b_bs1) && mult4(d.c_bs1))) return false;
-    if (d.nb2 > 1 && !(mult4(d.a_bs2) && mult4(d.b_bs2) && mult4(d.c_bs2))) return false;
-    if (d.m > (1ll << 31) - 512 || d.n > (1ll << 31) - 512 || d.k > (1ll << 31) - 512) return false;
-    return true;
-}
+// The split-bf16 kernel takes every problem the TMA GEMM takes that has at least two row tiles; everything else in
+// these modes runs the TF32 kernels of the same or better accuracy class (3xTF32 for bf16x3).
+bool gemm_tc_supported(const npm_gemm_desc& d);
+bool gemm_bx_supported(const npm_gemm_desc& d) { return d.m > kBM && gemm_tc_supported(d); }
 
 int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     const int nb1 = d.nb1 > 0 ? d.nb1 : 1, nb2 = d.nb2 > 0 ? d.nb2 : 1;
@@ -612,20 +569,50 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
         cudaError_t e = cudaMemsetAsync(d.c, 0, sizeof(float) * (size_t)d.m * d.n * nb1 * nb2, stream);
         if (e != cudaSuccess) { set_error("gemm split-K memset: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
     }
-    CUtensorMap tmC;
+    CUtensorMap tmA, tmB, tmC;
     auto bs = [](int nb, int64_t s, uint64_t natural) -> uint64_t { return nb > 1 ? (uint64_t)s : natural; };
+    const uint64_t M = d.m, N = d.n, K = d.k;
+    const bool a_chunked = a_mn && (d.m % 32 == 0), b_chunked = b_mn && (d.n % 32 == 0);
+    int rc;
+    // fp32 staging images: K-major = one box {32 k, rows}; MN-major = {32 mn, 32 k} boxes of 4 KB, all of a stage in one
+    // TMA instruction when the operand has the 5-D {32, K, MN/32, nb1, nb2} view (a box costs ~46 clk + bytes / 70 B/clk)
+    if (!a_mn) {
+        const uint64_t ld = d.a_rs, s2 = bs(nb1, d.a_bs1, ld * M), s3 = bs(nb2, d.a_bs2, s2 * nb1);
+        rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kKS, kBM, false, false);
+    } else {
+        const uint64_t ld = d.a_cs, s2 = bs(nb1, d.a_bs1, ld * K), s3 = bs(nb2, d.a_bs2, s2 * nb1);
+        if (a_chunked) {
+            const uint64_t dims[5] = {32, K, M / 32, (uint64_t)nb1, (uint64_t)nb2}, st[4] = {ld, 32, s2, s3};
+            const uint32_t box[5] = {32, kKS, kBM / 32, 1, 1};
+            rc = make_tensor_map_nd(&tmA, d.a, 5, dims, st, box, false, false);
+        } else {
+            rc = make_tensor_map_4d(&tmA, d.a, M, K, nb1, nb2, ld, s2, s3, 32, kKS, false, false);
+        }
+    }
+    if (rc) return rc;
+    if (!b_mn) {
+        const uint64_t ld = d.b_cs, s2 = bs(nb1, d.b_bs1, ld * N), s3 = bs(nb2, d.b_bs2, s2 * nb1);
+        rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kKS, bn / 2, false, false);
+    } else {
+        const uint64_t ld = d.b_rs, s2 = bs(nb1, d.b_bs1, ld * K), s3 = bs(nb2, d.b_bs2, s2 * nb1);
+        if (b_chunked) {
+            const uint64_t dims[5] = {32, K, N / 32, (uint64_t)nb1, (uint64_t)nb2}, st[4] = {ld, 32, s2, s3};
+            const uint32_t box[5] = {32, kKS, (uint32_t)bn / 2 / 32, 1, 1};
+            rc = make_tensor_map_nd(&tmB, d.b, 5, dims, st, box, false, false);
+        } else {
+            rc = make_tensor_map_4d(&tmB, d.b, N, K, nb1, nb2, ld, s2, s3, 32, kKS, false, false);
+        }
+    }
+    if (rc) return rc;
     {
         const uint64_t ld = d.ldc;
         const uint64_t s2 = bs(nb1, d.c_bs1, ld * d.m), s3 = bs(nb2, d.c_bs2, s2 * nb1);
-        int rc = make_tensor_map_4d(&tmC, d.c, d.n, d.m, nb1, nb2, ld, s2, s3, 32, 32, false, false);
+        rc = make_tensor_map_4d(&tmC, d.c, d.n, d.m, nb1, nb2, ld, s2, s3, 32, 32, false, false);
         if (rc) return rc;
     }
     GemmBxArgs args;
-    args.a = d.a; args.b = d.b;
-    args.a_ld = a_mn ? d.a_cs : d.a_rs;
-    args.b_ld = b_mn ? d.b_rs : d.b_cs;
-    args.a_bs1 = nb1 > 1 ? d.a_bs1 : 0; args.a_bs2 = nb2 > 1 ? d.a_bs2 : 0;
-    args.b_bs1 = nb1 > 1 ? d.b_bs1 : 0; args.b_bs2 = nb2 > 1 ? d.b_bs2 : 0;
+    args.a_chunked = a_chunked ? 1 : 0;
+    args.b_chunked = b_chunked ? 1 : 0;
     args.M = (int)d.m; args.N = (int)d.n; args.K = (int)d.k;
     args.tiles_m = (int)tiles_m; args.tiles_n = (int)tiles_n; args.nb1 = nb1;
     args.total_tiles = (int)total;
@@ -641,11 +628,11 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     args.dbg = nullptr;
     const int grid = 2 * (int)(total < units ? total : units);
     if (nterms == 3) {
-        if (bn == 256) return launch_bx_major<256, 3>(a_mn, b_mn, tmC, args, grid, stream);
-        return launch_bx_major<128, 3>(a_mn, b_mn, tmC, args, grid, stream);
+        if (bn == 256) return launch_bx_major<256, 3>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+        return launch_bx_major<128, 3>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
     }
-    if (bn == 256) return launch_bx_major<256, 1>(a_mn, b_mn, tmC, args, grid, stream);
-    return launch_bx_major<128, 1>(a_mn, b_mn, tmC, args, grid, stream);
+    if (bn == 256) return launch_bx_major<256, 1>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+    return launch_bx_major<128, 1>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
 }
 
 }  // namespace npm

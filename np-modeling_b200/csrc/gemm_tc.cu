@@ -803,6 +803,31 @@ int make_tensor_map_mn_chunked(CUtensorMap* tm, const float* base, uint64_t MN, 
     return NPM_OK;
 }
 
+// Split-bf16 planes [2][B, S, H, 64] (hi plane, then mid plane; token stride ld elements) as a 5-D bf16 tensor
+// {64 d, S, H, B, 2}: box {64, box_rows, 1, 1, 1} = box_rows rows of 128 bytes, 128-byte swizzle — one image that the
+// tensor core can read K-major (contraction over d) or MN-major (contraction over the rows).
+int make_tensor_map_bf16_planes(CUtensorMap* tm, const void* base, uint64_t S, uint64_t H, uint64_t B, uint64_t ld,
+                                uint64_t plane_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return NPM_ERR_CUDA;
+    }
+    cuuint64_t dims[5]    = {64, S, H, B, 2};
+    cuuint64_t strides[4] = {ld * 2, 64 * 2, S * ld * 2, plane_elems * 2};
+    cuuint32_t box[5]     = {64, box_rows, 1, 1, 1};
+    cuuint32_t estr[5]    = {1, 1, 1, 1, 1};
+    CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (bf16 planes) failed (%d): S=%llu H=%llu B=%llu ld=%llu", (int)rc,
+                  (unsigned long long)S, (unsigned long long)H, (unsigned long long)B, (unsigned long long)ld);
+        return NPM_ERR_CUDA;
+    }
+    return NPM_OK;
+}
+
 namespace {
 
 template <int BN, bool AMN, bool BMN, int NP>

@@ -153,10 +153,14 @@ class MultiHeadAttention(layer.StatefulLayer):
             self._qkv_ptrs = (q2.ptr, k2.ptr, v2.ptr)
             self._qkv_ld = (hd, hd, h * dv)
 
-        self._saved = device.workspace(C.npm_mha_core_saved_bytes(batch, h, sq, skv, dk, dv))
+        # the implementation (and with it the layout of `saved`) is chosen HERE, under the precision mode of the forward
+        # call, and pinned for the backward call: a set_precision() in between cannot make backward misread `saved`
+        self._path = int(C.npm_mha_core_path(batch, h, sq, skv, dk, dv))
+        self._saved = device.workspace(C.npm_mha_core_saved_bytes_for(self._path, batch, h, sq, skv, dk, dv))
         values = device.empty((batch, sq, h, dv))          # [B, Sq, H, dv] (reference keeps [B,H,Sq,dv])
         assert not self._causal or sq == skv, 'causal attention needs seq_len_q == seq_len_kv'
-        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], causal=int(self._causal))
+        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], causal=int(self._causal),
+                        path=1 + self._path)
         qp, kp, vp = self._qkv_ptrs
         C.npm_mha_core_fwd_strided(qp, kp, vp, values.ptr, self._saved.data_ptr(), batch, h, sq, skv, dk, dv,
                                    ctypes.byref(ld), device.stream())
@@ -235,9 +239,9 @@ class MultiHeadAttention(layer.StatefulLayer):
             dk2 = device.empty((batch * skv, hd))
             dv2 = device.empty((batch * skv, h * dv))
             dptrs, dld, dbufs = (dq2.ptr, dk2.ptr, dv2.ptr), (hd, hd, h * dv), (dq2, dk2, dv2)
-        scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes(batch, h, sq, skv, dk, dv))
+        scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes_for(self._path, batch, h, sq, skv, dk, dv))
         ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], dq=dld[0], dk=dld[1], dv=dld[2],
-                        causal=int(self._causal))
+                        causal=int(self._causal), path=1 + self._path)
         qp, kp, vp = self._qkv_ptrs
         C.npm_mha_core_bwd_strided(qp, kp, vp, self._values.ptr, dvalues.ptr, self._saved.data_ptr(), dptrs[0],
                                    dptrs[1], dptrs[2], scratch.data_ptr(), batch, h, sq, skv, dk, dv,

@@ -38,7 +38,7 @@ class GemmDesc(Structure):
 class MhaStrides(Structure):
     """npm_mha_strides (include/npm_b200.h): floats between consecutive tokens, 0 = dense."""
     _fields_ = [('q', c_int64), ('k', c_int64), ('v', c_int64), ('dq', c_int64), ('dk', c_int64), ('dv', c_int64),
-                ('causal', c_int64)]
+                ('causal', c_int64), ('path', c_int64)]
 
 
 class TensorEntry(Structure):
@@ -86,6 +86,9 @@ SIGNATURES = {
     'npm_add3': (c_int, [P, P, P, P, I64, P]),
     'npm_scale': (c_int, [P, F, I64, P]),
     'npm_fill': (c_int, [P, F, I64, P]),
+    'npm_mha_core_path': (c_int, [I64] * 6),
+    'npm_mha_core_saved_bytes_for': (c_size_t, [I] + [I64] * 6),
+    'npm_mha_core_bwd_scratch_bytes_for': (c_size_t, [I] + [I64] * 6),
     'npm_mha_core_saved_bytes': (c_size_t, [I64] * 6),
     'npm_mha_core_bwd_scratch_bytes': (c_size_t, [I64] * 6),
     'npm_mha_core_fwd': (c_int, [P, P, P, P, P] + [I64] * 6 + [P]),
@@ -142,7 +145,7 @@ class _Calls:
         lib = load()
         fn = getattr(lib, name)
         res = SIGNATURES[name][0]
-        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision', 'npm_dropout_layernorm_fused'):
+        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision', 'npm_dropout_layernorm_fused', 'npm_mha_core_path'):
             def call(*args, _fn=fn, _name=name):
                 rc = _fn(*args)
                 if rc != NPM_OK:

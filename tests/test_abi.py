@@ -44,7 +44,8 @@ def test_ctypes_table_matches_header():
 def test_struct_layouts_match_the_header():
     from npm_b200 import _lib
     assert ctypes.sizeof(_lib.TensorEntry) == 48          # 4 pointers + 2 int64
-    assert ctypes.sizeof(_lib.MhaStrides) == 7 * 8        # q k v dq dk dv causal
+    assert ctypes.sizeof(_lib.MhaStrides) == 8 * 8        # q k v dq dk dv causal path
+    assert _lib.MhaStrides.path.offset == 56
     assert _lib.MhaStrides.causal.offset == 48
     assert ctypes.sizeof(_lib.GemmDesc) == 4 * 8 + 3 * 8 + 5 * 8 + 2 * 4 + 6 * 8 + 3 * 4 + 4 + 2 * 8   # incl. padding before `residual`
     assert _lib.GemmDesc.residual.offset == ctypes.sizeof(_lib.GemmDesc) - 16

@@ -97,7 +97,8 @@ def run(B, H, Sq, Skv, bwd=False, timing=False, seed=0):
 
 
 if __name__ == '__main__':
-    npm_b200.set_precision('tf32')
+    prec = [a.split('=')[1] for a in sys.argv if a.startswith('--prec=')]
+    npm_b200.set_precision(prec[0] if prec else 'tf32')
     args = [a for a in sys.argv[1:] if not a.startswith('--')]
     dims = [int(a) for a in args] if args else [2, 4, 256, 384]
     run(*dims, bwd='--bwd' in sys.argv, timing='--time' in sys.argv)
