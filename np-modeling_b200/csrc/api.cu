@@ -14,7 +14,7 @@ namespace npm {
 // ------------------------------------------------------------------- state
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_precision{NPM_PREC_3XTF32};
+static std::atomic<int> g_precision{NPM_PREC_BF16X3};     // the default mode meets rtol 1e-3 / atol 1e-4 (as does 3xTF32)
 
 void set_error(const char* fmt, ...) {
     va_list ap;

@@ -22,8 +22,8 @@
 //                                    an MMA K16 slice is a 32-byte column of that row (hi: 0,32; mid: 64,96)
 //     MN-major operand [32 k, rows]: hi image then mid image, each rows/64 slabs of 32 k-rows x 128 B (64 mn), 128B
 //                                    swizzle; an MMA K16 slice is 16 k-rows = 2048 B of a slab
-//                              then fence.proxy.async and arrive on the pair leader's barrier
-//   warp 13     MMA issuer (leader CTA)
+//                              then arrive on their CTA's barrier
+//   warp 13     MMA issuer (leader CTA) / proxy-fence relay (peer CTA)
 // Why not convert on the way in from global memory (the first version of this kernel: LDG.128 into registers, two
 // stages in flight per thread, split, STS)?  Measured (NPM_GEMM_DEBUG_TIMES): the LSU path accepts ~18 B/clk/SM of
 // loads under load — issuing the 8 LDG.128 of a stage stalled 1800 clk — against the 42 B/clk/SM this kernel needs
@@ -185,11 +185,12 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bar_addr   = epi_addr + Cfg::kEpiBytes;
     auto tma_bar    = [&](int s) { return bar_addr + 8u * s; };                 // this CTA's fp32 tiles of stage s have landed
     auto empty_bar  = [&](int s) { return bar_addr + 8u * (S + s); };           // the MMAs that read stage s have completed
-    auto full_bar   = [&](int s) { return bar_addr + 8u * (2 * S + s); };       // leader: both CTAs converted stage s
-    auto tfull_bar  = [&](int a) { return bar_addr + 8u * (3 * S + a); };
-    auto tempty_bar = [&](int a) { return bar_addr + 8u * (3 * S + 2 + a); };
+    auto conv_bar   = [&](int s) { return bar_addr + 8u * (2 * S + s); };       // this CTA's converters have stored stage s
+    auto peer_bar   = [&](int s) { return bar_addr + 8u * (3 * S + s); };       // leader only: the peer's stage s is stored and fenced
+    auto tfull_bar  = [&](int a) { return bar_addr + 8u * (4 * S + a); };
+    auto tempty_bar = [&](int a) { return bar_addr + 8u * (4 * S + 2 + a); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
-        base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + 8 * (3 * S + 4));
+        base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + 8 * (4 * S + 4));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -208,7 +209,8 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int s = 0; s < S; ++s) {
                 ptx::mbar_init(tma_bar(s), 1);                     // this CTA's arrive.expect_tx
                 ptx::mbar_init(empty_bar(s), 1);                   // one multicast commit
-                ptx::mbar_init(full_bar(s), 2 * kConvWarps);       // one arrive per converter warp of each CTA
+                ptx::mbar_init(conv_bar(s), kConvWarps);           // one arrive per converter warp of this CTA
+                ptx::mbar_init(peer_bar(s), 1);                    // the peer relay's remote arrive
             }
             for (int a = 0; a < 2; ++a) {
                 ptx::mbar_init(tfull_bar(a), 1);
@@ -278,7 +280,6 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         OperandConverter<Cfg::kHalfN, B_MN, NTERMS> cb;
         ca.init(pw, lane);
         cb.init(pw, lane);
-        const uint32_t full_leader = ptx::mapa(full_bar(0), 0);
         int total_it = 0;
         for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
             const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
@@ -301,12 +302,11 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (dbg) t2 = clock64();
             ca.store(va, sA);
             cb.store(vb, sA + Cfg::kABytes);
-            ptx::fence_proxy_async_smem();                   // generic-proxy stores -> visible to the tensor core (async proxy)
+            // no proxy fence here: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR costs
+            // ~36 clk per store in flight (700 clk per stage measured with 16 STS per thread); the consumer of this
+            // barrier — a thread with nothing in flight — executes it (issuer / peer relay below)
             __syncwarp();
-            if (lane == 0) {
-                if (rank == 0) ptx::mbar_arrive(full_bar(stage));
-                else           mbar_arrive_remote(full_leader + 8u * stage);
-            }
+            if (lane == 0) ptx::mbar_arrive(conv_bar(stage));
             if (dbg) {
                 const long long t3 = clock64();
                 args.dbg[blockIdx.x * 16 + 0] += t1 - t0;            // wait for the TMA tiles
@@ -315,6 +315,25 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 args.dbg[blockIdx.x * 16 + 3] += 1;
             }
             if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == kMmaWarp && rank == 1) {
+        // ============ peer CTA: proxy-fence relay — the fence sits on the causality path stores -> conv_bar -> fence ->
+        // peer_bar -> MMA, which is what the PTX memory model asks of a proxy fence ============
+        if (ptx::elect_one()) {
+            int total_it = 0;
+            for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+                const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
+                total_it += min(num_kb, kb0 + args.kb_per_split) - kb0;
+            }
+            const uint32_t peer_leader = ptx::mapa(peer_bar(0), 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < total_it; ++it) {
+                ptx::mbar_wait(conv_bar(stage), phase);
+                ptx::fence_proxy_async_smem();
+                mbar_arrive_remote(peer_leader + 8u * stage);
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
         }
     } else if (warp == kMmaWarp) {
         // ============================= MMA issuer (leader CTA) =============================
@@ -340,7 +359,9 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     const long long t0 = args.dbg ? clock64() : 0;
-                    ptx::mbar_wait_cluster(full_bar(stage), phase);     // arrivals come from both CTAs of the pair
+                    ptx::mbar_wait(conv_bar(stage), phase);
+                    ptx::mbar_wait_cluster(peer_bar(stage), phase);
+                    ptx::fence_proxy_async_smem();                      // this CTA's converted stage -> async proxy
                     ptx::tc_fence_after();
                     if (args.dbg) {
                         args.dbg[blockIdx.x * 16 + 8] += clock64() - t0;     // issuer: wait for a converted stage
