@@ -20,12 +20,15 @@ int current_precision();
 bool conv_tc_supported(const void* p0, const void* p1, const void* p2, int64_t N, int64_t H, int64_t W, int64_t Cin,
                        int64_t Cout, int ks);
 int conv_tc_fprop_dgrad(bool dgrad, const float* act, const float* f, const float* bias, float* out, int64_t N, int64_t H,
-                        int64_t W, int64_t Cin, int64_t Cout, int ks, int relu, cudaStream_t stream);
+                        int64_t W, int64_t Cin, int64_t Cout, int ks, int relu, bool bx_mode, cudaStream_t stream);
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
-                  int ks, cudaStream_t stream);
+                  int ks, bool bx_mode, cudaStream_t stream);
+static bool bx_mode() { return current_precision() == NPM_PREC_BF16X3; }
 static bool use_tc(const void* p0, const void* p1, const void* p2, int64_t N, int64_t H, int64_t W, int64_t Cin,
                    int64_t Cout, int ks) {
-    return current_precision() == NPM_PREC_TF32 && getenv("NPM_CONV_SIMT") == nullptr &&
+    // tensor cores in the single-pass TF32 mode and in the split-bf16 mode (bf16 mode: the TF32 kernels)
+    const int prec = current_precision();
+    return (prec == NPM_PREC_TF32 || prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16) && getenv("NPM_CONV_SIMT") == nullptr &&
            conv_tc_supported(p0, p1, p2, N, H, W, Cin, Cout, ks);
 }
 size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
@@ -274,7 +277,7 @@ int npm_conv2d_fwd(const float* x, const float* f, const float* b, float* y, int
     if (rc) return rc;
     NPM_REQUIRE(x && f && y, "conv2d_fwd: NULL pointer");
     if (use_tc(x, f, y, N, H, W, Cin, Cout, ksize))
-        return conv_tc_fprop_dgrad(false, x, f, b, y, N, H, W, Cin, Cout, ksize, relu, (cudaStream_t)stream);
+        return conv_tc_fprop_dgrad(false, x, f, b, y, N, H, W, Cin, Cout, ksize, relu, bx_mode(), (cudaStream_t)stream);
     ConvArgs a{};
     a.act = x; a.other = f; a.out = y; a.bias = b;
     a.N = (int)N; a.H = (int)H; a.W = (int)W; a.Ca = (int)Cin; a.Co = (int)Cout;
@@ -292,7 +295,7 @@ int npm_conv2d_bwd_dx(const float* dy, const float* f, float* dx, int64_t N, int
     if (rc) return rc;
     NPM_REQUIRE(dy && f && dx, "conv2d_bwd_dx: NULL pointer");
     if (use_tc(dy, f, dx, N, H, W, Cin, Cout, ksize))
-        return conv_tc_fprop_dgrad(true, dy, f, nullptr, dx, N, H, W, Cin, Cout, ksize, 0, (cudaStream_t)stream);
+        return conv_tc_fprop_dgrad(true, dy, f, nullptr, dx, N, H, W, Cin, Cout, ksize, 0, bx_mode(), (cudaStream_t)stream);
     if (Cin <= 4 && Cout % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0 && N * H * W < (1ll << 31) &&
         (size_t)ksize * ksize * Cin * Cout * sizeof(float) <= 160 * 1024) {
         cudaStream_t s = (cudaStream_t)stream;
@@ -323,7 +326,7 @@ int npm_conv2d_bwd_dw_db(const float* x, const float* dy, float* dw, float* db, 
     const int64_t Mw = (int64_t)ksize * ksize * Cin;
     if ((rc = npm_fill(dw, 0.0f, Mw * Cout, stream))) return rc;
     if (use_tc(x, dy, dw, N, H, W, Cin, Cout, ksize)) {
-        if ((rc = conv_tc_wgrad(x, dy, dw, N, H, W, Cin, Cout, ksize, s))) return rc;
+        if ((rc = conv_tc_wgrad(x, dy, dw, N, H, W, Cin, Cout, ksize, bx_mode(), s))) return rc;
         if (db == nullptr) return NPM_OK;
         NPM_REQUIRE(workspace != nullptr, "conv2d_bwd_dw_db: workspace is NULL");
         return colsum_launch(dy, db, pixels, Cout, workspace, s);

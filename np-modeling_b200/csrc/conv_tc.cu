@@ -17,8 +17,13 @@
 // A 128-pixel M tile is a TW x TH rectangle of one image (TW = 32, TH = 4 for the 32 x 32 images of
 // BASELINE cfg2), so its box lands in shared memory as 128 rows of 32 channels = the K-major operand
 // layout of csrc/gemm_tc.cu; warp roles, ring, TMEM double buffering and epilogue are that kernel's.
-// Served in TF32 mode for Cin % 4 == 0, Cout % 4 == 0, W >= 8 (TMA needs 16-byte pixel strides — the
-// 3-channel input layer of cfg2 and the 3xTF32 / fp32 modes run the exact fp32 kernel in conv.cu).
+// Served in the TF32 and split-bf16 modes for Cin % 4 == 0, Cout % 4 == 0, W >= 8 (TMA needs 16-byte pixel strides —
+// the 3-channel input layer of cfg2 and the 3xTF32 / fp32 modes run the exact fp32 kernel in conv.cu).
+//
+// BX = true ("bf16x3" mode, rtol 1e-3 / atol 1e-4): the same boxes land as plain fp32 (128-byte swizzle), eight
+// converter warps rewrite every stage in place as bf16 hi / mid images (bx_convert.cuh, as in gemm_bx.cu) and the
+// issuer runs mid*hi + hi*mid + hi*hi with kind::f16.
+#include "bx_convert.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -89,8 +94,10 @@ __device__ __forceinline__ Tile decode(const ConvTcArgs& a, int tile) {
     return t;
 }
 
-template <int MODE, int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+constexpr int kFirstConvWarp = 6;           // BX: warps 6-13 convert
+
+template <int MODE, int BLOCK_N, bool BX>
+__global__ void __launch_bounds__(BX ? 32 * (kFirstConvWarp + bx::kConvWarps) : 192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvTcArgs args) {
     using Cfg = CCfg<BLOCK_N>;
@@ -109,8 +116,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto empty_bar  = [&](int s) { return bar_addr + 8u * (S + s); };
     auto tfull_bar  = [&](int a) { return bar_addr + 8u * (2 * S + a); };
     auto tempty_bar = [&](int a) { return bar_addr + 8u * (2 * S + 2 + a); };
+    auto conv_bar   = [&](int s) { return bar_addr + 8u * (2 * S + 4 + s); };   // BX: the converters have rewritten stage s
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
-        base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + 8 * (2 * S + 4));
+        base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + 8 * (3 * S + 4));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -122,7 +130,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 5) {
         if (lane == 0) {
-            for (int s = 0; s < S; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+            for (int s = 0; s < S; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); ptx::mbar_init(conv_bar(s), bx::kConvWarps); }
             for (int a = 0; a < 2; ++a) { ptx::mbar_init(tfull_bar(a), 1); ptx::mbar_init(tempty_bar(a), 4); }
             ptx::fence_mbar_init();
         }
@@ -185,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 5) {
         // ============================= MMA issuer =============================
-        constexpr uint32_t idesc = ptx::umma_idesc_tf32(kBlockM, BLOCK_N, A_MN, B_MN);
+        constexpr uint32_t idesc = BX ? ptx::umma_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN) : ptx::umma_idesc_tf32(kBlockM, BLOCK_N, A_MN, B_MN);
         constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;
         constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
         int stage = 0, acc = 0;
@@ -197,12 +205,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
             for (int kb = 0; kb < nkb; ++kb) {
-                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::mbar_wait(BX ? conv_bar(stage) : full_bar(stage), phase);
+                if (BX) ptx::fence_proxy_async_smem();       // the converters' generic-proxy stores -> async proxy (see gemm_bx.cu)
                 ptx::tc_fence_after();
                 __syncwarp();
                 if (ptx::elect_one()) {
                     const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
                     const uint32_t sB = sA + Cfg::kABytes;
+                    if (BX) {
+                        constexpr uint64_t dA = A_MN ? bx::kDescMN : bx::kDescK, dB = B_MN ? bx::kDescMN : bx::kDescK;
+#pragma unroll
+                        for (int t = 0; t < 3; ++t)            // mid*hi, hi*mid, hi*hi
+#pragma unroll
+                            for (int sl = 0; sl < 2; ++sl)
+                                ptx::umma_f16(d_tmem, ptx::umma_desc(dA, sA + bx::slice_off<kBlockM, A_MN>(t == 0 ? 1 : 0, sl)),
+                                              ptx::umma_desc(dB, sB + bx::slice_off<BLOCK_N, B_MN>(t == 1 ? 1 : 0, sl)), idesc,
+                                              (kb | t | sl) != 0 ? 1u : 0u);
+                    } else
 #pragma unroll
                     for (int kk = 0; kk < kBlockK / kUmmaK; ++kk)
                         ptx::umma_tf32(d_tmem, ptx::umma_desc(args.desc_a, sA + kk * a_kstep),
@@ -266,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (MODE == FPROP && args.relu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? -0.0f : f[j];
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] < 0.0f ? -0.0f : __uint_as_float(__float_as_uint(f[j]) & 0x7fffffffu);
                 }
                 const uint32_t buf = nstore & 1u;
                 if (lane == 0) ptx::tma_wait_group_read<1>();
@@ -291,6 +310,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (acc == 0) acc_phase ^= 1u;
         }
         if (lane == 0) ptx::tma_wait_group<0>();
+    } else if (BX && warp >= kFirstConvWarp) {
+        // ===================== converters: fp32 stage -> bf16 hi / mid images in place =====================
+        const int pw = warp - kFirstConvWarp;
+        bx::OperandConverter<kBlockM, A_MN, 3> ca;
+        bx::OperandConverter<BLOCK_N, B_MN, 3> cb;
+        ca.init(pw, lane);
+        cb.init(pw, lane);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+            int nkb = num_kb_fd;
+            if (MODE == WGRAD) { const Tile t = decode<MODE>(args, tile); nkb = t.kb1 - t.kb0; }
+            for (int kb = 0; kb < nkb; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
+                float4 va[bx::OperandConverter<kBlockM, A_MN, 3>::NLD];
+                float4 vb[bx::OperandConverter<BLOCK_N, B_MN, 3>::NLD];
+                ca.load(va, sA);
+                cb.load(vb, sA + Cfg::kABytes);
+                bx::bar_sync_conv();
+                ca.store(va, sA);
+                cb.store(vb, sA + Cfg::kABytes);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(conv_bar(stage));
+                if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+        }
     }
 
     ptx::tc_fence_before();
@@ -304,10 +350,10 @@ int pow2_floor(int64_t v, int cap) {
     return p;
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool BX>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const ConvTcArgs& args, cudaStream_t s) {
     using Cfg = CCfg<BN>;
-    auto kern = conv_tc_kernel<MODE, BN>;
+    auto kern = conv_tc_kernel<MODE, BN, BX>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -315,15 +361,20 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, con
         configured = true;
     }
     const int grid = args.total_tiles < num_sms() ? args.total_tiles : num_sms();
-    kern<<<grid, 192, Cfg::kSmemBytes, s>>>(a, b, c, args);
+    kern<<<grid, BX ? 32 * (kFirstConvWarp + bx::kConvWarps) : 192, Cfg::kSmemBytes, s>>>(a, b, c, args);
     count_launch();
     return check_launch("conv_tc_kernel");
 }
 template <int MODE>
-int launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const ConvTcArgs& args, cudaStream_t s) {
-    if (bn == 256) return launch<MODE, 256>(a, b, c, args, s);
-    if (bn == 128) return launch<MODE, 128>(a, b, c, args, s);
-    return launch<MODE, 64>(a, b, c, args, s);
+int launch_bn(int bn, bool bx_mode, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const ConvTcArgs& args, cudaStream_t s) {
+    if (bx_mode) {
+        if (bn == 256) return launch<MODE, 256, true>(a, b, c, args, s);
+        if (bn == 128) return launch<MODE, 128, true>(a, b, c, args, s);
+        return launch<MODE, 64, true>(a, b, c, args, s);
+    }
+    if (bn == 256) return launch<MODE, 256, false>(a, b, c, args, s);
+    if (bn == 128) return launch<MODE, 128, false>(a, b, c, args, s);
+    return launch<MODE, 64, false>(a, b, c, args, s);
 }
 int pick_bn(int64_t n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
 
@@ -338,7 +389,8 @@ bool conv_tc_supported(const void* p0, const void* p1, const void* p2, int64_t N
 
 // fprop (act = x, Ca = Cin, Cn = Cout) and dgrad (act = dy, Ca = Cout, Cn = Cin)
 int conv_tc_fprop_dgrad(bool dgrad, const float* act, const float* f, const float* bias, float* out, int64_t N, int64_t H,
-                        int64_t W, int64_t Cin, int64_t Cout, int ks, int relu, cudaStream_t stream) {
+                        int64_t W, int64_t Cin, int64_t Cout, int ks, int relu, bool bx_mode, cudaStream_t stream) {
+    const bool rnd = !bx_mode;          // TF32 mode: TMA rounds to tf32; split-bf16 mode: plain fp32, 16-byte swizzle atoms
     const int64_t Ca = dgrad ? Cout : Cin, Cn = dgrad ? Cin : Cout;
     ConvTcArgs a{};
     a.H = (int)H; a.W = (int)W; a.NB = (int)N; a.ks = ks; a.pad = ks / 2; a.taps = ks * ks;
@@ -362,18 +414,18 @@ int conv_tc_fprop_dgrad(bool dgrad, const float* act, const float* f, const floa
         const uint64_t dims[4] = {(uint64_t)Ca, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t str[3] = {(uint64_t)Ca, (uint64_t)Ca * W, (uint64_t)Ca * W * H};
         const uint32_t box[4] = {32, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-        if ((rc = make_tensor_map_4d_box(&tA, act, dims, str, box, true, false))) return rc;
+        if ((rc = make_tensor_map_4d_box(&tA, act, dims, str, box, rnd, false))) return rc;
     }
     {   // filters f[kh, kw, Cin, Cout]
         const uint64_t str[3] = {(uint64_t)Cout, (uint64_t)Cout * Cin, (uint64_t)Cout * Cin * ks};
         if (!dgrad) {
             const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ks, (uint64_t)ks};
             const uint32_t box[4] = {32, 32, 1, 1};
-            if ((rc = make_tensor_map_4d_box(&tB, f, dims, str, box, true, true))) return rc;
+            if ((rc = make_tensor_map_4d_box(&tB, f, dims, str, box, rnd, !bx_mode))) return rc;
         } else {
             const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ks, (uint64_t)ks};
             const uint32_t box[4] = {32, (uint32_t)bn, 1, 1};
-            if ((rc = make_tensor_map_4d_box(&tB, f, dims, str, box, true, false))) return rc;
+            if ((rc = make_tensor_map_4d_box(&tB, f, dims, str, box, rnd, false))) return rc;
         }
     }
     {
@@ -382,12 +434,13 @@ int conv_tc_fprop_dgrad(bool dgrad, const float* act, const float* f, const floa
         const uint32_t box[4] = {32, (uint32_t)a.PW, (uint32_t)a.PH, 1};
         if ((rc = make_tensor_map_4d_box(&tC, out, dims, str, box, false, false))) return rc;
     }
-    return dgrad ? launch_bn<DGRAD>(bn, tA, tB, tC, a, stream) : launch_bn<FPROP>(bn, tA, tB, tC, a, stream);
+    return dgrad ? launch_bn<DGRAD>(bn, bx_mode, tA, tB, tC, a, stream) : launch_bn<FPROP>(bn, bx_mode, tA, tB, tC, a, stream);
 }
 
 // dw[kh, kw, Cin, Cout] (must be zero on entry: partial sums are TMA-reduced into it)
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
-                  int ks, cudaStream_t stream) {
+                  int ks, bool bx_mode, cudaStream_t stream) {
+    const bool rnd = !bx_mode;
     ConvTcArgs a{};
     a.H = (int)H; a.W = (int)W; a.NB = (int)N; a.ks = ks; a.pad = ks / 2; a.taps = ks * ks;
     a.Nn = (int)Cout; a.Mw = (int)Cin;
@@ -416,13 +469,13 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int64_t N, int64_t
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t str[3] = {(uint64_t)Cin, (uint64_t)Cin * W, (uint64_t)Cin * W * H};
         const uint32_t box[4] = {32, (uint32_t)a.PW, (uint32_t)a.PH, 1};
-        if ((rc = make_tensor_map_4d_box(&tA, x, dims, str, box, true, true))) return rc;
+        if ((rc = make_tensor_map_4d_box(&tA, x, dims, str, box, rnd, !bx_mode))) return rc;
     }
     {
         const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t str[3] = {(uint64_t)Cout, (uint64_t)Cout * W, (uint64_t)Cout * W * H};
         const uint32_t box[4] = {32, (uint32_t)a.PW, (uint32_t)a.PH, 1};
-        if ((rc = make_tensor_map_4d_box(&tB, dy, dims, str, box, true, true))) return rc;
+        if ((rc = make_tensor_map_4d_box(&tB, dy, dims, str, box, rnd, !bx_mode))) return rc;
     }
     {
         const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)Cin, (uint64_t)ks, (uint64_t)ks};
@@ -430,7 +483,7 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int64_t N, int64_t
         const uint32_t box[4] = {32, 32, 1, 1};
         if ((rc = make_tensor_map_4d_box(&tC, dw, dims, str, box, false, false))) return rc;
     }
-    return launch_bn<WGRAD>(bn, tA, tB, tC, a, stream);
+    return launch_bn<WGRAD>(bn, bx_mode, tA, tB, tC, a, stream);
 }
 
 }  // namespace npm
