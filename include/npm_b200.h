@@ -220,6 +220,15 @@ int npm_add3(const float* a, const float* b, const float* c, float* out,
 int npm_scale(float* x, float s, int64_t n, npm_stream_t stream);
 int npm_fill(float* x, float v, int64_t n, npm_stream_t stream);
 
+/* ---- token embedding (the reference has none) ------------- */
+/* out[i,:] = table[ids[i],:] for n int32 token ids (clamped to [0, vocab)). */
+int npm_embedding_fwd(const float* table, const int32_t* ids, float* out,
+                      int64_t n, int64_t d, int64_t vocab, npm_stream_t stream);
+/* dtable = 0; dtable[ids[i],:] += dy[i,:] (red.global.add: the order in which
+ * rows of the same id are summed is not fixed). */
+int npm_embedding_bwd(const float* dy, const int32_t* ids, float* dtable,
+                      int64_t n, int64_t d, int64_t vocab, npm_stream_t stream);
+
 /* ---- attention core (layers/attentions.py:103-112, :146-162) -------------- */
 /* q [B,Sq,H,dk], k [B,Skv,H,dk], v [B,Skv,H,dv]  → o [B,Sq,H,dv]
  * o = softmax(q k^T / sqrt(dk)) v per (b,h); unmasked (the reference's mask

@@ -182,6 +182,37 @@ int dropout_apply(const float* x, float* y, int64_t n, float keep_prob, uint64_t
 
 using namespace npm;
 
+
+namespace npm {
+namespace {
+// Token embedding (beyond the reference: the reference has no embedding layer).  One warp per token
+// row: out[i, :] = table[ids[i], :] (+ pos[i % S, :]); the backward scatters dy rows into dtable with red.global.add
+// (rows of the same token id collide, so the sum order — and the last bits — depend on scheduling).
+__global__ void __launch_bounds__(256) embedding_fwd_kernel(const float* __restrict__ table, const int32_t* __restrict__ ids,
+                                                            float* __restrict__ out, int64_t n, int d, int vocab) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        int id = ids[i];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const float* src = table + (int64_t)id * d;
+        float* dst = out + i * d;
+        for (int c = lane; c < d; c += 32) dst[c] = __ldg(src + c);
+    }
+}
+__global__ void __launch_bounds__(256) embedding_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ ids,
+                                                            float* __restrict__ dtable, int64_t n, int d, int vocab) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        int id = ids[i];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        float* dst = dtable + (int64_t)id * d;
+        const float* src = dy + i * d;
+        for (int c = lane; c < d; c += 32) atomicAdd(dst + c, src[c]);
+    }
+}
+}  // namespace
+}  // namespace npm
+
 extern "C" {
 
 int npm_relu_fwd(const float* x, float* y, int64_t n, npm_stream_t stream) {
@@ -210,6 +241,22 @@ int npm_add3(const float* a, const float* b, const float* c, float* out, int64_t
 }
 int npm_scale(float* x, float s, int64_t n, npm_stream_t stream) {
     return launch_ew1("scale", x, x, n, ScaleF{s}, (cudaStream_t)stream);
+}
+int npm_embedding_fwd(const float* table, const int32_t* ids, float* out, int64_t n, int64_t d, int64_t vocab, npm_stream_t stream) {
+    NPM_REQUIRE(table && ids && out && d > 0 && vocab > 0 && d < (1ll << 30) && vocab < (1ll << 31), "embedding_fwd: bad arguments");
+    if (n <= 0) return NPM_OK;
+    npm::embedding_fwd_kernel<<<bw_grid((size_t)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(table, ids, out, n, (int)d, (int)vocab);
+    count_launch();
+    return check_launch("embedding_fwd_kernel");
+}
+int npm_embedding_bwd(const float* dy, const int32_t* ids, float* dtable, int64_t n, int64_t d, int64_t vocab, npm_stream_t stream) {
+    NPM_REQUIRE(dy && ids && dtable && d > 0 && vocab > 0 && d < (1ll << 30) && vocab < (1ll << 31), "embedding_bwd: bad arguments");
+    cudaError_t e = cudaMemsetAsync(dtable, 0, sizeof(float) * (size_t)vocab * d, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("embedding_bwd memset: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+    if (n <= 0) return NPM_OK;
+    npm::embedding_bwd_kernel<<<bw_grid((size_t)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(dy, ids, dtable, n, (int)d, (int)vocab);
+    count_launch();
+    return check_launch("embedding_bwd_kernel");
 }
 int npm_fill(float* x, float v, int64_t n, npm_stream_t stream) {
     if (n <= 0) return NPM_OK;

@@ -21,6 +21,21 @@ def _add3(parts):
     return out
 
 
+class KVCache:
+    """Decode-time cache of one MultiHeadAttention (the reference's `# TODO: support cache`,
+    transformer.py:120).  Self-attention: the projected keys / values of every token decoded so far, TIME-major
+    `[max_len, B, H*d]` — with the batch folded into the head axis this is the `[S, B*H, d]` layout the attention core
+    already takes (token stride B*H*d), so a step attends over the first `length` rows without any copy.
+    Cross-attention: the projected memory, computed once."""
+
+    def __init__(self, max_len: int, batch: int, hk: int, hv: int):
+        self.k = device.empty((max_len, batch, hk))
+        self.v = device.empty((max_len, batch, hv))
+        self.max_len = max_len
+        self.length = 0
+        self.memory_kv = None      # cross-attention: [B*Skv, 2*H*d] projected memory (k | v)
+
+
 class MultiHeadAttention(layer.StatefulLayer):
     def __init__(self, num_heads: int, *args, causal: bool = False, **kwargs):
         """`causal=True` (keyword-only, BEYOND the reference — SURVEY.md §8 f1): key position t > query position s is
@@ -168,6 +183,51 @@ class MultiHeadAttention(layer.StatefulLayer):
 
         o = self._project(values.reshape(batch * sq, h * dv), wo, bo, wo.shape[0], _residual)
         return o.reshape(batch, sq, wo.shape[0])
+
+    # ---- decode-time step with a key/value cache (inference) ---------------------------------------
+    def decode_step(self, x_t, cache: KVCache, memory=None, _residual=None):
+        """One new token per sequence: `x_t` [B, 1, D].  memory is None: causal self-attention over the tokens decoded so
+        far (the new token's k / v are appended to `cache`); else cross-attention over `memory` [B, Skv, D], whose k / v
+        projections are computed on the first call and kept in `cache`.  Equals row t of `forward` on the full
+        sequence with `causal=True` (tests/test_parity_gpu.py::test_kv_cache_decode_equals_full_forward)."""
+        x_t = device.asdevice(x_t)
+        batch, one, dmodel = x_t.shape
+        assert one == 1, 'decode_step takes one token per sequence'
+        h, dk, dv = self._num_heads, self._key_dim, self._value_dim
+        assert dk == dv, 'the cached path keeps k | v packed'
+        hd = h * dk
+        packs = self._packed_params()
+        assert packs is not None
+        wq, wo, bq, bo = self._p('_wq'), self._p('_wo'), self._p('_bq'), self._p('_bo')
+        x2 = x_t.reshape(batch, dmodel)
+        q2 = self._project(x2, wq, bq, hd)                                            # [B, H*dk]
+        values = device.empty((batch, 1, h, dv))
+        s = device.stream()
+        if memory is None:
+            assert cache.length < cache.max_len, 'KVCache is full'
+            kv2 = self._project(x2, packs[0][1:3], packs[1][1:3], 2 * hd)             # [B, 2*H*dk]: k_t | v_t
+            t = cache.length
+            cache.k.t[t].copy_(kv2.t[:, :hd])
+            cache.v.t[t].copy_(kv2.t[:, hd:])
+            cache.length = t + 1
+            # batch folded into heads: q [1, 1, B*H, d], k / v [length, B*H, d] with token stride B*H*d
+            fb, fh, skv = 1, batch * h, cache.length
+            ld = MhaStrides(q=batch * hd, k=batch * hd, v=batch * hd, causal=0)       # the last position sees every cached token
+            kp, vp = cache.k.ptr, cache.v.ptr
+        else:
+            memory = device.asdevice(memory)
+            skv = memory.shape[1]
+            if cache.memory_kv is None:
+                cache.memory_kv = self._project(memory.reshape(batch * skv, memory.shape[2]), packs[0][1:3], packs[1][1:3], 2 * hd)
+            fb, fh = batch, h
+            ld = MhaStrides(q=hd, k=2 * hd, v=2 * hd, causal=0)
+            kp, vp = cache.memory_kv.ptr, cache.memory_kv.ptr + 4 * hd
+        path = int(C.npm_mha_core_path(fb, fh, 1, skv, dk, dv))
+        ld.path = 1 + path
+        saved = device.workspace(C.npm_mha_core_saved_bytes_for(path, fb, fh, 1, skv, dk, dv))
+        C.npm_mha_core_fwd_strided(q2.ptr, kp, vp, values.ptr, saved.data_ptr(), fb, fh, 1, skv, dk, dv, ctypes.byref(ld), s)
+        o = self._project(values.reshape(batch, h * dv), wo, bo, wo.shape[0], _residual)
+        return o.reshape(batch, 1, wo.shape[0])
 
     def backward(self, dy, optimizer_: optimizer.Optimizer, _sum_inputs: bool = False):
         """Returns `(dquery, dkey, dvalue)` (attentions.py:199).  `_sum_inputs=True` (B200 extension used by

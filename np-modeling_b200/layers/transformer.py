@@ -158,6 +158,37 @@ class TransformerDecoder(layer.Layer):
 
         return out.reshape(batch, seq_len_q, features)
 
+    # ---- decode-time step with key/value caches (inference; SURVEY.md §8 f4, transformer.py:120 "TODO: support cache")
+    def new_cache(self, batch: int, max_len: int):
+        h, dk = self._self_attention._num_heads, self._self_attention._key_dim
+        return (attentions.KVCache(max_len, batch, h * dk, h * dk), attentions.KVCache(0, batch, h * dk, h * dk))
+
+    def decode_step(self, x_t, kv, cache):
+        """`forward` for ONE new token per sequence (`x_t` [B, 1, D]) given the tokens already decoded into `cache`
+        (from `new_cache`); dropout is the identity (inference).  The layer must have been initialised by a forward
+        call (or a loaded checkpoint) with `causal=True` semantics in mind: position t sees positions <= t."""
+        x_t = device.asdevice(x_t)
+        batch, one, features = x_t.shape
+        self_cache, cross_cache = cache
+        skip = x_t
+        out = self._norm1(x_t) if self._norm_first else x_t
+        out = self._self_attention.decode_step(out, self_cache, _residual=skip)
+        if not self._norm_first:
+            out = self._norm1(out)
+        skip = out
+        h = self._norm2(out) if self._norm_first else out
+        out = self._cross_attention.decode_step(h, cross_cache, memory=kv, _residual=skip)
+        if not self._norm_first:
+            out = self._norm2(out)
+        out = out.reshape(-1, features)
+        skip = out
+        h = self._norm3(out) if self._norm_first else out
+        h = self._dense1(h, _alias_ok=True)
+        out = self._dense2(h, _residual=skip)
+        if not self._norm_first:
+            out = self._norm3(out)
+        return out.reshape(batch, 1, features)
+
     def backward(self, dy, optimizer_):
         dy = device.asdevice(dy)
         batch, seq_len_q, features = dy.shape

@@ -86,6 +86,8 @@ SIGNATURES = {
     'npm_add3': (c_int, [P, P, P, P, I64, P]),
     'npm_scale': (c_int, [P, F, I64, P]),
     'npm_fill': (c_int, [P, F, I64, P]),
+    'npm_embedding_fwd': (c_int, [P, P, P, I64, I64, I64, P]),
+    'npm_embedding_bwd': (c_int, [P, P, P, I64, I64, I64, P]),
     'npm_mha_core_path': (c_int, [I64] * 6),
     'npm_mha_core_saved_bytes_for': (c_size_t, [I] + [I64] * 6),
     'npm_mha_core_bwd_scratch_bytes_for': (c_size_t, [I] + [I64] * 6),
