@@ -342,6 +342,9 @@ def run_b200(args):
         for _ in range(steps):
             trainer.train(inputs, targets, 1, adam)
             if read_loss:
+                # the input pipeline's job: start the NEXT step's host->device copies (copy stream) before blocking on
+                # this step's loss; the same bytes still cross PCIe every step
+                trainer.prefetch(inputs, targets)
                 float(trainer.last_loss)
         e1.record()
         torch.cuda.synchronize()

@@ -45,6 +45,7 @@ constexpr int kD   = 64;          // head dim
 constexpr int kTileBytes  = kBlk * kD * 4;   // 32 KB
 constexpr int kChunkBytes = 16384;           // one {32 d, 128 rows} TMA box
 constexpr int kThreads = 384;       // 4 control warps + 4 exp warps + 4 dS warps
+constexpr int kThreadsBx = 640;     // split-bf16 variant: 8 exp warps + 8 dS warps (two warps per TMEM lane quarter, each half the columns)
 
 struct BwdArgs {
     int B, H, Sq, Skv;
@@ -69,8 +70,9 @@ __device__ __forceinline__ uint32_t cvt_tf32(float x) {
 }
 // fp32 → tf32 round-to-nearest on the integer ALU (kind::tf32 ignores the low 13 bits); see attn_fwd.cu
 __device__ __forceinline__ uint32_t rna_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
-__device__ __forceinline__ void bar_sync_128(int id) {
-    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+template <int N>
+__device__ __forceinline__ void bar_sync_n(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
 }
 // both 16 KB boxes of a [128 rows, 64] tile: fp32 = d 0..31 and d 32..63; split bf16 = hi plane and mid plane
 template <bool BX>
@@ -107,14 +109,14 @@ __device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_
 template <bool BX>
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool accumulate) {
     if (BX) {
-        // A: per 64-k half [32 columns hi | 32 columns mid], two bf16 per column; a K16 step = 8 columns of A and 16
+        // A: per 32-k quarter [16 columns hi | 16 columns mid], two bf16 per column; a K16 step = 8 columns of A and 16
         // rows (2048 B) of the B image (plain 128-byte swizzle, N = 64 = one 128-byte chunk, 8-row groups 1024 B apart)
         const uint64_t desc_mn = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, kChunkBytes, 1024);
 #pragma unroll
         for (int t = 0; t < 3; ++t)
 #pragma unroll
             for (int kk = 0; kk < kBlk / 16; ++kk)
-                ptx::umma_f16_ts(d_tmem, a_tmem + (kk >> 2) * 64 + (t == 0 ? 32 : 0) + (kk & 3) * 8,
+                ptx::umma_f16_ts(d_tmem, a_tmem + (kk >> 1) * 32 + (t == 0 ? 16 : 0) + (kk & 1) * 8,
                                  ptx::umma_desc(desc_mn, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 2048), idesc,
                                  (accumulate || (t | kk) != 0) ? 1u : 0u);
         return;
@@ -134,6 +136,19 @@ __device__ __forceinline__ void split_pack(float p0, float p1, uint32_t& hi, uin
 __device__ __forceinline__ float unpack_lo(uint32_t hi, uint32_t mid) { return __uint_as_float(hi << 16) + __uint_as_float(mid << 16); }
 __device__ __forceinline__ float unpack_hi(uint32_t hi, uint32_t mid) {
     return __uint_as_float(hi & 0xffff0000u) + __uint_as_float(mid & 0xffff0000u);
+}
+// 32 columns of one accumulator row → 128 contiguous bytes of global memory
+__device__ __forceinline__ void store_acc_half(uint32_t taddr, float* dst, bool live) {
+    uint32_t o[32];
+    ptx::tmem_ld_32x32(taddr, o);
+    ptx::tmem_ld_wait();
+    if (live) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            d4[k] = make_float4(__uint_as_float(o[4 * k]), __uint_as_float(o[4 * k + 1]), __uint_as_float(o[4 * k + 2]),
+                                __uint_as_float(o[4 * k + 3]));
+    }
 }
 // one accumulator row (64 fp32 in TMEM) → 256 contiguous bytes of global memory
 __device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool live) {
@@ -163,7 +178,7 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, float* dst, bool l
 constexpr int kKvSmem = 6 * kTileBytes + 2 * 2 * kBlk * 4 + 1024 + 256;
 
 template <bool CAUSAL, bool BX>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(BX ? kThreadsBx : kThreads, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmQt,
                      const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmVr,
                      const __grid_constant__ CUtensorMap tmDOr, const __grid_constant__ CUtensorMap tmDOt,
@@ -195,7 +210,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
     if (warp == 3) {
         if (lane == 0) {
             for (int i = 0; i < NBAR; ++i)
-                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DS_READY) ? 128 : 1);
+                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DS_READY) ? (BX ? 256 : 128) : 1);
             ptx::fence_mbar_init();
         }
         __syncwarp();
@@ -352,8 +367,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
         // ============ warps 4-7: P^T = exp2(c S^T - L[q]) in place.  warps 8-11: dS^T = P^T o (dP^T - D[q]) / sqrt(dk)
         // in place over dP^T.  Thread = kv row = TMEM lane; the two groups run one block apart, so the
         // exponentials of block g+1 overlap the dS / dK / dP^T chain of block g. ============
-        const bool exp_group = warp < 8;
+        // BX: 8 warps per group — warps w and w + 4 of a group share a TMEM lane quarter and take half of the 128
+        // columns each (quarters q0..q1 of 32 columns), which halves the serial elementwise time on the
+        // S^T -> P^T -> dV and dP^T -> dS^T -> dK chains (the split to bf16 hi / mid doubles the work per element)
+        constexpr int NSET = BX ? 2 : 1;
+        const bool exp_group = warp < 4 + 4 * NSET;
         const int wq = warp & 3;
+        const int hsel = BX ? ((warp - 4) >> 2) & 1 : 0;
+        const int q0 = BX ? 2 * hsel : 0, q1 = BX ? 2 * hsel + 2 : 4;
         const int tid = wq * 32 + lane;             // kv row within the tile (also: which q column's L / D this thread stages)
         const uint32_t lane_off = uint32_t(wq * 32) << 16;
         const float c = args.c, scale = args.scale;
@@ -376,18 +397,43 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             for (int i = first_q(item); i < n_q; ++i, ++g) {
                 const uint32_t buf = g & 1u;
                 // stage this block's L (or D) — fetched one block ago — and prefetch the next block's
-                stage[buf * kBlk + tid] = next;
+                if (hsel == 0) stage[buf * kBlk + tid] = next;
                 {
                     int ni = i + 1, nitem = item;
                     if (ni == n_q) { nitem = item + gridDim.x; ni = nitem < args.total_items ? first_q(nitem) : 0; }
                     if (nitem < args.total_items) next = fetch(nitem, ni);
                 }
-                bar_sync_128(bar_id);
+                bar_sync_n<128 * NSET>(bar_id);
                 const float4* V4 = reinterpret_cast<const float4*>(stage + buf * kBlk);
                 if (exp_group) {
                     ptx::mbar_wait(bar(ST_FULL0 + buf), (g >> 1) & 1);
                     ptx::tc_fence_after();
                     const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
+                    if (BX) {
+#pragma unroll
+                        for (int qt = q0; qt < q1; ++qt) {          // 32 columns: S^T in, [16 columns hi | 16 columns mid] of P^T out
+                            float p[32];
+                            ptx::tmem_ld_32x32(s_tmem + qt * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 32; k += 4) {
+                                const float4 l4 = V4[(qt * 32 + k) >> 2];
+                                p[k]     = ptx::ex2(fmaf(p[k], c, -l4.x));
+                                p[k + 1] = ptx::ex2(fmaf(p[k + 1], c, -l4.y));
+                                p[k + 2] = ptx::ex2(fmaf(p[k + 2], c, -l4.z));
+                                p[k + 3] = ptx::ex2(fmaf(p[k + 3], c, -l4.w));
+                            }
+                            if (CAUSAL && i == nt) {
+#pragma unroll
+                                for (int k = 0; k < 32; ++k)
+                                    if (qt * 32 + k < tid) p[k] = 0.0f;
+                            }
+                            uint32_t hm[32];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) split_pack(p[2 * k], p[2 * k + 1], hm[k], hm[16 + k]);
+                            ptx::tmem_st_32x32(s_tmem + qt * 32, hm);
+                        }
+                    } else
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         if (args.debug_skip & 1) break;
@@ -412,16 +458,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                             for (int k = 0; k < 64; ++k)
                                 if (hf * 64 + k < tid) p[k] = 0.0f;
                         }
-                        if (BX) {
-                            uint32_t hi[32], mid[32];
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) split_pack(p[2 * k], p[2 * k + 1], hi[k], mid[k]);
-                            ptx::tmem_st_32x32(s_tmem + hf * 64, hi);
-                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, mid);
-                        } else {
-                            ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
-                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
-                        }
+                        ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
                     }
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before();
@@ -433,25 +471,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     const uint32_t p_tmem = tmem_base + lane_off + buf * kBlk;
                     if (BX) {
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            uint32_t ph[32], pm[32], dp[64];
-                            ptx::tmem_ld_32x32(p_tmem + hf * 64, ph);
-                            ptx::tmem_ld_32x32(p_tmem + hf * 64 + 32, pm);
-                            ptx::tmem_ld_32x32(tm_dpt + lane_off + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
-                            ptx::tmem_ld_32x32(tm_dpt + lane_off + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+                        for (int qt = q0; qt < q1; ++qt) {
+                            uint32_t pm[32], dp[32];               // pm: [16 hi | 16 mid] of P^T, then of dS^T
+                            ptx::tmem_ld_32x32(p_tmem + qt * 32, pm);
+                            ptx::tmem_ld_32x32(tm_dpt + lane_off + qt * 32, dp);
                             ptx::tmem_ld_wait();
 #pragma unroll
-                            for (int k = 0; k < 32; k += 2) {          // pairs (2k, 2k+1), (2k+2, 2k+3) = one float4 of D
-                                const float4 d4 = V4[(hf * 64 + 2 * k) >> 2];
-                                const float s0 = unpack_lo(ph[k], pm[k]) * ((__uint_as_float(dp[2 * k]) - d4.x) * scale);
-                                const float s1 = unpack_hi(ph[k], pm[k]) * ((__uint_as_float(dp[2 * k + 1]) - d4.y) * scale);
-                                const float s2 = unpack_lo(ph[k + 1], pm[k + 1]) * ((__uint_as_float(dp[2 * k + 2]) - d4.z) * scale);
-                                const float s3 = unpack_hi(ph[k + 1], pm[k + 1]) * ((__uint_as_float(dp[2 * k + 3]) - d4.w) * scale);
-                                split_pack(s0, s1, ph[k], pm[k]);
-                                split_pack(s2, s3, ph[k + 1], pm[k + 1]);
+                            for (int k = 0; k < 16; k += 2) {      // packed columns k, k+1 = elements 2k .. 2k+3 = one float4 of D
+                                const float4 d4 = V4[(qt * 32 + 2 * k) >> 2];
+                                const float s0 = unpack_lo(pm[k], pm[16 + k]) * ((__uint_as_float(dp[2 * k]) - d4.x) * scale);
+                                const float s1 = unpack_hi(pm[k], pm[16 + k]) * ((__uint_as_float(dp[2 * k + 1]) - d4.y) * scale);
+                                const float s2 = unpack_lo(pm[k + 1], pm[17 + k]) * ((__uint_as_float(dp[2 * k + 2]) - d4.z) * scale);
+                                const float s3 = unpack_hi(pm[k + 1], pm[17 + k]) * ((__uint_as_float(dp[2 * k + 3]) - d4.w) * scale);
+                                split_pack(s0, s1, pm[k], pm[16 + k]);
+                                split_pack(s2, s3, pm[k + 1], pm[17 + k]);
                             }
-                            ptx::tmem_st_32x32(tm_dpt + lane_off + hf * 64, ph);
-                            ptx::tmem_st_32x32(tm_dpt + lane_off + hf * 64 + 32, pm);
+                            ptx::tmem_st_32x32(tm_dpt + lane_off + qt * 32, pm);
                         }
                     } else
 #pragma unroll
@@ -482,8 +517,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             const int t = nt * kBlk + tid;
             const bool live = t < args.Skv;
             const size_t tok = (size_t)b * args.Skv + (live ? t : 0);
-            if (exp_group) store_acc_row(tm_dv + lane_off, args.dv + tok * args.lddv + (size_t)h * kD, live);
-            else           store_acc_row(tm_dk + lane_off, args.dk + tok * args.lddk + (size_t)h * kD, live);
+            if (BX) {       // each of the two warp sets stores 32 of the 64 columns
+                if (exp_group) store_acc_half(tm_dv + lane_off + 32 * hsel, args.dv + tok * args.lddv + (size_t)h * kD + 32 * hsel, live);
+                else           store_acc_half(tm_dk + lane_off + 32 * hsel, args.dk + tok * args.lddk + (size_t)h * kD + 32 * hsel, live);
+            } else {
+                if (exp_group) store_acc_row(tm_dv + lane_off, args.dv + tok * args.lddv + (size_t)h * kD, live);
+                else           store_acc_row(tm_dk + lane_off, args.dk + tok * args.lddk + (size_t)h * kD, live);
+            }
             ptx::tc_fence_before();
         }
     }
@@ -498,7 +538,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
 constexpr int kDqSmem = 7 * kTileBytes + 1024 + 256;
 
 template <bool CAUSAL, bool BX>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(BX ? kThreadsBx : kThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_constant__ CUtensorMap tmDOr,
                    const __grid_constant__ CUtensorMap tmKr, const __grid_constant__ CUtensorMap tmKt,
                    const __grid_constant__ CUtensorMap tmVr, const BwdArgs args) {
@@ -527,7 +567,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
     if (warp == 3) {
         if (lane == 0) {
             for (int i = 0; i < NBAR; ++i)
-                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DS_READY) ? 128 : 1);
+                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DS_READY) ? (BX ? 256 : 128) : 1);
             ptx::fence_mbar_init();
         }
         __syncwarp();
@@ -645,8 +685,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
     } else if (warp >= 4) {
         // ============ warps 4-7: P = exp2(c S - L) in place.  warps 8-11: dS = P o (dP - D) / sqrt(dk) in place over
         // dP, then the dQ epilogue.  Thread = q row = TMEM lane; the groups run one block apart. ============
-        const bool exp_group = warp < 8;
+        constexpr int NSET = BX ? 2 : 1;               // BX: two warps per TMEM lane quarter, half of the columns each (see dkdv)
+        const bool exp_group = warp < 4 + 4 * NSET;
         const int wq = warp & 3;
+        const int hsel = BX ? ((warp - 4) >> 2) & 1 : 0;
+        const int q0 = BX ? 2 * hsel : 0, q1 = BX ? 2 * hsel + 2 : 4;
         const int tid = wq * 32 + lane;
         const uint32_t lane_off = uint32_t(wq * 32) << 16;
         const float c = args.c, scale = args.scale;
@@ -673,6 +716,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                     ptx::mbar_wait(bar(S_FULL0 + buf), (g >> 1) & 1);
                     ptx::tc_fence_after();
                     const int kv_left = args.Skv - j * kBlk;
+                    if (BX) {
+#pragma unroll
+                        for (int qt = q0; qt < q1; ++qt) {
+                            float p[32];
+                            ptx::tmem_ld_32x32(s_tmem + qt * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const float e = ptx::ex2(fmaf(p[k], c, -mine));
+                                const bool masked = CAUSAL && j == mt && qt * 32 + k > tid;          // kv position after q position
+                                p[k] = (qt * 32 + k < kv_left && !masked) ? e : 0.0f;   // zero-filled K rows past Skv
+                            }
+                            uint32_t hm[32];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) split_pack(p[2 * k], p[2 * k + 1], hm[k], hm[16 + k]);
+                            ptx::tmem_st_32x32(s_tmem + qt * 32, hm);
+                        }
+                    } else
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         float p[64];
@@ -681,21 +742,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int k = 0; k < 64; ++k) {
-                            const float e0 = ptx::ex2(fmaf(p[k], c, -mine));
-                            const float e = BX ? e0 : __uint_as_float(rna_tf32(e0));
+                            const float e = __uint_as_float(rna_tf32(ptx::ex2(fmaf(p[k], c, -mine))));
                             const bool masked = CAUSAL && j == mt && hf * 64 + k > tid;          // kv position after q position
                             p[k] = (hf * 64 + k < kv_left && !masked) ? e : 0.0f;   // zero-filled K rows past Skv
                         }
-                        if (BX) {
-                            uint32_t hi[32], mid[32];
-#pragma unroll
-                            for (int k = 0; k < 32; ++k) split_pack(p[2 * k], p[2 * k + 1], hi[k], mid[k]);
-                            ptx::tmem_st_32x32(s_tmem + hf * 64, hi);
-                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, mid);
-                        } else {
-                            ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
-                            ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
-                        }
+                        ptx::tmem_st_32x32(s_tmem + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_st_32x32(s_tmem + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&p[32]));
                     }
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before();
@@ -707,21 +759,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                     const float dscale = mine * scale;
                     if (BX) {
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            uint32_t ph[32], pm[32], dp[64];
-                            ptx::tmem_ld_32x32(s_tmem + hf * 64, ph);
-                            ptx::tmem_ld_32x32(s_tmem + hf * 64 + 32, pm);
-                            ptx::tmem_ld_32x32(tm_dp + lane_off + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&dp[0]));
-                            ptx::tmem_ld_32x32(tm_dp + lane_off + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&dp[32]));
+                        for (int qt = q0; qt < q1; ++qt) {
+                            uint32_t pm[32], dp[32];               // pm: [16 hi | 16 mid] of P, then of dS
+                            ptx::tmem_ld_32x32(s_tmem + qt * 32, pm);
+                            ptx::tmem_ld_32x32(tm_dp + lane_off + qt * 32, dp);
                             ptx::tmem_ld_wait();
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) {
-                                const float s0 = unpack_lo(ph[k], pm[k]) * fmaf(__uint_as_float(dp[2 * k]), scale, -dscale);
-                                const float s1 = unpack_hi(ph[k], pm[k]) * fmaf(__uint_as_float(dp[2 * k + 1]), scale, -dscale);
-                                split_pack(s0, s1, ph[k], pm[k]);
+                            for (int k = 0; k < 16; ++k) {
+                                const float s0 = unpack_lo(pm[k], pm[16 + k]) * fmaf(__uint_as_float(dp[2 * k]), scale, -dscale);
+                                const float s1 = unpack_hi(pm[k], pm[16 + k]) * fmaf(__uint_as_float(dp[2 * k + 1]), scale, -dscale);
+                                split_pack(s0, s1, pm[k], pm[16 + k]);
                             }
-                            ptx::tmem_st_32x32(tm_dp + lane_off + hf * 64, ph);
-                            ptx::tmem_st_32x32(tm_dp + lane_off + hf * 64 + 32, pm);
+                            ptx::tmem_st_32x32(tm_dp + lane_off + qt * 32, pm);
                         }
                     } else
 #pragma unroll
@@ -746,7 +795,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 ptx::tc_fence_after();
                 const int sq = mt * kBlk + tid;
                 const bool live = sq < args.Sq;
-                store_acc_row(tm_dq + lane_off, args.dq + ((size_t)b * args.Sq + (live ? sq : 0)) * args.lddq + (size_t)h * kD, live);
+                float* drow = args.dq + ((size_t)b * args.Sq + (live ? sq : 0)) * args.lddq + (size_t)h * kD;
+                if (BX) store_acc_half(tm_dq + lane_off + 32 * hsel, drow + 32 * hsel, live);      // two warp sets, 32 columns each
+                else    store_acc_row(tm_dq + lane_off, drow, live);
                 ptx::tc_fence_before();
             }
         }
@@ -935,7 +986,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         if (causal) while (grid > 1 && gcd_int(grid, a.n_kv) != 1) --grid;     // see attn_fwd_launch
         auto kern = causal ? (bx ? attn_bwd_dkdv_kernel<true, true> : attn_bwd_dkdv_kernel<true, false>)
                            : (bx ? attn_bwd_dkdv_kernel<false, true> : attn_bwd_dkdv_kernel<false, false>);
-        launch_pdl(kern, dim3(grid), dim3(kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dkdv_kernel"))) return rc;
         if (dbg_times) {
@@ -962,7 +1013,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         if (causal) while (grid > 1 && gcd_int(grid, a.n_q) != 1) --grid;
         auto kern = causal ? (bx ? attn_bwd_dq_kernel<true, true> : attn_bwd_dq_kernel<true, false>)
                            : (bx ? attn_bwd_dq_kernel<false, true> : attn_bwd_dq_kernel<false, false>);
-        launch_pdl(kern, dim3(grid), dim3(kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
+        launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
         count_launch();
         if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
     }

@@ -195,9 +195,11 @@ def empty(shape) -> DeviceArray:
 
 
 def zeros(shape) -> DeviceArray:
-    if isinstance(shape, int):
-        shape = (shape,)
-    return DeviceArray(torch.zeros(tuple(int(s) for s in shape), dtype=torch.float32, device=_device()))
+    """Zero-filled by this library's own fill kernel (torch is the allocator only)."""
+    out = empty(shape)
+    if out.size:
+        C.npm_fill(out.ptr, 0.0, out.size, stream())
+    return out
 
 
 def workspace(nbytes: int) -> torch.Tensor:

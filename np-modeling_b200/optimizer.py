@@ -14,6 +14,7 @@ data-parallel training all-reduces a few large contiguous blocks (see train.py).
 """
 import abc
 import dataclasses
+import os
 
 import numpy as np
 import torch
@@ -58,7 +59,10 @@ class _Arena:
     i.e. backward, order), so a data-parallel all-reduce touches whole blocks."""
 
     ALIGN = 64            # floats (256 B)
-    MAX_BLOCK = 1 << 26   # 64 Mi floats = 256 MiB
+    # Largest block = largest all-reduce bucket.  The arena is filled in backward order, so the LAST block holds the
+    # first layers' gradients and its all-reduce cannot overlap any compute: 64 MiB keeps that exposed tail at ~0.25 ms
+    # on NVLink 5 (256 MiB blocks left ~1 ms of it exposed, 3.5 ms of the 8-GPU step).  NPM_DP_BUCKET_MB: A/B switch.
+    MAX_BLOCK = (int(os.environ.get('NPM_DP_BUCKET_MB', '64')) << 20) // 4
 
     def __init__(self):
         self.blocks = []   # [tensor, used]
@@ -71,7 +75,7 @@ class _Arena:
         need = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         if not self.blocks or self.blocks[-1][1] + need > self.blocks[-1][0].numel():
             size = max(need, min(self.MAX_BLOCK, max(1 << 20, 2 * self.total)))
-            self.blocks.append([torch.zeros(size, dtype=torch.float32, device=device._device()), 0])
+            self.blocks.append([device.zeros(size).t, 0])
         blk = self.blocks[-1]
         view = blk[0][blk[1]:blk[1] + n].view(*shape)
         blk[1] += need

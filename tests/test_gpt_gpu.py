@@ -4,7 +4,7 @@ key/value caches against the full causal forward."""
 import numpy as np
 import pytest
 
-from helpers import Recorder, close, grads_of, param_values
+from helpers import Recorder, close, grads_of, param_values, use_device_relu_gates
 
 pytestmark = pytest.mark.gpu
 
@@ -80,6 +80,7 @@ def test_three_layer_gpt_stack_vs_chained_oracle(heads, features):
     odkv = 0.0
     ograds = [None] * L
     for i in reversed(range(L)):
+        use_device_relu_gates(model._stack._layers[i], caches[i])
         (dx, d), ograds[i] = O.decoder_bwd(ps[i], caches[i], dx, True)
         odkv = odkv + d
     close(dkv, odkv)
