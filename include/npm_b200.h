@@ -87,6 +87,18 @@ typedef struct npm_gemm_desc {
                                * `out += skip` of layers/transformer.py:39,53 in the epilogue;
                                * unbatched problems only                            */
     int64_t ldr;
+    float*  a_colsum;         /* NULL, or [m]: receives sum_k A[m,k] (overwritten).  For the dW GEMM of a
+                               * projection (dw = dy^T x, A = dy^T) this is the bias gradient
+                               * np.sum(dy, axis=0) of attentions.py:129-135 / mlp.py:34, taken from the
+                               * operand tiles the GEMM stages anyway.  Served by the split-bf16 kernel
+                               * (precision NPM_PREC_BF16X3 / BF16, A m-contiguous, unbatched, m > 128);
+                               * otherwise NPM_ERR_UNSUPPORTED — npm_linear_bwd_dw_db chooses.      */
+    const void* b_split;      /* NULL, or the bf16 hi / mid planes of B written by npm_weight_split
+                               * (same element (k,n) addressing as `b`, in bf16; the mid plane starts
+                               * b_split_plane elements after the hi plane).  A hint: the split-bf16
+                               * kernel then lands B without converting it; every other path ignores it
+                               * and reads `b`.                                                       */
+    int64_t b_split_plane;
 } npm_gemm_desc;
 int npm_gemm(const npm_gemm_desc* d, npm_stream_t stream);
 
@@ -105,6 +117,24 @@ int npm_linear_fwd_residual(const float* x, const float* w, const float* b,
                             const float* residual, float* y, int64_t m,
                             int64_t k, int64_t n, int w_out_major,
                             npm_stream_t stream);
+/* Split-bf16 planes of a weight matrix for the NPM_PREC_BF16X3 mode: hi = bf16_rn(w),
+ * mid = bf16_rn(w - hi), as two [rows, cols] bf16 matrices (mid plane right after the hi plane:
+ * npm_weight_split_bytes = 4 * rows * cols).  A weight is the B operand of its forward GEMM and
+ * of its dX GEMM; split once per step it is landed by TMA in tensor-core layout instead of being
+ * converted in shared memory by both.  The *_presplit entry points take the planes as a hint
+ * (`w_planes` may be NULL; `plane` = elements between the hi and the mid plane, so that a row
+ * block of a packed weight can be addressed); they compute exactly what npm_linear_fwd /
+ * npm_linear_fwd_residual / npm_linear_bwd_dx compute. */
+size_t npm_weight_split_bytes(int64_t rows, int64_t cols);
+int npm_weight_split(const float* w, void* planes, int64_t rows, int64_t cols,
+                     npm_stream_t stream);
+int npm_linear_fwd_presplit(const float* x, const float* w, const void* w_planes,
+                            int64_t plane, const float* b, const float* residual,
+                            float* y, int64_t m, int64_t k, int64_t n,
+                            int w_out_major, int relu, npm_stream_t stream);
+int npm_linear_bwd_dx_presplit(const float* dy, const float* w, const void* w_planes,
+                               int64_t plane, float* dx, int64_t m, int64_t k,
+                               int64_t n, int w_out_major, npm_stream_t stream);
 /* dx[m,k] = dy[m,n] @ W^T.                                         mlp.py:36 */
 int npm_linear_bwd_dx(const float* dy, const float* w, float* dx,
                       int64_t m, int64_t k, int64_t n, int w_out_major,

@@ -108,7 +108,10 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     int rc = require_sm100();
     if (rc) return rc;
     int prec = d.precision >= 0 ? d.precision : g_precision.load();
-    if (prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16) {
+    const bool bx_mode = prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16;
+    NPM_REQUIRE(d.a_colsum == nullptr || (bx_mode && !(getenv("NPM_GEMM_NO_BX")) && gemm_bx_supported(d) && d.a_rs == 1 && d.nb1 <= 1 && d.nb2 <= 1),
+                "gemm: a_colsum is served by the split-bf16 kernel only (precision bf16x3 / bf16, m-contiguous A, unbatched, m > 128)");
+    if (bx_mode) {
         // split-bf16 CTA-pair kernel; problems it does not take (a single row tile, ragged 16-byte chunks) run the
         // TF32 kernels at the same or better accuracy class (3xTF32 for bf16x3, one TF32 pass for bf16)
         static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
@@ -220,6 +223,38 @@ int npm_linear_fwd_residual(const float* x, const float* w, const float* b, cons
     return gemm_dispatch(d, (cudaStream_t)stream);
 }
 
+size_t npm_weight_split_bytes(int64_t rows, int64_t cols) { return (size_t)rows * cols * 4; }
+int npm_weight_split(const float* w, void* planes, int64_t rows, int64_t cols, npm_stream_t stream) {
+    NPM_REQUIRE(w && planes && rows > 0 && cols > 0 && (rows * cols) % 4 == 0 && rows * cols < (1ll << 32),
+                "weight_split: needs a multiple of 4 (and fewer than 2^32) elements");
+    return attn_split_launch(w, rows * cols, planes, 1, rows * cols, (cudaStream_t)stream);     // one "row" of rows * cols elements
+}
+int npm_linear_fwd_presplit(const float* x, const float* w, const void* w_planes, int64_t plane, const float* b,
+                            const float* residual, float* y, int64_t m, int64_t k, int64_t n, int w_out_major, int relu,
+                            npm_stream_t stream) {
+    npm_gemm_desc d = blank_desc();
+    d.a = x; d.b = w; d.c = y; d.bias = b;
+    d.m = m; d.n = n; d.k = k;
+    d.a_rs = k; d.a_cs = 1;
+    if (w_out_major) { d.b_rs = 1; d.b_cs = k; } else { d.b_rs = n; d.b_cs = 1; }
+    d.ldc = n;
+    d.flags = relu ? NPM_GEMM_RELU : 0;
+    d.residual = residual; d.ldr = n;
+    d.b_split = w_planes; d.b_split_plane = plane;
+    return gemm_dispatch(d, (cudaStream_t)stream);
+}
+int npm_linear_bwd_dx_presplit(const float* dy, const float* w, const void* w_planes, int64_t plane, float* dx, int64_t m,
+                               int64_t k, int64_t n, int w_out_major, npm_stream_t stream) {
+    npm_gemm_desc d = blank_desc();
+    d.a = dy; d.b = w; d.c = dx;
+    d.m = m; d.n = k; d.k = n;
+    d.a_rs = n; d.a_cs = 1;
+    if (w_out_major) { d.b_rs = k; d.b_cs = 1; } else { d.b_rs = 1; d.b_cs = n; }
+    d.ldc = k;
+    d.b_split = w_planes; d.b_split_plane = plane;
+    return gemm_dispatch(d, (cudaStream_t)stream);
+}
+
 int npm_linear_bwd_dx(const float* dy, const float* w, float* dx, int64_t m, int64_t k, int64_t n, int w_out_major,
                       npm_stream_t stream) {
     // dx[m,k] = sum_n dy[m,n] * W(k,n): contraction over n
@@ -251,8 +286,14 @@ int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db, 
         d.b_rs = k; d.b_cs = 1;
         d.ldc = k;
     }
+    // split-bf16 mode, output-major weights: dy is the MN-major A operand of this GEMM, and its column sums come out
+    // of the operand tiles the kernel converts anyway (gemm_bx.cu) — no separate pass over dy
+    static const bool fold_off = getenv("NPM_NO_COLSUM_FOLD") != nullptr || getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch
+    const int prec = g_precision.load();
+    const bool fold = db != nullptr && w_out_major && !fold_off && (prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16) && gemm_bx_supported(d);
+    if (fold) d.a_colsum = db;
     int rc = gemm_dispatch(d, (cudaStream_t)stream);
-    if (rc || db == nullptr) return rc;
+    if (rc || db == nullptr || fold) return rc;
     return colsum_launch(dy, db, m, n, workspace, (cudaStream_t)stream);
 }
 

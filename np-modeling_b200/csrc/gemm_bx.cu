@@ -69,6 +69,7 @@ struct GemmBxArgs {
     const float* residual;
     int64_t ldr;
     int relu, accum;
+    float* a_colsum;           // optional [M] (A MN-major only): += sum over k of A[m, k] — the bias gradient of a dW GEMM
     long long* dbg;            // tools only (NPM_GEMM_DEBUG_TIMES): 16 wait-cycle counters per CTA
 };
 
@@ -81,9 +82,10 @@ struct BxCfg {
     static constexpr int kEpiBytes   = 4 * 2 * 4096;
     static constexpr int kBarBytes   = 512;
     static constexpr int kBudget     = 232448 - 1024;
-    static constexpr int kStagesRaw  = (kBudget - kEpiBytes - kBarBytes) / kStageBytes;
+    static constexpr int kStagesRaw  = (kBudget - kEpiBytes - kBarBytes - 1024) / kStageBytes;
     static constexpr int kStages     = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr int kSmemBytes  = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+    static constexpr int kCsBytes    = 1024;                           // column-sum exchange between converter warp pairs
+    static constexpr int kSmemBytes  = kStages * kStageBytes + kEpiBytes + kBarBytes + kCsBytes + 1024;
     static constexpr int kTmemCols   = 2 * BLOCK_N;
 };
 
@@ -96,7 +98,13 @@ __device__ __forceinline__ void tile_coords_bx(int r, int tiles_m, int tiles_n, 
     tn = idx / width;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int NTERMS>
+// B_PRE: the B operand (a weight matrix) arrives already split — bf16 hi / mid planes written once per step by
+// split_planes_kernel — and is landed by TMA directly as the image the tensor core reads: no LDS / STS for it, which
+// is what bounds this kernel (the shared-memory data pipe: 32 KB LDS + 32 KB STS + 48 KB of MMA operand reads per
+// stage = 896 wavefronts + arbitration against the 768 clk of its six MMAs, profiles/r02_ncu_gemm_bx_ffn.txt).
+//   K-major  B_PRE: box {32 k, rows, 2 planes}, 64-byte swizzle: hi image rows x 64 B, then the mid image
+//   MN-major B_PRE: box {64 n, 32 k, rows/64 slabs, 2 planes}, 128-byte swizzle: the same image the converters write
+template <int BLOCK_N, bool A_MN, bool B_MN, int NTERMS, bool B_PRE>
 __global__ void __launch_bounds__(kThreadsBx, 1)
 gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
@@ -190,7 +198,10 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int c = 0; c < kBM / 32; ++c) ptx::tma_load_4d(sA + c * 4096, &tmA, fb, m0 + c * 32, k0, z1, z2);
                     }
-                    if (!B_MN) {
+                    if (B_PRE) {
+                        if (!B_MN) ptx::tma_load_4d(sB, &tmB, fb, k0, n0, 0, 0);           // {k, rows, plane, 1}
+                        else       ptx::tma_load_4d(sB, &tmB, fb, 0, k0, n0 / 64, 0);      // {64 n, k, slab, plane}
+                    } else if (!B_MN) {
                         ptx::tma_load_4d(sB, &tmB, fb, k0, n0, z1, z2);
                     } else if (args.b_chunked) {
                         ptx::tma_load_5d(sB, &tmB, fb, 0, k0, n0 / 32, z1, z2);
@@ -209,14 +220,24 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         OperandConverter<Cfg::kHalfN, B_MN, NTERMS> cb;
         ca.init(pw, lane);
         cb.init(pw, lane);
-        int total_it = 0;
-        for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
-            const int kb0 = (tile / args.items_per_split) * args.kb_per_split;
-            total_it += min(num_kb, kb0 + args.kb_per_split) - kb0;
-        }
+        // Bias gradient folded into the dW GEMM (layers/attentions.py:129-135, mlp.py:34: db = sum over tokens of dy): for
+        // dW = dy^T x the A operand IS dy, MN-major, and every element of it passes through these registers as fp32 —
+        // a thread always holds the same four columns (mn = 32 * (pw / 2) + 4 * (lane & 7) ..+3), so one float4
+        // accumulates them; the tiles of the first column of N tiles add their sums to args.a_colsum (zeroed by the
+        // launcher; red.global.add, the splits of a split-K launch each contribute their rows).
+        const bool do_colsum = A_MN && args.a_colsum != nullptr;
+        float4* cs_smem = reinterpret_cast<float4*>(base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kBarBytes);
         int stage = 0;
         uint32_t phase = 0;
-        for (int it = 0; it < total_it; ++it) {
+        for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
+            const int sp = tile / args.items_per_split, t2i = tile - sp * args.items_per_split;
+            const int kb0 = sp * args.kb_per_split;
+            const int nkb = min(num_kb, kb0 + args.kb_per_split) - kb0;
+            int tm = 0, tn = 1;
+            if (do_colsum) tile_coords_bx(t2i % tiles_mn, args.tiles_m, args.tiles_n, args.band_m, tm, tn);
+            const bool sum_tile = do_colsum && tn == 0;
+            float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < nkb; ++it) {
             const bool dbg = args.dbg != nullptr && pw == 0 && lane == 0;
             long long t0 = 0, t1 = 0, t2 = 0;
             if (dbg) t0 = clock64();
@@ -226,16 +247,22 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float4 va[OperandConverter<kBM, A_MN, NTERMS>::NLD];
             float4 vb[OperandConverter<Cfg::kHalfN, B_MN, NTERMS>::NLD];
             ca.load(va, sA);
-            cb.load(vb, sA + Cfg::kABytes);
+            if (!B_PRE) cb.load(vb, sA + Cfg::kABytes);
             bar_sync_conv();                                 // every fp32 chunk of the stage is in registers: overwrite it
             if (dbg) t2 = clock64();
             ca.store(va, sA);
-            cb.store(vb, sA + Cfg::kABytes);
+            if (!B_PRE) cb.store(vb, sA + Cfg::kABytes);
             // no proxy fence here: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR costs
             // ~36 clk per store in flight (700 clk per stage measured with 16 STS per thread); the consumer of this
             // barrier — a thread with nothing in flight — executes it (issuer / peer relay below)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(conv_bar(stage));
+            if (sum_tile) {
+#pragma unroll
+                for (int i = 0; i < OperandConverter<kBM, A_MN, NTERMS>::NLD; ++i) {
+                    csum.x += va[i].x; csum.y += va[i].y; csum.z += va[i].z; csum.w += va[i].w;
+                }
+            }
             if (dbg) {
                 const long long t3 = clock64();
                 args.dbg[blockIdx.x * 16 + 0] += t1 - t0;            // wait for the TMA tiles
@@ -244,6 +271,30 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 args.dbg[blockIdx.x * 16 + 3] += 1;
             }
             if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+            if (do_colsum) {       // uniform over the 256 converter threads of the CTA (tile coordinates are CTA-wide)
+                if (sum_tile) {
+                    // rows of one warp instruction sit in the lane groups q = lane >> 3: fold them, then the warp pair
+                    // (pw, pw ^ 1) that shares the 32-column chunk through shared memory
+#pragma unroll
+                    for (int o = 8; o <= 16; o <<= 1) {
+                        csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+                        csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+                    }
+                    if (lane < 8) cs_smem[pw * 8 + lane] = csum;
+                }
+                bar_sync_conv();
+                if (sum_tile && (pw & 1) == 0 && lane < 8) {
+                    const float4 o = cs_smem[(pw + 1) * 8 + lane];
+                    const int m = tm * (2 * kBM) + (int)rank * kBM + (pw >> 1) * 32 + 4 * lane;
+                    float* dst = args.a_colsum + m;
+                    if (m < args.M)     atomicAdd(dst, csum.x + o.x);
+                    if (m + 1 < args.M) atomicAdd(dst + 1, csum.y + o.y);
+                    if (m + 2 < args.M) atomicAdd(dst + 2, csum.z + o.z);
+                    if (m + 3 < args.M) atomicAdd(dst + 3, csum.w + o.w);
+                }
+                bar_sync_conv();       // cs_smem is reused by the next tile
+            }
         }
     } else if (warp == kMmaWarp && rank == 1) {
         // ============ peer CTA: proxy-fence relay — the fence sits on the causality path stores -> conv_bar -> fence ->
@@ -270,10 +321,14 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kBM, BLOCK_N, A_MN, B_MN);
             constexpr uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
             constexpr uint64_t desc_mn = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 4096, 1024);   // LBO: next 64-mn slab, SBO: next 8 k-rows
-            constexpr uint64_t descA = A_MN ? desc_mn : desc_k, descB = B_MN ? desc_mn : desc_k;
+            constexpr uint64_t desc_k64 = ptx::umma_desc_base(4 /*SWIZZLE_64B*/, 16, 512);      // pre-split K-major: 64-byte rows, 8-row groups 512 B apart
+            constexpr uint64_t descA = A_MN ? desc_mn : desc_k, descB = B_MN ? desc_mn : (B_PRE ? desc_k64 : desc_k);
             // byte offset of K16 slice s of the hi (t = 0) / mid (t = 1) image
             auto a_off = [](int t, int s) -> uint32_t { return A_MN ? uint32_t(t) * (kBM / 64) * 4096u + uint32_t(s) * 2048u : uint32_t(t) * 64u + uint32_t(s) * 32u; };
-            auto b_off = [](int t, int s) -> uint32_t { return B_MN ? uint32_t(t) * (Cfg::kHalfN / 64) * 4096u + uint32_t(s) * 2048u : uint32_t(t) * 64u + uint32_t(s) * 32u; };
+            auto b_off = [](int t, int s) -> uint32_t {
+                return B_MN ? uint32_t(t) * (Cfg::kHalfN / 64) * 4096u + uint32_t(s) * 2048u
+                            : (B_PRE ? uint32_t(t) * (Cfg::kHalfN * 64u) + uint32_t(s) * 32u : uint32_t(t) * 64u + uint32_t(s) * 32u);
+            };
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int tile = cluster_id; tile < args.total_tiles; tile += num_clusters) {
@@ -424,10 +479,10 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == kMmaWarp) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
 }
 
-template <int BN, bool AMN, bool BMN, int NT>
+template <int BN, bool AMN, bool BMN, int NT, bool BPRE>
 int launch_bx(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream_t stream) {
     using Cfg = BxCfg<BN>;
-    auto kern = gemm_bx_kernel<BN, AMN, BMN, NT>;
+    auto kern = gemm_bx_kernel<BN, AMN, BMN, NT, BPRE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -462,12 +517,16 @@ int launch_bx(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, 
 }
 
 template <int BN, int NT>
-int launch_bx_major(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args, int grid,
-                    cudaStream_t s) {
-    if (!amn && !bmn) return launch_bx<BN, false, false, NT>(a, b, c, args, grid, s);
-    if (!amn && bmn) return launch_bx<BN, false, true, NT>(a, b, c, args, grid, s);
-    if (amn && !bmn) return launch_bx<BN, true, false, NT>(a, b, c, args, grid, s);
-    return launch_bx<BN, true, true, NT>(a, b, c, args, grid, s);
+int launch_bx_major(bool amn, bool bmn, bool bpre, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args,
+                    int grid, cudaStream_t s) {
+    if (bpre && NT == 3) {        // pre-split weights: the B operand of a forward / dX GEMM (A is an activation, K-major)
+        if (!amn && !bmn) return launch_bx<BN, false, false, 3, true>(a, b, c, args, grid, s);
+        if (!amn && bmn) return launch_bx<BN, false, true, 3, true>(a, b, c, args, grid, s);
+    }
+    if (!amn && !bmn) return launch_bx<BN, false, false, NT, false>(a, b, c, args, grid, s);
+    if (!amn && bmn) return launch_bx<BN, false, true, NT, false>(a, b, c, args, grid, s);
+    if (amn && !bmn) return launch_bx<BN, true, false, NT, false>(a, b, c, args, grid, s);
+    return launch_bx<BN, true, true, NT, false>(a, b, c, args, grid, s);
 }
 
 }  // namespace
@@ -476,6 +535,9 @@ int launch_bx_major(bool amn, bool bmn, const CUtensorMap& a, const CUtensorMap&
 // these modes runs the TF32 kernels of the same or better accuracy class (3xTF32 for bf16x3).
 bool gemm_tc_supported(const npm_gemm_desc& d);
 bool gemm_bx_supported(const npm_gemm_desc& d) { return d.m > kBM && gemm_tc_supported(d); }
+
+int make_tensor_map_bf16_nd(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                            const uint32_t* box, int swizzle_bytes);
 
 int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     const int nb1 = d.nb1 > 0 ? d.nb1 : 1, nb2 = d.nb2 > 0 ? d.nb2 : 1;
@@ -540,7 +602,18 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
         }
     }
     if (rc) return rc;
-    if (!b_mn) {
+    // pre-split B (weights): unbatched, A K-major, three terms; MN-major needs whole 64-column slabs
+    const bool b_pre = d.b_split != nullptr && nterms == 3 && !a_mn && nb1 == 1 && nb2 == 1 && (!b_mn || d.n % 64 == 0) &&
+                       aligned16(d.b_split) && d.b_split_plane % 8 == 0 && (b_mn ? d.b_rs : d.b_cs) % 8 == 0;   // TMA: 16-byte strides in bf16
+    if (b_pre && !b_mn) {
+        const uint64_t dims[4] = {K, N, 2, 1}, st[3] = {(uint64_t)d.b_cs, (uint64_t)d.b_split_plane, (uint64_t)d.b_split_plane * 2};
+        const uint32_t box[4] = {kKS, (uint32_t)bn / 2, 2, 1};
+        rc = make_tensor_map_bf16_nd(&tmB, d.b_split, 4, dims, st, box, 64);
+    } else if (b_pre) {
+        const uint64_t dims[4] = {64, K, N / 64, 2}, st[3] = {(uint64_t)d.b_rs, 64, (uint64_t)d.b_split_plane};
+        const uint32_t box[4] = {64, kKS, (uint32_t)bn / 2 / 64, 2};
+        rc = make_tensor_map_bf16_nd(&tmB, d.b_split, 4, dims, st, box, 128);
+    } else if (!b_mn) {
         const uint64_t ld = d.b_cs, s2 = bs(nb1, d.b_bs1, ld * N), s3 = bs(nb2, d.b_bs2, s2 * nb1);
         rc = make_tensor_map_4d(&tmB, d.b, K, N, nb1, nb2, ld, s2, s3, kKS, bn / 2, false, false);
     } else {
@@ -575,14 +648,21 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     args.ldr = d.ldr;
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
     args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
+    args.a_colsum = nullptr;
+    if (d.a_colsum != nullptr) {
+        NPM_REQUIRE(a_mn && nb1 == 1 && nb2 == 1, "gemm: a_colsum needs an unbatched problem with an MN-major A");
+        cudaError_t e = cudaMemsetAsync(d.a_colsum, 0, sizeof(float) * (size_t)d.m, stream);
+        if (e != cudaSuccess) { set_error("gemm a_colsum memset: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
+        args.a_colsum = d.a_colsum;
+    }
     args.dbg = nullptr;
     const int grid = 2 * (int)(total < units ? total : units);
     if (nterms == 3) {
-        if (bn == 256) return launch_bx_major<256, 3>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
-        return launch_bx_major<128, 3>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+        if (bn == 256) return launch_bx_major<256, 3>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
+        return launch_bx_major<128, 3>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
     }
-    if (bn == 256) return launch_bx_major<256, 1>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
-    return launch_bx_major<128, 1>(a_mn, b_mn, tmA, tmB, tmC, args, grid, stream);
+    if (bn == 256) return launch_bx_major<256, 1>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
+    return launch_bx_major<128, 1>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
 }
 
 }  // namespace npm

@@ -110,15 +110,36 @@ class MultiHeadAttention(layer.StatefulLayer):
         self._packs = (wp, bp)
         return self._packs
 
-    def _project(self, x2d, w, b, n, residual=None):
+    def _project(self, x2d, w, b, n, residual=None, planes=None):
+        """y = x @ W^T + b (+ residual) for an output-major W [n, k]; `planes` = (pointer, plane stride) of W's bf16
+        hi / mid split (bf16x3 mode) or None."""
         m, k = x2d.shape
         y = device.empty((m, n))
-        if residual is not None:
-            assert residual.size == m * n, 'residual must match the attention output'
-            C.npm_linear_fwd_residual(x2d.ptr, w.ptr, b.ptr, residual.ptr, y.ptr, m, k, n, 1, device.stream())
-        else:
-            C.npm_linear_fwd(x2d.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 1, 0, device.stream())
+        assert residual is None or residual.size == m * n, 'residual must match the attention output'
+        pp, ps = planes if planes is not None else (None, 0)
+        C.npm_linear_fwd_presplit(x2d.ptr, w.ptr, pp, ps, b.ptr, residual.ptr if residual is not None else None, y.ptr, m, k, n,
+                                  1, 0, device.stream())
         return y
+
+    def _split_params(self, packs, wo, tokens):
+        """bf16x3 mode: split the packed projection block and `_wo` once per forward; returns a function
+        (weight DeviceArray) -> (pointer, plane stride) that also resolves row blocks of the packed block."""
+        self._planes = None
+        if tokens <= 128:
+            return lambda w: None
+        blocks = []
+        for w in ([packs[0]] if packs is not None else [self._p('_wq'), self._p('_wk'), self._p('_wv')]) + [wo]:
+            t = device.split_weight(w)
+            if t is not None:
+                blocks.append((w.ptr, w.size, t))
+        self._planes = blocks
+
+        def find(w):
+            for base, size, t in self._planes or ():
+                if base <= w.ptr and w.ptr + 4 * w.size <= base + 4 * size:
+                    return (t.data_ptr() + (w.ptr - base) // 2, size)       # bf16: half the byte offset of the fp32 block
+            return None
+        return find
 
     def forward(self, query, key=None, value=None, mask=None, _residual=None):
         # _residual (B200 extension): the `out += skip` of the transformer blocks, run in the epilogue of the
@@ -144,26 +165,28 @@ class MultiHeadAttention(layer.StatefulLayer):
         hd = h * dk
         query2 = query.reshape(batch * sq, dmodel)
         key2 = key.reshape(batch * skv, key.shape[2])
+        pl = self._find_planes = self._split_params(packs, wo, min(batch * sq, batch * skv))
 
         # input projections (attentions.py:88-100); q/k/v are [B,S,H,dk] row blocks of `bufs`, token stride ld
         if packs is not None and key is query and value is query:
             self._mode = 'qkv'
-            qkv = self._project(query2, packs[0], packs[1], 3 * hd)                    # [B*S, 3*H*dk]
+            qkv = self._project(query2, packs[0], packs[1], 3 * hd, planes=pl(packs[0]))   # [B*S, 3*H*dk]
             self._proj = (qkv,)
             self._qkv_ptrs = (qkv.ptr, qkv.ptr + 4 * hd, qkv.ptr + 8 * hd)
             self._qkv_ld = (3 * hd, 3 * hd, 3 * hd)
         elif packs is not None and value is key:
             self._mode = 'kv'
-            q2 = self._project(query2, wq, bq, hd)
-            kv2 = self._project(key2, packs[0][1:3], packs[1][1:3], 2 * hd)              # [B*Skv, 2*H*dk]
+            q2 = self._project(query2, wq, bq, hd, planes=pl(wq))
+            kv_w = packs[0][1:3]
+            kv2 = self._project(key2, kv_w, packs[1][1:3], 2 * hd, planes=pl(kv_w))      # [B*Skv, 2*H*dk]
             self._proj = (q2, kv2)
             self._qkv_ptrs = (q2.ptr, kv2.ptr, kv2.ptr + 4 * hd)
             self._qkv_ld = (hd, 2 * hd, 2 * hd)
         else:
             self._mode = 'separate'
-            q2 = self._project(query2, wq, bq, hd)
-            k2 = self._project(key2, wk, bk, hd)
-            v2 = self._project(value.reshape(batch * skv, value.shape[2]), wv, bv, h * dv)
+            q2 = self._project(query2, wq, bq, hd, planes=pl(wq))
+            k2 = self._project(key2, wk, bk, hd, planes=pl(wk))
+            v2 = self._project(value.reshape(batch * skv, value.shape[2]), wv, bv, h * dv, planes=pl(wv))
             self._proj = (q2, k2, v2)
             self._qkv_ptrs = (q2.ptr, k2.ptr, v2.ptr)
             self._qkv_ld = (hd, hd, h * dv)
@@ -181,7 +204,7 @@ class MultiHeadAttention(layer.StatefulLayer):
                                    ctypes.byref(ld), device.stream())
         self._values = values
 
-        o = self._project(values.reshape(batch * sq, h * dv), wo, bo, wo.shape[0], _residual)
+        o = self._project(values.reshape(batch * sq, h * dv), wo, bo, wo.shape[0], _residual, planes=pl(wo))
         return o.reshape(batch, sq, wo.shape[0])
 
     # ---- decode-time step with a key/value cache (inference) ---------------------------------------
@@ -272,11 +295,14 @@ class MultiHeadAttention(layer.StatefulLayer):
             m = dy2d.shape[0]
             n = dy2d.shape[1] if n is None else n
             dx = device.empty((m, k))
+            find = getattr(self, '_find_planes', None)
+            pp, ps = (find(w) if find is not None else None) or (None, 0)
             if ld is None:
-                C.npm_linear_bwd_dx(dy2d.ptr, w.ptr, dx.ptr, m, k, n, 1, s)
+                C.npm_linear_bwd_dx_presplit(dy2d.ptr, w.ptr, pp, ps, dx.ptr, m, k, n, 1, s)
             else:
                 d = GemmDesc(a=ptr, b=w.ptr, c=dx.ptr, bias=None, m=m, n=k, k=n, a_rs=ld, a_cs=1, b_rs=k, b_cs=1,
-                             ldc=k, nb1=1, nb2=1, alpha=1.0, flags=0, precision=-1, residual=None, ldr=0)
+                             ldc=k, nb1=1, nb2=1, alpha=1.0, flags=0, precision=-1, residual=None, ldr=0,
+                             b_split=pp, b_split_plane=ps)
                 C.npm_gemm(ctypes.byref(d), s)
             return dx
 

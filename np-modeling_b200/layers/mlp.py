@@ -28,11 +28,13 @@ class Linear(layer.StatefulLayer):
         n = w.shape[1]
         assert w.shape[0] == k, f'{w.shape} vs input features {k}'
         y = device.empty((m, n))
-        if _residual is not None:
-            assert not _relu and _residual.size == m * n, 'residual must match the output'
-            C.npm_linear_fwd_residual(x.ptr, w.ptr, b.ptr, _residual.ptr, y.ptr, m, k, n, 0, device.stream())
-        else:
-            C.npm_linear_fwd(x.ptr, w.ptr, b.ptr, y.ptr, m, k, n, 0, 1 if _relu else 0, device.stream())
+        assert _residual is None or (not _relu and _residual.size == m * n), 'residual must match the output'
+        # bf16x3 mode: the weight is split once here and serves this GEMM and the dX GEMM of backward (the optimizer
+        # applies updates after the whole backward pass, so the weight cannot change in between)
+        self._w_planes = device.split_weight(w) if m > 128 else None
+        C.npm_linear_fwd_presplit(x.ptr, w.ptr, self._w_planes.data_ptr() if self._w_planes is not None else None, w.size,
+                                  b.ptr, _residual.ptr if _residual is not None else None, y.ptr, m, k, n, 0,
+                                  1 if _relu else 0, device.stream())
         return y
 
     def backward(self, dy, optimizer_: optimizer.Optimizer, _db=None):
@@ -59,7 +61,9 @@ class Linear(layer.StatefulLayer):
             db = _db
             C.npm_linear_bwd_dw_db(x.ptr, dy.ptr, dw.ptr, None, m, k, n, 0, None, s)
         dx = device.empty((m, k))
-        C.npm_linear_bwd_dx(dy.ptr, w.ptr, dx.ptr, m, k, n, 0, s)
+        planes = getattr(self, '_w_planes', None)
+        C.npm_linear_bwd_dx_presplit(dy.ptr, w.ptr, planes.data_ptr() if planes is not None else None, w.size, dx.ptr, m, k, n,
+                                     0, s)
         assert dx.shape == x.shape
         optimizer_.update(self, '_w', dw)
         optimizer_.update(self, '_b', db)

@@ -31,7 +31,7 @@ class GemmDesc(Structure):
         ('a_bs1', c_int64), ('a_bs2', c_int64), ('b_bs1', c_int64), ('b_bs2', c_int64),
         ('c_bs1', c_int64), ('c_bs2', c_int64),
         ('alpha', c_float), ('flags', c_int32), ('precision', c_int32),
-        ('residual', c_void_p), ('ldr', c_int64),
+        ('residual', c_void_p), ('ldr', c_int64), ('a_colsum', c_void_p), ('b_split', c_void_p), ('b_split_plane', c_int64),
     ]
 
 
@@ -62,6 +62,10 @@ SIGNATURES = {
     'npm_linear_fwd': (c_int, [P, P, P, P, I64, I64, I64, I, I, P]),
     'npm_linear_fwd_residual': (c_int, [P, P, P, P, P, I64, I64, I64, I, P]),
     'npm_linear_bwd_dx': (c_int, [P, P, P, I64, I64, I64, I, P]),
+    'npm_weight_split_bytes': (c_size_t, [I64, I64]),
+    'npm_weight_split': (c_int, [P, P, I64, I64, P]),
+    'npm_linear_fwd_presplit': (c_int, [P, P, P, I64, P, P, P, I64, I64, I64, I, I, P]),
+    'npm_linear_bwd_dx_presplit': (c_int, [P, P, P, I64, P, I64, I64, I64, I, P]),
     'npm_linear_bwd_dw_db': (c_int, [P, P, P, P, I64, I64, I64, I, P, P]),
     'npm_colsum_workspace': (c_size_t, [I64, I64]),
     'npm_colsum': (c_int, [P, P, I64, I64, P, P]),

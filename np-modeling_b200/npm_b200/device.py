@@ -202,6 +202,19 @@ def zeros(shape) -> DeviceArray:
     return out
 
 
+def split_weight(w: 'DeviceArray'):
+    """bf16 hi / mid planes of a weight for the split-bf16 ('bf16x3') contraction mode (npm_weight_split), or None in
+    the other modes.  A layer computes them once per forward call; its forward GEMM and its dX GEMM both take them as
+    their B operand without converting it again (gemm_bx.cu, B_PRE)."""
+    from ._lib import PREC_BF16X3, load
+    if load().npm_get_precision() != PREC_BF16X3 or w.size % 4 or w.ndim < 2:
+        return None
+    rows, cols = w.shape[0], w.size // w.shape[0]
+    planes = torch.empty(int(C.npm_weight_split_bytes(rows, cols)), dtype=torch.uint8, device=_device())
+    C.npm_weight_split(w.ptr, planes.data_ptr(), rows, cols, stream())
+    return planes
+
+
 def workspace(nbytes: int) -> torch.Tensor:
     """Scratch bytes for a *_workspace() query (caller-owned, per the C-ABI contract)."""
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=_device())

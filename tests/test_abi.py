@@ -47,8 +47,10 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.MhaStrides) == 8 * 8        # q k v dq dk dv causal path
     assert _lib.MhaStrides.path.offset == 56
     assert _lib.MhaStrides.causal.offset == 48
-    assert ctypes.sizeof(_lib.GemmDesc) == 4 * 8 + 3 * 8 + 5 * 8 + 2 * 4 + 6 * 8 + 3 * 4 + 4 + 2 * 8   # incl. padding before `residual`
-    assert _lib.GemmDesc.residual.offset == ctypes.sizeof(_lib.GemmDesc) - 16
+    # incl. padding before `residual`; then a_colsum, b_split, b_split_plane
+    assert ctypes.sizeof(_lib.GemmDesc) == 4 * 8 + 3 * 8 + 5 * 8 + 2 * 4 + 6 * 8 + 3 * 4 + 4 + 2 * 8 + 3 * 8
+    assert _lib.GemmDesc.residual.offset == ctypes.sizeof(_lib.GemmDesc) - 16 - 24
+    assert _lib.GemmDesc.a_colsum.offset == ctypes.sizeof(_lib.GemmDesc) - 24
     assert _lib.GemmDesc.alpha.offset == 4 * 8 + 3 * 8 + 5 * 8 + 8 + 6 * 8
 
 

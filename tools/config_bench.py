@@ -1,5 +1,5 @@
 """tools/config_bench.py — step time of BASELINE.json's configs 1-4 (SURVEY.md §8d shapes) on one B200.
-cfg5 is bench.py's workload.  usage: python tools/config_bench.py [tf32|3xtf32]"""
+cfg5 is bench.py's workload.  usage: python tools/config_bench.py [bf16x3|tf32|3xtf32]"""
 import os
 import sys
 
@@ -16,7 +16,8 @@ from layers.adapters import EncoderStack  # noqa: E402
 from npm_b200 import device  # noqa: E402
 from train import Trainer, iter_parameters  # noqa: E402
 
-prec = sys.argv[1] if len(sys.argv) > 1 else 'tf32'
+prec = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'
+print(f'# contraction mode {prec}', flush=True)
 npm_b200.set_precision(prec)
 rng = np.random.default_rng(0)
 

@@ -29,13 +29,13 @@ def main():
         y = torch.empty(N, H, W, Co, device='cuda'); dx = torch.empty_like(x); dw = torch.empty_like(f); db = torch.empty(Co, device='cuda')
         ws = torch.empty(max(C.npm_conv2d_workspace(N, H, W, Ci, Co, k), 16), dtype=torch.uint8, device='cuda')
         fl = 2.0 * N * H * W * k * k * Ci * Co
-        for mode in ('tf32', '3xtf32'):
+        for mode in ('bf16x3', 'tf32', '3xtf32'):
             npm_b200.set_precision(mode)
             p = lambda a: a.data_ptr()
             a = t(lambda: C.npm_conv2d_fwd(p(x), p(f), p(b), p(y), N, H, W, Ci, Co, k, 0, p(ws), st))
             bb = t(lambda: C.npm_conv2d_bwd_dx(p(dy), p(f), p(dx), N, H, W, Ci, Co, k, p(ws), st))
             c = t(lambda: C.npm_conv2d_bwd_dw_db(p(x), p(dy), p(dw), p(db), N, H, W, Ci, Co, k, p(ws), st))
-            path = 'tcgen05 implicit GEMM' if mode == 'tf32' and Ci % 4 == 0 else 'fp32 CUDA-core kernel'
+            path = 'tcgen05 implicit GEMM' if mode in ('tf32', 'bf16x3') and Ci % 4 == 0 else 'fp32 CUDA-core kernel'
             print(f'x[{N},{H},{W},{Ci}] k{k} -> {Co}  {mode:7s} ({path}): fprop {a:7.3f} ms {fl / a / 1e9:6.1f} TF | '
                   f'dgrad {bb:7.3f} ms {fl / bb / 1e9:6.1f} TF | wgrad+db {c:7.3f} ms {fl / c / 1e9:6.1f} TF', flush=True)
 
