@@ -109,12 +109,12 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     if (rc) return rc;
     int prec = d.precision >= 0 ? d.precision : g_precision.load();
     const bool bx_mode = prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16;
-    NPM_REQUIRE(d.a_colsum == nullptr || (bx_mode && !(getenv("NPM_GEMM_NO_BX")) && gemm_bx_supported(d) && d.a_rs == 1 && d.nb1 <= 1 && d.nb2 <= 1),
+    static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
+    NPM_REQUIRE(d.a_colsum == nullptr || (bx_mode && !bx_off && gemm_bx_supported(d) && d.a_rs == 1 && d.nb1 <= 1 && d.nb2 <= 1),
                 "gemm: a_colsum is served by the split-bf16 kernel only (precision bf16x3 / bf16, m-contiguous A, unbatched, m > 128)");
     if (bx_mode) {
         // split-bf16 CTA-pair kernel; problems it does not take (a single row tile, ragged 16-byte chunks) run the
         // TF32 kernels at the same or better accuracy class (3xTF32 for bf16x3, one TF32 pass for bf16)
-        static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
         if (!bx_off && gemm_bx_supported(d)) return gemm_bx_launch(d, prec == NPM_PREC_BF16X3 ? 3 : 1, stream);
         prec = prec == NPM_PREC_BF16X3 ? NPM_PREC_3XTF32 : NPM_PREC_TF32;
     }

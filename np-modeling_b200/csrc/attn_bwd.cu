@@ -950,9 +950,10 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
     a.lse = lse; a.dsum = dsum; a.dq = dq; a.dk = dk; a.dv = dv;
     a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
     a.causal = causal ? 1 : 0;
-    a.debug_skip = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
+    static const int debug_skip_env = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
+    a.debug_skip = debug_skip_env;
     a.dbg = nullptr;
-    const bool dbg_times = getenv("NPM_ATTN_DEBUG_TIMES") != nullptr;       // tools only: synchronises and prints
+    static const bool dbg_times = getenv("NPM_ATTN_DEBUG_TIMES") != nullptr;       // tools only: synchronises and prints
     if (dbg_times) {
         cudaMalloc(&a.dbg, sizeof(long long) * 12 * num_sms());
         cudaMemset(a.dbg, 0, sizeof(long long) * 12 * num_sms());

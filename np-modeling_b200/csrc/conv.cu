@@ -28,7 +28,8 @@ static bool use_tc(const void* p0, const void* p1, const void* p2, int64_t N, in
                    int64_t Cout, int ks) {
     // tensor cores in the single-pass TF32 mode and in the split-bf16 mode (bf16 mode: the TF32 kernels)
     const int prec = current_precision();
-    return (prec == NPM_PREC_TF32 || prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16) && getenv("NPM_CONV_SIMT") == nullptr &&
+    static const bool simt_only = getenv("NPM_CONV_SIMT") != nullptr;      // A/B switch for tools/
+    return (prec == NPM_PREC_TF32 || prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16) && !simt_only &&
            conv_tc_supported(p0, p1, p2, N, H, W, Cin, Cout, ks);
 }
 size_t colsum_workspace_bytes(int64_t rows, int64_t cols);

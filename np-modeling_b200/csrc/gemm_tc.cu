@@ -897,7 +897,7 @@ int launch_one2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
         configured = true;
     }
     GemmTcArgs largs = args;
-    const bool dbg_times = getenv("NPM_GEMM_DEBUG_TIMES") != nullptr;      // tools only: synchronises and prints
+    static const bool dbg_times = getenv("NPM_GEMM_DEBUG_TIMES") != nullptr;      // tools only: synchronises and prints
     if (dbg_times) {
         cudaMalloc(&largs.dbg, sizeof(long long) * 8 * grid);
         cudaMemset(largs.dbg, 0, sizeof(long long) * 8 * grid);
@@ -982,11 +982,15 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     const int64_t tiles_m = (d.m + tile_m - 1) / tile_m;
     const int num_kb_total = (int)((d.k + kBlockK - 1) / kBlockK);
     const bool c_dense = (d.ldc == d.n) && (nb1 == 1 || d.c_bs1 == d.m * d.n) && (nb2 == 1 || d.c_bs2 == d.m * d.n * nb1);
-    const bool may_split = c_dense && !(d.flags & (NPM_GEMM_RELU | NPM_GEMM_ACCUM)) && !getenv("NPM_GEMM_NO_SPLITK");
+    // environment switches are tools-only and read once per process (this function runs ~1000 times per training step)
+    static const bool no_splitk = getenv("NPM_GEMM_NO_SPLITK") != nullptr;
+    static const int forced_bn = getenv("NPM_GEMM_BLOCK_N_DYN") ? atoi(getenv("NPM_GEMM_BLOCK_N_DYN")) : 0;
+    static const int dbg_mode_env = getenv("NPM_GEMM_DEBUG_MODE") ? atoi(getenv("NPM_GEMM_DEBUG_MODE")) : 0;
+    static const int mn_lbo_env = getenv("NPM_MN_LBO") ? atoi(getenv("NPM_MN_LBO")) : 0;
+    const bool may_split = c_dense && !(d.flags & (NPM_GEMM_RELU | NPM_GEMM_ACCUM)) && !no_splitk;
     int best_bn = 64, best_splits = 1;
     {
-        const char* fe = getenv("NPM_GEMM_BLOCK_N_DYN");
-        const int forced = fe ? atoi(fe) : 0;   // tuning hook (tools/gemm_bench.py)
+        const int forced = forced_bn;           // tuning hook (tools/gemm_bench.py)
         double best_cost = 1e300;
         const int cands[3] = {256, 128, 64};
         const double kstep[3] = {512.0, 400.0, 300.0};
@@ -1081,7 +1085,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
         static const int band_env = getenv("NPM_GEMM_BAND") ? atoi(getenv("NPM_GEMM_BAND")) : 8;
         args.band_m = (pair && tiles_m > band_env && tiles_n > 1) ? band_env : 0;
     }
-    args.dbg_mode = getenv("NPM_GEMM_DEBUG_MODE") ? atoi(getenv("NPM_GEMM_DEBUG_MODE")) : 0;
+    args.dbg_mode = dbg_mode_env;
     args.a_chunked = a_chunked ? 1 : 0;
     args.b_chunked = b_chunked ? 1 : 0;
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
@@ -1094,7 +1098,7 @@ int gemm_tc_launch(const npm_gemm_desc& d, int precision, cudaStream_t stream) {
     //                    each {32 mn, 32 k} box as 32 K-rows of 128 B; UMMA layout
     //                    SWIZZLE_128B_BASE32B, 32-element MN chunks 4096 B apart (LBO), 4-row K groups
     //                    512 B apart (SBO).
-    const uint32_t mn_lbo = getenv("NPM_MN_LBO") ? (uint32_t)atoi(getenv("NPM_MN_LBO")) : ks * 128u;   // one {32 mn, ks k} chunk
+    const uint32_t mn_lbo = mn_lbo_env ? (uint32_t)mn_lbo_env : ks * 128u;   // one {32 mn, ks k} chunk
     static const uint32_t mn_sbo = getenv("NPM_MN_SBO") ? (uint32_t)atoi(getenv("NPM_MN_SBO")) : 512u;
     const uint64_t desc_k  = k_atom32 ? ptx::umma_desc_base(1, 16, 1024) : ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
     const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, mn_lbo, mn_sbo);

@@ -60,9 +60,10 @@ class _Arena:
 
     ALIGN = 64            # floats (256 B)
     # Largest block = largest all-reduce bucket.  The arena is filled in backward order, so the LAST block holds the
-    # first layers' gradients and its all-reduce cannot overlap any compute: 64 MiB keeps that exposed tail at ~0.25 ms
-    # on NVLink 5 (256 MiB blocks left ~1 ms of it exposed, 3.5 ms of the 8-GPU step).  NPM_DP_BUCKET_MB: A/B switch.
-    MAX_BLOCK = (int(os.environ.get('NPM_DP_BUCKET_MB', '64')) << 20) // 4
+    # first layers' gradients and its all-reduce cannot overlap any compute.  A/B on 8 x B200 (NPM_DP_BUCKET_MB,
+    # profiles/r02_bench_8gpu.txt): 64 MiB buckets 93.3 ms/step, 256 MiB 92.5 ms/step — the exposed tail shrinks, the
+    # number of NCCL launches that contend with the persistent tcgen05 kernels for SMs grows; 256 MiB stays.
+    MAX_BLOCK = (int(os.environ.get('NPM_DP_BUCKET_MB', '256')) << 20) // 4
 
     def __init__(self):
         self.blocks = []   # [tensor, used]

@@ -28,7 +28,7 @@ def time_fn(fn, iters=6):
     return ts[len(ts) // 2]
 
 
-def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, timing=False, seed=0):
+def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, timing=False, seed=0, presplit=False):
     g = torch.Generator(device='cuda').manual_seed(seed)
     a = torch.randn(nb, M, K, device='cuda', generator=g) if majors[0] == 'k' else torch.randn(nb, K, M, device='cuda', generator=g)
     b = torch.randn(nb, N, K, device='cuda', generator=g) if majors[1] == 'k' else torch.randn(nb, K, N, device='cuda', generator=g)
@@ -47,6 +47,10 @@ def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, tim
     d.alpha, d.flags, d.precision = 1.0, (1 if relu else 0), PREC[prec]
     d.residual = rv.data_ptr() if residual else None
     d.ldr = N
+    if presplit:      # B's bf16 hi / mid planes (npm_weight_split), as the layers pass them for weights
+        planes = torch.empty(b.numel() * 4, dtype=torch.uint8, device='cuda')
+        C.npm_weight_split(b.data_ptr(), planes.data_ptr(), b.shape[-2], b.shape[-1], torch.cuda.current_stream().cuda_stream)
+        d.b_split, d.b_split_plane = planes.data_ptr(), b.numel()
     st = torch.cuda.current_stream().cuda_stream
     C.npm_gemm(d, st)
     torch.cuda.synchronize()
@@ -75,6 +79,8 @@ def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, tim
 
 def main():
     bad = 0
+    for mj, M, N, K in [('kk', 256, 256, 64), ('km', 256, 256, 64), ('kk', 300, 520, 1024), ('km', 300, 512, 104), ('km', 1000, 1024, 1000), ('kk', 513, 36, 96)]:
+        bad += run(mj, 'bf16x3', M, N, K, presplit=True, bias=True) > 1.0 and M * K < 100000
     quick = [('kk', 256, 256, 64), ('km', 256, 256, 64), ('mk', 256, 256, 64), ('mm', 256, 256, 64),
              ('kk', 300, 520, 1024), ('km', 300, 520, 100), ('mk', 260, 36, 516), ('mm', 1024, 1024, 1024),
              ('kk', 129, 8, 4), ('km', 1000, 1000, 1000), ('mm', 516, 260, 132)]

@@ -4,6 +4,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'tools'))
 import bx_check  # noqa: E402
-mj, M, N, K = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-prec = sys.argv[5] if len(sys.argv) > 5 else 'bf16x3'
-bx_check.run(mj, prec, M, N, K, timing=not os.environ.get('NPM_GEMM_DEBUG_TIMES'))
+argv = [a for a in sys.argv if not a.startswith('--')]
+mj, M, N, K = argv[1], int(argv[2]), int(argv[3]), int(argv[4])
+prec = argv[5] if len(argv) > 5 else 'bf16x3'
+bx_check.run(mj, prec, M, N, K, timing=not os.environ.get('NPM_GEMM_DEBUG_TIMES'), presplit='--presplit' in sys.argv)

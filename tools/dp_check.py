@@ -48,7 +48,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl')
     import npm_b200
-    npm_b200.set_precision('3xtf32')
+    npm_b200.set_precision(os.environ.get('NPM_DP_CHECK_PRECISION', 'bf16x3'))
     sharded, loss_s = run(True)
     full, loss_f = run(False)
     worst = 0.0
@@ -63,7 +63,7 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         ok = ok and bool(torch.equal(lo, hi))
     if dist.get_rank() == 0:
-        print(f'world={dist.get_world_size()} overlap={"off" if os.environ.get("NPM_DP_NO_OVERLAP") else "on"} '
+        print(f'precision={npm_b200.get_precision()} world={dist.get_world_size()} overlap={"off" if os.environ.get("NPM_DP_NO_OVERLAP") else "on"} '
               f'max rel param diff sharded vs full-batch = {worst:.3e}, loss {loss_s:.6f} vs {loss_f:.6f}')
         print('DP_CHECK_OK' if ok else 'DP_CHECK_FAILED', flush=True)
     dist.destroy_process_group()
