@@ -131,7 +131,7 @@ static int attn_path_now(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t 
     static const bool off = getenv("NPM_ATTN_UNFUSED") != nullptr;     // A/B switch for tools/ and tests
     if (off || !attn_fused_supported(B, H, Sq, Skv, dk, dv)) return ATTN_MATERIALISED;
     const int prec = g_precision.load();
-    if (prec == NPM_PREC_TF32) return ATTN_FUSED_TF32;
+    if (prec == NPM_PREC_TF32 || prec == NPM_PREC_BF16) return ATTN_FUSED_TF32;     // single-pass modes: the TF32 kernels
     if (prec == NPM_PREC_BF16X3) return ATTN_FUSED_BX;
     return ATTN_MATERIALISED;
 }

@@ -173,7 +173,7 @@ def test_tf32_mode_stated_tolerance():
     kv = rng.standard_normal((b, skv, d)).astype(np.float32)
     dy = rng.standard_normal((b, sq, d)).astype(np.float32)
     errs = {}
-    for mode in ('tf32', '3xtf32', 'bf16x3'):
+    for mode in ('tf32', '3xtf32', 'bf16x3', 'bf16'):
         npm_b200.set_precision(mode)
         np.random.seed(0)
         layer = TransformerDecoder(h, f, True, 0.0)
@@ -201,6 +201,9 @@ def test_tf32_mode_stated_tolerance():
     assert errs['3xtf32'] < 1e-5, errs
     assert errs['3xtf32'] * 30 < errs['tf32'], errs
     assert errs['bf16x3'] < 2e-5 and errs['bf16x3'] * 30 < errs['tf32'], errs      # the mode bench.py reports
+    # bf16 tensor-core operands (8-bit mantissas) for the GEMMs, fp32 storage / accumulation; attention and
+    # convolution run their single-pass TF32 kernels.  Stated tolerance: relative Frobenius error below 1e-2.
+    assert errs['bf16'] < 1e-2, errs
 
 
 @pytest.mark.parametrize('mode', ['bf16x3', 'tf32'])
