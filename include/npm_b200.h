@@ -99,6 +99,12 @@ typedef struct npm_gemm_desc {
                                * kernel then lands B without converting it; every other path ignores it
                                * and reads `b`.                                                       */
     int64_t b_split_plane;
+    void*   c_split;          /* NULL, or bf16 planes [2][m, ldc] (mid plane c_split_plane elements after
+                               * the hi plane): the result is written ONLY in this split form (c may be
+                               * NULL) — what the fused split-bf16 attention reads, so a q | k | v
+                               * projection feeds it without an fp32 round trip.  Split-bf16 kernel only
+                               * (else NPM_ERR_UNSUPPORTED); unbatched, no ACCUM / residual.          */
+    int64_t c_split_plane;
 } npm_gemm_desc;
 int npm_gemm(const npm_gemm_desc* d, npm_stream_t stream);
 
@@ -135,6 +141,14 @@ int npm_linear_fwd_presplit(const float* x, const float* w, const void* w_planes
 int npm_linear_bwd_dx_presplit(const float* dy, const float* w, const void* w_planes,
                                int64_t plane, float* dx, int64_t m, int64_t k,
                                int64_t n, int w_out_major, npm_stream_t stream);
+/* y = x @ W + b written ONLY as bf16 hi / mid planes (y_planes: [2][m, n], mid plane y_plane
+ * elements after the hi plane): the projections in front of the fused split-bf16 attention
+ * (attentions.py:90-100).  NPM_ERR_UNSUPPORTED when the split-bf16 GEMM does not take the
+ * problem (m <= 128, n % 8 != 0, other precision modes): the caller then projects to fp32. */
+int npm_linear_fwd_planes(const float* x, const float* w, const void* w_planes,
+                          int64_t plane, const float* b, void* y_planes, int64_t y_plane,
+                          int64_t m, int64_t k, int64_t n, int w_out_major,
+                          npm_stream_t stream);
 /* dx[m,k] = dy[m,n] @ W^T.                                         mlp.py:36 */
 int npm_linear_bwd_dx(const float* dy, const float* w, float* dx,
                       int64_t m, int64_t k, int64_t n, int w_out_major,
@@ -309,6 +323,11 @@ typedef struct npm_mha_strides {
                                * 1 + the value npm_mha_core_path() returned when the forward ran — pins
                                * forward, backward and the layout of `saved` to one implementation even if
                                * the precision mode changes in between.                              */
+    int64_t planes;           /* != 0 (path 2 only): q / k / v are NOT fp32 but the hi planes of bf16 hi / mid
+                               * planes (npm_linear_fwd_planes), token strides q / k / v in bf16 elements, the
+                               * mid plane `planes` elements (per tensor: q_plane, k_plane, v_plane below)
+                               * after the hi plane; the core then skips its own operand split.       */
+    int64_t q_plane, k_plane, v_plane;
 } npm_mha_strides;
 int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v,
                              float* o, void* saved, int64_t B, int64_t H,

@@ -55,13 +55,14 @@ size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
 // attn_fwd.cu / attn_bwd.cu
 bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv);
 int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, bool bx, cudaStream_t stream);
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv,
+                    int causal, bool bx, cudaStream_t stream);
 size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, bool bx);
 int attn_split_launch(const float* x, int64_t ld, void* planes, int64_t rows, int64_t HD, cudaStream_t stream);
 int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal, bool bx,
-                    cudaStream_t stream);
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv, int64_t lddq, int64_t lddk,
+                    int64_t lddv, int causal, bool bx, cudaStream_t stream);
 int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
 
@@ -98,7 +99,7 @@ static int require_sm100() {
 }
 
 int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
-    NPM_REQUIRE(d.a && d.b && d.c, "gemm: NULL operand");
+    NPM_REQUIRE(d.a && d.b && (d.c || d.c_split), "gemm: NULL operand");
     NPM_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem m=%lld n=%lld k=%lld", (long long)d.m,
                 (long long)d.n, (long long)d.k);
     NPM_REQUIRE((d.a_rs == 1 || d.a_cs == 1) && (d.b_rs == 1 || d.b_cs == 1),
@@ -112,6 +113,10 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
     NPM_REQUIRE(d.a_colsum == nullptr || (bx_mode && !bx_off && gemm_bx_supported(d) && d.a_rs == 1 && d.nb1 <= 1 && d.nb2 <= 1),
                 "gemm: a_colsum is served by the split-bf16 kernel only (precision bf16x3 / bf16, m-contiguous A, unbatched, m > 128)");
+    if (d.c_split != nullptr && !(bx_mode && !bx_off && gemm_bx_supported(d))) {
+        set_error("gemm: c_split (split-bf16 output) is served by the split-bf16 kernel only (precision bf16x3 / bf16, m > 128)");
+        return NPM_ERR_UNSUPPORTED;
+    }
     if (bx_mode) {
         // split-bf16 CTA-pair kernel; problems it does not take (a single row tile, ragged 16-byte chunks) run the
         // TF32 kernels at the same or better accuracy class (3xTF32 for bf16x3, one TF32 pass for bf16)
@@ -243,6 +248,20 @@ int npm_linear_fwd_presplit(const float* x, const float* w, const void* w_planes
     d.b_split = w_planes; d.b_split_plane = plane;
     return gemm_dispatch(d, (cudaStream_t)stream);
 }
+int npm_linear_fwd_planes(const float* x, const float* w, const void* w_planes, int64_t plane, const float* b, void* y_planes,
+                          int64_t y_plane, int64_t m, int64_t k, int64_t n, int w_out_major, npm_stream_t stream) {
+    NPM_REQUIRE(y_planes != nullptr, "linear_fwd_planes: NULL output");
+    if (n % 8 != 0 || y_plane % 8 != 0) { set_error("linear_fwd_planes: n and the plane stride must be multiples of 8"); return NPM_ERR_UNSUPPORTED; }
+    npm_gemm_desc d = blank_desc();
+    d.a = x; d.b = w; d.c = nullptr; d.bias = b;
+    d.m = m; d.n = n; d.k = k;
+    d.a_rs = k; d.a_cs = 1;
+    if (w_out_major) { d.b_rs = 1; d.b_cs = k; } else { d.b_rs = n; d.b_cs = 1; }
+    d.ldc = n;
+    d.b_split = w_planes; d.b_split_plane = plane;
+    d.c_split = y_planes; d.c_split_plane = y_plane;
+    return gemm_dispatch(d, (cudaStream_t)stream);
+}
 int npm_linear_bwd_dx_presplit(const float* dy, const float* w, const void* w_planes, int64_t plane, float* dx, int64_t m,
                                int64_t k, int64_t n, int w_out_major, npm_stream_t stream) {
     npm_gemm_desc d = blank_desc();
@@ -339,14 +358,18 @@ int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v, flo
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_fwd: the causal mask needs Sq == Skv");
     const int path = attn_path_of(ld, B, H, Sq, Skv, dk, dv);
     NPM_REQUIRE(path == ATTN_MATERIALISED || attn_fused_supported(B, H, Sq, Skv, dk, dv), "mha_core_fwd: the pinned path does not serve this shape");
-    if (path == ATTN_FUSED_TF32) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, causal, false, s);
+    NPM_REQUIRE(!(ld && ld->planes) || path == ATTN_FUSED_BX, "mha_core_fwd: pre-split q / k / v need the split-bf16 path (strides.path = 3)");
+    if (path == ATTN_FUSED_TF32) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, 0, 0, 0, causal, false, s);
+    if (path == ATTN_FUSED_BX && ld && ld->planes)      // q / k / v already are bf16 planes (npm_linear_fwd_planes); saved = the log-sum-exp
+        return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, ld->q_plane, ld->k_plane, ld->v_plane, causal, true, s);
     if (path == ATTN_FUSED_BX) {
         const BxSaved sv = bx_saved(saved, B, H, Sq, Skv);
         int rc;
         if ((rc = attn_split_launch(q, ldq, sv.q, B * Sq, H * dk, s))) return rc;
         if ((rc = attn_split_launch(k, ldk, sv.k, B * Skv, H * dk, s))) return rc;
         if ((rc = attn_split_launch(v, ldv, sv.v, B * Skv, H * dv, s))) return rc;
-        return attn_fwd_launch(sv.q, sv.k, sv.v, o, sv.lse, B, H, Sq, Skv, 0, 0, 0, causal, true, s);
+        return attn_fwd_launch(sv.q, sv.k, sv.v, o, sv.lse, B, H, Sq, Skv, H * dk, H * dk, H * dv, B * Sq * H * dk, B * Skv * H * dk,
+                               B * Skv * H * dv, causal, true, s);
     }
     // S[b,h] = (1/sqrt(dk)) q[b,:,h,:] k[b,:,h,:]^T
     npm_gemm_desc d = blank_desc();
@@ -403,14 +426,20 @@ int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v, con
                 "mha_core_bwd: token strides must be >= H*d");
     const int path = attn_path_of(ld, B, H, Sq, Skv, dk, dv);
     NPM_REQUIRE(path == ATTN_MATERIALISED || attn_fused_supported(B, H, Sq, Skv, dk, dv), "mha_core_bwd: the pinned path does not serve this shape");
+    NPM_REQUIRE(!(ld && ld->planes) || path == ATTN_FUSED_BX, "mha_core_bwd: pre-split q / k / v need the split-bf16 path (strides.path = 3)");
     if (path == ATTN_FUSED_TF32)
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
-                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, lddq, lddk, lddv,
+                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, 0, 0, 0, lddq, lddk, lddv,
                                ld && ld->causal ? 1 : 0, false, s);
+    if (path == ATTN_FUSED_BX && ld && ld->planes)
+        return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
+                               reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, ld->q_plane, ld->k_plane, ld->v_plane,
+                               lddq, lddk, lddv, ld->causal ? 1 : 0, true, s);
     if (path == ATTN_FUSED_BX) {
         const BxSaved sv = bx_saved(const_cast<void*>(saved), B, H, Sq, Skv);
         return attn_bwd_launch(sv.q, sv.k, sv.v, o, d_o, sv.lse, dq, dk_out, dv_out, reinterpret_cast<float*>(scratch), B, H,
-                               Sq, Skv, 0, 0, 0, lddq, lddk, lddv, ld && ld->causal ? 1 : 0, true, s);
+                               Sq, Skv, H * dk, H * dk, H * dv, B * Sq * H * dk, B * Skv * H * dk, B * Skv * H * dv, lddq, lddk, lddv,
+                               ld && ld->causal ? 1 : 0, true, s);
     }
     const float* P = reinterpret_cast<const float*>(saved);
     float* dP = reinterpret_cast<float*>(scratch);

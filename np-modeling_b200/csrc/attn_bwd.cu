@@ -907,8 +907,8 @@ int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_
 // saved ([2][B,S,H,64]); dO is split into `scratch` behind D by the dsum kernel.
 int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddq, int64_t lddk, int64_t lddv, int causal, bool bx,
-                    cudaStream_t stream) {
+                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv, int64_t lddq, int64_t lddk,
+                    int64_t lddv, int causal, bool bx, cudaStream_t stream) {
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_bwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(o != nullptr, "mha_core_bwd: the fused path needs the forward output o");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
@@ -921,9 +921,11 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
     uint2* do_planes = nullptr;
     if (bx) {
         do_planes = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dsum) + (((size_t)B * H * Sq * sizeof(float) + 255) & ~(size_t)255));
-        if ((rc = make_tensor_map_bf16_planes(&tQr, q, Sq, H, B, HD, (uint64_t)B * Sq * HD, kBlk))) return rc;
-        if ((rc = make_tensor_map_bf16_planes(&tKr, k, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBlk))) return rc;
-        if ((rc = make_tensor_map_bf16_planes(&tVr, v, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBlk))) return rc;
+        NPM_REQUIRE(ldq >= (int64_t)HD && ldk >= (int64_t)HD && ldv >= (int64_t)HD && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+                    plq % 8 == 0 && plk % 8 == 0 && plv % 8 == 0, "mha_core_bwd: plane strides must be multiples of 8 bf16 elements");
+        if ((rc = make_tensor_map_bf16_planes(&tQr, q, Sq, H, B, ldq, plq, kBlk))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tKr, k, Skv, H, B, ldk, plk, kBlk))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tVr, v, Skv, H, B, ldv, plv, kBlk))) return rc;
         if ((rc = make_tensor_map_bf16_planes(&tDOr, do_planes, Sq, H, B, HD, (uint64_t)B * Sq * HD, kBlk))) return rc;
         tQt = tQr; tKt = tKr; tDOt = tDOr;          // one bf16 image serves as the R and the T operand
     } else {

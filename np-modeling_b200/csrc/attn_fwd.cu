@@ -416,19 +416,22 @@ bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t
            Sq < (1ll << 30) && Skv < (1ll << 30);
 }
 
-// bx = false: q / k / v are fp32 (token strides ld*).  bx = true: q / k / v point at split-bf16 planes [2][B,S,H,64]
-// (dense; hi plane, then mid plane) and ld* are ignored.
+// bx = false: q / k / v are fp32 (token strides ld*).  bx = true: q / k / v point at the hi plane of split-bf16 planes
+// (token strides ld* in bf16 elements, the mid plane pl* elements after the hi plane).
 int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float* lse, int64_t B, int64_t H,
-                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int causal, bool bx, cudaStream_t stream) {
+                    int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv,
+                    int causal, bool bx, cudaStream_t stream) {
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_fwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "mha_core_fwd: pointers must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
     int rc;
     const uint64_t HD = (uint64_t)H * kD;
     if (bx) {
-        if ((rc = make_tensor_map_bf16_planes(&tmQ, q, Sq, H, B, HD, (uint64_t)B * Sq * HD, kBM))) return rc;
-        if ((rc = make_tensor_map_bf16_planes(&tmK, k, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBN))) return rc;
-        if ((rc = make_tensor_map_bf16_planes(&tmV, v, Skv, H, B, HD, (uint64_t)B * Skv * HD, kBN))) return rc;
+        NPM_REQUIRE(ldq >= (int64_t)HD && ldk >= (int64_t)HD && ldv >= (int64_t)HD && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+                    plq % 8 == 0 && plk % 8 == 0 && plv % 8 == 0, "mha_core_fwd: plane strides must be multiples of 8 bf16 elements");
+        if ((rc = make_tensor_map_bf16_planes(&tmQ, q, Sq, H, B, ldq, plq, kBM))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tmK, k, Skv, H, B, ldk, plk, kBN))) return rc;
+        if ((rc = make_tensor_map_bf16_planes(&tmV, v, Skv, H, B, ldv, plv, kBN))) return rc;
     } else {
     NPM_REQUIRE(ldq >= (int64_t)HD && ldk >= (int64_t)HD && ldv >= (int64_t)HD && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0,
                 "mha_core_fwd: token strides must be >= H*d and multiples of 4 floats");

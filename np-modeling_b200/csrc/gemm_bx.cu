@@ -69,6 +69,7 @@ struct GemmBxArgs {
     const float* residual;
     int64_t ldr;
     int relu, accum;
+    int c_planes;              // the result is written as bf16 hi / mid planes (tmC is a bf16 {N, M, 2 planes} map) instead of fp32
     float* a_colsum;           // optional [M] (A MN-major only): += sum over k of A[m, k] — the bias gradient of a dW GEMM
     long long* dbg;            // tools only (NPM_GEMM_DEBUG_TIMES): 16 wait-cycle counters per CTA
 };
@@ -445,6 +446,32 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t buf = nstore & 1u;
                 if (lane == 0) ptx::tma_wait_group_read<1>();
                 __syncwarp();
+                if (args.c_planes) {
+                    // split-bf16 output (the q | k | v projection feeding the fused attention): hi rows of 64 B in the first
+                    // half of the staging buffer, mid rows in the second, two TMA stores into the planes
+                    uint8_t* hrow = stg_base + buf * 4096 + lane * 64;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t h[4], m[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float a = f[8 * j + 2 * q], b = f[8 * j + 2 * q + 1];
+                            h[q] = bx::bf16x2_rn(a, b);
+                            m[q] = bx::bf16x2_rn(a - __uint_as_float(h[q] << 16), b - __uint_as_float(h[q] & 0xffff0000u));
+                        }
+                        *reinterpret_cast<uint4*>(hrow + j * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(hrow + 2048 + j * 16) = make_uint4(m[0], m[1], m[2], m[3]);
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (ptx::elect_one()) {
+                        ptx::tma_store_4d(&tmC, stg_addr + buf * 4096, nc, m0 + warp * 32, 0, 0);
+                        ptx::tma_store_4d(&tmC, stg_addr + buf * 4096 + 2048, nc, m0 + warp * 32, 1, 0);
+                        ptx::tma_commit_group();
+                    }
+                    ++nstore;
+                    continue;
+                }
                 uint8_t* row = stg_base + buf * 4096 + lane * 128;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -548,7 +575,11 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     const bool c_dense = (d.ldc == d.n) && (nb1 == 1 || d.c_bs1 == d.m * d.n) && (nb2 == 1 || d.c_bs2 == d.m * d.n * nb1);
     static const bool no_splitk = getenv("NPM_GEMM_NO_SPLITK") != nullptr;
     static const int forced_bn = getenv("NPM_GEMM_BLOCK_N_DYN") ? atoi(getenv("NPM_GEMM_BLOCK_N_DYN")) : 0;
-    const bool may_split = c_dense && !(d.flags & (NPM_GEMM_RELU | NPM_GEMM_ACCUM)) && !no_splitk;
+    const bool c_planes = d.c_split != nullptr;
+    if (c_planes)
+        NPM_REQUIRE(nb1 == 1 && nb2 == 1 && !(d.flags & NPM_GEMM_ACCUM) && d.residual == nullptr && aligned16(d.c_split) && d.ldc % 8 == 0 &&
+                    d.c_split_plane % 8 == 0, "gemm: c_split needs an unbatched, non-accumulating problem and 16-byte aligned bf16 rows");
+    const bool may_split = c_dense && !(d.flags & (NPM_GEMM_RELU | NPM_GEMM_ACCUM)) && !no_splitk && !c_planes;
     int best_bn = 128, best_splits = 1;
     {
         // cycles per K stage of one pair: 2 * nterms MMAs of N x K16 at N/2 clk each (tensor floor)
@@ -630,7 +661,13 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     {
         const uint64_t ld = d.ldc;
         const uint64_t s2 = bs(nb1, d.c_bs1, ld * d.m), s3 = bs(nb2, d.c_bs2, s2 * nb1);
-        rc = make_tensor_map_4d(&tmC, d.c, d.n, d.m, nb1, nb2, ld, s2, s3, 32, 32, false, false);
+        if (c_planes) {
+            const uint64_t dims[4] = {N, M, 2, 1}, st[3] = {ld, (uint64_t)d.c_split_plane, (uint64_t)d.c_split_plane * 2};
+            const uint32_t box[4] = {32, 32, 1, 1};
+            rc = make_tensor_map_bf16_nd(&tmC, d.c_split, 4, dims, st, box, 0);
+        } else {
+            rc = make_tensor_map_4d(&tmC, d.c, d.n, d.m, nb1, nb2, ld, s2, s3, 32, 32, false, false);
+        }
         if (rc) return rc;
     }
     GemmBxArgs args;
@@ -648,6 +685,7 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     args.ldr = d.ldr;
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
     args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
+    args.c_planes = c_planes ? 1 : 0;
     args.a_colsum = nullptr;
     if (d.a_colsum != nullptr) {
         NPM_REQUIRE(a_mn && nb1 == 1 && nb2 == 1, "gemm: a_colsum needs an unbatched problem with an MN-major A");

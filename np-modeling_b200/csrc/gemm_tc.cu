@@ -828,7 +828,7 @@ int make_tensor_map_bf16_planes(CUtensorMap* tm, const void* base, uint64_t S, u
     return NPM_OK;
 }
 
-// General bf16 tensor map of rank 3..5 (dims[0] contiguous; strides of dims 1.. in ELEMENTS), 64- or 128-byte swizzle.
+// General bf16 tensor map of rank 3..5 (dims[0] contiguous; strides of dims 1.. in ELEMENTS); swizzle 0 (none), 64 or 128 bytes.
 int make_tensor_map_bf16_nd(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                             const uint32_t* box, int swizzle_bytes) {
     EncodeTiledFn fn = encode_fn();
@@ -841,7 +841,8 @@ int make_tensor_map_bf16_nd(CUtensorMap* tm, const void* base, int rank, const u
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) st[i] = strides_elems[i] * 2;
     CUresult rc = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (bf16, rank %d) failed (%d): dims0..2=(%llu,%llu,%llu) box0..2=(%u,%u,%u) base=%p", rank, (int)rc,

@@ -8,11 +8,16 @@ gradients are single tcgen05 GEMMs on the arrays as stored; the attention core r
 `npm_mha_core_fwd/bwd`.
 """
 import ctypes
+import os
 
 import optimizer
 from layers import activations, layer
 from npm_b200 import device
+from npm_b200 import _lib
 from npm_b200._lib import C, GemmDesc, MhaStrides
+
+
+_NO_QKV_PLANES = bool(os.environ.get('NPM_NO_QKV_PLANES'))      # A/B switch for tools
 
 
 def _add3(parts):
@@ -167,38 +172,68 @@ class MultiHeadAttention(layer.StatefulLayer):
         key2 = key.reshape(batch * skv, key.shape[2])
         pl = self._find_planes = self._split_params(packs, wo, min(batch * sq, batch * skv))
 
-        # input projections (attentions.py:88-100); q/k/v are [B,S,H,dk] row blocks of `bufs`, token stride ld
+        # the implementation (and with it the layout of `saved`) is chosen HERE, under the precision mode of the forward
+        # call, and pinned for the backward call: a set_precision() in between cannot make backward misread `saved`
+        self._path = int(C.npm_mha_core_path(batch, h, sq, skv, dk, dv))
+        # split-bf16 fused attention (path 2): the projections write q / k / v directly as the bf16 hi / mid planes the
+        # attention kernels read (npm_linear_fwd_planes) — no fp32 q / k / v, no separate split pass
+        self._planes_mode = (self._path == 2 and dk == dv and hd % 8 == 0 and min(batch * sq, batch * skv) > 128
+                             and not _NO_QKV_PLANES)
+
+        def project(x2d, w, b, n):
+            """-> (buffer, pointer of q-like column 0, elements per token, elements between hi and mid plane)"""
+            if self._planes_mode:
+                m, k = x2d.shape
+                buf = device.workspace(4 * m * n)                         # [2][m, n] bf16
+                pp, ps = pl(w) or (None, 0)
+                rc = _lib.load().npm_linear_fwd_planes(x2d.ptr, w.ptr, pp, ps, b.ptr, buf.data_ptr(), m * n, m, k, n, 1,
+                                                       device.stream())
+                if rc == 0:
+                    return buf, buf.data_ptr(), 2
+                if rc != -3:                                               # NPM_ERR_UNSUPPORTED: project to fp32 instead
+                    raise _lib.NpmError(f'npm_linear_fwd_planes failed (rc={rc}): {_lib.last_error()}')
+                self._planes_mode = False
+            y = self._project(x2d, w, b, n, planes=pl(w))
+            return y, y.ptr, 4
+
+        # input projections (attentions.py:88-100); q/k/v are [B,S,H,dk] column blocks of the outputs, token stride ld
         if packs is not None and key is query and value is query:
             self._mode = 'qkv'
-            qkv = self._project(query2, packs[0], packs[1], 3 * hd, planes=pl(packs[0]))   # [B*S, 3*H*dk]
+            qkv, p0, es = project(query2, packs[0], packs[1], 3 * hd)                      # [B*S, 3*H*dk]
             self._proj = (qkv,)
-            self._qkv_ptrs = (qkv.ptr, qkv.ptr + 4 * hd, qkv.ptr + 8 * hd)
+            self._qkv_ptrs = (p0, p0 + es * hd, p0 + 2 * es * hd)
             self._qkv_ld = (3 * hd, 3 * hd, 3 * hd)
+            self._qkv_plane = (batch * sq * 3 * hd,) * 3
         elif packs is not None and value is key:
             self._mode = 'kv'
-            q2 = self._project(query2, wq, bq, hd, planes=pl(wq))
+            q2, pq, es = project(query2, wq, bq, hd)
             kv_w = packs[0][1:3]
-            kv2 = self._project(key2, kv_w, packs[1][1:3], 2 * hd, planes=pl(kv_w))      # [B*Skv, 2*H*dk]
+            if es == 2:
+                kv2, pk, es2 = project(key2, kv_w, packs[1][1:3], 2 * hd)                  # [B*Skv, 2*H*dk]
+                assert es2 == 2, 'q projected to planes but k | v could not be'
+            else:
+                kv2 = self._project(key2, kv_w, packs[1][1:3], 2 * hd, planes=pl(kv_w))
+                pk = kv2.ptr
             self._proj = (q2, kv2)
-            self._qkv_ptrs = (q2.ptr, kv2.ptr, kv2.ptr + 4 * hd)
+            self._qkv_ptrs = (pq, pk, pk + es * hd)
             self._qkv_ld = (hd, 2 * hd, 2 * hd)
+            self._qkv_plane = (batch * sq * hd, batch * skv * 2 * hd, batch * skv * 2 * hd)
         else:
             self._mode = 'separate'
+            self._planes_mode = False
             q2 = self._project(query2, wq, bq, hd, planes=pl(wq))
             k2 = self._project(key2, wk, bk, hd, planes=pl(wk))
             v2 = self._project(value.reshape(batch * skv, value.shape[2]), wv, bv, h * dv, planes=pl(wv))
             self._proj = (q2, k2, v2)
             self._qkv_ptrs = (q2.ptr, k2.ptr, v2.ptr)
             self._qkv_ld = (hd, hd, h * dv)
+            self._qkv_plane = (0, 0, 0)
 
-        # the implementation (and with it the layout of `saved`) is chosen HERE, under the precision mode of the forward
-        # call, and pinned for the backward call: a set_precision() in between cannot make backward misread `saved`
-        self._path = int(C.npm_mha_core_path(batch, h, sq, skv, dk, dv))
-        self._saved = device.workspace(C.npm_mha_core_saved_bytes_for(self._path, batch, h, sq, skv, dk, dv))
+        # planes mode: `saved` is only the log-sum-exp (the size the TF32 fused path reports)
+        self._saved = device.workspace(C.npm_mha_core_saved_bytes_for(1 if self._planes_mode else self._path, batch, h, sq, skv, dk, dv))
         values = device.empty((batch, sq, h, dv))          # [B, Sq, H, dv] (reference keeps [B,H,Sq,dv])
         assert not self._causal or sq == skv, 'causal attention needs seq_len_q == seq_len_kv'
-        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], causal=int(self._causal),
-                        path=1 + self._path)
+        ld = self._strides()
         qp, kp, vp = self._qkv_ptrs
         C.npm_mha_core_fwd_strided(qp, kp, vp, values.ptr, self._saved.data_ptr(), batch, h, sq, skv, dk, dv,
                                    ctypes.byref(ld), device.stream())
@@ -206,6 +241,12 @@ class MultiHeadAttention(layer.StatefulLayer):
 
         o = self._project(values.reshape(batch * sq, h * dv), wo, bo, wo.shape[0], _residual, planes=pl(wo))
         return o.reshape(batch, sq, wo.shape[0])
+
+    def _strides(self, **grads):
+        pm = self._planes_mode
+        return MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], causal=int(self._causal), path=1 + self._path,
+                          planes=int(pm), q_plane=self._qkv_plane[0] if pm else 0, k_plane=self._qkv_plane[1] if pm else 0,
+                          v_plane=self._qkv_plane[2] if pm else 0, **grads)
 
     # ---- decode-time step with a key/value cache (inference) ---------------------------------------
     def decode_step(self, x_t, cache: KVCache, memory=None, _residual=None):
@@ -326,8 +367,7 @@ class MultiHeadAttention(layer.StatefulLayer):
             dv2 = device.empty((batch * skv, h * dv))
             dptrs, dld, dbufs = (dq2.ptr, dk2.ptr, dv2.ptr), (hd, hd, h * dv), (dq2, dk2, dv2)
         scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes_for(self._path, batch, h, sq, skv, dk, dv))
-        ld = MhaStrides(q=self._qkv_ld[0], k=self._qkv_ld[1], v=self._qkv_ld[2], dq=dld[0], dk=dld[1], dv=dld[2],
-                        causal=int(self._causal), path=1 + self._path)
+        ld = self._strides(dq=dld[0], dk=dld[1], dv=dld[2])
         qp, kp, vp = self._qkv_ptrs
         C.npm_mha_core_bwd_strided(qp, kp, vp, self._values.ptr, dvalues.ptr, self._saved.data_ptr(), dptrs[0],
                                    dptrs[1], dptrs[2], scratch.data_ptr(), batch, h, sq, skv, dk, dv,
@@ -400,6 +440,13 @@ class MultiHeadAttention(layer.StatefulLayer):
         """Dense copy of projected q (0) / k (1) / v (2) as [B, S, H, d] (reference `_q,_k,_v`, attentions.py:92-100)."""
         h, d = self._num_heads, (self._key_dim if i < 2 else self._value_dim)
         batch = self._query.shape[0]
+        if getattr(self, '_planes_mode', False):
+            # the projections exist only as bf16 hi / mid planes: hi + mid is the value the attention kernels used
+            import torch
+            j, width = (0, 1) if (self._mode == 'kv' and i == 0) else ((1, 2) if self._mode == 'kv' else (0, 3))
+            pl2 = self._proj[j].view(torch.bfloat16).view(2, batch * seq, width * h * d).float().sum(0)
+            col = i if self._mode == 'qkv' else (0 if i == 0 else i - 1)
+            return device.DeviceArray(pl2.view(batch, seq, width, h, d)[:, :, col].contiguous())
         if self._mode == 'qkv':
             t = self._proj[0].t.view(batch, seq, 3, h, d)[:, :, i]
         elif self._mode == 'kv' and i > 0:

@@ -293,3 +293,69 @@ def test_conv_tensor_core_path_vs_oracle(shape, mode):
             close(got, want, rtol=1e-3, atol=1e-4 * (np.sqrt(n * hh * ww) if name in ('dw', 'db') else 1.0))
         else:
             assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())
+
+
+@pytest.mark.parametrize('mode', ['bf16x3', 'tf32'])
+def test_conv_cfg2_full_batch(mode):
+    """BASELINE cfg2 at its full batch (x [256,32,32,64] -> 128, 3x3; the Cin = 3 first layer too): a convolution treats
+    images independently (conv.py:104-105), so the oracle is evaluated on images 0, 1, 254, 255 and compared with those
+    slices of the full-batch device result; the filter gradient, a sum over all 256 images, is compared with this
+    library's exact fp32 CUDA-core kernel (precision 'fp32') and, for the four-image sub-batch, with the oracle."""
+    import npm_b200
+    from layers import Conv2D
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(256)
+    for c0, c1 in ((64, 128), (3, 64)):
+        x = rng.standard_normal((256, 32, 32, c0)).astype(np.float32)
+        dy = rng.standard_normal((256, 32, 32, c1)).astype(np.float32)
+        f = (rng.standard_normal((3, 3, c0, c1)) / np.sqrt(9 * c0)).astype(np.float32)
+        # biases well above the pre-activation spread: every ReLU gate is open in both runs, so the filter gradients of
+        # the two kernels can be compared element by element (a gate at rounding level would move dw by an outer product)
+        b = (np.abs(rng.standard_normal(c1)) + 8.0).astype(np.float32)
+        res = {}
+        for prec in (mode, 'fp32'):
+            npm_b200.set_precision(prec)
+            layer = Conv2D(c1, 3)
+            layer(x[:1])
+            bind(layer, {'_w': f, '_b': b})
+            y = np.asarray(layer(x))
+            rec = Recorder()
+            dx = np.asarray(layer(dy, backprop=True, optimizer_=rec))
+            res[prec] = (y, dx, grads_of(layer, rec, ['_w', '_b']))
+        y, dx, g = res[mode]
+        sel = [0, 1, 254, 255]
+        oy, oz = O.conv_layer_fwd(x[sel], f, b)
+        tight = mode == 'bf16x3'
+        tol = dict(rtol=1e-3, atol=1e-4) if tight else dict(rtol=5e-3, atol=5e-3)
+        close(y[sel], oy, **tol)
+        odx, _, _ = O.conv_layer_bwd(x[sel], f, np.where(y[sel] > 0, 1.0, -1.0), dy[sel])
+        close(dx[sel], odx, **tol)
+        # dw / db over the full batch: against the exact fp32 kernel (ReLU gates may differ at rounding level between
+        # the two runs, each flip moves dw by one outer product of O(1): judged in relative Frobenius norm)
+        for k in ('_w', '_b'):
+            a, r = np.asarray(g[k], dtype=np.float64), np.asarray(res['fp32'][2][k], dtype=np.float64)
+            err = np.linalg.norm(a - r) / np.linalg.norm(r)
+            assert err < (1e-4 if tight else 2e-3), (c0, k, err)     # incl. the fp32 kernel's own rounding over 262144 summed pixels
+
+
+def test_adam_fp32_moments_do_not_drift_over_500_steps():
+    """optimizer.py:53-67 keeps m and v in float64; the fused kernel keeps them in fp32.  500 steps with fresh random
+    gradients: the parameters stay within 2e-5 (relative to the update scale) of the float64 recurrence."""
+    import optimizer
+    from npm_b200 import device
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(500)
+
+    class Box:
+        pass
+
+    box = Box()
+    host = rng.standard_normal(4099).astype(np.float32)
+    box.p = device.asdevice(host)
+    opt = optimizer.AdamOptimizer(learning_rate=1e-3)
+    p64, m, v = host.astype(np.float64), np.zeros(4099), np.zeros(4099)
+    for t in range(1, 501):
+        g = (rng.standard_normal(4099) * (1.0 + np.sin(t / 17.0))).astype(np.float32)
+        opt.update(box, 'p', g)
+        p64, m, v = O.adam_step(p64, g, m, v, t, 1e-3)
+    close(box.p, p64, rtol=0, atol=2e-5)
