@@ -45,6 +45,7 @@ constexpr int kChunkBytes = 16384;
 constexpr int kKS = 3, kVS = 2;              // K / V ring depth (K is consumed one block ahead of V)
 constexpr int kSmemBytes = (2 + kKS + kVS) * kTileBytes + 1024 /*align*/ + 512 /*barriers*/;
 constexpr int kThreads = 256;
+constexpr int kThreadsBx = 384;               // split-bf16 variant: 8 softmax warps (two per TMEM lane quarter, 64 columns each)
 constexpr float kRescaleThreshold = 8.0f;    // log2 units
 
 struct FwdArgs {
@@ -69,8 +70,19 @@ __device__ __forceinline__ void split_pack(float p0, float p1, uint32_t& hi, uin
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
 }
 
+// one 32-bit TMEM cell per lane: how the two softmax warps of a lane quarter exchange row maxima / row sums
+__device__ __forceinline__ void tmem_st_x1(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bar_sync_64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 template <bool CAUSAL, bool BX>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(BX ? kThreadsBx : kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
     pdl_trigger();
@@ -109,7 +121,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int i = 0; i < 2; ++i) { ptx::mbar_init(q_full(i), 1); ptx::mbar_init(q_empty(i), 1); }
             for (int i = 0; i < kKS; ++i) { ptx::mbar_init(k_full(i), 1); ptx::mbar_init(k_empty(i), 1); }
             for (int i = 0; i < kVS; ++i) { ptx::mbar_init(v_full(i), 1); ptx::mbar_init(v_empty(i), 1); }
-            for (int i = 0; i < 2; ++i) { ptx::mbar_init(s_full(i), 1); ptx::mbar_init(p_ready(i), 128); }
+            for (int i = 0; i < 2; ++i) { ptx::mbar_init(s_full(i), 1); ptx::mbar_init(p_ready(i), BX ? 256 : 128); }
             ptx::mbar_init(o_done, 1);
             ptx::fence_mbar_init();
         }
@@ -278,6 +290,125 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 ptx::umma_commit(v_empty(st));
                 ptx::umma_commit(o_done);
+            }
+        }
+    } else if (BX && warp >= 4) {
+        // ===== softmax, split-bf16 variant: TWO warps per TMEM lane quarter (warps 4+wq and 8+wq), 64 of the 128 columns
+        // each.  The split to bf16 hi / mid doubles the per-element work of these warps (cvt.rn.bf16x2 shares the XU pipe
+        // with ex2) and with four warps they, not the tensor pipe, bounded the kernel.  The two threads of a row agree on
+        // the running maximum through one TMEM cell each per block (columns 320.. of their own lane) and add their row
+        // sums the same way in the epilogue. =====
+        const int wq = warp & 3, hsel = ((warp - 4) >> 2) & 1;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_off = uint32_t(wq * 32) << 16;
+        const uint32_t tmem_x = tmem_base + lane_off + 320;
+        const int c0 = hsel * 64;
+        const float c = args.c;
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+            const int mt = item % args.q_tiles;
+            const int bh = item / args.q_tiles;
+            const int h = bh % args.H, b = bh / args.H;
+            float m_ref = -INFINITY, l = 0.0f;
+            const int nb = blocks_of(item);
+            for (int j = 0; j < nb; ++j, ++g) {
+                const uint32_t buf = g & 1u;
+                ptx::mbar_wait(s_full(buf), (g >> 1) & 1);
+                ptx::tc_fence_after();
+                float s[64];
+                const uint32_t s_tmem = tmem_base + lane_off + buf * kBN + c0;
+                ptx::tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+                ptx::tmem_ld_32x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+                ptx::tmem_ld_wait();
+                const int kv_left = args.Skv - j * kBN;
+                if (kv_left < kBN) {
+#pragma unroll
+                    for (int k = 0; k < 64; ++k)
+                        if (c0 + k >= kv_left) s[k] = -INFINITY;
+                }
+                if (CAUSAL && j == mt) {
+#pragma unroll
+                    for (int k = 0; k < 64; ++k)
+                        if (c0 + k > row) s[k] = -INFINITY;
+                }
+                float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+                for (int k = 4; k < 64; k += 4) {
+                    mx0 = fmaxf(mx0, s[k]); mx1 = fmaxf(mx1, s[k + 1]);
+                    mx2 = fmaxf(mx2, s[k + 2]); mx3 = fmaxf(mx3, s[k + 3]);
+                }
+                float pm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                // exchange with the thread that holds the other 64 columns of this row
+                tmem_st_x1(tmem_x + buf * 2 + hsel, __float_as_uint(pm));
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                bar_sync_64(1 + wq);
+                ptx::tc_fence_after();
+                pm = fmaxf(pm, __uint_as_float(tmem_ld_x1(tmem_x + buf * 2 + (hsel ^ 1))));
+                ptx::tmem_ld_wait();
+                const float mb = pm * c;
+                const bool need = mb > m_ref + kRescaleThreshold;
+                if (__any_sync(0xffffffffu, need)) {
+                    float alpha = 1.0f;
+                    if (need) {
+                        alpha = ptx::ex2(m_ref - mb);
+                        m_ref = mb;
+                        l *= alpha;
+                    }
+                    if (j > 0) {       // see the four-warp variant below for why parity (g-1)&1 is unambiguous
+                        ptx::mbar_wait(o_done, (g - 1) & 1);
+                        ptx::tc_fence_after();
+                        uint32_t o[32];                       // this thread rescales its 32 of the 64 O columns
+                        ptx::tmem_ld_32x32(tmem_o + lane_off + hsel * 32, o);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                        ptx::tmem_st_32x32(tmem_o + lane_off + hsel * 32, o);
+                    }
+                }
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 64; k += 4) {
+                    s[k] = ptx::ex2(fmaf(s[k], c, -m_ref));         s[k + 1] = ptx::ex2(fmaf(s[k + 1], c, -m_ref));
+                    s[k + 2] = ptx::ex2(fmaf(s[k + 2], c, -m_ref)); s[k + 3] = ptx::ex2(fmaf(s[k + 3], c, -m_ref));
+                    l0 += s[k]; l1 += s[k + 1]; l2 += s[k + 2]; l3 += s[k + 3];
+                }
+                l += (l0 + l1) + (l2 + l3);
+                {
+                    uint32_t hi[32], mid[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) split_pack(s[2 * i], s[2 * i + 1], hi[i], mid[i]);
+                    ptx::tmem_st_32x32(s_tmem, hi);                // this 64-k half: [32 columns hi | 32 columns mid]
+                    ptx::tmem_st_32x32(s_tmem + 32, mid);
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(p_ready(buf));
+            }
+            // ---- epilogue: add the two partial row sums, O / l -> global (32 columns each), log-sum-exp -> saved ----
+            tmem_st_x1(tmem_x + 4 + hsel, __float_as_uint(l));
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            bar_sync_64(1 + wq);
+            ptx::tc_fence_after();
+            l += __uint_as_float(tmem_ld_x1(tmem_x + 4 + (hsel ^ 1)));
+            ptx::tmem_ld_wait();
+            ptx::mbar_wait(o_done, (g - 1) & 1);
+            ptx::tc_fence_after();
+            uint32_t o[32];
+            ptx::tmem_ld_32x32(tmem_o + lane_off + hsel * 32, o);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            bar_sync_64(1 + wq);          // both partial sums have been read: the exchange cells may be rewritten (next item)
+            const int sq = mt * kBM + row;
+            if (sq < args.Sq) {
+                const float inv = 1.0f / l;
+                float4* dst = reinterpret_cast<float4*>(args.o + (((size_t)b * args.Sq + sq) * args.H + h) * kD + hsel * 32);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    dst[k] = make_float4(__uint_as_float(o[4 * k]) * inv, __uint_as_float(o[4 * k + 1]) * inv,
+                                         __uint_as_float(o[4 * k + 2]) * inv, __uint_as_float(o[4 * k + 3]) * inv);
+                if (hsel == 0) args.lse[((size_t)b * args.H + h) * args.Sq + sq] = m_ref + ptx::lg2(l);
             }
         }
     } else if (warp >= 4) {
@@ -471,7 +602,7 @@ int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float
     if (causal) while (grid > 1 && gcd_int(grid, a.q_tiles) != 1) --grid;
     auto kern = causal ? (bx ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
                        : (bx ? attn_fwd_kernel<false, true> : attn_fwd_kernel<false, false>);
-    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a);
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a);
     if (le != cudaSuccess) { set_error("attn_fwd_kernel launch: %s", cudaGetErrorString(le)); return NPM_ERR_CUDA; }
     count_launch();
     return check_launch("attn_fwd_kernel");
