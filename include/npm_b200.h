@@ -99,6 +99,10 @@ typedef struct npm_gemm_desc {
                                * kernel then lands B without converting it; every other path ignores it
                                * and reads `b`.                                                       */
     int64_t b_split_plane;
+    const void* a_split;      /* the same hint for A: an activation that exists as bf16 planes because its
+                               * producer wrote it that way (c_split of the GEMM before it, the split
+                               * output of npm_relu_bwd_colsum_planes); `a` may then be NULL.            */
+    int64_t a_split_plane;
     void*   c_split;          /* NULL, or bf16 planes [2][m, ldc] (mid plane c_split_plane elements after
                                * the hi plane): the result is written ONLY in this split form (c may be
                                * NULL) — what the fused split-bf16 attention reads, so a q | k | v

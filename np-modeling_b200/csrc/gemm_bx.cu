@@ -105,7 +105,10 @@ __device__ __forceinline__ void tile_coords_bx(int r, int tiles_m, int tiles_n, 
 // stage = 896 wavefronts + arbitration against the 768 clk of its six MMAs, profiles/r02_ncu_gemm_bx_ffn.txt).
 //   K-major  B_PRE: box {32 k, rows, 2 planes}, 64-byte swizzle: hi image rows x 64 B, then the mid image
 //   MN-major B_PRE: box {64 n, 32 k, rows/64 slabs, 2 planes}, 128-byte swizzle: the same image the converters write
-template <int BLOCK_N, bool A_MN, bool B_MN, int NTERMS, bool B_PRE>
+// A_PRE: the same for the A operand — an activation whose producer wrote it as bf16 planes in the first place (the FFN
+// hidden activation out of the first FFN GEMM's epilogue, its gradient out of the ReLU backward kernel): with both
+// operands pre-split the converters only pass the TMA completion on and the main loop is TMA -> MMA.
+template <int BLOCK_N, bool A_MN, bool B_MN, int NTERMS, bool B_PRE, bool A_PRE = false>
 __global__ void __launch_bounds__(kThreadsBx, 1)
 gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmBxArgs args) {
@@ -191,7 +194,10 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t fb = tma_bar(stage);
                     ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
                     const int k0 = kb * kKS;
-                    if (!A_MN) {
+                    if (A_PRE) {
+                        if (!A_MN) ptx::tma_load_4d(sA, &tmA, fb, k0, m0, 0, 0);           // {k, rows, plane, 1}
+                        else       ptx::tma_load_4d(sA, &tmA, fb, 0, k0, m0 / 64, 0);      // {64 m, k, slab, plane}
+                    } else if (!A_MN) {
                         ptx::tma_load_4d(sA, &tmA, fb, k0, m0, z1, z2);
                     } else if (args.a_chunked) {
                         ptx::tma_load_5d(sA, &tmA, fb, 0, k0, m0 / 32, z1, z2);
@@ -226,7 +232,7 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // a thread always holds the same four columns (mn = 32 * (pw / 2) + 4 * (lane & 7) ..+3), so one float4
         // accumulates them; the tiles of the first column of N tiles add their sums to args.a_colsum (zeroed by the
         // launcher; red.global.add, the splits of a split-K launch each contribute their rows).
-        const bool do_colsum = A_MN && args.a_colsum != nullptr;
+        const bool do_colsum = A_MN && !A_PRE && args.a_colsum != nullptr;
         float4* cs_smem = reinterpret_cast<float4*>(base_ptr + S * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kBarBytes);
         int stage = 0;
         uint32_t phase = 0;
@@ -247,18 +253,18 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t sA = stage_addr + stage * Cfg::kStageBytes;
             float4 va[OperandConverter<kBM, A_MN, NTERMS>::NLD];
             float4 vb[OperandConverter<Cfg::kHalfN, B_MN, NTERMS>::NLD];
-            ca.load(va, sA);
+            if (!A_PRE) ca.load(va, sA);
             if (!B_PRE) cb.load(vb, sA + Cfg::kABytes);
-            bar_sync_conv();                                 // every fp32 chunk of the stage is in registers: overwrite it
+            if (!(A_PRE && B_PRE)) bar_sync_conv();          // every fp32 chunk of the stage is in registers: overwrite it
             if (dbg) t2 = clock64();
-            ca.store(va, sA);
+            if (!A_PRE) ca.store(va, sA);
             if (!B_PRE) cb.store(vb, sA + Cfg::kABytes);
             // no proxy fence here: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR costs
             // ~36 clk per store in flight (700 clk per stage measured with 16 STS per thread); the consumer of this
             // barrier — a thread with nothing in flight — executes it (issuer / peer relay below)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(conv_bar(stage));
-            if (sum_tile) {
+            if (!A_PRE && sum_tile) {
 #pragma unroll
                 for (int i = 0; i < OperandConverter<kBM, A_MN, NTERMS>::NLD; ++i) {
                     csum.x += va[i].x; csum.y += va[i].y; csum.z += va[i].z; csum.w += va[i].w;
@@ -323,9 +329,12 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint64_t desc_k  = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
             constexpr uint64_t desc_mn = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 4096, 1024);   // LBO: next 64-mn slab, SBO: next 8 k-rows
             constexpr uint64_t desc_k64 = ptx::umma_desc_base(4 /*SWIZZLE_64B*/, 16, 512);      // pre-split K-major: 64-byte rows, 8-row groups 512 B apart
-            constexpr uint64_t descA = A_MN ? desc_mn : desc_k, descB = B_MN ? desc_mn : (B_PRE ? desc_k64 : desc_k);
+            constexpr uint64_t descA = A_MN ? desc_mn : (A_PRE ? desc_k64 : desc_k), descB = B_MN ? desc_mn : (B_PRE ? desc_k64 : desc_k);
             // byte offset of K16 slice s of the hi (t = 0) / mid (t = 1) image
-            auto a_off = [](int t, int s) -> uint32_t { return A_MN ? uint32_t(t) * (kBM / 64) * 4096u + uint32_t(s) * 2048u : uint32_t(t) * 64u + uint32_t(s) * 32u; };
+            auto a_off = [](int t, int s) -> uint32_t {
+                return A_MN ? uint32_t(t) * (kBM / 64) * 4096u + uint32_t(s) * 2048u
+                            : (A_PRE ? uint32_t(t) * (kBM * 64u) + uint32_t(s) * 32u : uint32_t(t) * 64u + uint32_t(s) * 32u);
+            };
             auto b_off = [](int t, int s) -> uint32_t {
                 return B_MN ? uint32_t(t) * (Cfg::kHalfN / 64) * 4096u + uint32_t(s) * 2048u
                             : (B_PRE ? uint32_t(t) * (Cfg::kHalfN * 64u) + uint32_t(s) * 32u : uint32_t(t) * 64u + uint32_t(s) * 32u);
@@ -506,10 +515,10 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == kMmaWarp) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
 }
 
-template <int BN, bool AMN, bool BMN, int NT, bool BPRE>
+template <int BN, bool AMN, bool BMN, int NT, bool BPRE, bool APRE = false>
 int launch_bx(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args, int grid, cudaStream_t stream) {
     using Cfg = BxCfg<BN>;
-    auto kern = gemm_bx_kernel<BN, AMN, BMN, NT, BPRE>;
+    auto kern = gemm_bx_kernel<BN, AMN, BMN, NT, BPRE, APRE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -543,17 +552,27 @@ int launch_bx(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, 
     return check_launch("gemm_bx_kernel");
 }
 
+template <int BN, bool AMN, bool BMN>
+int launch_bx_pre(bool apre, bool bpre, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args, int grid,
+                  cudaStream_t s) {
+    if (apre && bpre) return launch_bx<BN, AMN, BMN, 3, true, true>(a, b, c, args, grid, s);
+    if (apre) return launch_bx<BN, AMN, BMN, 3, false, true>(a, b, c, args, grid, s);
+    if (bpre) return launch_bx<BN, AMN, BMN, 3, true, false>(a, b, c, args, grid, s);
+    return launch_bx<BN, AMN, BMN, 3, false, false>(a, b, c, args, grid, s);
+}
 template <int BN, int NT>
-int launch_bx_major(bool amn, bool bmn, bool bpre, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmBxArgs& args,
-                    int grid, cudaStream_t s) {
-    if (bpre && NT == 3) {        // pre-split weights: the B operand of a forward / dX GEMM (A is an activation, K-major)
-        if (!amn && !bmn) return launch_bx<BN, false, false, 3, true>(a, b, c, args, grid, s);
-        if (!amn && bmn) return launch_bx<BN, false, true, 3, true>(a, b, c, args, grid, s);
+int launch_bx_major(bool amn, bool bmn, bool apre, bool bpre, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                    const GemmBxArgs& args, int grid, cudaStream_t s) {
+    if (NT == 3) {
+        if (!amn && !bmn) return launch_bx_pre<BN, false, false>(apre, bpre, a, b, c, args, grid, s);
+        if (!amn && bmn) return launch_bx_pre<BN, false, true>(apre, bpre, a, b, c, args, grid, s);
+        if (amn && !bmn) return launch_bx_pre<BN, true, false>(apre, bpre, a, b, c, args, grid, s);
+        return launch_bx_pre<BN, true, true>(apre, bpre, a, b, c, args, grid, s);
     }
-    if (!amn && !bmn) return launch_bx<BN, false, false, NT, false>(a, b, c, args, grid, s);
-    if (!amn && bmn) return launch_bx<BN, false, true, NT, false>(a, b, c, args, grid, s);
-    if (amn && !bmn) return launch_bx<BN, true, false, NT, false>(a, b, c, args, grid, s);
-    return launch_bx<BN, true, true, NT, false>(a, b, c, args, grid, s);
+    if (!amn && !bmn) return launch_bx<BN, false, false, 1, false>(a, b, c, args, grid, s);
+    if (!amn && bmn) return launch_bx<BN, false, true, 1, false>(a, b, c, args, grid, s);
+    if (amn && !bmn) return launch_bx<BN, true, false, 1, false>(a, b, c, args, grid, s);
+    return launch_bx<BN, true, true, 1, false>(a, b, c, args, grid, s);
 }
 
 }  // namespace
@@ -619,7 +638,19 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     int rc;
     // fp32 staging images: K-major = one box {32 k, rows}; MN-major = {32 mn, 32 k} boxes of 4 KB, all of a stage in one
     // TMA instruction when the operand has the 5-D {32, K, MN/32, nb1, nb2} view (a box costs ~46 clk + bytes / 70 B/clk)
-    if (!a_mn) {
+    // pre-split A (an activation its producer wrote as bf16 planes): unbatched, three terms; MN-major needs whole 64-row slabs
+    const bool a_pre = d.a_split != nullptr && nterms == 3 && nb1 == 1 && nb2 == 1 && (!a_mn || d.m % 64 == 0) && aligned16(d.a_split) &&
+                       d.a_split_plane % 8 == 0 && (a_mn ? d.a_cs : d.a_rs) % 8 == 0 && d.a_colsum == nullptr;
+    NPM_REQUIRE(d.a != nullptr || a_pre, "gemm: a_split cannot be used for this problem (alignment / shape) and no fp32 A was given");
+    if (a_pre && !a_mn) {
+        const uint64_t dims[4] = {K, M, 2, 1}, st[3] = {(uint64_t)d.a_rs, (uint64_t)d.a_split_plane, (uint64_t)d.a_split_plane * 2};
+        const uint32_t box[4] = {kKS, kBM, 2, 1};
+        rc = make_tensor_map_bf16_nd(&tmA, d.a_split, 4, dims, st, box, 64);
+    } else if (a_pre) {
+        const uint64_t dims[4] = {64, K, M / 64, 2}, st[3] = {(uint64_t)d.a_cs, 64, (uint64_t)d.a_split_plane};
+        const uint32_t box[4] = {64, kKS, kBM / 64, 2};
+        rc = make_tensor_map_bf16_nd(&tmA, d.a_split, 4, dims, st, box, 128);
+    } else if (!a_mn) {
         const uint64_t ld = d.a_rs, s2 = bs(nb1, d.a_bs1, ld * M), s3 = bs(nb2, d.a_bs2, s2 * nb1);
         rc = make_tensor_map_4d(&tmA, d.a, K, M, nb1, nb2, ld, s2, s3, kKS, kBM, false, false);
     } else {
@@ -634,7 +665,7 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     }
     if (rc) return rc;
     // pre-split B (weights): unbatched, A K-major, three terms; MN-major needs whole 64-column slabs
-    const bool b_pre = d.b_split != nullptr && nterms == 3 && !a_mn && nb1 == 1 && nb2 == 1 && (!b_mn || d.n % 64 == 0) &&
+    const bool b_pre = d.b_split != nullptr && nterms == 3 && nb1 == 1 && nb2 == 1 && (!b_mn || d.n % 64 == 0) &&
                        aligned16(d.b_split) && d.b_split_plane % 8 == 0 && (b_mn ? d.b_rs : d.b_cs) % 8 == 0;   // TMA: 16-byte strides in bf16
     if (b_pre && !b_mn) {
         const uint64_t dims[4] = {K, N, 2, 1}, st[3] = {(uint64_t)d.b_cs, (uint64_t)d.b_split_plane, (uint64_t)d.b_split_plane * 2};
@@ -696,11 +727,11 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     args.dbg = nullptr;
     const int grid = 2 * (int)(total < units ? total : units);
     if (nterms == 3) {
-        if (bn == 256) return launch_bx_major<256, 3>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
-        return launch_bx_major<128, 3>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
+        if (bn == 256) return launch_bx_major<256, 3>(a_mn, b_mn, a_pre, b_pre, tmA, tmB, tmC, args, grid, stream);
+        return launch_bx_major<128, 3>(a_mn, b_mn, a_pre, b_pre, tmA, tmB, tmC, args, grid, stream);
     }
-    if (bn == 256) return launch_bx_major<256, 1>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
-    return launch_bx_major<128, 1>(a_mn, b_mn, b_pre, tmA, tmB, tmC, args, grid, stream);
+    if (bn == 256) return launch_bx_major<256, 1>(a_mn, b_mn, a_pre, b_pre, tmA, tmB, tmC, args, grid, stream);
+    return launch_bx_major<128, 1>(a_mn, b_mn, a_pre, b_pre, tmA, tmB, tmC, args, grid, stream);
 }
 
 }  // namespace npm

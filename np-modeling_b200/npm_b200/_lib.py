@@ -32,7 +32,7 @@ class GemmDesc(Structure):
         ('c_bs1', c_int64), ('c_bs2', c_int64),
         ('alpha', c_float), ('flags', c_int32), ('precision', c_int32),
         ('residual', c_void_p), ('ldr', c_int64), ('a_colsum', c_void_p), ('b_split', c_void_p), ('b_split_plane', c_int64),
-        ('c_split', c_void_p), ('c_split_plane', c_int64),
+        ('a_split', c_void_p), ('a_split_plane', c_int64), ('c_split', c_void_p), ('c_split_plane', c_int64),
     ]
 
 

@@ -48,10 +48,10 @@ def test_struct_layouts_match_the_header():
     assert _lib.MhaStrides.path.offset == 56
     assert _lib.MhaStrides.causal.offset == 48
     # incl. padding before `residual`; then a_colsum, b_split, b_split_plane
-    # incl. c_split, c_split_plane
-    assert ctypes.sizeof(_lib.GemmDesc) == 4 * 8 + 3 * 8 + 5 * 8 + 2 * 4 + 6 * 8 + 3 * 4 + 4 + 2 * 8 + 5 * 8
-    assert _lib.GemmDesc.residual.offset == ctypes.sizeof(_lib.GemmDesc) - 16 - 40
-    assert _lib.GemmDesc.a_colsum.offset == ctypes.sizeof(_lib.GemmDesc) - 40
+    # incl. a_split, a_split_plane, c_split, c_split_plane
+    assert ctypes.sizeof(_lib.GemmDesc) == 4 * 8 + 3 * 8 + 5 * 8 + 2 * 4 + 6 * 8 + 3 * 4 + 4 + 2 * 8 + 7 * 8
+    assert _lib.GemmDesc.residual.offset == ctypes.sizeof(_lib.GemmDesc) - 16 - 56
+    assert _lib.GemmDesc.a_colsum.offset == ctypes.sizeof(_lib.GemmDesc) - 56
     assert _lib.GemmDesc.c_split.offset == ctypes.sizeof(_lib.GemmDesc) - 16
     assert _lib.GemmDesc.alpha.offset == 4 * 8 + 3 * 8 + 5 * 8 + 8 + 6 * 8
 

@@ -988,3 +988,47 @@ def test_trainer_prefetch_overlaps_and_matches_plain_training():
         return np.asarray(layer.linear.w)
 
     np.testing.assert_array_equal(run(True), run(False))
+
+
+@pytest.mark.parametrize('majors', ['kk', 'km', 'mk', 'mm'])
+@pytest.mark.parametrize('pre', ['a', 'b', 'ab', 'c'])
+def test_gemm_split_planes_as_operands_and_output(majors, pre):
+    """npm_gemm_desc.a_split / b_split / c_split (split-bf16 kernel): operands handed over as bf16 hi / mid planes
+    (npm_weight_split) and the result written as planes give what the fp32 entry computes — against float64."""
+    import ctypes
+    import torch
+    from npm_b200 import device
+    from npm_b200._lib import C, GemmDesc
+    M, N, K = 384, 320, 264
+    rng = np.random.default_rng(40)
+    a = rng.standard_normal((M, K) if majors[0] == 'k' else (K, M)).astype(np.float32)
+    b = rng.standard_normal((N, K) if majors[1] == 'k' else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ta, tb, tbias = (torch.from_numpy(x).cuda() for x in (a, b, bias))
+    tc = torch.full((M, N), float('nan'), device='cuda')
+    st = device.stream()
+
+    def planes(t):
+        p = torch.empty(t.numel() * 4, dtype=torch.uint8, device='cuda')
+        C.npm_weight_split(t.data_ptr(), p.data_ptr(), t.shape[0], t.shape[1], st)
+        return p
+
+    d = GemmDesc(a=ta.data_ptr(), b=tb.data_ptr(), c=tc.data_ptr(), bias=tbias.data_ptr(), m=M, n=N, k=K,
+                 a_rs=K if majors[0] == 'k' else 1, a_cs=1 if majors[0] == 'k' else M,
+                 b_rs=1 if majors[1] == 'k' else N, b_cs=K if majors[1] == 'k' else 1, ldc=N, nb1=1, nb2=1, alpha=1.0, flags=0,
+                 precision=3)
+    keep = []
+    if 'a' in pre:
+        keep.append(planes(ta)); d.a_split, d.a_split_plane, d.a = keep[-1].data_ptr(), M * K, None
+    if 'b' in pre:
+        keep.append(planes(tb)); d.b_split, d.b_split_plane = keep[-1].data_ptr(), N * K
+    if pre == 'c':
+        out = torch.empty(2, M, N, dtype=torch.bfloat16, device='cuda')
+        d.c_split, d.c_split_plane, d.c = out.data_ptr(), M * N, None
+    C.npm_gemm(ctypes.byref(d), st)
+    torch.cuda.synchronize()
+    A = a.astype(np.float64) if majors[0] == 'k' else a.astype(np.float64).T
+    B = b.astype(np.float64).T if majors[1] == 'k' else b.astype(np.float64)
+    want = A @ B + bias
+    got = out.float().sum(0).cpu().numpy() if pre == 'c' else tc.cpu().numpy()
+    close(got, want, rtol=1e-3, atol=4e-4)

@@ -28,7 +28,7 @@ def time_fn(fn, iters=6):
     return ts[len(ts) // 2]
 
 
-def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, timing=False, seed=0, presplit=False):
+def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, timing=False, seed=0, presplit=False, presplit_a=False):
     g = torch.Generator(device='cuda').manual_seed(seed)
     a = torch.randn(nb, M, K, device='cuda', generator=g) if majors[0] == 'k' else torch.randn(nb, K, M, device='cuda', generator=g)
     b = torch.randn(nb, N, K, device='cuda', generator=g) if majors[1] == 'k' else torch.randn(nb, K, N, device='cuda', generator=g)
@@ -51,6 +51,10 @@ def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, tim
         planes = torch.empty(b.numel() * 4, dtype=torch.uint8, device='cuda')
         C.npm_weight_split(b.data_ptr(), planes.data_ptr(), b.shape[-2], b.shape[-1], torch.cuda.current_stream().cuda_stream)
         d.b_split, d.b_split_plane = planes.data_ptr(), b.numel()
+    if presplit_a:    # A as bf16 planes, no fp32 pointer at all (what a producer that writes planes hands over)
+        planes_a = torch.empty(a.numel() * 4, dtype=torch.uint8, device='cuda')
+        C.npm_weight_split(a.data_ptr(), planes_a.data_ptr(), a.shape[-2], a.shape[-1], torch.cuda.current_stream().cuda_stream)
+        d.a_split, d.a_split_plane, d.a = planes_a.data_ptr(), a.numel(), None
     st = torch.cuda.current_stream().cuda_stream
     C.npm_gemm(d, st)
     torch.cuda.synchronize()
@@ -68,7 +72,8 @@ def run(majors, prec, M, N, K, nb=1, bias=False, residual=False, relu=False, tim
     tol = 1e-4 + 1e-3 * want.abs()
     viol = float((err / tol).max())
     rel = float(err.max() / want.abs().max())
-    out = f'{prec:7s} {majors} M={M:5d} N={N:5d} K={K:5d} nb={nb:3d} b{int(bias)}r{int(residual)}relu{int(relu)}: max|err|={float(err.max()):.3e} ' \
+    tag = prec + ('+A' if presplit_a else '') + ('+B' if presplit else '')
+    out = f'{tag:11s} {majors} M={M:5d} N={N:5d} K={K:5d} nb={nb:3d} b{int(bias)}r{int(residual)}relu{int(relu)}: max|err|={float(err.max()):.3e} ' \
           f'rel-to-max={rel:.2e} worst err/tol={viol:.3f} nan={int(torch.isnan(c).sum())}'
     if timing:
         ms = time_fn(lambda: C.npm_gemm(d, st))
@@ -81,6 +86,10 @@ def main():
     bad = 0
     for mj, M, N, K in [('kk', 256, 256, 64), ('km', 256, 256, 64), ('kk', 300, 520, 1024), ('km', 300, 512, 104), ('km', 1000, 1024, 1000), ('kk', 513, 36, 96)]:
         bad += run(mj, 'bf16x3', M, N, K, presplit=True, bias=True) > 1.0 and M * K < 100000
+    for mj, M, N, K in [('kk', 256, 256, 64), ('km', 256, 256, 64), ('mk', 256, 256, 64), ('mm', 256, 256, 64), ('kk', 300, 520, 1024),
+                        ('mm', 1024, 1024, 1000), ('mk', 512, 104, 264), ('km', 1000, 1024, 1000)]:
+        for pa, pb in ((True, False), (True, True)):
+            bad += run(mj, 'bf16x3', M, N, K, presplit=pb, presplit_a=pa, bias=True) > 1.0 and K < 200
     quick = [('kk', 256, 256, 64), ('km', 256, 256, 64), ('mk', 256, 256, 64), ('mm', 256, 256, 64),
              ('kk', 300, 520, 1024), ('km', 300, 520, 100), ('mk', 260, 36, 516), ('mm', 1024, 1024, 1024),
              ('kk', 129, 8, 4), ('km', 1000, 1000, 1000), ('mm', 516, 260, 132)]
@@ -99,6 +108,9 @@ def main():
     for mj, M, N, K in cases:
         for prec in ('bf16x3', 'bf16', 'tf32', '3xtf32'):
             run(mj, prec, M, N, K, timing=True)
+        run(mj, 'bf16x3', M, N, K, timing=True, presplit=True)
+        run(mj, 'bf16x3', M, N, K, timing=True, presplit_a=True)
+        run(mj, 'bf16x3', M, N, K, timing=True, presplit=True, presplit_a=True)
     print('BX_CHECK', 'FAIL' if bad else 'OK', bad, flush=True)
 
 
