@@ -473,12 +473,14 @@ def run_b200(args):
     alt = None
     if not args.no_alt:
         alt = []
-        for other in [m for m in ('tf32', '3xtf32') if m != args.precision]:
+        for other in [m for m in ('tf32', 'bf16', '3xtf32') if m != args.precision]:
             a = measure(other, max(2, args.steps // 4), 3, with_e2e=False)
             atf, _ = gemm_roofline(other)
             alt.append(dict(precision=other, value=a['value'], ms_per_step=a['ms_per_step'], gemm_tflops=atf,
-                            tolerance=('single tensor-core pass, 10-bit operand mantissas: stated 2e-3 relative Frobenius, NOT north_star\'s'
-                                       if other == 'tf32' else 'rtol 1e-3 / atol 1e-4 (as the headline mode)')))
+                            tolerance={'tf32': 'single tensor-core pass, 10-bit operand mantissas: stated 2e-3 relative Frobenius, NOT north_star\'s',
+                                       'bf16': 'bf16 tensor-core operands (8-bit mantissas) on fp32 storage, fp32 accumulate (SURVEY f3): stated '
+                                               '1e-2 relative Frobenius, NOT north_star\'s',
+                                       '3xtf32': 'rtol 1e-3 / atol 1e-4 (as the headline mode)'}[other]))
     npm_b200.set_precision(args.precision)
 
     # data parallel: the replicas must hold bit-identical parameters after the timed steps (same reduced gradients, same update)

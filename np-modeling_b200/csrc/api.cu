@@ -56,13 +56,13 @@ size_t colsum_workspace_bytes(int64_t rows, int64_t cols);
 bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv);
 int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float* lse, int64_t B, int64_t H,
                     int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv,
-                    int causal, bool bx, cudaStream_t stream);
+                    int causal, bool bx, int nterms, cudaStream_t stream);
 size_t attn_bwd_scratch_bytes(int64_t B, int64_t H, int64_t Sq, bool bx);
 int attn_split_launch(const float* x, int64_t ld, void* planes, int64_t rows, int64_t HD, cudaStream_t stream);
 int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
                     int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv, int64_t lddq, int64_t lddk,
-                    int64_t lddv, int causal, bool bx, cudaStream_t stream);
+                    int64_t lddv, int causal, bool bx, int nterms, cudaStream_t stream);
 int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
 
@@ -113,8 +113,8 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
     NPM_REQUIRE(d.a_colsum == nullptr || (bx_mode && !bx_off && gemm_bx_supported(d) && d.a_rs == 1 && d.nb1 <= 1 && d.nb2 <= 1),
                 "gemm: a_colsum is served by the split-bf16 kernel only (precision bf16x3 / bf16, m-contiguous A, unbatched, m > 128)");
-    if ((d.c_split != nullptr || d.a == nullptr) && !(bx_mode && prec == NPM_PREC_BF16X3 && !bx_off && gemm_bx_supported(d))) {
-        set_error("gemm: split-bf16 input / output planes are served by the split-bf16 kernel only (precision bf16x3, m > 128)");
+    if ((d.c_split != nullptr || d.a == nullptr) && !(bx_mode && !bx_off && gemm_bx_supported(d))) {
+        set_error("gemm: split-bf16 input / output planes are served by the split-bf16 kernel only (precision bf16x3 / bf16, m > 128)");
         return NPM_ERR_UNSUPPORTED;
     }
     if (bx_mode) {
@@ -136,8 +136,8 @@ static int attn_path_now(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t 
     static const bool off = getenv("NPM_ATTN_UNFUSED") != nullptr;     // A/B switch for tools/ and tests
     if (off || !attn_fused_supported(B, H, Sq, Skv, dk, dv)) return ATTN_MATERIALISED;
     const int prec = g_precision.load();
-    if (prec == NPM_PREC_TF32 || prec == NPM_PREC_BF16) return ATTN_FUSED_TF32;     // single-pass modes: the TF32 kernels
-    if (prec == NPM_PREC_BF16X3) return ATTN_FUSED_BX;
+    if (prec == NPM_PREC_TF32) return ATTN_FUSED_TF32;
+    if (prec == NPM_PREC_BF16X3 || prec == NPM_PREC_BF16) return ATTN_FUSED_BX;      // bf16: the same kernels, hi*hi term only
     return ATTN_MATERIALISED;
 }
 // the path a call runs: the one pinned in the strides struct (1 + path), else the current mode's
@@ -145,6 +145,7 @@ static int attn_path_of(const npm_mha_strides* ld, int64_t B, int64_t H, int64_t
     if (ld && ld->path > 0) return (int)ld->path - 1;
     return attn_path_now(B, H, Sq, Skv, dk, dv);
 }
+static int attn_terms() { return g_precision.load() == NPM_PREC_BF16 ? 1 : 3; }
 static size_t pad256(size_t n) { return (n + 255) & ~(size_t)255; }
 // split-bf16 path: `saved` = log-sum-exp | q planes | k planes | v planes (each [2][B,S,H,64] bf16)
 struct BxSaved { float* lse; uint8_t* q; uint8_t* k; uint8_t* v; };
@@ -359,9 +360,9 @@ int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v, flo
     const int path = attn_path_of(ld, B, H, Sq, Skv, dk, dv);
     NPM_REQUIRE(path == ATTN_MATERIALISED || attn_fused_supported(B, H, Sq, Skv, dk, dv), "mha_core_fwd: the pinned path does not serve this shape");
     NPM_REQUIRE(!(ld && ld->planes) || path == ATTN_FUSED_BX, "mha_core_fwd: pre-split q / k / v need the split-bf16 path (strides.path = 3)");
-    if (path == ATTN_FUSED_TF32) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, 0, 0, 0, causal, false, s);
+    if (path == ATTN_FUSED_TF32) return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, 0, 0, 0, causal, false, 3, s);
     if (path == ATTN_FUSED_BX && ld && ld->planes)      // q / k / v already are bf16 planes (npm_linear_fwd_planes); saved = the log-sum-exp
-        return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, ld->q_plane, ld->k_plane, ld->v_plane, causal, true, s);
+        return attn_fwd_launch(q, k, v, o, P, B, H, Sq, Skv, ldq, ldk, ldv, ld->q_plane, ld->k_plane, ld->v_plane, causal, true, attn_terms(), s);
     if (path == ATTN_FUSED_BX) {
         const BxSaved sv = bx_saved(saved, B, H, Sq, Skv);
         int rc;
@@ -369,7 +370,7 @@ int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v, flo
         if ((rc = attn_split_launch(k, ldk, sv.k, B * Skv, H * dk, s))) return rc;
         if ((rc = attn_split_launch(v, ldv, sv.v, B * Skv, H * dv, s))) return rc;
         return attn_fwd_launch(sv.q, sv.k, sv.v, o, sv.lse, B, H, Sq, Skv, H * dk, H * dk, H * dv, B * Sq * H * dk, B * Skv * H * dk,
-                               B * Skv * H * dv, causal, true, s);
+                               B * Skv * H * dv, causal, true, attn_terms(), s);
     }
     // S[b,h] = (1/sqrt(dk)) q[b,:,h,:] k[b,:,h,:]^T
     npm_gemm_desc d = blank_desc();
@@ -430,16 +431,16 @@ int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v, con
     if (path == ATTN_FUSED_TF32)
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
                                reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, 0, 0, 0, lddq, lddk, lddv,
-                               ld && ld->causal ? 1 : 0, false, s);
+                               ld && ld->causal ? 1 : 0, false, 3, s);
     if (path == ATTN_FUSED_BX && ld && ld->planes)
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
                                reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, ld->q_plane, ld->k_plane, ld->v_plane,
-                               lddq, lddk, lddv, ld->causal ? 1 : 0, true, s);
+                               lddq, lddk, lddv, ld->causal ? 1 : 0, true, attn_terms(), s);
     if (path == ATTN_FUSED_BX) {
         const BxSaved sv = bx_saved(const_cast<void*>(saved), B, H, Sq, Skv);
         return attn_bwd_launch(sv.q, sv.k, sv.v, o, d_o, sv.lse, dq, dk_out, dv_out, reinterpret_cast<float*>(scratch), B, H,
                                Sq, Skv, H * dk, H * dk, H * dv, B * Sq * H * dk, B * Skv * H * dk, B * Skv * H * dv, lddq, lddk, lddv,
-                               ld && ld->causal ? 1 : 0, true, s);
+                               ld && ld->causal ? 1 : 0, true, attn_terms(), s);
     }
     const float* P = reinterpret_cast<const float*>(saved);
     float* dP = reinterpret_cast<float*>(scratch);

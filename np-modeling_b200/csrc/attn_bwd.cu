@@ -58,6 +58,7 @@ struct BwdArgs {
     float* dk;                // [B, Skv, H, 64]  token stride lddk
     float* dv;                // [B, Skv, H, 64]  token stride lddv
     int64_t lddq, lddk, lddv;
+    int t0;                   // split-bf16 variant: first term to run (0 = bf16x3: mid*hi, hi*mid, hi*hi; 2 = plain bf16: hi*hi only)
     int causal;               // kv position t > q position s is masked (Sq == Skv): blocks above the diagonal are skipped
     long long* dbg;           // tools only: per-CTA cycle counters of the dK/dV MMA issuer's waits (NPM_ATTN_DEBUG_TIMES)
     int debug_skip;           // tools only: 1 = exp warps do no work, 2 = dS warps do no work, 3 = both (timing experiments)
@@ -87,15 +88,17 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* tm, u
 }
 // D[tmem] (=|+=) A[smem, K-major R image] * B[smem, K-major R image]^T over the 64-wide head dim
 template <bool BX>
-__device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc) {
+__device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int t0 = 0) {
     const uint64_t desc_k = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
     if (BX) {
 #pragma unroll
-        for (int t = 0; t < 3; ++t)            // mid*hi, hi*mid, hi*hi (the mid image follows the hi image)
+        for (int t = 0; t < 3; ++t) {          // mid*hi, hi*mid, hi*hi (the mid image follows the hi image); t0 = 2: hi*hi only
+            if (t < t0) continue;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
                 ptx::umma_f16(d_tmem, ptx::umma_desc(desc_k, a_addr + (t == 0 ? kChunkBytes : 0) + kk * 32),
-                              ptx::umma_desc(desc_k, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 32), idesc, (t | kk) != 0 ? 1u : 0u);
+                              ptx::umma_desc(desc_k, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 32), idesc, (t > t0 || kk != 0) ? 1u : 0u);
+        }
         return;
     }
 #pragma unroll
@@ -107,18 +110,20 @@ __device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_
 }
 // D[tmem, 128 x 64] (=|+=) A[tmem, 128 lanes x 128 cols] * B[smem T image: 128 rows (k) x 64 (n)]
 template <bool BX>
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool accumulate, int t0 = 0) {
     if (BX) {
         // A: per 32-k quarter [16 columns hi | 16 columns mid], two bf16 per column; a K16 step = 8 columns of A and 16
         // rows (2048 B) of the B image (plain 128-byte swizzle, N = 64 = one 128-byte chunk, 8-row groups 1024 B apart)
         const uint64_t desc_mn = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, kChunkBytes, 1024);
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+        for (int t = 0; t < 3; ++t) {
+            if (t < t0) continue;
 #pragma unroll
             for (int kk = 0; kk < kBlk / 16; ++kk)
                 ptx::umma_f16_ts(d_tmem, a_tmem + (kk >> 1) * 32 + (t == 0 ? 16 : 0) + (kk & 1) * 8,
                                  ptx::umma_desc(desc_mn, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 2048), idesc,
-                                 (accumulate || (t | kk) != 0) ? 1u : 0u);
+                                 (accumulate || t > t0 || kk != 0) ? 1u : 0u);
+        }
         return;
     }
     const uint64_t desc_mn = ptx::umma_desc_base(1 /*SWIZZLE_128B_BASE32B*/, kChunkBytes, 512);
@@ -318,7 +323,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 if (first) twait(0, K_FULL, it & 1);
                 twait(1, QR_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_rr<BX>(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s);
+                mma_rr<BX>(tmem_base + (g & 1u) * kBlk, kr_addr, qr_addr, idesc_s, args.t0);
                 ptx::umma_commit(bar(QR_EMPTY));
                 ptx::umma_commit(bar(ST_FULL0 + (g & 1u)));
                 if (i == n_q - 1) ptx::umma_commit(bar(K_EMPTY));
@@ -330,7 +335,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 if (first) twait(2, V_FULL, it & 1);
                 twait(3, DOR_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_rr<BX>(tm_dpt, vr_addr, dor_addr, idesc_s);
+                mma_rr<BX>(tm_dpt, vr_addr, dor_addr, idesc_s, args.t0);
                 ptx::umma_commit(bar(DOR_EMPTY));
                 ptx::umma_commit(bar(DPT_FULL));
                 if (i == n_q - 1) ptx::umma_commit(bar(V_EMPTY));
@@ -345,13 +350,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 twait(4, P_READY0 + (g & 1u), (g >> 1) & 1);
                 twait(5, DOT_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_ts<BX>(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, !first);    // dV += P^T dO
+                mma_ts<BX>(tm_dv, tmem_base + (g & 1u) * kBlk, dot_addr, idesc_ts, !first, args.t0);    // dV += P^T dO
                 ptx::umma_commit(bar(DOT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DV_DONE));
                 twait(6, DS_READY, g & 1);
                 twait(7, QT_FULL, g & 1);
                 ptx::tc_fence_after();
-                mma_ts<BX>(tm_dk, tm_dpt, qt_addr, idesc_ts, !first);                          // dK += dS^T Q
+                mma_ts<BX>(tm_dk, tm_dpt, qt_addr, idesc_ts, !first, args.t0);                          // dK += dS^T Q
                 ptx::umma_commit(bar(QT_EMPTY));
                 if (i == n_q - 1) ptx::umma_commit(bar(DK_DONE));
                 if (g + 1 < G) issue_dpt(g + 1);
@@ -651,7 +656,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 if (j == 0) ptx::mbar_wait(bar(QDO_FULL0 + (it & 1)), (it >> 1) & 1);
                 ptx::mbar_wait(bar(KR_FULL), g & 1);
                 ptx::tc_fence_after();
-                mma_rr<BX>(tmem_base + (g & 1u) * kBlk, qr_addr + (it & 1) * kTileBytes, kr_addr, idesc_s);
+                mma_rr<BX>(tmem_base + (g & 1u) * kBlk, qr_addr + (it & 1) * kTileBytes, kr_addr, idesc_s, args.t0);
                 ptx::umma_commit(bar(KR_EMPTY));
                 ptx::umma_commit(bar(S_FULL0 + (g & 1u)));
             };
@@ -661,7 +666,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 cur_next(c_dp);
                 ptx::mbar_wait(bar(VR_FULL), g & 1);
                 ptx::tc_fence_after();
-                mma_rr<BX>(tm_dp, dor_addr + (it & 1) * kTileBytes, vr_addr, idesc_s);
+                mma_rr<BX>(tm_dp, dor_addr + (it & 1) * kTileBytes, vr_addr, idesc_s, args.t0);
                 ptx::umma_commit(bar(VR_EMPTY));
                 ptx::umma_commit(bar(DP_FULL));
                 if (last) ptx::umma_commit(bar(QDO_EMPTY0 + (it & 1)));
@@ -675,7 +680,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                 ptx::mbar_wait(bar(DS_READY), g & 1);
                 ptx::mbar_wait(bar(KT_FULL), g & 1);
                 ptx::tc_fence_after();
-                mma_ts<BX>(tm_dq, tm_dp, kt_addr, idesc_ts, j != 0);                           // dQ += dS K
+                mma_ts<BX>(tm_dq, tm_dp, kt_addr, idesc_ts, j != 0, args.t0);                           // dQ += dS K
                 ptx::umma_commit(bar(KT_EMPTY));
                 if (last) ptx::umma_commit(bar(ACC_DONE));
                 if (g + 1 < G) issue_dp(g + 1);
@@ -908,7 +913,7 @@ int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_
 int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
                     int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv, int64_t lddq, int64_t lddk,
-                    int64_t lddv, int causal, bool bx, cudaStream_t stream) {
+                    int64_t lddv, int causal, bool bx, int nterms, cudaStream_t stream) {
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_bwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(o != nullptr, "mha_core_bwd: the fused path needs the forward output o");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
@@ -952,6 +957,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
     a.lse = lse; a.dsum = dsum; a.dq = dq; a.dk = dk; a.dv = dv;
     a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
     a.causal = causal ? 1 : 0;
+    a.t0 = nterms == 1 ? 2 : 0;
     static const int debug_skip_env = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
     a.debug_skip = debug_skip_env;
     a.dbg = nullptr;

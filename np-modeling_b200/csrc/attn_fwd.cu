@@ -51,6 +51,7 @@ constexpr float kRescaleThreshold = 8.0f;    // log2 units
 struct FwdArgs {
     int B, H, Sq, Skv;
     int q_tiles, n_kv, total_items;
+    int t0;                  // split-bf16 variant: first of the three terms (mid*hi, hi*mid, hi*hi) to run: 0 = bf16x3, 2 = plain bf16 (hi*hi only)
     int causal;              // scores of kv position t > query position s are masked (Sq == Skv): kv blocks past the
                              // diagonal are never visited, the diagonal block is masked element-wise
     float c;                 // log2(e) / sqrt(dk)
@@ -234,13 +235,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (BX) {
                     // (A image, B image): mid*hi, hi*mid, hi*hi; the mid image of a tile follows its hi image
 #pragma unroll
-                    for (int t = 0; t < 3; ++t)
+                    for (int t = 0; t < 3; ++t) {
+                        if (t < args.t0) continue;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             const uint64_t da = ptx::umma_desc(desc_k, qa + (t == 0 ? kChunkBytes : 0) + kk * 32);
                             const uint64_t db = ptx::umma_desc(desc_k, ka + (t == 1 ? kChunkBytes : 0) + kk * 32);
-                            ptx::umma_f16(d_tmem, da, db, idesc_s, (t | kk) != 0 ? 1u : 0u);
+                            ptx::umma_f16(d_tmem, da, db, idesc_s, (t > args.t0 || kk != 0) ? 1u : 0u);
                         }
+                    }
                 } else {
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb)
@@ -274,13 +277,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     // P in TMEM: per 64-k half [32 columns hi | 32 columns mid], two bf16 per column; a K16 step is 8 columns
                     // of P and 16 rows (2048 B) of the V image
 #pragma unroll
-                    for (int t = 0; t < 3; ++t)
+                    for (int t = 0; t < 3; ++t) {
+                        if (t < args.t0) continue;
 #pragma unroll
                         for (int kk = 0; kk < kBN / 16; ++kk) {
                             const uint32_t pa = p_tmem + (kk >> 2) * 64 + (t == 0 ? 32 : 0) + (kk & 3) * 8;
                             const uint64_t db = ptx::umma_desc(desc_mn, va + (t == 1 ? kChunkBytes : 0) + kk * 2048);
-                            ptx::umma_f16_ts(tmem_o, pa, db, idesc_pv, (j | t | kk) != 0 ? 1u : 0u);
+                            ptx::umma_f16_ts(tmem_o, pa, db, idesc_pv, (j != 0 || t > args.t0 || kk != 0) ? 1u : 0u);
                         }
+                    }
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < kBN / 8; ++kk) {
@@ -551,7 +556,7 @@ bool attn_fused_supported(int64_t B, int64_t H, int64_t Sq, int64_t Skv, int64_t
 // (token strides ld* in bf16 elements, the mid plane pl* elements after the hi plane).
 int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float* lse, int64_t B, int64_t H,
                     int64_t Sq, int64_t Skv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv,
-                    int causal, bool bx, cudaStream_t stream) {
+                    int causal, bool bx, int nterms, cudaStream_t stream) {
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_fwd: the causal mask needs Sq == Skv");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "mha_core_fwd: pointers must be 16-byte aligned");
     CUtensorMap tmQ, tmK, tmV;
@@ -582,6 +587,7 @@ int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float
     NPM_REQUIRE(items < (1ll << 30), "mha_core_fwd: too many tiles");
     a.total_items = (int)items;
     a.causal = causal ? 1 : 0;
+    a.t0 = nterms == 1 ? 2 : 0;
     a.c = (float)(1.4426950408889634 / sqrt((double)kD));
     a.o = o; a.lse = lse;
     static bool configured = false;

@@ -206,7 +206,7 @@ def test_tf32_mode_stated_tolerance():
     assert errs['bf16'] < 1e-2, errs
 
 
-@pytest.mark.parametrize('mode', ['bf16x3', 'tf32'])
+@pytest.mark.parametrize('mode', ['bf16x3', 'tf32', 'bf16'])
 @pytest.mark.parametrize('B,H,Sq,Skv', [(1, 1, 128, 128), (2, 4, 256, 384), (2, 3, 200, 300), (1, 2, 1, 130), (3, 2, 129, 64)])
 def test_fused_attention_vs_oracle(B, H, Sq, Skv, mode):
     """The fused tcgen05 attention kernels (dk = dv = 64) against the float64 oracle (oracle/np_oracle.py softmax /
@@ -225,7 +225,7 @@ def test_fused_attention_vs_oracle(B, H, Sq, Skv, mode):
     tq, tk, tv, tdo = (torch.from_numpy(a).cuda() for a in (q, k, v, do))
     o = torch.full((B, Sq, H, D), float('nan'), device='cuda')
     st = device.stream()
-    assert C.npm_mha_core_path(B, H, Sq, Skv, D, D) == (2 if mode == 'bf16x3' else 1)
+    assert C.npm_mha_core_path(B, H, Sq, Skv, D, D) == (1 if mode == 'tf32' else 2)
     if mode == 'tf32':
         assert C.npm_mha_core_saved_bytes(B, H, Sq, Skv, D, D) == B * H * Sq * 4       # only the log-sum-exp is saved
     else:       # + the bf16 hi / mid planes of q, k, v (4 bytes per element, as the fp32 tensors they replace)
@@ -252,8 +252,9 @@ def test_fused_attention_vs_oracle(B, H, Sq, Skv, mode):
         assert np.isfinite(got).all(), name
         if mode == 'bf16x3':
             close(got, want, rtol=1e-3, atol=1e-4)
-        else:
-            assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())
+        else:       # single-pass modes: 10-bit (tf32) / 8-bit (bf16: the hi*hi term of the split kernels only) operand mantissas
+            bound = 2e-3 if mode == 'tf32' else 1.5e-2
+            assert np.abs(got - want).max() <= bound * np.abs(want).max(), (name, np.abs(got - want).max(), np.abs(want).max())
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 32, 64, 128, 3), (3, 12, 28, 16, 20, 5), (2, 16, 16, 32, 32, 1), (2, 9, 8, 8, 260, 3),
