@@ -21,6 +21,7 @@
 // 128B-swizzled tiles exactly as TMA lands them, so no transposes are ever materialised.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -672,7 +673,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn encode_fn() {
+EncodeTiledFn driver_encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -683,6 +684,49 @@ EncodeTiledFn encode_fn() {
     }
     return fn;
 }
+
+// Per-thread tensor-map cache (the one piece of hidden state SURVEY.md §8b allows): a tensor map is a pure function of
+// (base pointer, data type, dims, strides, box, swizzle), and a training step re-creates the same ~3000 of them every
+// step (three per GEMM launch) — torch's caching allocator hands the same addresses back.  Direct mapped, 2048 entries,
+// the full key is compared on a hit.  NPM_NO_TMAP_CACHE=1 disables it (A/B).
+struct TmKey {
+    void* addr;
+    cuuint64_t dims[5];
+    cuuint64_t strides[4];
+    cuuint32_t box[5];
+    uint32_t meta;       // data type | rank << 8 | swizzle << 16 | interleave << 24
+};
+struct TmEntry { TmKey key; CUtensorMap map; bool valid; };
+constexpr int kTmCacheSize = 2048;
+
+CUresult cached_encode(CUtensorMap* tm, CUtensorMapDataType dt, cuuint32_t rank, void* addr, const cuuint64_t* dims,
+                       const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                       CUtensorMapSwizzle sw, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+    static const bool off = getenv("NPM_NO_TMAP_CACHE") != nullptr;
+    EncodeTiledFn fn = driver_encode_fn();
+    bool plain = off || rank > 5;
+    for (cuuint32_t i = 0; i < rank && !plain; ++i) plain = estr[i] != 1;
+    if (plain || l2 != CU_TENSOR_MAP_L2_PROMOTION_L2_256B || oob != CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+        return fn(tm, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
+    static thread_local TmEntry* cache = nullptr;
+    if (!cache) cache = new TmEntry[kTmCacheSize]();
+    TmKey k;
+    memset(&k, 0, sizeof(k));
+    k.addr = addr;
+    for (cuuint32_t i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+    for (cuuint32_t i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+    k.meta = (uint32_t)dt | (rank << 8) | ((uint32_t)sw << 16) | ((uint32_t)il << 24);
+    uint64_t h = 1469598103934665603ull;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    for (size_t i = 0; i < sizeof(k) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    TmEntry& e = cache[(h >> 20) & (kTmCacheSize - 1)];
+    if (e.valid && memcmp(&e.key, &k, sizeof(k)) == 0) { *tm = e.map; return CUDA_SUCCESS; }
+    const CUresult rc = fn(tm, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
+    if (rc == CUDA_SUCCESS) { e.key = k; e.map = *tm; e.valid = true; }
+    return rc;
+}
+
+EncodeTiledFn encode_fn() { return driver_encode_fn() ? &cached_encode : nullptr; }
 
 }  // namespace
 
