@@ -91,13 +91,14 @@ template <bool BX>
 __device__ __forceinline__ void mma_rr(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int t0 = 0) {
     const uint64_t desc_k = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, 16, 1024);
     if (BX) {
+        const uint64_t da0 = ptx::umma_desc(desc_k, a_addr), db0 = ptx::umma_desc(desc_k, b_addr);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {          // mid*hi, hi*mid, hi*hi (the mid image follows the hi image); t0 = 2: hi*hi only
             if (t < t0) continue;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-                ptx::umma_f16(d_tmem, ptx::umma_desc(desc_k, a_addr + (t == 0 ? kChunkBytes : 0) + kk * 32),
-                              ptx::umma_desc(desc_k, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 32), idesc, (t > t0 || kk != 0) ? 1u : 0u);
+                ptx::umma_f16(d_tmem, ptx::umma_desc_off(da0, (t == 0 ? kChunkBytes : 0) + kk * 32),
+                              ptx::umma_desc_off(db0, (t == 1 ? kChunkBytes : 0) + kk * 32), idesc, (t > t0 || kk != 0) ? 1u : 0u);
         }
         return;
     }
@@ -114,14 +115,14 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_
     if (BX) {
         // A: per 32-k quarter [16 columns hi | 16 columns mid], two bf16 per column; a K16 step = 8 columns of A and 16
         // rows (2048 B) of the B image (plain 128-byte swizzle, N = 64 = one 128-byte chunk, 8-row groups 1024 B apart)
-        const uint64_t desc_mn = ptx::umma_desc_base(2 /*SWIZZLE_128B*/, kChunkBytes, 1024);
+        const uint64_t db0 = ptx::umma_desc(ptx::umma_desc_base(2 /*SWIZZLE_128B*/, kChunkBytes, 1024), b_addr);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             if (t < t0) continue;
 #pragma unroll
             for (int kk = 0; kk < kBlk / 16; ++kk)
                 ptx::umma_f16_ts(d_tmem, a_tmem + (kk >> 1) * 32 + (t == 0 ? 16 : 0) + (kk & 1) * 8,
-                                 ptx::umma_desc(desc_mn, b_addr + (t == 1 ? kChunkBytes : 0) + kk * 2048), idesc,
+                                 ptx::umma_desc_off(db0, (t == 1 ? kChunkBytes : 0) + kk * 2048), idesc,
                                  (accumulate || t > t0 || kk != 0) ? 1u : 0u);
         }
         return;
@@ -365,7 +366,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             if (dbg) {
                 acc[8] = clock64() - t_begin;
                 acc[9] = G;
-                for (int k = 0; k < 12; ++k) dbg[blockIdx.x * 12 + k] = acc[k];
+                for (int k = 0; k < 12; ++k) dbg[blockIdx.x * 24 + k] = acc[k];
             }
         }
     } else if (warp >= 4) {
@@ -402,6 +403,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
             for (int i = first_q(item); i < n_q; ++i, ++g) {
                 const uint32_t buf = g & 1u;
                 // stage this block's L (or D) — fetched one block ago — and prefetch the next block's
+                const bool rec = args.dbg != nullptr && lane == 0 && (warp == 4 || warp == 4 + 4 * NSET);
+                long long* const dbg = args.dbg + blockIdx.x * 24 + (exp_group ? 12 : 15);
+                long long t0 = rec ? clock64() : 0, t1;
+#define BWD_STAMP(i) { if (rec) { t1 = clock64(); dbg[i] += t1 - t0; t0 = t1; } __syncwarp(); }
                 if (hsel == 0) stage[buf * kBlk + tid] = next;
                 {
                     int ni = i + 1, nitem = item;
@@ -409,9 +414,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     if (nitem < args.total_items) next = fetch(nitem, ni);
                 }
                 bar_sync_n<128 * NSET>(bar_id);
+                BWD_STAMP(0)
                 const float4* V4 = reinterpret_cast<const float4*>(stage + buf * kBlk);
                 if (exp_group) {
                     ptx::mbar_wait(bar(ST_FULL0 + buf), (g >> 1) & 1);
+                    BWD_STAMP(1)
                     ptx::tc_fence_after();
                     const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
                     if (BX) {
@@ -469,9 +476,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(bar(P_READY0 + buf));
+                    BWD_STAMP(2)
                 } else {
                     ptx::mbar_wait(bar(P_READY0 + buf), (g >> 1) & 1);
+                    BWD_STAMP(1)
                     ptx::mbar_wait(bar(DPT_FULL), g & 1);
+                    BWD_STAMP(2)
                     ptx::tc_fence_after();
                     const uint32_t p_tmem = tmem_base + lane_off + buf * kBlk;
                     if (BX) {
@@ -514,9 +524,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(bar(DS_READY));
+                    BWD_STAMP(3)
                 }
+#undef BWD_STAMP
             }
             // ---- epilogue: the exp warps store this kv tile's dV rows, the dS warps its dK rows ----
+            const bool rec_e = args.dbg != nullptr && lane == 0 && (warp == 4 || warp == 4 + 4 * NSET);
+            const long long te = rec_e ? clock64() : 0;
             ptx::mbar_wait(bar(exp_group ? DV_DONE : DK_DONE), it & 1);
             ptx::tc_fence_after();
             const int t = nt * kBlk + tid;
@@ -530,6 +544,376 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_cons
                 else           store_acc_row(tm_dk + lane_off, args.dk + tok * args.lddk + (size_t)h * kD, live);
             }
             ptx::tc_fence_before();
+            if (rec_e) args.dbg[blockIdx.x * 24 + (exp_group ? 19 : 20)] += clock64() - te;
+            __syncwarp();
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 3) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================== dK, dV (split-bf16)
+// The split-bf16 variant is its own kernel.  Measured on the shared-template version (NPM_ATTN_DEBUG_TIMES, B8 H16
+// S1024, cycles per q block of 5700-6400): the dS warps work 2500 clk on a block and then wait 2100 clk for
+// dK(g) (1080 clk of MMAs) -> dP^T(g+1) (768 clk) to pass through the single dP^T buffer — the period of a block is that
+// serial chain, the tensor pipe is busy 56 % of it.  Three changes:
+//   * HALF-TILE CHAIN.  dP^T is produced and consumed as two 64-column halves (q rows 0..63 / 64..127 of the block), each
+//     with its own full / ready barrier and its own set of dS warps (the two warp sets of the BX layout already own one
+//     half each).  dK(g) runs its four K16 steps of half A, then dP^T_A(g+1) overwrites half A while the steps of half B
+//     still read theirs: per set the chain is dS -> 540 clk -> 384 clk -> dS instead of dS -> 1080 -> 768 -> dS, and
+//     the two sets run staggered, so the other 3700 clk of MMAs per block (S^T, dV, the other half) fill the pipe
+//     while a set computes.
+//   * ONE IMAGE PER TILE.  A bf16 [128, 64] tile with the 128-byte swizzle is the K-major ("R") and the MN-major ("T")
+//     operand at once, so Q and dO are loaded once per block instead of twice (64 KB instead of 128 KB per block; the
+//     shared-template version measured ~3700 clk per block for its loads alone).  Q lives in a ring of three (S^T runs
+//     two blocks ahead of dK), dO in a ring of two (dP^T runs one block ahead of dV).
+//   * The L / D vectors are staged per warp set (128-thread named barriers), so the sets never meet.
+// smem: K, V (resident per item) | Q ring x3 | dO ring x2 | L / D staging | barriers = all 227 KB of the SM.
+constexpr int kKvBxStage = 2 * 2 * kBlk * 4;
+constexpr int kKvBxUsed  = 7 * kTileBytes + kKvBxStage + 256;
+constexpr int kKvBxSmem  = 232448;
+
+// D[tmem, 128 x 64] (=|+=) A[tmem, K16 steps kk0..kk1 of a packed 128-column tile] * B[smem, the same rows of the bf16 image]
+__device__ __forceinline__ void mma_ts_bx_range(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t idesc, bool accumulate,
+                                                int t0, int kk0, int kk1) {
+    const uint64_t db0 = ptx::umma_desc(ptx::umma_desc_base(2 /*SWIZZLE_128B*/, kChunkBytes, 1024), b_addr);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        if (t < t0) continue;
+#pragma unroll
+        for (int kk = kk0; kk < kk1; ++kk)
+            ptx::umma_f16_ts(d_tmem, a_tmem + (kk >> 1) * 32 + (t == 0 ? 16 : 0) + (kk & 1) * 8,
+                             ptx::umma_desc_off(db0, (t == 1 ? kChunkBytes : 0) + kk * 2048), idesc,
+                             (accumulate || t > t0 || kk != kk0) ? 1u : 0u);
+    }
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(kThreadsBx, 1)
+attn_bwd_dkdv_bx_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const BwdArgs args) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+    {
+        uint32_t dyn;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (base_addr - raw_addr + kKvBxUsed > dyn) __trap();      // the launch gives the kernel the whole SM; fail loudly if the base moved
+    }
+    const uint32_t kr_addr = base_addr, vr_addr = kr_addr + kTileBytes;
+    const uint32_t q_addr = vr_addr + kTileBytes;                    // ring of 3
+    const uint32_t do_addr = q_addr + 3 * kTileBytes;                // ring of 2
+    float* lsm = reinterpret_cast<float*>(base_ptr + 7 * kTileBytes);   // [2][128] L, then [2][128] D
+    float* dsm = lsm + 2 * kBlk;
+    const uint32_t bar_addr = base_addr + 7 * kTileBytes + kKvBxStage;
+    enum { K_FULL = 0, K_EMPTY, V_FULL, V_EMPTY, Q_FULL0, Q_FULL1, Q_FULL2, Q_EMPTY0, Q_EMPTY1, Q_EMPTY2, DO_FULL0, DO_FULL1,
+           DO_EMPTY0, DO_EMPTY1, ST_FULL0, ST_FULL1, P_READY0, P_READY1, DPT_FULL_A, DPT_FULL_B, DS_READY_A, DS_READY_B,
+           DV_DONE, DK_DONE, DK_FREE, NBAR };
+    static_assert(8 * NBAR + 4 <= 256, "barrier block");
+    auto bar = [&](int i) { return bar_addr + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 7 * kTileBytes + kKvBxStage + 8 * NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV); ptx::prefetch_tensormap(&tmDO);
+    }
+    if (warp == 3) {
+        if (lane == 0) {
+            for (int i = 0; i < NBAR; ++i)
+                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DK_FREE) ? 256 : (i == DS_READY_A || i == DS_READY_B) ? 128 : 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();               // only shared memory / TMEM set-up above
+    const uint32_t tm_dpt = tmem_base + 256, tm_dv = tmem_base + 384, tm_dk = tmem_base + 448;
+
+    const int n_q = args.n_q;
+    auto first_q = [&](int item) -> int { return CAUSAL ? item % args.n_kv : 0; };
+    uint32_t G = 0;                                            // q blocks this CTA walks, over all its items
+    for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) G += (uint32_t)(n_q - first_q(item));
+
+    if (warp == 0) {
+        // ============ producer: K, V per item; Q per q block (ring of 3) ============
+        if (ptx::elect_one()) {
+            uint32_t g = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+                const int nt = item % args.n_kv;
+                const int bh = item / args.n_kv;
+                const int h = bh % args.H, b = bh / args.H;
+                ptx::mbar_wait(bar(K_EMPTY), (it & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(bar(K_FULL), kTileBytes);
+                load_tile<true>(kr_addr, &tmK, bar(K_FULL), nt * kBlk, h, b);
+                const int i0 = first_q(item);
+                for (int i = i0; i < n_q; ++i, ++g) {
+                    const uint32_t slot = g % 3u;
+                    ptx::mbar_wait(bar(Q_EMPTY0 + slot), ((g / 3u) & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(Q_FULL0 + slot), kTileBytes);
+                    load_tile<true>(q_addr + slot * kTileBytes, &tmQ, bar(Q_FULL0 + slot), i * kBlk, h, b);
+                    if (i == i0) {
+                        ptx::mbar_wait(bar(V_EMPTY), (it & 1) ^ 1u);
+                        ptx::mbar_arrive_expect_tx(bar(V_FULL), kTileBytes);
+                        load_tile<true>(vr_addr, &tmV, bar(V_FULL), nt * kBlk, h, b);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============ producer: dO per q block (ring of 2) ============
+        if (ptx::elect_one()) {
+            uint32_t g = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+                const int bh = item / args.n_kv;
+                const int h = bh % args.H, b = bh / args.H;
+                for (int i = first_q(item); i < n_q; ++i, ++g) {
+                    const uint32_t slot = g & 1u;
+                    ptx::mbar_wait(bar(DO_EMPTY0 + slot), ((g >> 1) & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(DO_FULL0 + slot), kTileBytes);
+                    load_tile<true>(do_addr + slot * kTileBytes, &tmDO, bar(DO_FULL0 + slot), i * kBlk, h, b);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ============ MMA issuer ============
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc_s   = ptx::umma_idesc_bf16(kBlk, kBlk, false, false);
+            constexpr uint32_t idesc_s64 = ptx::umma_idesc_bf16(kBlk, kBlk / 2, false, false);
+            constexpr uint32_t idesc_ts  = ptx::umma_idesc_bf16(kBlk, kD, false, true);
+            long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            long long* const dbg = args.dbg;
+            auto twait = [&](int slot, int which, uint32_t parity) {
+                if (dbg) {
+                    const long long t0 = clock64();
+                    ptx::mbar_wait(bar(which), parity);
+                    acc[slot] += clock64() - t0;
+                } else {
+                    ptx::mbar_wait(bar(which), parity);
+                }
+            };
+            struct Cur { int item, it, i, i0; };
+            auto cur_init = [&](Cur& c) {
+                c.item = blockIdx.x; c.it = 0;
+                c.i0 = c.item < args.total_items ? first_q(c.item) : 0;
+                c.i = c.i0;
+            };
+            auto cur_next = [&](Cur& c) {
+                if (++c.i == n_q) {
+                    c.item += gridDim.x; ++c.it;
+                    c.i0 = c.item < args.total_items ? first_q(c.item) : 0;
+                    c.i = c.i0;
+                }
+            };
+            Cur c_st, c_dpt, c_main;
+            cur_init(c_st); cur_init(c_dpt); cur_init(c_main);
+            auto issue_st = [&](uint32_t g) {        // S^T(g) = K Q^T
+                const int it = c_st.it, i = c_st.i;
+                const bool first = i == c_st.i0;
+                cur_next(c_st);
+                if (first) twait(0, K_FULL, it & 1);
+                twait(1, Q_FULL0 + g % 3u, (g / 3u) & 1u);
+                ptx::tc_fence_after();
+                mma_rr<true>(tmem_base + (g & 1u) * kBlk, kr_addr, q_addr + (g % 3u) * kTileBytes, idesc_s, args.t0);
+                ptx::umma_commit(bar(ST_FULL0 + (g & 1u)));
+                if (i == n_q - 1) ptx::umma_commit(bar(K_EMPTY));
+            };
+            auto issue_dpt = [&](uint32_t g, int half) {       // dP^T(g)[:, half] = V dO[64 q rows of the half]^T
+                const int it = c_dpt.it, i = c_dpt.i;
+                const bool first = i == c_dpt.i0;
+                if (half == 0) {
+                    if (first) twait(2, V_FULL, it & 1);
+                    twait(3, DO_FULL0 + (g & 1u), (g >> 1) & 1u);
+                    ptx::tc_fence_after();
+                } else {
+                    cur_next(c_dpt);
+                }
+                mma_rr<true>(tm_dpt + half * 64, vr_addr, do_addr + (g & 1u) * kTileBytes + half * 8192, idesc_s64, args.t0);
+                ptx::umma_commit(bar(DPT_FULL_A + half));
+                if (half == 1 && i == n_q - 1) ptx::umma_commit(bar(V_EMPTY));
+            };
+            const long long t_begin = dbg ? clock64() : 0;
+            if (G > 0) { issue_st(0); issue_dpt(0, 0); issue_dpt(0, 1); }
+            if (G > 1) issue_st(1);
+            for (uint32_t g = 0; g < G; ++g) {
+                const int i = c_main.i, it_main = c_main.it;
+                const bool first = i == c_main.i0, last = i == n_q - 1;
+                cur_next(c_main);
+                const uint32_t qa = q_addr + (g % 3u) * kTileBytes, da = do_addr + (g & 1u) * kTileBytes;
+                twait(4, P_READY0 + (g & 1u), (g >> 1) & 1);
+                ptx::tc_fence_after();
+                mma_ts<true>(tm_dv, tmem_base + (g & 1u) * kBlk, da, idesc_ts, !first, args.t0);          // dV += P^T dO
+                ptx::umma_commit(bar(DO_EMPTY0 + (g & 1u)));
+                if (last) ptx::umma_commit(bar(DV_DONE));
+                twait(5, DS_READY_A, g & 1);
+                // the first dK product of an item overwrites the accumulator: BOTH warp sets must have stored the previous
+                // item's dK rows (set B arrives on DS_READY_B later than this point)
+                if (first && it_main > 0) twait(7, DK_FREE, (it_main - 1) & 1);
+                ptx::tc_fence_after();
+                mma_ts_bx_range(tm_dk, tm_dpt, qa, idesc_ts, !first, args.t0, 0, 4);                      // dK += dS^T Q, q rows 0..63
+                if (g + 1 < G) issue_dpt(g + 1, 0);
+                twait(6, DS_READY_B, g & 1);
+                ptx::tc_fence_after();
+                mma_ts_bx_range(tm_dk, tm_dpt, qa, idesc_ts, true, args.t0, 4, 8);                        // q rows 64..127
+                ptx::umma_commit(bar(Q_EMPTY0 + g % 3u));
+                if (last) ptx::umma_commit(bar(DK_DONE));
+                if (g + 1 < G) issue_dpt(g + 1, 1);
+                if (g + 2 < G) issue_st(g + 2);
+            }
+            if (dbg) {
+                acc[8] = clock64() - t_begin;
+                acc[9] = G;
+                for (int k = 0; k < 12; ++k) dbg[blockIdx.x * 24 + k] = acc[k];
+            }
+        }
+    } else if (warp >= 4) {
+        // ============ warps 4-11: P^T = exp2(c S^T - L[q]) in place, packed.  warps 12-19: dS^T = P^T o (dP^T - D[q]) /
+        // sqrt(dk) in place over dP^T.  Thread = kv row = TMEM lane; warps w and w + 4 of a group share a TMEM lane quarter,
+        // set A (hsel = 0) owns q columns 0..63 of every block, set B columns 64..127. ============
+        const bool exp_group = warp < 12;
+        const int wq = warp & 3;
+        const int hsel = ((warp - 4) >> 2) & 1;
+        const int q0 = 2 * hsel, q1 = 2 * hsel + 2;
+        const int tid = wq * 32 + lane;             // kv row within the tile
+        const uint32_t lane_off = uint32_t(wq * 32) << 16;
+        const float c = args.c, scale = args.scale;
+        const float* vec = exp_group ? args.lse : args.dsum;      // per-q-row vector this group consumes
+        float* stage = (exp_group ? lsm : dsm) + hsel * 64;       // this set's 64 columns of either buffer
+        const float pad = exp_group ? INFINITY : 0.0f;            // exp2(-inf) = 0 for padded q columns
+        const int bar_id = (exp_group ? 1 : 3) + hsel;
+        const bool stager = tid < 64;                             // these threads fetch one L / D value per block
+        auto fetch = [&](int item, int i) -> float {
+            const int bh = item / args.n_kv;
+            const int qi = i * kBlk + hsel * 64 + tid;
+            return qi < args.Sq ? __ldg(vec + (size_t)bh * args.Sq + qi) : pad;
+        };
+        uint32_t g = 0;
+        int it = 0;
+        float next = (stager && (int)blockIdx.x < args.total_items) ? fetch(blockIdx.x, first_q(blockIdx.x)) : 0.0f;
+        const bool rec = args.dbg != nullptr && lane == 0 && (warp == 4 || warp == 12);
+        long long racc[5] = {0, 0, 0, 0, 0};          // tools only: kept in registers, written once at the end
+        // Epilogue of a finished item: the exp warps store its dV rows, the dS warps its dK rows (32 columns per warp set).
+        // It is DEFERRED into the first block of the next item, between that block's TMEM stores and its barrier arrival:
+        // the accumulator is only overwritten by the MMA that this arrival releases, and the elementwise work of the
+        // next item's first blocks no longer waits for the last MMA of this one (measured: the exp warps sat 7300 clk
+        // per item in the epilogue wait and the issuer 750 clk per block on P_READY behind it).
+        int prev_item = -1;
+        auto epilogue = [&](int item, uint32_t parity) {
+            const long long te = rec ? clock64() : 0;
+            const int nt = item % args.n_kv;
+            const int bh = item / args.n_kv;
+            const int h = bh % args.H, b = bh / args.H;
+            ptx::mbar_wait(bar(exp_group ? DV_DONE : DK_DONE), parity);
+            ptx::tc_fence_after();
+            const int t = nt * kBlk + tid;
+            const bool live = t < args.Skv;
+            const size_t tok = (size_t)b * args.Skv + (live ? t : 0);
+            if (exp_group) store_acc_half(tm_dv + lane_off + 32 * hsel, args.dv + tok * args.lddv + (size_t)h * kD + 32 * hsel, live);
+            else           store_acc_half(tm_dk + lane_off + 32 * hsel, args.dk + tok * args.lddk + (size_t)h * kD + 32 * hsel, live);
+            ptx::tc_fence_before();
+            if (!exp_group) ptx::mbar_arrive(bar(DK_FREE));
+            if (rec) racc[4] += clock64() - te;
+        };
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+            const int nt = item % args.n_kv;
+            for (int i = first_q(item); i < n_q; ++i, ++g) {
+                const uint32_t buf = g & 1u;
+                long long t0 = rec ? clock64() : 0, t1;
+#define BWD_STAMP(i) { if (rec) { t1 = clock64(); racc[i] += t1 - t0; t0 = t1; } }
+                // stage this block's L (or D) — fetched one block ago — and prefetch the next block's
+                if (stager) {
+                    stage[buf * kBlk + tid] = next;
+                    int ni = i + 1, nitem = item;
+                    if (ni == n_q) { nitem = item + gridDim.x; ni = nitem < args.total_items ? first_q(nitem) : 0; }
+                    if (nitem < args.total_items) next = fetch(nitem, ni);
+                }
+                bar_sync_n<128>(bar_id);
+                BWD_STAMP(0)
+                const float4* V4 = reinterpret_cast<const float4*>(stage + buf * kBlk) - hsel * 16;   // indexed by block column / 4
+                if (exp_group) {
+                    ptx::mbar_wait(bar(ST_FULL0 + buf), (g >> 1) & 1);
+                    BWD_STAMP(1)
+                    ptx::tc_fence_after();
+                    const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
+#pragma unroll
+                    for (int qt = q0; qt < q1; ++qt) {          // 32 columns: S^T in, [16 columns hi | 16 columns mid] of P^T out
+                        float p[32];
+                        ptx::tmem_ld_32x32(s_tmem + qt * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) {
+                            const float4 l4 = V4[(qt * 32 + k) >> 2];
+                            p[k]     = ptx::ex2(fmaf(p[k], c, -l4.x));
+                            p[k + 1] = ptx::ex2(fmaf(p[k + 1], c, -l4.y));
+                            p[k + 2] = ptx::ex2(fmaf(p[k + 2], c, -l4.z));
+                            p[k + 3] = ptx::ex2(fmaf(p[k + 3], c, -l4.w));
+                        }
+                        if (CAUSAL && i == nt) {            // diagonal block: q position (column) before kv position (lane)
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (qt * 32 + k < tid) p[k] = 0.0f;
+                        }
+                        uint32_t hm[32];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) split_pack(p[2 * k], p[2 * k + 1], hm[k], hm[16 + k]);
+                        ptx::tmem_st_32x32(s_tmem + qt * 32, hm);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    if (prev_item >= 0) { epilogue(prev_item, (it - 1) & 1); prev_item = -1; }
+                    ptx::mbar_arrive(bar(P_READY0 + buf));
+                    BWD_STAMP(2)
+                } else {
+                    ptx::mbar_wait(bar(P_READY0 + buf), (g >> 1) & 1);
+                    BWD_STAMP(1)
+                    ptx::mbar_wait(bar(DPT_FULL_A + hsel), g & 1);
+                    BWD_STAMP(2)
+                    ptx::tc_fence_after();
+                    const uint32_t p_tmem = tmem_base + lane_off + buf * kBlk;
+#pragma unroll
+                    for (int qt = q0; qt < q1; ++qt) {
+                        uint32_t pm[32], dp[32];               // pm: [16 hi | 16 mid] of P^T, then of dS^T
+                        ptx::tmem_ld_32x32(p_tmem + qt * 32, pm);
+                        ptx::tmem_ld_32x32(tm_dpt + lane_off + qt * 32, dp);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 16; k += 2) {      // packed columns k, k+1 = elements 2k .. 2k+3 = one float4 of D
+                            const float4 d4 = V4[(qt * 32 + 2 * k) >> 2];
+                            const float s0 = unpack_lo(pm[k], pm[16 + k]) * ((__uint_as_float(dp[2 * k]) - d4.x) * scale);
+                            const float s1 = unpack_hi(pm[k], pm[16 + k]) * ((__uint_as_float(dp[2 * k + 1]) - d4.y) * scale);
+                            const float s2 = unpack_lo(pm[k + 1], pm[17 + k]) * ((__uint_as_float(dp[2 * k + 2]) - d4.z) * scale);
+                            const float s3 = unpack_hi(pm[k + 1], pm[17 + k]) * ((__uint_as_float(dp[2 * k + 3]) - d4.w) * scale);
+                            split_pack(s0, s1, pm[k], pm[16 + k]);
+                            split_pack(s2, s3, pm[k + 1], pm[17 + k]);
+                        }
+                        ptx::tmem_st_32x32(tm_dpt + lane_off + qt * 32, pm);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    if (prev_item >= 0) { epilogue(prev_item, (it - 1) & 1); prev_item = -1; }
+                    ptx::mbar_arrive(bar(DS_READY_A + hsel));
+                    BWD_STAMP(3)
+                }
+#undef BWD_STAMP
+            }
+            prev_item = item;
+        }
+        if (prev_item >= 0) epilogue(prev_item, (it - 1) & 1);
+        if (rec) {
+            long long* const dbg = args.dbg + blockIdx.x * 24;
+            for (int k = 0; k < (exp_group ? 3 : 4); ++k) dbg[(exp_group ? 12 : 15) + k] = racc[k];
+            dbg[exp_group ? 19 : 20] = racc[4];
         }
     }
 
@@ -707,10 +1091,25 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
         uint32_t g = 0;
         int it = 0;
         float next = (int)blockIdx.x < args.total_items ? fetch(blockIdx.x) : 0.0f;
-        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+        // dQ rows of a finished q tile (dS warps).  Deferred into the first block of the next item, between that block's
+        // TMEM stores and its DS_READY arrival (which releases the MMA that overwrites the accumulator): the next item's
+        // first dS no longer waits for the last dQ product of this one.
+        int prev_item = -1;
+        auto epilogue = [&](int item, uint32_t parity) {
             const int mt = item % args.n_q;
             const int bh = item / args.n_q;
             const int h = bh % args.H, b = bh / args.H;
+            ptx::mbar_wait(bar(ACC_DONE), parity);
+            ptx::tc_fence_after();
+            const int sq = mt * kBlk + tid;
+            const bool live = sq < args.Sq;
+            float* drow = args.dq + ((size_t)b * args.Sq + (live ? sq : 0)) * args.lddq + (size_t)h * kD;
+            if (BX) store_acc_half(tm_dq + lane_off + 32 * hsel, drow + 32 * hsel, live);      // two warp sets, 32 columns each
+            else    store_acc_row(tm_dq + lane_off, drow, live);
+            ptx::tc_fence_before();
+        };
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+            const int mt = item % args.n_q;
             const float mine = next;                              // L (exp warps) or D (dS warps) of this thread's q row
             if (item + (int)gridDim.x < args.total_items) next = fetch(item + gridDim.x);
             const int nb = blocks_of(item);
@@ -733,10 +1132,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                                 const bool masked = CAUSAL && j == mt && qt * 32 + k > tid;          // kv position after q position
                                 p[k] = (qt * 32 + k < kv_left && !masked) ? e : 0.0f;   // zero-filled K rows past Skv
                             }
-                            uint32_t hm[32];
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) split_pack(p[2 * k], p[2 * k + 1], hm[k], hm[16 + k]);
-                            ptx::tmem_st_32x32(s_tmem + qt * 32, hm);
+                            // P is no MMA operand in this kernel (only dS is): it goes back as plain fp32, no split
+                            ptx::tmem_st_32x32(s_tmem + qt * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
                         }
                     } else
 #pragma unroll
@@ -765,17 +1162,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                     if (BX) {
 #pragma unroll
                         for (int qt = q0; qt < q1; ++qt) {
-                            uint32_t pm[32], dp[32];               // pm: [16 hi | 16 mid] of P, then of dS
+                            uint32_t pm[32], dp[32];               // pm: P (fp32) in, [16 hi | 16 mid] of dS out
                             ptx::tmem_ld_32x32(s_tmem + qt * 32, pm);
                             ptx::tmem_ld_32x32(tm_dp + lane_off + qt * 32, dp);
                             ptx::tmem_ld_wait();
+                            uint32_t ds[32];
 #pragma unroll
                             for (int k = 0; k < 16; ++k) {
-                                const float s0 = unpack_lo(pm[k], pm[16 + k]) * fmaf(__uint_as_float(dp[2 * k]), scale, -dscale);
-                                const float s1 = unpack_hi(pm[k], pm[16 + k]) * fmaf(__uint_as_float(dp[2 * k + 1]), scale, -dscale);
-                                split_pack(s0, s1, pm[k], pm[16 + k]);
+                                const float s0 = __uint_as_float(pm[2 * k]) * fmaf(__uint_as_float(dp[2 * k]), scale, -dscale);
+                                const float s1 = __uint_as_float(pm[2 * k + 1]) * fmaf(__uint_as_float(dp[2 * k + 1]), scale, -dscale);
+                                split_pack(s0, s1, ds[k], ds[16 + k]);
                             }
-                            ptx::tmem_st_32x32(tm_dp + lane_off + qt * 32, pm);
+                            ptx::tmem_st_32x32(tm_dp + lane_off + qt * 32, ds);
                         }
                     } else
 #pragma unroll
@@ -791,21 +1189,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
                     }
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before();
+                    if (prev_item >= 0) { epilogue(prev_item, (it - 1) & 1); prev_item = -1; }
                     ptx::mbar_arrive(bar(DS_READY));
                 }
             }
-            if (!exp_group) {
-                // ---- epilogue: dQ rows of this q tile ----
-                ptx::mbar_wait(bar(ACC_DONE), it & 1);
-                ptx::tc_fence_after();
-                const int sq = mt * kBlk + tid;
-                const bool live = sq < args.Sq;
-                float* drow = args.dq + ((size_t)b * args.Sq + (live ? sq : 0)) * args.lddq + (size_t)h * kD;
-                if (BX) store_acc_half(tm_dq + lane_off + 32 * hsel, drow + 32 * hsel, live);      // two warp sets, 32 columns each
-                else    store_acc_row(tm_dq + lane_off, drow, live);
-                ptx::tc_fence_before();
-            }
+            if (!exp_group) prev_item = item;
         }
+        if (prev_item >= 0) epilogue(prev_item, (it - 1) & 1);
     }
 
     ptx::tc_fence_before();
@@ -963,8 +1353,8 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
     a.dbg = nullptr;
     static const bool dbg_times = getenv("NPM_ATTN_DEBUG_TIMES") != nullptr;       // tools only: synchronises and prints
     if (dbg_times) {
-        cudaMalloc(&a.dbg, sizeof(long long) * 12 * num_sms());
-        cudaMemset(a.dbg, 0, sizeof(long long) * 12 * num_sms());
+        cudaMalloc(&a.dbg, sizeof(long long) * 24 * num_sms());
+        cudaMemset(a.dbg, 0, sizeof(long long) * 24 * num_sms());
     }
 
     static bool configured = false;
@@ -973,6 +1363,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         auto set = [&](auto kern, int bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); };
         set(attn_bwd_dkdv_kernel<false, false>, kKvSmem); set(attn_bwd_dkdv_kernel<true, false>, kKvSmem);
         set(attn_bwd_dkdv_kernel<false, true>, kKvSmem);  set(attn_bwd_dkdv_kernel<true, true>, kKvSmem);
+        set(attn_bwd_dkdv_bx_kernel<false>, kKvBxSmem);   set(attn_bwd_dkdv_bx_kernel<true>, kKvBxSmem);
         set(attn_bwd_dq_kernel<false, false>, kDqSmem);   set(attn_bwd_dq_kernel<true, false>, kDqSmem);
         set(attn_bwd_dq_kernel<false, true>, kDqSmem);    set(attn_bwd_dq_kernel<true, true>, kDqSmem);
         if (e != cudaSuccess) { set_error("attn_bwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
@@ -993,23 +1384,35 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         a.total_items = (int)items;
         int grid = (int)(items < num_sms() ? items : num_sms());
         if (causal) while (grid > 1 && gcd_int(grid, a.n_kv) != 1) --grid;     // see attn_fwd_launch
-        auto kern = causal ? (bx ? attn_bwd_dkdv_kernel<true, true> : attn_bwd_dkdv_kernel<true, false>)
-                           : (bx ? attn_bwd_dkdv_kernel<false, true> : attn_bwd_dkdv_kernel<false, false>);
-        launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        static const bool old_bx = getenv("NPM_ATTN_OLD_DKDV") != nullptr;      // A/B: the shared-template split-bf16 kernel
+        if (bx && !old_bx) {
+            auto kern = causal ? attn_bwd_dkdv_bx_kernel<true> : attn_bwd_dkdv_bx_kernel<false>;
+            launch_pdl(kern, dim3(grid), dim3(kThreadsBx), kKvBxSmem, stream, 1, tQr, tKr, tVr, tDOr, a);
+        } else {
+            auto kern = causal ? (bx ? attn_bwd_dkdv_kernel<true, true> : attn_bwd_dkdv_kernel<true, false>)
+                               : (bx ? attn_bwd_dkdv_kernel<false, true> : attn_bwd_dkdv_kernel<false, false>);
+            launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kKvSmem, stream, 1, tQr, tQt, tKr, tVr, tDOr, tDOt, a);
+        }
         count_launch();
         if ((rc = check_launch("attn_bwd_dkdv_kernel"))) return rc;
         if (dbg_times) {
             cudaStreamSynchronize(stream);
-            std::vector<long long> h(12 * (size_t)grid);
+            std::vector<long long> h(24 * (size_t)grid);
             cudaMemcpy(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
-            static const char* names[10] = {"K_FULL", "QR_FULL", "V_FULL", "DOR_FULL", "P_READY", "DOT_FULL", "DS_READY",
-                                            "QT_FULL", "total", "blocks"};
-            double sum[12] = {0};
-            for (int c = 0; c < grid; ++c) for (int k = 0; k < 12; ++k) sum[k] += (double)h[12 * c + k];
+            static const char* names_old[10] = {"K_FULL", "QR_FULL", "V_FULL", "DOR_FULL", "P_READY", "DOT_FULL", "DS_READY",
+                                                "QT_FULL", "total", "blocks"};
+            static const char* names_bx[10] = {"K_FULL", "Q_FULL", "V_FULL", "DO_FULL", "P_READY", "DS_READY_A", "DS_READY_B",
+                                               "DK_FREE", "total", "blocks"};
+            const char** names = (bx && !old_bx) ? names_bx : names_old;
+            double sum[24] = {0};
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 24; ++k) sum[k] += (double)h[24 * c + k];
             const double blocks = sum[9] > 0 ? sum[9] : 1;
             fprintf(stderr, "[attn_bwd_dkdv issuer, cycles per q block, mean over %d CTAs]", grid);
             for (int k = 0; k < 9; ++k) fprintf(stderr, " %s=%.0f", names[k], sum[k] / blocks);
-            fprintf(stderr, "\n");
+            fprintf(stderr, "\n  elementwise warps, cycles per q block: exp(w4) stage+bar %.0f, wait S^T %.0f, work %.0f | dS(first warp) stage+bar %.0f, "
+                    "wait P %.0f, wait dP^T %.0f, work %.0f | epilogues per item: dV %.0f dK %.0f\n",
+                    sum[12] / blocks, sum[13] / blocks, sum[14] / blocks, sum[15] / blocks, sum[16] / blocks, sum[17] / blocks, sum[18] / blocks,
+                    sum[19] * 8 / blocks, sum[20] * 8 / blocks);
             cudaFree(a.dbg);
             a.dbg = nullptr;
         }

@@ -23,6 +23,10 @@
 // pairs, per 64-column half [32 columns hi | 32 columns mid].  In bf16 a [rows, 64] tile with the 128-byte swizzle is
 // at once a K-major operand over its 64 columns and an MN-major operand over its rows, so V needs no second layout.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -57,6 +61,7 @@ struct FwdArgs {
     float c;                 // log2(e) / sqrt(dk)
     float* o;                // [B, Sq, H, 64]
     float* lse;              // [B, H, Sq]  log2-domain: m + log2(sum)
+    long long* dbg;          // tools only (NPM_ATTN_DEBUG_TIMES): 16 cycle counters per CTA
 };
 
 // Round-to-nearest (ties away) fp32 → tf32 on the integer ALU: kind::tf32 reads only the upper 19 bits
@@ -228,19 +233,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int qb = it & 1;
                 if (j == 0) ptx::mbar_wait(q_full(qb), (it >> 1) & 1);
                 const int st = gs % kKS;
+                const long long tk = args.dbg ? clock64() : 0;
                 ptx::mbar_wait(k_full(st), (gs / kKS) & 1);
+                if (args.dbg) args.dbg[blockIdx.x * 16 + 0] += clock64() - tk;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (gs & 1u) * kBN;
                 const uint32_t qa = q_addr + qb * kTileBytes, ka = k_addr + st * kTileBytes;
                 if (BX) {
                     // (A image, B image): mid*hi, hi*mid, hi*hi; the mid image of a tile follows its hi image
+                    const uint64_t da0 = ptx::umma_desc(desc_k, qa), db0 = ptx::umma_desc(desc_k, ka);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         if (t < args.t0) continue;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t da = ptx::umma_desc(desc_k, qa + (t == 0 ? kChunkBytes : 0) + kk * 32);
-                            const uint64_t db = ptx::umma_desc(desc_k, ka + (t == 1 ? kChunkBytes : 0) + kk * 32);
+                            const uint64_t da = ptx::umma_desc_off(da0, (t == 0 ? kChunkBytes : 0) + kk * 32);
+                            const uint64_t db = ptx::umma_desc_off(db0, (t == 1 ? kChunkBytes : 0) + kk * 32);
                             ptx::umma_f16(d_tmem, da, db, idesc_s, (t > args.t0 || kk != 0) ? 1u : 0u);
                         }
                     }
@@ -268,21 +276,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int j = cm.j;
                 cur_next(cm);
                 const int st = g % kVS;
+                const long long tp = args.dbg ? clock64() : 0;
                 ptx::mbar_wait(p_ready(g & 1u), (g >> 1) & 1);
+                const long long tv = args.dbg ? clock64() : 0;
                 ptx::mbar_wait(v_full(st), (g / kVS) & 1);
+                if (args.dbg) {
+                    args.dbg[blockIdx.x * 16 + 1] += tv - tp;
+                    args.dbg[blockIdx.x * 16 + 2] += clock64() - tv;
+                    args.dbg[blockIdx.x * 16 + 3] += 1;
+                }
                 ptx::tc_fence_after();
                 const uint32_t p_tmem = tmem_base + (g & 1u) * kBN;
                 const uint32_t va = v_addr + st * kTileBytes;
                 if (BX) {
                     // P in TMEM: per 64-k half [32 columns hi | 32 columns mid], two bf16 per column; a K16 step is 8 columns
                     // of P and 16 rows (2048 B) of the V image
+                    const uint64_t db0 = ptx::umma_desc(desc_mn, va);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         if (t < args.t0) continue;
 #pragma unroll
                         for (int kk = 0; kk < kBN / 16; ++kk) {
                             const uint32_t pa = p_tmem + (kk >> 2) * 64 + (t == 0 ? 32 : 0) + (kk & 3) * 8;
-                            const uint64_t db = ptx::umma_desc(desc_mn, va + (t == 1 ? kChunkBytes : 0) + kk * 2048);
+                            const uint64_t db = ptx::umma_desc_off(db0, (t == 1 ? kChunkBytes : 0) + kk * 2048);
                             ptx::umma_f16_ts(tmem_o, pa, db, idesc_pv, (j != 0 || t > args.t0 || kk != 0) ? 1u : 0u);
                         }
                     }
@@ -310,21 +326,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int c0 = hsel * 64;
         const float c = args.c;
         uint32_t g = 0;
-        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+        // Epilogue of a finished item (add the two partial row sums, O / l -> global, log-sum-exp -> saved).  DEFERRED into
+        // the first kv block of the next item, between that block's P stores and its p_ready arrival — the arrival is what
+        // releases the P V product that overwrites O — so the softmax of the next item's first block no longer waits for the
+        // last P V product of this one (measured: 4700 clk per item in this epilogue, most of it that wait).
+        int prev_item = -1;
+        float prev_l = 0.0f, prev_m = 0.0f;
+        auto epilogue = [&](int item, float l, float m_ref, uint32_t parity) {
+            const long long te = (args.dbg != nullptr && warp == 4 && lane == 0) ? clock64() : 0;
             const int mt = item % args.q_tiles;
             const int bh = item / args.q_tiles;
             const int h = bh % args.H, b = bh / args.H;
+            tmem_st_x1(tmem_x + 4 + hsel, __float_as_uint(l));
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            bar_sync_64(1 + wq);
+            ptx::tc_fence_after();
+            l += __uint_as_float(tmem_ld_x1(tmem_x + 4 + (hsel ^ 1)));
+            ptx::tmem_ld_wait();
+            ptx::mbar_wait(o_done, parity);
+            ptx::tc_fence_after();
+            uint32_t o[32];
+            ptx::tmem_ld_32x32(tmem_o + lane_off + hsel * 32, o);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            bar_sync_64(1 + wq);          // both partial sums have been read: the exchange cells may be rewritten
+            const int sq = mt * kBM + row;
+            if (sq < args.Sq) {
+                const float inv = 1.0f / l;
+                float4* dst = reinterpret_cast<float4*>(args.o + (((size_t)b * args.Sq + sq) * args.H + h) * kD + hsel * 32);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    dst[k] = make_float4(__uint_as_float(o[4 * k]) * inv, __uint_as_float(o[4 * k + 1]) * inv,
+                                         __uint_as_float(o[4 * k + 2]) * inv, __uint_as_float(o[4 * k + 3]) * inv);
+                if (hsel == 0) args.lse[((size_t)b * args.H + h) * args.Sq + sq] = m_ref + ptx::lg2(l);
+            }
+            if (args.dbg != nullptr && warp == 4 && lane == 0) args.dbg[blockIdx.x * 16 + 10] += clock64() - te;
+            __syncwarp();
+        };
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) {
+            const int mt = item % args.q_tiles;
             float m_ref = -INFINITY, l = 0.0f;
             const int nb = blocks_of(item);
             for (int j = 0; j < nb; ++j, ++g) {
                 const uint32_t buf = g & 1u;
+                const bool rec = args.dbg != nullptr && warp == 4 && lane == 0;
+                long long* dbg = args.dbg + blockIdx.x * 16;
+                long long t0 = rec ? clock64() : 0, t1;
+#define ATTN_STAMP(i) { if (rec) { t1 = clock64(); dbg[i] += t1 - t0; t0 = t1; } __syncwarp(); }
                 ptx::mbar_wait(s_full(buf), (g >> 1) & 1);
+                ATTN_STAMP(4)
                 ptx::tc_fence_after();
                 float s[64];
                 const uint32_t s_tmem = tmem_base + lane_off + buf * kBN + c0;
                 ptx::tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
                 ptx::tmem_ld_32x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
                 ptx::tmem_ld_wait();
+                ATTN_STAMP(5)
                 const int kv_left = args.Skv - j * kBN;
                 if (kv_left < kBN) {
 #pragma unroll
@@ -351,6 +409,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 ptx::tc_fence_after();
                 pm = fmaxf(pm, __uint_as_float(tmem_ld_x1(tmem_x + buf * 2 + (hsel ^ 1))));
                 ptx::tmem_ld_wait();
+                ATTN_STAMP(6)
                 const float mb = pm * c;
                 const bool need = mb > m_ref + kRescaleThreshold;
                 if (__any_sync(0xffffffffu, need)) {
@@ -371,6 +430,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         ptx::tmem_st_32x32(tmem_o + lane_off + hsel * 32, o);
                     }
                 }
+                ATTN_STAMP(7)
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
                 for (int k = 0; k < 64; k += 4) {
@@ -379,6 +439,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     l0 += s[k]; l1 += s[k + 1]; l2 += s[k + 2]; l3 += s[k + 3];
                 }
                 l += (l0 + l1) + (l2 + l3);
+                ATTN_STAMP(8)
                 {
                     uint32_t hi[32], mid[32];
 #pragma unroll
@@ -388,34 +449,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
+                if (prev_item >= 0) { epilogue(prev_item, prev_l, prev_m, (g - 1) & 1); prev_item = -1; }
                 ptx::mbar_arrive(p_ready(buf));
+                ATTN_STAMP(9)
+                if (rec) dbg[11] += 1;
+                __syncwarp();
+#undef ATTN_STAMP
             }
-            // ---- epilogue: add the two partial row sums, O / l -> global (32 columns each), log-sum-exp -> saved ----
-            tmem_st_x1(tmem_x + 4 + hsel, __float_as_uint(l));
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            bar_sync_64(1 + wq);
-            ptx::tc_fence_after();
-            l += __uint_as_float(tmem_ld_x1(tmem_x + 4 + (hsel ^ 1)));
-            ptx::tmem_ld_wait();
-            ptx::mbar_wait(o_done, (g - 1) & 1);
-            ptx::tc_fence_after();
-            uint32_t o[32];
-            ptx::tmem_ld_32x32(tmem_o + lane_off + hsel * 32, o);
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            bar_sync_64(1 + wq);          // both partial sums have been read: the exchange cells may be rewritten (next item)
-            const int sq = mt * kBM + row;
-            if (sq < args.Sq) {
-                const float inv = 1.0f / l;
-                float4* dst = reinterpret_cast<float4*>(args.o + (((size_t)b * args.Sq + sq) * args.H + h) * kD + hsel * 32);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    dst[k] = make_float4(__uint_as_float(o[4 * k]) * inv, __uint_as_float(o[4 * k + 1]) * inv,
-                                         __uint_as_float(o[4 * k + 2]) * inv, __uint_as_float(o[4 * k + 3]) * inv);
-                if (hsel == 0) args.lse[((size_t)b * args.H + h) * args.Sq + sq] = m_ref + ptx::lg2(l);
-            }
+            prev_item = item; prev_l = l; prev_m = m_ref;
         }
+        if (prev_item >= 0) epilogue(prev_item, prev_l, prev_m, (g - 1) & 1);
     } else if (warp >= 4) {
         // ========================= softmax =========================
         const int wq = warp & 3;                         // TMEM lane quarter this warp may access
@@ -590,6 +633,8 @@ int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float
     a.t0 = nterms == 1 ? 2 : 0;
     a.c = (float)(1.4426950408889634 / sqrt((double)kD));
     a.o = o; a.lse = lse;
+    a.dbg = nullptr;
+    static const bool dbg_times = getenv("NPM_ATTN_DEBUG_TIMES") != nullptr;      // tools only: synchronises and prints
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -608,9 +653,26 @@ int attn_fwd_launch(const void* q, const void* k, const void* v, float* o, float
     if (causal) while (grid > 1 && gcd_int(grid, a.q_tiles) != 1) --grid;
     auto kern = causal ? (bx ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
                        : (bx ? attn_fwd_kernel<false, true> : attn_fwd_kernel<false, false>);
+    if (dbg_times && bx) {
+        cudaMalloc(&a.dbg, sizeof(long long) * 16 * grid);
+        cudaMemset(a.dbg, 0, sizeof(long long) * 16 * grid);
+    }
     cudaError_t le = launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kSmemBytes, stream, 1, tmQ, tmK, tmV, a);
     if (le != cudaSuccess) { set_error("attn_fwd_kernel launch: %s", cudaGetErrorString(le)); return NPM_ERR_CUDA; }
     count_launch();
+    if (a.dbg != nullptr) {
+        cudaStreamSynchronize(stream);
+        std::vector<long long> h(16 * (size_t)grid);
+        cudaMemcpy(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+        double t[16] = {0};
+        for (int cta = 0; cta < grid; ++cta)
+            for (int i = 0; i < 16; ++i) t[i] += (double)h[16 * cta + i];
+        fprintf(stderr, "[attn_fwd bx] cycles per kv block: issuer waits k %.0f, p_ready %.0f, v %.0f | softmax(w4): s_full wait %.0f, "
+                "tmem ld %.0f, max+exchange %.0f, rescale %.0f, exp %.0f, split+st+arrive %.0f; epilogue per item %.0f\n",
+                t[0] / t[3], t[1] / t[3], t[2] / t[3], t[4] / t[11], t[5] / t[11], t[6] / t[11], t[7] / t[11], t[8] / t[11], t[9] / t[11],
+                t[10] * 8 / t[11]);
+        cudaFree(a.dbg);
+    }
     return check_launch("attn_fwd_kernel");
 }
 

@@ -380,6 +380,15 @@ __host__ __device__ constexpr uint64_t umma_desc_base(uint32_t layout_type, uint
 __device__ __forceinline__ uint64_t umma_desc(uint64_t base, uint32_t smem_addr) {
     return base | uint64_t((smem_addr >> 4) & 0x3fffu);
 }
+// The descriptor `off_bytes` further into the same operand, from the low word of a descriptor built once: one 32-bit add
+// per MMA instead of the shift / mask / or chain (the single issuing thread of the attention kernels spends ~11 uniform
+// instructions per tcgen05.mma otherwise, and its MMAs are only 32-64 clk long).  No carry out of the 14-bit address field:
+// shared-memory addresses stay below 256 KB.
+__device__ __forceinline__ uint64_t umma_desc_off(uint64_t desc0, uint32_t off_bytes) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(uint32_t(desc0) + (off_bytes >> 4)), "r"(uint32_t(desc0 >> 32)));
+    return d;
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor):
 //   [4,6) c_format=1(F32) [7,10) a_format=2(TF32) [10,13) b_format=2 [15] a_major [16] b_major
 //   [17,23) N>>3 [24,29) M>>4       (major: 0 = K-major, 1 = MN-major)
