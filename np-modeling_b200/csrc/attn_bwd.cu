@@ -62,6 +62,7 @@ struct BwdArgs {
     int causal;               // kv position t > q position s is masked (Sq == Skv): blocks above the diagonal are skipped
     long long* dbg;           // tools only: per-CTA cycle counters of the dK/dV MMA issuer's waits (NPM_ATTN_DEBUG_TIMES)
     int debug_skip;           // tools only: 1 = exp warps do no work, 2 = dS warps do no work, 3 = both (timing experiments)
+    int halves;               // split-bf16 kernels: dP / dP^T as two N = 64 products interleaved with the dQ / dK halves (1) or one N = 128 product (0)
 };
 
 __device__ __forceinline__ uint32_t cvt_tf32(float x) {
@@ -729,9 +730,22 @@ attn_bwd_dkdv_bx_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 ptx::umma_commit(bar(ST_FULL0 + (g & 1u)));
                 if (i == n_q - 1) ptx::umma_commit(bar(K_EMPTY));
             };
+            const bool halves = args.halves != 0;
             auto issue_dpt = [&](uint32_t g, int half) {       // dP^T(g)[:, half] = V dO[64 q rows of the half]^T
                 const int it = c_dpt.it, i = c_dpt.i;
                 const bool first = i == c_dpt.i0;
+                if (!halves) {             // one N = 128 product when called for half 1, nothing for half 0
+                    if (half == 0) return;
+                    cur_next(c_dpt);
+                    if (first) twait(2, V_FULL, it & 1);
+                    twait(3, DO_FULL0 + (g & 1u), (g >> 1) & 1u);
+                    ptx::tc_fence_after();
+                    mma_rr<true>(tm_dpt, vr_addr, do_addr + (g & 1u) * kTileBytes, idesc_s, args.t0);
+                    ptx::umma_commit(bar(DPT_FULL_A));
+                    ptx::umma_commit(bar(DPT_FULL_B));
+                    if (i == n_q - 1) ptx::umma_commit(bar(V_EMPTY));
+                    return;
+                }
                 if (half == 0) {
                     if (first) twait(2, V_FULL, it & 1);
                     twait(3, DO_FULL0 + (g & 1u), (g >> 1) & 1u);
@@ -1203,6 +1217,319 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQr, const __grid_consta
     if (warp == 3) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// =============================================================================== dQ (split-bf16)
+// The split-bf16 dQ kernel, restructured like attn_bwd_dkdv_bx_kernel: dP is produced and consumed as two 64-column halves
+// (kv rows 0..63 / 64..127 of the block; per warp set the chain is dS -> 4 K16 steps of dQ -> dP half -> dS), K is loaded
+// once per block into a ring of three (S runs two blocks ahead of dQ, and the bf16 image is the K-major operand of S and
+// the MN-major operand of dQ at once), the dQ epilogue is deferred into the next item's first block.
+// smem: Q x2 (per item) | dO | K ring x3 | V | barriers.
+constexpr int kDqBxUsed = 7 * kTileBytes + 256;
+constexpr int kDqBxSmem = 7 * kTileBytes + 1024 + 256;
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(kThreadsBx, 1)
+attn_bwd_dq_bx_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdArgs args) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr  = ptx::smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr        = smem_raw + (base_addr - raw_addr);
+
+    const uint32_t q_addr = base_addr;                        // 2 x 32 KB (items alternate)
+    const uint32_t do_addr = q_addr + 2 * kTileBytes;
+    const uint32_t k_addr = do_addr + kTileBytes;             // ring of 3
+    const uint32_t v_addr = k_addr + 3 * kTileBytes;
+    const uint32_t bar_addr = base_addr + 7 * kTileBytes;
+    enum { Q_FULL0 = 0, Q_FULL1, Q_EMPTY0, Q_EMPTY1, DO_FULL, DO_EMPTY, K_FULL0, K_FULL1, K_FULL2, K_EMPTY0, K_EMPTY1, K_EMPTY2,
+           V_FULL, V_EMPTY, S_FULL0, S_FULL1, P_READY0, P_READY1, DP_FULL_A, DP_FULL_B, DS_READY_A, DS_READY_B, ACC_DONE,
+           DQ_FREE, NBAR };
+    static_assert(8 * NBAR + 4 <= 256, "barrier block");
+    auto bar = [&](int i) { return bar_addr + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 7 * kTileBytes + 8 * NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmDO); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV);
+    }
+    if (warp == 3) {
+        if (lane == 0) {
+            for (int i = 0; i < NBAR; ++i)
+                ptx::mbar_init(bar(i), (i == P_READY0 || i == P_READY1 || i == DQ_FREE) ? 256 : (i == DS_READY_A || i == DS_READY_B) ? 128 : 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();               // only shared memory / TMEM set-up above
+    const uint32_t tm_dp = tmem_base + 256, tm_dq = tmem_base + 384;
+
+    const int n_kv = args.n_kv;
+    auto blocks_of = [&](int item) -> int { return CAUSAL ? (item % args.n_q) + 1 : n_kv; };
+    uint32_t G = 0;
+    for (int item = blockIdx.x; item < args.total_items; item += gridDim.x) G += (uint32_t)blocks_of(item);
+
+    if (warp == 0) {
+        // ============ producer of the streams that run ahead: Q per item, K per kv block (ring of 3) ============
+        if (ptx::elect_one()) {
+            uint32_t g = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+                const int mt = item % args.n_q;
+                const int bh = item / args.n_q;
+                const int h = bh % args.H, b = bh / args.H;
+                const int qb = it & 1;
+                ptx::mbar_wait(bar(Q_EMPTY0 + qb), ((it >> 1) & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(bar(Q_FULL0 + qb), kTileBytes);
+                load_tile<true>(q_addr + qb * kTileBytes, &tmQ, bar(Q_FULL0 + qb), mt * kBlk, h, b);
+                const int nb = blocks_of(item);
+                for (int j = 0; j < nb; ++j, ++g) {
+                    const uint32_t slot = g % 3u;
+                    ptx::mbar_wait(bar(K_EMPTY0 + slot), ((g / 3u) & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(K_FULL0 + slot), kTileBytes);
+                    load_tile<true>(k_addr + slot * kTileBytes, &tmK, bar(K_FULL0 + slot), j * kBlk, h, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============ producer of the streams consumed one block ahead: dO per item, V per kv block ============
+        if (ptx::elect_one()) {
+            uint32_t g = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+                const int mt = item % args.n_q;
+                const int bh = item / args.n_q;
+                const int h = bh % args.H, b = bh / args.H;
+                ptx::mbar_wait(bar(DO_EMPTY), (it & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(bar(DO_FULL), kTileBytes);
+                load_tile<true>(do_addr, &tmDO, bar(DO_FULL), mt * kBlk, h, b);
+                const int nb = blocks_of(item);
+                for (int j = 0; j < nb; ++j, ++g) {
+                    ptx::mbar_wait(bar(V_EMPTY), (g & 1) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(V_FULL), kTileBytes);
+                    load_tile<true>(v_addr, &tmV, bar(V_FULL), j * kBlk, h, b);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ============ MMA issuer ============
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc_s   = ptx::umma_idesc_bf16(kBlk, kBlk, false, false);
+            constexpr uint32_t idesc_s64 = ptx::umma_idesc_bf16(kBlk, kBlk / 2, false, false);
+            constexpr uint32_t idesc_ts  = ptx::umma_idesc_bf16(kBlk, kD, false, true);
+            struct Cur { int item, it, j, cnt; };
+            auto cur_init = [&](Cur& c) {
+                c.item = blockIdx.x; c.it = 0; c.j = 0;
+                c.cnt = c.item < args.total_items ? blocks_of(c.item) : 0;
+            };
+            auto cur_next = [&](Cur& c) {
+                if (++c.j == c.cnt) {
+                    c.j = 0; c.item += gridDim.x; ++c.it;
+                    c.cnt = c.item < args.total_items ? blocks_of(c.item) : 0;
+                }
+            };
+            Cur c_s, c_dp, c_main;
+            cur_init(c_s); cur_init(c_dp); cur_init(c_main);
+            long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            long long* const dbg = args.dbg;
+            auto twait = [&](int slot, int which, uint32_t parity) {
+                if (dbg) {
+                    const long long t0 = clock64();
+                    ptx::mbar_wait(bar(which), parity);
+                    acc[slot] += clock64() - t0;
+                } else {
+                    ptx::mbar_wait(bar(which), parity);
+                }
+            };
+            const long long t_begin = dbg ? clock64() : 0;
+            auto issue_s = [&](uint32_t g) {         // S(g) = Q K^T
+                const int it = c_s.it, j = c_s.j;
+                const bool last = j == c_s.cnt - 1;
+                cur_next(c_s);
+                if (j == 0) twait(0, Q_FULL0 + (it & 1), (it >> 1) & 1);
+                twait(1, K_FULL0 + g % 3u, (g / 3u) & 1u);
+                ptx::tc_fence_after();
+                mma_rr<true>(tmem_base + (g & 1u) * kBlk, q_addr + (it & 1) * kTileBytes, k_addr + (g % 3u) * kTileBytes, idesc_s, args.t0);
+                ptx::umma_commit(bar(S_FULL0 + (g & 1u)));
+                if (last) ptx::umma_commit(bar(Q_EMPTY0 + (it & 1)));
+            };
+            const bool halves = args.halves != 0;
+            auto issue_dp = [&](uint32_t g, int half) {        // dP(g)[:, half] = dO V[64 kv rows of the half]^T
+                const int it = c_dp.it, j = c_dp.j;
+                const bool last = j == c_dp.cnt - 1;
+                if (!halves) {             // one N = 128 product when called for half 1, nothing for half 0
+                    if (half == 0) return;
+                    cur_next(c_dp);
+                    if (j == 0) twait(2, DO_FULL, it & 1);
+                    twait(3, V_FULL, g & 1);
+                    ptx::tc_fence_after();
+                    mma_rr<true>(tm_dp, do_addr, v_addr, idesc_s, args.t0);
+                    ptx::umma_commit(bar(DP_FULL_A));
+                    ptx::umma_commit(bar(DP_FULL_B));
+                    ptx::umma_commit(bar(V_EMPTY));
+                    if (last) ptx::umma_commit(bar(DO_EMPTY));
+                    return;
+                }
+                if (half == 0) {
+                    if (j == 0) twait(2, DO_FULL, it & 1);
+                    twait(3, V_FULL, g & 1);
+                    ptx::tc_fence_after();
+                } else {
+                    cur_next(c_dp);
+                }
+                mma_rr<true>(tm_dp + half * 64, do_addr, v_addr + half * 8192, idesc_s64, args.t0);
+                ptx::umma_commit(bar(DP_FULL_A + half));
+                if (half == 1) {
+                    ptx::umma_commit(bar(V_EMPTY));
+                    if (last) ptx::umma_commit(bar(DO_EMPTY));
+                }
+            };
+            if (G > 0) { issue_s(0); issue_dp(0, 0); issue_dp(0, 1); }
+            if (G > 1) issue_s(1);
+            for (uint32_t g = 0; g < G; ++g) {
+                const int j = c_main.j, it_main = c_main.it;
+                const bool last = j == c_main.cnt - 1;
+                cur_next(c_main);
+                const uint32_t ka = k_addr + (g % 3u) * kTileBytes;
+                twait(4, DS_READY_A, g & 1);
+                // the first dQ product of an item overwrites the accumulator: both warp sets must have stored the previous item's rows
+                if (j == 0 && it_main > 0) twait(6, DQ_FREE, (it_main - 1) & 1);
+                ptx::tc_fence_after();
+                mma_ts_bx_range(tm_dq, tm_dp, ka, idesc_ts, j != 0, args.t0, 0, 4);                       // dQ += dS K, kv rows 0..63
+                if (g + 1 < G) issue_dp(g + 1, 0);
+                twait(5, DS_READY_B, g & 1);
+                ptx::tc_fence_after();
+                mma_ts_bx_range(tm_dq, tm_dp, ka, idesc_ts, true, args.t0, 4, 8);                         // kv rows 64..127
+                ptx::umma_commit(bar(K_EMPTY0 + g % 3u));
+                if (last) ptx::umma_commit(bar(ACC_DONE));
+                if (g + 1 < G) issue_dp(g + 1, 1);
+                if (g + 2 < G) issue_s(g + 2);
+            }
+            if (dbg) {
+                acc[8] = clock64() - t_begin;
+                acc[9] = G;
+                for (int k = 0; k < 12; ++k) dbg[blockIdx.x * 24 + k] = acc[k];
+            }
+        }
+    } else if (warp >= 4) {
+        // ============ warps 4-11: P = exp2(c S - L) in place (fp32: P is no MMA operand here).  warps 12-19: dS = P o (dP - D) /
+        // sqrt(dk), packed, in place over dP, then the dQ epilogue.  Thread = q row = TMEM lane; set A (hsel = 0) owns kv
+        // columns 0..63 of every block, set B columns 64..127. ============
+        const bool exp_group = warp < 12;
+        const int wq = warp & 3;
+        const int hsel = ((warp - 4) >> 2) & 1;
+        const int q0 = 2 * hsel, q1 = 2 * hsel + 2;
+        const int tid = wq * 32 + lane;
+        const uint32_t lane_off = uint32_t(wq * 32) << 16;
+        const float c = args.c, scale = args.scale;
+        const float* vec = exp_group ? args.lse : args.dsum;
+        const float pad = exp_group ? INFINITY : 0.0f;
+        auto fetch = [&](int item) -> float {
+            const int sq = (item % args.n_q) * kBlk + tid;
+            return sq < args.Sq ? __ldg(vec + (size_t)(item / args.n_q) * args.Sq + sq) : pad;
+        };
+        uint32_t g = 0;
+        int it = 0;
+        float next = (int)blockIdx.x < args.total_items ? fetch(blockIdx.x) : 0.0f;
+        const bool rec = args.dbg != nullptr && lane == 0 && (warp == 4 || warp == 12);
+        long long racc[5] = {0, 0, 0, 0, 0};
+        int prev_item = -1;
+        auto epilogue = [&](int item, uint32_t parity) {      // dQ rows of a finished q tile (dS warps), 32 columns per warp set
+            const int mt = item % args.n_q;
+            const int bh = item / args.n_q;
+            const int h = bh % args.H, b = bh / args.H;
+            ptx::mbar_wait(bar(ACC_DONE), parity);
+            ptx::tc_fence_after();
+            const int sq = mt * kBlk + tid;
+            const bool live = sq < args.Sq;
+            float* drow = args.dq + ((size_t)b * args.Sq + (live ? sq : 0)) * args.lddq + (size_t)h * kD;
+            store_acc_half(tm_dq + lane_off + 32 * hsel, drow + 32 * hsel, live);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar(DQ_FREE));
+        };
+        for (int item = blockIdx.x; item < args.total_items; item += gridDim.x, ++it) {
+            const int mt = item % args.n_q;
+            const float mine = next;                              // L (exp warps) or D (dS warps) of this thread's q row
+            if (item + (int)gridDim.x < args.total_items) next = fetch(item + gridDim.x);
+            const int nb = blocks_of(item);
+            for (int j = 0; j < nb; ++j, ++g) {
+                const uint32_t buf = g & 1u;
+                const uint32_t s_tmem = tmem_base + lane_off + buf * kBlk;
+                long long t0 = rec ? clock64() : 0, t1;
+#define BWD_STAMP(i) { if (rec) { t1 = clock64(); racc[i] += t1 - t0; t0 = t1; } }
+                if (exp_group) {
+                    ptx::mbar_wait(bar(S_FULL0 + buf), (g >> 1) & 1);
+                    BWD_STAMP(0)
+                    ptx::tc_fence_after();
+                    const int kv_left = args.Skv - j * kBlk;
+#pragma unroll
+                    for (int qt = q0; qt < q1; ++qt) {
+                        float p[32];
+                        ptx::tmem_ld_32x32(s_tmem + qt * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const float e = ptx::ex2(fmaf(p[k], c, -mine));
+                            const bool masked = CAUSAL && j == mt && qt * 32 + k > tid;          // kv position after q position
+                            p[k] = (qt * 32 + k < kv_left && !masked) ? e : 0.0f;   // zero-filled K rows past Skv
+                        }
+                        ptx::tmem_st_32x32(s_tmem + qt * 32, *reinterpret_cast<uint32_t(*)[32]>(&p[0]));
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(bar(P_READY0 + buf));
+                    BWD_STAMP(1)
+                } else {
+                    ptx::mbar_wait(bar(P_READY0 + buf), (g >> 1) & 1);
+                    BWD_STAMP(0)
+                    ptx::mbar_wait(bar(DP_FULL_A + hsel), g & 1);
+                    BWD_STAMP(1)
+                    ptx::tc_fence_after();
+                    const float dscale = mine * scale;
+#pragma unroll
+                    for (int qt = q0; qt < q1; ++qt) {
+                        uint32_t pm[32], dp[32];               // pm: P (fp32) in, [16 hi | 16 mid] of dS out
+                        ptx::tmem_ld_32x32(s_tmem + qt * 32, pm);
+                        ptx::tmem_ld_32x32(tm_dp + lane_off + qt * 32, dp);
+                        ptx::tmem_ld_wait();
+                        uint32_t ds[32];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const float s0 = __uint_as_float(pm[2 * k]) * fmaf(__uint_as_float(dp[2 * k]), scale, -dscale);
+                            const float s1 = __uint_as_float(pm[2 * k + 1]) * fmaf(__uint_as_float(dp[2 * k + 1]), scale, -dscale);
+                            split_pack(s0, s1, ds[k], ds[16 + k]);
+                        }
+                        ptx::tmem_st_32x32(tm_dp + lane_off + qt * 32, ds);
+                    }
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    if (prev_item >= 0) { epilogue(prev_item, (it - 1) & 1); prev_item = -1; }
+                    ptx::mbar_arrive(bar(DS_READY_A + hsel));
+                    BWD_STAMP(2)
+                }
+#undef BWD_STAMP
+            }
+            if (!exp_group) prev_item = item;
+        }
+        if (prev_item >= 0) epilogue(prev_item, (it - 1) & 1);
+        if (rec) {
+            long long* const dbg = args.dbg + blockIdx.x * 24;
+            for (int k = 0; k < (exp_group ? 2 : 3); ++k) dbg[(exp_group ? 12 : 15) + k] = racc[k];
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 3) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 // D[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]: 16 lanes x float4 per (b,s,h) row.  A separate 18 us launch: computing D
 // inside the dQ kernel (by its dS warps at item start, or by its exp warps one item ahead) was measured and costs the
 // dQ kernel as much as or more than this launch (0.267 / 0.279 ms vs 0.265 ms for the whole backward at B8 H16 S1024).
@@ -1350,6 +1677,8 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
     a.t0 = nterms == 1 ? 2 : 0;
     static const int debug_skip_env = getenv("NPM_ATTN_DEBUG_SKIP") ? atoi(getenv("NPM_ATTN_DEBUG_SKIP")) : 0;
     a.debug_skip = debug_skip_env;
+    static const int halves_env = getenv("NPM_ATTN_HALVES") ? atoi(getenv("NPM_ATTN_HALVES")) : 3;   // bit 0: dK/dV kernel, bit 1: dQ kernel
+    const int halves_mask = halves_env;
     a.dbg = nullptr;
     static const bool dbg_times = getenv("NPM_ATTN_DEBUG_TIMES") != nullptr;       // tools only: synchronises and prints
     if (dbg_times) {
@@ -1364,6 +1693,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         set(attn_bwd_dkdv_kernel<false, false>, kKvSmem); set(attn_bwd_dkdv_kernel<true, false>, kKvSmem);
         set(attn_bwd_dkdv_kernel<false, true>, kKvSmem);  set(attn_bwd_dkdv_kernel<true, true>, kKvSmem);
         set(attn_bwd_dkdv_bx_kernel<false>, kKvBxSmem);   set(attn_bwd_dkdv_bx_kernel<true>, kKvBxSmem);
+        set(attn_bwd_dq_bx_kernel<false>, kDqBxSmem);     set(attn_bwd_dq_bx_kernel<true>, kDqBxSmem);
         set(attn_bwd_dq_kernel<false, false>, kDqSmem);   set(attn_bwd_dq_kernel<true, false>, kDqSmem);
         set(attn_bwd_dq_kernel<false, true>, kDqSmem);    set(attn_bwd_dq_kernel<true, true>, kDqSmem);
         if (e != cudaSuccess) { set_error("attn_bwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
@@ -1385,6 +1715,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         int grid = (int)(items < num_sms() ? items : num_sms());
         if (causal) while (grid > 1 && gcd_int(grid, a.n_kv) != 1) --grid;     // see attn_fwd_launch
         static const bool old_bx = getenv("NPM_ATTN_OLD_DKDV") != nullptr;      // A/B: the shared-template split-bf16 kernel
+        a.halves = halves_mask & 1;
         if (bx && !old_bx) {
             auto kern = causal ? attn_bwd_dkdv_bx_kernel<true> : attn_bwd_dkdv_bx_kernel<false>;
             launch_pdl(kern, dim3(grid), dim3(kThreadsBx), kKvBxSmem, stream, 1, tQr, tKr, tVr, tDOr, a);
@@ -1423,11 +1754,36 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         a.total_items = (int)items;
         int grid = (int)(items < num_sms() ? items : num_sms());
         if (causal) while (grid > 1 && gcd_int(grid, a.n_q) != 1) --grid;
-        auto kern = causal ? (bx ? attn_bwd_dq_kernel<true, true> : attn_bwd_dq_kernel<true, false>)
-                           : (bx ? attn_bwd_dq_kernel<false, true> : attn_bwd_dq_kernel<false, false>);
-        launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
+        static const bool old_dq = getenv("NPM_ATTN_OLD_DQ") != nullptr;      // A/B: the shared-template split-bf16 kernel
+        if (dbg_times && bx && !old_dq) {
+            cudaMalloc(&a.dbg, sizeof(long long) * 24 * num_sms());
+            cudaMemset(a.dbg, 0, sizeof(long long) * 24 * num_sms());
+        }
+        a.halves = (halves_mask >> 1) & 1;
+        if (bx && !old_dq) {
+            auto kern = causal ? attn_bwd_dq_bx_kernel<true> : attn_bwd_dq_bx_kernel<false>;
+            launch_pdl(kern, dim3(grid), dim3(kThreadsBx), kDqBxSmem, stream, 1, tQr, tDOr, tKr, tVr, a);
+        } else {
+            auto kern = causal ? (bx ? attn_bwd_dq_kernel<true, true> : attn_bwd_dq_kernel<true, false>)
+                               : (bx ? attn_bwd_dq_kernel<false, true> : attn_bwd_dq_kernel<false, false>);
+            launch_pdl(kern, dim3(grid), dim3(bx ? kThreadsBx : kThreads), kDqSmem, stream, 1, tQr, tDOr, tKr, tKt, tVr, a);
+        }
         count_launch();
         if ((rc = check_launch("attn_bwd_dq_kernel"))) return rc;
+        if (dbg_times && a.dbg != nullptr) {
+            cudaStreamSynchronize(stream);
+            std::vector<long long> h(24 * (size_t)grid);
+            cudaMemcpy(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+            double sum[24] = {0};
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 24; ++k) sum[k] += (double)h[24 * c + k];
+            const double blocks = sum[9] > 0 ? sum[9] : 1;
+            fprintf(stderr, "[attn_bwd_dq issuer, cycles per kv block] Q_FULL=%.0f K_FULL=%.0f DO_FULL=%.0f V_FULL=%.0f DS_READY_A=%.0f DS_READY_B=%.0f "
+                    "DQ_FREE=%.0f total=%.0f\n  exp(w4): wait S %.0f, work %.0f | dS(first warp): wait P %.0f, wait dP %.0f, work %.0f\n",
+                    sum[0] / blocks, sum[1] / blocks, sum[2] / blocks, sum[3] / blocks, sum[4] / blocks, sum[5] / blocks, sum[6] / blocks,
+                    sum[8] / blocks, sum[12] / blocks, sum[13] / blocks, sum[15] / blocks, sum[16] / blocks, sum[17] / blocks);
+            cudaFree(a.dbg);
+            a.dbg = nullptr;
+        }
     }
     return NPM_OK;
 }

@@ -431,22 +431,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     }
                 }
                 ATTN_STAMP(7)
+                // exponentials (XU pipe, 16 lanes / clk / SM: the 64 of a thread keep it busy ~1000 clk per block) interleaved
+                // with the split of the PREVIOUS chunk of eight (ALU / FMA pipes), so the split rides in the XU shadow
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                uint32_t hi[32], mid[32];
 #pragma unroll
-                for (int k = 0; k < 64; k += 4) {
-                    s[k] = ptx::ex2(fmaf(s[k], c, -m_ref));         s[k + 1] = ptx::ex2(fmaf(s[k + 1], c, -m_ref));
-                    s[k + 2] = ptx::ex2(fmaf(s[k + 2], c, -m_ref)); s[k + 3] = ptx::ex2(fmaf(s[k + 3], c, -m_ref));
-                    l0 += s[k]; l1 += s[k + 1]; l2 += s[k + 2]; l3 += s[k + 3];
+                for (int ch = 0; ch <= 8; ++ch) {
+                    if (ch < 8) {
+#pragma unroll
+                        for (int k = 8 * ch; k < 8 * ch + 8; ++k) s[k] = ptx::ex2(fmaf(s[k], c, -m_ref));
+                    }
+                    if (ch > 0) {
+                        const int k0 = 8 * (ch - 1);
+                        l0 += s[k0] + s[k0 + 4]; l1 += s[k0 + 1] + s[k0 + 5]; l2 += s[k0 + 2] + s[k0 + 6]; l3 += s[k0 + 3] + s[k0 + 7];
+#pragma unroll
+                        for (int i = k0 / 2; i < k0 / 2 + 4; ++i) split_pack(s[2 * i], s[2 * i + 1], hi[i], mid[i]);
+                    }
                 }
                 l += (l0 + l1) + (l2 + l3);
                 ATTN_STAMP(8)
-                {
-                    uint32_t hi[32], mid[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) split_pack(s[2 * i], s[2 * i + 1], hi[i], mid[i]);
-                    ptx::tmem_st_32x32(s_tmem, hi);                // this 64-k half: [32 columns hi | 32 columns mid]
-                    ptx::tmem_st_32x32(s_tmem + 32, mid);
-                }
+                ptx::tmem_st_32x32(s_tmem, hi);                // this 64-k half: [32 columns hi | 32 columns mid]
+                ptx::tmem_st_32x32(s_tmem + 32, mid);
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 if (prev_item >= 0) { epilogue(prev_item, prev_l, prev_m, (g - 1) & 1); prev_item = -1; }
