@@ -48,6 +48,7 @@ struct ConvTcArgs {
     int tiles_w, tiles_h, tiles_n, tiles_m;
     int rect_w, rect_h;        // wgrad: 32-pixel rectangles per image row / column
     int kb_total, kb_per_split, splits;   // wgrad K blocks (= rectangles over the whole batch)
+    int tap_pack;              // wgrad with Cin <= 64: 128 / Cin filter taps share one M tile (rows = [tap][channel]), else 1
     int total_tiles;
     const float* bias;
     int relu;
@@ -178,11 +179,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         int r = kb;
                         const int rw = r % args.rect_w; r /= args.rect_w;
                         const int rh = r % args.rect_h; r /= args.rect_h;
-                        const int ti = t.tap / args.ks, tj = t.tap - ti * args.ks;
                         const int w = rw * args.PW, h = rh * args.PH;
 #pragma unroll
-                        for (int c = 0; c < kBlockM / 32; ++c)
-                            ptx::tma_load_4d(sA + c * 4096, &tmA, fb, t.m0 + c * 32, w + tj - args.pad, h + ti - args.pad, r);
+                        for (int c = 0; c < kBlockM / 32; ++c) {
+                            // 32 rows of the M tile: channels c*32.. of the tile's tap, or (packed) of tap group*pack + (c*32)/Cin —
+                            // a tap past the last one loads a valid window whose rows the epilogue drops
+                            int tap = t.tap, ch = t.m0 + c * 32;
+                            if (args.tap_pack > 1) {
+                                tap = min(t.tap * args.tap_pack + (c * 32) / args.Mw, args.taps - 1);
+                                ch = (c * 32) % args.Mw;
+                            }
+                            const int ti = tap / args.ks, tj = tap - ti * args.ks;
+                            ptx::tma_load_4d(sA + c * 4096, &tmA, fb, ch, w + tj - args.pad, h + ti - args.pad, r);
+                        }
 #pragma unroll
                         for (int c = 0; c < BLOCK_N / 32; ++c)
                             ptx::tma_load_4d(sB + c * 4096, &tmB, fb, n0 + c * 32, w, h, r);
@@ -253,9 +262,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 c1 = t.w0 + p0 % args.TW; c2 = t.h0 + p0 / args.TW; c3 = t.n_img;
                 rows_live = c1 < args.W && c2 < args.H;
             } else {
-                const int ti = t.tap / args.ks, tj = t.tap - ti * args.ks;
-                c1 = t.m0 + warp * 32; c2 = tj; c3 = ti;
-                rows_live = c1 < args.Mw;
+                int tap = t.tap;
+                c1 = t.m0 + warp * 32;
+                if (args.tap_pack > 1) {
+                    tap = t.tap * args.tap_pack + (warp * 32) / args.Mw;
+                    c1 = (warp * 32) % args.Mw;
+                }
+                const int ti = tap / args.ks, tj = tap - ti * args.ks;
+                c2 = tj; c3 = ti;
+                rows_live = c1 < args.Mw && tap < args.taps;
             }
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
@@ -452,8 +467,14 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int64_t N, int64_t
     const int bn = pick_bn(Cout);
     a.tiles_n = (int)((Cout + bn - 1) / bn);
     a.tiles_m = (int)((Cin + kBlockM - 1) / kBlockM);
-    const int64_t base_items = (int64_t)a.taps * a.tiles_m * a.tiles_n;
-    int64_t splits = ((int64_t)num_sms() * 2 + base_items - 1) / base_items;     // ~2 work items per SM
+    // Cin = 32 / 64: the 128-row M tile would be 1/4 / 1/2 empty — 4 / 2 taps share it (their A boxes are the same
+    // channels at differently shifted pixel coordinates), 9 taps in 3 / 5 tiles instead of 9
+    static const bool no_pack = getenv("NPM_CONV_NO_TAP_PACK") != nullptr;
+    a.tap_pack = (!no_pack && (Cin == 32 || Cin == 64)) ? (int)(kBlockM / Cin) : 1;
+    const int tap_groups = (a.taps + a.tap_pack - 1) / a.tap_pack;
+    const int64_t base_items = (int64_t)tap_groups * a.tiles_m * a.tiles_n;
+    static const int waves_env = getenv("NPM_CONV_WGRAD_WAVES") ? atoi(getenv("NPM_CONV_WGRAD_WAVES")) : 2;
+    int64_t splits = ((int64_t)num_sms() * waves_env) / base_items;              // at most `waves` whole waves of work items
     const int64_t max_splits = (kb_total + 15) / 16;                            // >= 16 K blocks per item
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
