@@ -109,6 +109,16 @@ typedef struct npm_gemm_desc {
                                * projection feeds it without an fp32 round trip.  Split-bf16 kernel only
                                * (else NPM_ERR_UNSUPPORTED); unbatched, no ACCUM / residual.          */
     int64_t c_split_plane;
+    const float* rowdot_x;    /* NULL, or [m, n] fp32 (leading dimension rowdot_ld): together with c_split, the epilogue
+                               * also writes rowdot_out[(row / rowdot_seq) * (n / 64) + j][row % rowdot_seq] =
+                               * sum over the 64 columns of column group j of C[row, .] * rowdot_x[row, .] (the fp32
+                               * result, before the split).  For the dX GEMM of the attention output projection
+                               * (C = dO, rowdot_x = O, rowdot_seq = Sq) that is D = rowsum(dO o O) per head, the row
+                               * term of Softmax.backward (activations.py:42-45 in closed form) in the [B, H, Sq]
+                               * layout npm_mha_core_bwd reads — no separate pass over dO and O.  n % 64 == 0.        */
+    int64_t rowdot_ld;
+    float*  rowdot_out;
+    int64_t rowdot_seq;
 } npm_gemm_desc;
 int npm_gemm(const npm_gemm_desc* d, npm_stream_t stream);
 
@@ -160,6 +170,14 @@ int npm_linear_bwd_dx(const float* dy, const float* w, float* dx,
 /* dw = x^T @ dy (layout per w_out_major), db[n] = sum_m dy (db may be NULL).
  * workspace: npm_colsum_workspace(m, n) bytes (may be NULL when db is NULL).
  *                                                               mlp.py:34-35 */
+/* dx = dy @ W^T written ONLY as bf16 hi / mid planes [2][m, k] (mid plane dx_plane elements after the hi plane), plus the
+ * per-64-column row dots with `o` (npm_gemm_desc.rowdot_*): the backward of MultiHeadAttention's output projection
+ * (attentions.py:129-136) feeding the fused split-bf16 attention backward, whose `scratch` (D, then the planes) it fills.
+ * NPM_ERR_UNSUPPORTED when the split-bf16 GEMM does not take the problem (callers then use npm_linear_bwd_dx). */
+int npm_linear_bwd_dx_planes_rowdot(const float* dy, const float* w, const void* w_planes, int64_t plane,
+                                    void* dx_planes, int64_t dx_plane, int64_t m, int64_t k, int64_t n,
+                                    int w_out_major, const float* o, int64_t ldo, float* rowdot_out,
+                                    int64_t seq, npm_stream_t stream);
 int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db,
                          int64_t m, int64_t k, int64_t n, int w_out_major,
                          void* workspace, npm_stream_t stream);
@@ -332,6 +350,10 @@ typedef struct npm_mha_strides {
                                * mid plane `planes` elements (per tensor: q_plane, k_plane, v_plane below)
                                * after the hi plane; the core then skips its own operand split.       */
     int64_t q_plane, k_plane, v_plane;
+    int64_t do_ready;         /* != 0 (path 2 backward only): `scratch` already holds D [B,H,Sq] and, 256-byte aligned
+                               * behind it, dO as bf16 hi / mid planes [2][B*Sq, H*64] — written by
+                               * npm_linear_bwd_dx_planes_rowdot, the output projection's dX GEMM; d_o may be NULL
+                               * and the core skips its own D / split pass.                                        */
 } npm_mha_strides;
 int npm_mha_core_fwd_strided(const float* q, const float* k, const float* v,
                              float* o, void* saved, int64_t B, int64_t H,

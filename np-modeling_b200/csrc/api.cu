@@ -62,7 +62,7 @@ int attn_split_launch(const float* x, int64_t ld, void* planes, int64_t rows, in
 int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
                     int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv, int64_t lddq, int64_t lddk,
-                    int64_t lddv, int causal, bool bx, int nterms, cudaStream_t stream);
+                    int64_t lddv, int causal, bool bx, int nterms, bool do_ready, cudaStream_t stream);
 int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_t cols, cudaStream_t stream);
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s);
 
@@ -113,7 +113,7 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
     NPM_REQUIRE(d.a_colsum == nullptr || (bx_mode && !bx_off && gemm_bx_supported(d) && d.a_rs == 1 && d.nb1 <= 1 && d.nb2 <= 1),
                 "gemm: a_colsum is served by the split-bf16 kernel only (precision bf16x3 / bf16, m-contiguous A, unbatched, m > 128)");
-    if ((d.c_split != nullptr || d.a == nullptr) && !(bx_mode && !bx_off && gemm_bx_supported(d))) {
+    if ((d.c_split != nullptr || d.a == nullptr || d.rowdot_x != nullptr) && !(bx_mode && !bx_off && gemm_bx_supported(d))) {
         set_error("gemm: split-bf16 input / output planes are served by the split-bf16 kernel only (precision bf16x3 / bf16, m > 128)");
         return NPM_ERR_UNSUPPORTED;
     }
@@ -275,6 +275,26 @@ int npm_linear_bwd_dx_presplit(const float* dy, const float* w, const void* w_pl
     return gemm_dispatch(d, (cudaStream_t)stream);
 }
 
+int npm_linear_bwd_dx_planes_rowdot(const float* dy, const float* w, const void* w_planes, int64_t plane, void* dx_planes,
+                                    int64_t dx_plane, int64_t m, int64_t k, int64_t n, int w_out_major, const float* o, int64_t ldo,
+                                    float* rowdot_out, int64_t seq, npm_stream_t stream) {
+    NPM_REQUIRE(dy && w && dx_planes && o && rowdot_out, "linear_bwd_dx_planes_rowdot: NULL pointer");
+    if (k % 64 != 0 || dx_plane % 8 != 0 || seq <= 0 || m % seq != 0) {
+        set_error("linear_bwd_dx_planes_rowdot: k must be a multiple of 64, m of seq, the plane stride of 8");
+        return NPM_ERR_UNSUPPORTED;
+    }
+    npm_gemm_desc d = blank_desc();
+    d.a = dy; d.b = w; d.c = nullptr;
+    d.m = m; d.n = k; d.k = n;
+    d.a_rs = n; d.a_cs = 1;
+    if (w_out_major) { d.b_rs = k; d.b_cs = 1; } else { d.b_rs = 1; d.b_cs = n; }
+    d.ldc = k;
+    d.b_split = w_planes; d.b_split_plane = plane;
+    d.c_split = dx_planes; d.c_split_plane = dx_plane;
+    d.rowdot_x = o; d.rowdot_ld = ldo; d.rowdot_out = rowdot_out; d.rowdot_seq = seq;
+    return gemm_dispatch(d, (cudaStream_t)stream);
+}
+
 int npm_linear_bwd_dx(const float* dy, const float* w, float* dx, int64_t m, int64_t k, int64_t n, int w_out_major,
                       npm_stream_t stream) {
     // dx[m,k] = sum_n dy[m,n] * W(k,n): contraction over n
@@ -418,7 +438,8 @@ int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v, con
                              const void* saved, float* dq, float* dk_out, float* dv_out, void* scratch, int64_t B,
                              int64_t H, int64_t Sq, int64_t Skv, int64_t dk, int64_t dv, const npm_mha_strides* ld,
                              npm_stream_t stream) {
-    NPM_REQUIRE(q && k && v && d_o && saved && dq && dk_out && dv_out && scratch, "mha_core_bwd: NULL pointer");
+    const bool do_ready = ld && ld->do_ready;
+    NPM_REQUIRE(q && k && v && (d_o || do_ready) && saved && dq && dk_out && dv_out && scratch, "mha_core_bwd: NULL pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ldq = ld && ld->q ? ld->q : H * dk, ldk = ld && ld->k ? ld->k : H * dk,
                   ldv = ld && ld->v ? ld->v : H * dv, lddq = ld && ld->dq ? ld->dq : H * dk,
@@ -428,19 +449,20 @@ int npm_mha_core_bwd_strided(const float* q, const float* k, const float* v, con
     const int path = attn_path_of(ld, B, H, Sq, Skv, dk, dv);
     NPM_REQUIRE(path == ATTN_MATERIALISED || attn_fused_supported(B, H, Sq, Skv, dk, dv), "mha_core_bwd: the pinned path does not serve this shape");
     NPM_REQUIRE(!(ld && ld->planes) || path == ATTN_FUSED_BX, "mha_core_bwd: pre-split q / k / v need the split-bf16 path (strides.path = 3)");
+    NPM_REQUIRE(!do_ready || path == ATTN_FUSED_BX, "mha_core_bwd: do_ready needs the split-bf16 path (strides.path = 3)");
     if (path == ATTN_FUSED_TF32)
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
                                reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, 0, 0, 0, lddq, lddk, lddv,
-                               ld && ld->causal ? 1 : 0, false, 3, s);
+                               ld && ld->causal ? 1 : 0, false, 3, false, s);
     if (path == ATTN_FUSED_BX && ld && ld->planes)
         return attn_bwd_launch(q, k, v, o, d_o, reinterpret_cast<const float*>(saved), dq, dk_out, dv_out,
                                reinterpret_cast<float*>(scratch), B, H, Sq, Skv, ldq, ldk, ldv, ld->q_plane, ld->k_plane, ld->v_plane,
-                               lddq, lddk, lddv, ld->causal ? 1 : 0, true, attn_terms(), s);
+                               lddq, lddk, lddv, ld->causal ? 1 : 0, true, attn_terms(), do_ready, s);
     if (path == ATTN_FUSED_BX) {
         const BxSaved sv = bx_saved(const_cast<void*>(saved), B, H, Sq, Skv);
         return attn_bwd_launch(sv.q, sv.k, sv.v, o, d_o, sv.lse, dq, dk_out, dv_out, reinterpret_cast<float*>(scratch), B, H,
                                Sq, Skv, H * dk, H * dk, H * dv, B * Sq * H * dk, B * Skv * H * dk, B * Skv * H * dv, lddq, lddk, lddv,
-                               ld && ld->causal ? 1 : 0, true, attn_terms(), s);
+                               ld && ld->causal ? 1 : 0, true, attn_terms(), do_ready, s);
     }
     const float* P = reinterpret_cast<const float*>(saved);
     float* dP = reinterpret_cast<float*>(scratch);

@@ -1630,9 +1630,10 @@ int attn_scores_from_lse_launch(float* p, const float* lse, int64_t rows, int64_
 int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o, const float* d_o, const float* lse,
                     float* dq, float* dk, float* dv, float* dsum, int64_t B, int64_t H, int64_t Sq, int64_t Skv,
                     int64_t ldq, int64_t ldk, int64_t ldv, int64_t plq, int64_t plk, int64_t plv, int64_t lddq, int64_t lddk,
-                    int64_t lddv, int causal, bool bx, int nterms, cudaStream_t stream) {
+                    int64_t lddv, int causal, bool bx, int nterms, bool do_ready, cudaStream_t stream) {
     NPM_REQUIRE(!causal || Sq == Skv, "mha_core_bwd: the causal mask needs Sq == Skv");
-    NPM_REQUIRE(o != nullptr, "mha_core_bwd: the fused path needs the forward output o");
+    NPM_REQUIRE(o != nullptr || do_ready, "mha_core_bwd: the fused path needs the forward output o");
+    NPM_REQUIRE(!do_ready || bx, "mha_core_bwd: do_ready is a split-bf16 feature");
     NPM_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
                 aligned16(dk) && aligned16(dv), "mha_core_bwd: pointers must be 16-byte aligned");
     const uint64_t HD = (uint64_t)H * kD;
@@ -1699,7 +1700,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const float* o,
         if (e != cudaSuccess) { set_error("attn_bwd smem attribute: %s", cudaGetErrorString(e)); return NPM_ERR_CUDA; }
         configured = true;
     }
-    {
+    if (!do_ready) {     // else: the output projection's dX GEMM already wrote D and the dO planes (npm_gemm_desc.rowdot_*)
         const int64_t rows = B * Sq * H;
         int grid = (int)((rows * 16 + 255) / 256);
         const int cap = num_sms() * 8;

@@ -71,6 +71,10 @@ struct GemmBxArgs {
     int relu, accum;
     int c_planes;              // the result is written as bf16 hi / mid planes (tmC is a bf16 {N, M, 2 planes} map) instead of fp32
     float* a_colsum;           // optional [M] (A MN-major only): += sum over k of A[m, k] — the bias gradient of a dW GEMM
+    const float* rowdot_x;     // optional (c_planes only): [M, N] fp32, leading dimension rowdot_ld; the epilogue writes
+    int64_t rowdot_ld;         // rowdot_out[(row / rowdot_seq) * (N / 64) + col / 64][row % rowdot_seq] = sum over the 64 columns of
+    float* rowdot_out;         // the group of C[row, .] * rowdot_x[row, .] — D = rowsum(dO o O) of the attention backward
+    int rowdot_seq;
     long long* dbg;            // tools only (NPM_GEMM_DEBUG_TIMES): 16 wait-cycle counters per CTA
 };
 
@@ -406,6 +410,7 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(tfull_bar(acc), acc_phase);
             ptx::tc_fence_after();
             const bool rows_live = (m0 + warp * 32) < args.M;
+            float rowdot_acc = 0.0f;            // the even chunk's half of a 64-column row dot (rowdot_x)
 #pragma unroll 1
             for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
                 const int nc = n0 + chunk * 32;
@@ -455,6 +460,27 @@ gemm_bx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t buf = nstore & 1u;
                 if (lane == 0) ptx::tma_wait_group_read<1>();
                 __syncwarp();
+                if (args.c_planes && args.rowdot_x != nullptr) {
+                    // this thread holds 32 consecutive fp32 results of row row_g: their dot with the same 32 elements of
+                    // rowdot_x; two consecutive chunks are one 64-column group (N % 64 == 0 is checked by the launcher)
+                    const int64_t row_g = (int64_t)m0 + warp * 32 + lane;
+                    if (row_g < args.M) {
+                        const float4* xr = reinterpret_cast<const float4*>(args.rowdot_x + row_g * args.rowdot_ld + nc);
+                        float p0 = 0.0f, p1 = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            const float4 a = __ldg(xr + j), b = __ldg(xr + j + 1);
+                            p0 += (f[4 * j] * a.x + f[4 * j + 1] * a.y) + (f[4 * j + 2] * a.z + f[4 * j + 3] * a.w);
+                            p1 += (f[4 * j + 4] * b.x + f[4 * j + 5] * b.y) + (f[4 * j + 6] * b.z + f[4 * j + 7] * b.w);
+                        }
+                        if ((chunk & 1) == 0) {
+                            rowdot_acc = p0 + p1;
+                        } else {
+                            const int64_t bi = row_g / args.rowdot_seq, si = row_g - bi * args.rowdot_seq;
+                            args.rowdot_out[(bi * (args.N >> 6) + (nc >> 6)) * args.rowdot_seq + si] = rowdot_acc + (p0 + p1);
+                        }
+                    }
+                }
                 if (args.c_planes) {
                     // split-bf16 output (the q | k | v projection feeding the fused attention): hi rows of 64 B in the first
                     // half of the staging buffer, mid rows in the second, two TMA stores into the planes
@@ -717,6 +743,13 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     args.relu = (d.flags & NPM_GEMM_RELU) ? 1 : 0;
     args.accum = (d.flags & NPM_GEMM_ACCUM) ? 1 : 0;
     args.c_planes = c_planes ? 1 : 0;
+    args.rowdot_x = nullptr; args.rowdot_ld = 0; args.rowdot_out = nullptr; args.rowdot_seq = 1;
+    if (d.rowdot_x != nullptr) {
+        NPM_REQUIRE(c_planes && d.rowdot_out != nullptr && d.n % 64 == 0 && d.rowdot_ld % 4 == 0 && d.rowdot_ld >= d.n && aligned16(d.rowdot_x) &&
+                    d.rowdot_seq > 0 && d.rowdot_seq < (1ll << 31) && d.m % d.rowdot_seq == 0,
+                    "gemm: rowdot needs the c_split output, n %% 64 == 0, a 16-byte aligned rowdot_x and m a multiple of rowdot_seq");
+        args.rowdot_x = d.rowdot_x; args.rowdot_ld = d.rowdot_ld; args.rowdot_out = d.rowdot_out; args.rowdot_seq = (int)d.rowdot_seq;
+    }
     args.a_colsum = nullptr;
     if (d.a_colsum != nullptr) {
         NPM_REQUIRE(a_mn && nb1 == 1 && nb2 == 1, "gemm: a_colsum needs an unbatched problem with an MN-major A");

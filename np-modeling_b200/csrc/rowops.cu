@@ -143,9 +143,6 @@ __device__ __forceinline__ uint32_t drop4(float4& v, const DropArgs& d, uint64_t
     v.z = (k & 4u) ? v.z * d.inv_keep : 0.0f; v.w = (k & 8u) ? v.w * d.inv_keep : 0.0f;
     return k;
 }
-// Persistent: the grid is one wave (ln_fwd_grid), a warp walks rows `stride` apart and issues the loads of its NEXT row
-// before it reduces the current one — with one row per warp and a grid of rows / 8 CTAs the kernel ran as 1.15 waves of
-// load -> reduce -> store with nothing in flight during the reductions (0.60 of the HBM rate at [8192, 1024]).
 template <int NV, bool DROP = false>
 __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
@@ -156,57 +153,48 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float*
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
-    int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (row >= rows) return;
-    RowRegs<NV> r, nx;
+    RowRegs<NV> r;
     r.load(x + row * cols, cols, lane, 0.0f);
-    for (; row < rows; row += stride) {
-        const int64_t nrow = row + stride;
-        if (nrow < rows) nx.load(x + nrow * cols, cols, lane, 0.0f);
-        if (DROP) {
-            uint32_t keep_bits = 0;      // 4 bits per float4 of this lane; saved so that backward need not redo Philox
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = (i * 32 + lane) * 4;
-                if (c < cols) keep_bits |= drop4(r.v[i], drop, (uint64_t)row * cols + c) << (4 * i);
-            }
-            maskbits[row * 32 + lane] = keep_bits;
-        }
-        float s = 0.0f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
-        const float mean = warp_sum(s) / (float)cols;
-        float q = 0.0f;
+    if (DROP) {
+        uint32_t keep_bits = 0;      // 4 bits per float4 of this lane; saved so that backward need not redo Philox
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 4;
-            if (c < cols) {
-                const float a = r.v[i].x - mean, b = r.v[i].y - mean, cc = r.v[i].z - mean, d = r.v[i].w - mean;
-                q += (a * a + b * b) + (cc * cc + d * d);
-            }
+            if (c < cols) keep_bits |= drop4(r.v[i], drop, (uint64_t)row * cols + c) << (4 * i);
         }
-        const float var = warp_sum(q) / (float)cols;
-        const float rstd = 1.0f / sqrtf(var + eps);
+        maskbits[row * 32 + lane] = keep_bits;
+    }
+    float s = 0.0f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = (i * 32 + lane) * 4;
-            if (c < cols) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-                r.v[i].x = g.x * ((r.v[i].x - mean) * rstd) + b.x;
-                r.v[i].y = g.y * ((r.v[i].y - mean) * rstd) + b.y;
-                r.v[i].z = g.z * ((r.v[i].z - mean) * rstd) + b.z;
-                r.v[i].w = g.w * ((r.v[i].w - mean) * rstd) + b.w;
-            }
-        }
-        r.store(out + row * cols, cols, lane);
-        if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
-        if (nrow < rows) {
+    for (int i = 0; i < NV; ++i) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+    const float mean = warp_sum(s) / (float)cols;
+    float q = 0.0f;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) r.v[i] = nx.v[i];
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+            const float a = r.v[i].x - mean, b = r.v[i].y - mean, cc = r.v[i].z - mean, d = r.v[i].w - mean;
+            q += (a * a + b * b) + (cc * cc + d * d);
         }
     }
+    const float var = warp_sum(q) / (float)cols;
+    const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < cols) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            r.v[i].x = g.x * ((r.v[i].x - mean) * rstd) + b.x;
+            r.v[i].y = g.y * ((r.v[i].y - mean) * rstd) + b.y;
+            r.v[i].z = g.z * ((r.v[i].z - mean) * rstd) + b.z;
+            r.v[i].w = g.w * ((r.v[i].w - mean) * rstd) + b.w;
+        }
+    }
+    r.store(out + row * cols, cols, lane);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
 __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_generic(const float* x, const float* gamma, const float* beta,
@@ -227,6 +215,12 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_generic(const float
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
+// Measured and rejected (round 2): a persistent forward (one wave of CTAs, the next row's loads issued before the
+// current row is reduced) and a backward with one CTA per SM holding the next row's x / dz / statistics in flight.  Under
+// ncu (one launch, cold L2) the fused dropout+LayerNorm backward went 39.1 -> 32.9 us and the plain backward 33.9 -> 31.3 us,
+// the forward was unchanged and the Philox variant slower (21.6 -> 28.3 us: issue-bound, wants every warp the SM holds);
+// inside the cfg5 step — inputs warm in L2, neighbours overlapped by PDL — the same library was 0.4 ms per step SLOWER
+// (three alternating same-box runs: 87.23 vs 86.83 ms).  The occupancy-heavy forms below stay.
 // Backward.  Each warp walks rows (grid-stride), writes dx, and accumulates its columns of
 // dgamma/dbeta in registers; warps of a CTA are combined through shared memory and each CTA
 // writes one partial row pair to the workspace [grid][2][cols]; colsum-style second stage
@@ -234,10 +228,8 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_generic(const float
 // XSUM: also accumulate the column sums of the dx this kernel writes (third partial row): dx is the gradient of the
 // residual stream, whose column sum is the bias gradient of the projection / FFN layer that produced that stream
 // (attentions.py:129, mlp.py:34) — summed here from registers instead of re-reading dx in a colsum launch.
-// One CTA per SM (ln_bwd_grid); a warp has the x / dz rows, statistics and keep bits of its NEXT row in flight while it
-// works on the current one, and the residual-gradient row of the current one is requested before the reductions.
 template <int NV, bool DROP = false, bool XSUM = false>
-__global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x,
+__global__ void __launch_bounds__(kRowThreads, 2) layernorm_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     float* __restrict__ dx, float* __restrict__ partial,
@@ -262,28 +254,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(const flo
         if (XSUM) *reinterpret_cast<float4*>(my + 2 * cpad + c) = make_float4(0, 0, 0, 0);
     }
     const float inv_c = 1.0f / (float)cols;
-    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
-    int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-    RowRegs<NV> rx, rz, nx, nz;
-    float mu = 0.0f, rs = 0.0f, nmu = 0.0f, nrs = 0.0f;
-    uint32_t keep_bits = 0, nkeep = 0;          // 4 bits per float4 of this lane (NV <= 8), written by the fused forward
-    if (row < rows) {
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < rows; row += (int64_t)gridDim.x * kWarpsPerCta) {
+        RowRegs<NV> rx, rz;
         rx.load(x + row * cols, cols, lane, 0.0f);
         rz.load(dz + row * cols, cols, lane, 0.0f);
-        mu = mean[row]; rs = rstd[row];
-        if (DROP) keep_bits = __ldg(maskbits + row * 32 + lane);
-    }
-    for (; row < rows; row += stride) {
-        const int64_t nrow = row + stride;
-        if (nrow < rows) {
-            nx.load(x + nrow * cols, cols, lane, 0.0f);
-            nz.load(dz + nrow * cols, cols, lane, 0.0f);
-            nmu = mean[nrow]; nrs = rstd[nrow];
-            if (DROP) nkeep = __ldg(maskbits + nrow * 32 + lane);
-        }
-        RowRegs<NV> rk;                  // the residual-branch gradient of this row, in flight during the reductions
-        if (dskip != nullptr) rk.load(dskip + row * cols, cols, lane, 0.0f);
+        uint32_t keep_bits = 0;          // 4 bits per float4 of this lane (NV <= 8), written by the fused forward
         if (DROP) {
+            keep_bits = __ldg(maskbits + row * 32 + lane);
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const uint32_t k = keep_bits >> (4 * i);
@@ -293,6 +270,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(const flo
                 rx.v[i].w = (k & 8u) ? rx.v[i].w * drop.inv_keep : 0.0f;
             }
         }
+        const float mu = mean[row], rs = rstd[row];
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -334,7 +312,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(const flo
         if (dskip != nullptr) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
-                rz.v[i].x += rk.v[i].x; rz.v[i].y += rk.v[i].y; rz.v[i].z += rk.v[i].z; rz.v[i].w += rk.v[i].w;
+                const int c = (i * 32 + lane) * 4;
+                if (c < cols) {
+                    const float4 a = ld_stream(reinterpret_cast<const float4*>(dskip + row * cols + c));
+                    rz.v[i].x += a.x; rz.v[i].y += a.y; rz.v[i].z += a.z; rz.v[i].w += a.w;
+                }
             }
         }
         if (XSUM) {
@@ -349,11 +331,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(const flo
             }
         }
         rz.store(dx + row * cols, cols, lane);
-        if (nrow < rows) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) { rx.v[i] = nx.v[i]; rz.v[i] = nz.v[i]; }
-            mu = nmu; rs = nrs; keep_bits = nkeep;
-        }
     }
     // CTA reduce of the parameter-gradient partials
     __syncthreads();
@@ -660,26 +637,14 @@ int npm_softmax_bwd(const float* y, const float* dy, float* dx, int64_t rows, in
     return check_launch("softmax_bwd");
 }
 
-// one wave of CTAs for the persistent row kernels: enough warps per SM to keep ~64 KB of row loads in flight (a warp
-// holds its current row and has the next one in flight), at most 6 CTAs of 8 warps
-static unsigned ln_fwd_grid(int64_t rows, int64_t cols) {
-    const int64_t all = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-    int64_t per_sm = (65536 / (cols * 4 * 2) + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 6) per_sm = 6;
-    const int64_t cap = (int64_t)num_sms() * per_sm;
-    return (unsigned)(all < cap ? all : cap);
-}
-
 int npm_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
                       int64_t rows, int64_t cols, float epsilon, npm_stream_t stream) {
     if (rows <= 0 || cols <= 0) return NPM_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
     int nv = nv_for(cols);
     if (nv > 16) nv = 0;
-    const bool fast = nv && (cols & 3) == 0 && aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta);
-    const unsigned grid = fast ? ln_fwd_grid(rows, cols) : (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
-    if (fast) {
+    if (nv && (cols & 3) == 0 && aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta)) {
         switch (nv) {
             case 1: layernorm_fwd_kernel<1><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon); break;
             case 2: layernorm_fwd_kernel<2><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon); break;
@@ -696,7 +661,7 @@ int npm_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
 
 static int ln_bwd_grid(int64_t rows) {
     int64_t g = (rows + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int64_t cap = (int64_t)num_sms();          // one resident CTA per SM (two rows of x / dz per warp in registers), one wave
+    const int64_t cap = (int64_t)num_sms() * 2;      // two resident CTAs per SM, one wave
     return (int)(g < cap ? g : cap);
 }
 static int ln_generic_slabs(int64_t rows) {
@@ -799,8 +764,6 @@ int npm_dropout_layernorm_fwd(const float* x, const float* gamma, const float* b
         return NPM_ERR_UNSUPPORTED;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    // one row per warp here: the Philox rounds make this variant issue-bound, it wants every warp the SM can hold
-    // (measured at [8192, 1024]: 21.6 us with rows / 8 CTAs, 28.3 us with the one-wave persistent grid of the plain kernel)
     const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
     const DropArgs d = make_drop(keep_prob, seed, offset);
     switch (nv_for(cols)) {

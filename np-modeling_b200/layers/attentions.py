@@ -17,6 +17,11 @@ from npm_b200 import _lib
 from npm_b200._lib import C, GemmDesc, MhaStrides
 
 
+# Opt-in (NPM_DO_ROWDOT=1; tests flip the attribute): the output projection's dX GEMM writes dO as bf16 planes and
+# D = rowsum(dO o O) from its epilogue (npm_linear_bwd_dx_planes_rowdot) instead of fp32 dO + the D / split kernel.
+# Measured neutral-to-slower inside the cfg5 step (87.4-87.9 vs 87.1-87.7 ms, same box): the K = 1024 GEMM's epilogue
+# becomes its bottleneck with the extra 32 x 128-byte row loads of O per chunk.
+_NO_DO_ROWDOT = not os.environ.get('NPM_DO_ROWDOT')
 _NO_QKV_PLANES = bool(os.environ.get('NPM_NO_QKV_PLANES'))      # A/B switch for tools
 
 
@@ -351,7 +356,22 @@ class MultiHeadAttention(layer.StatefulLayer):
         dy2 = dy.reshape(batch * sq, dmodel)
         values2 = self._values.reshape(batch * sq, h * dv)
         dwo, dbo = grads(values2, dy2, '_wo', '_bo')
-        dvalues = dinput(dy2, wo, h * dv)                     # [B*Sq, H*dv]
+        scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes_for(self._path, batch, h, sq, skv, dk, dv))
+        # split-bf16 fused path: the dX GEMM writes dO straight as the bf16 planes the backward kernels read, and
+        # D = rowsum(dO o O) per head from its epilogue registers, both into `scratch` — no fp32 dO, no D / split pass
+        do_ready = 0
+        if self._path == 2 and (h * dv) % 64 == 0 and batch * sq > 128 and not _NO_DO_ROWDOT:
+            find = getattr(self, '_find_planes', None)
+            pp, ps = (find(wo) if find is not None else None) or (None, 0)
+            d_bytes = (batch * h * sq * 4 + 255) & ~255
+            rc = _lib.load().npm_linear_bwd_dx_planes_rowdot(dy2.ptr, wo.ptr, pp, ps, scratch.data_ptr() + d_bytes,
+                                                             batch * sq * h * dv, batch * sq, h * dv, dmodel, 1,
+                                                             values2.ptr, h * dv, scratch.data_ptr(), sq, s)
+            if rc == 0:
+                do_ready = 1
+            elif rc != -3:                                     # NPM_ERR_UNSUPPORTED: the fp32 route below
+                raise _lib.NpmError(f'npm_linear_bwd_dx_planes_rowdot failed (rc={rc}): {_lib.last_error()}')
+        dvalues = None if do_ready else dinput(dy2, wo, h * dv)                     # [B*Sq, H*dv]
 
         # attention core (attentions.py:146-162): dq / dk / dv are written as row blocks mirroring forward's layout
         if mode == 'qkv':
@@ -366,10 +386,10 @@ class MultiHeadAttention(layer.StatefulLayer):
             dk2 = device.empty((batch * skv, hd))
             dv2 = device.empty((batch * skv, h * dv))
             dptrs, dld, dbufs = (dq2.ptr, dk2.ptr, dv2.ptr), (hd, hd, h * dv), (dq2, dk2, dv2)
-        scratch = device.workspace(C.npm_mha_core_bwd_scratch_bytes_for(self._path, batch, h, sq, skv, dk, dv))
-        ld = self._strides(dq=dld[0], dk=dld[1], dv=dld[2])
+        ld = self._strides(dq=dld[0], dk=dld[1], dv=dld[2], do_ready=do_ready)
         qp, kp, vp = self._qkv_ptrs
-        C.npm_mha_core_bwd_strided(qp, kp, vp, self._values.ptr, dvalues.ptr, self._saved.data_ptr(), dptrs[0],
+        C.npm_mha_core_bwd_strided(qp, kp, vp, self._values.ptr, dvalues.ptr if dvalues is not None else None,
+                                   self._saved.data_ptr(), dptrs[0],
                                    dptrs[1], dptrs[2], scratch.data_ptr(), batch, h, sq, skv, dk, dv,
                                    ctypes.byref(ld), s)
 

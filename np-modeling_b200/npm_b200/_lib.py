@@ -33,6 +33,7 @@ class GemmDesc(Structure):
         ('alpha', c_float), ('flags', c_int32), ('precision', c_int32),
         ('residual', c_void_p), ('ldr', c_int64), ('a_colsum', c_void_p), ('b_split', c_void_p), ('b_split_plane', c_int64),
         ('a_split', c_void_p), ('a_split_plane', c_int64), ('c_split', c_void_p), ('c_split_plane', c_int64),
+        ('rowdot_x', c_void_p), ('rowdot_ld', c_int64), ('rowdot_out', c_void_p), ('rowdot_seq', c_int64),
     ]
 
 
@@ -40,7 +41,7 @@ class MhaStrides(Structure):
     """npm_mha_strides (include/npm_b200.h): floats between consecutive tokens, 0 = dense."""
     _fields_ = [('q', c_int64), ('k', c_int64), ('v', c_int64), ('dq', c_int64), ('dk', c_int64), ('dv', c_int64),
                 ('causal', c_int64), ('path', c_int64), ('planes', c_int64), ('q_plane', c_int64), ('k_plane', c_int64),
-                ('v_plane', c_int64)]
+                ('v_plane', c_int64), ('do_ready', c_int64)]
 
 
 class TensorEntry(Structure):
@@ -70,6 +71,7 @@ SIGNATURES = {
     'npm_linear_bwd_dx_presplit': (c_int, [P, P, P, I64, P, I64, I64, I64, I, P]),
     'npm_linear_fwd_planes': (c_int, [P, P, P, I64, P, P, I64, I64, I64, I64, I, P]),
     'npm_linear_bwd_dw_db': (c_int, [P, P, P, P, I64, I64, I64, I, P, P]),
+    'npm_linear_bwd_dx_planes_rowdot': (c_int, [P, P, P, I64, P, I64, I64, I64, I64, I, P, I64, P, I64, P]),
     'npm_colsum_workspace': (c_size_t, [I64, I64]),
     'npm_colsum': (c_int, [P, P, I64, I64, P, P]),
     'npm_relu_fwd': (c_int, [P, P, I64, P]),
@@ -154,7 +156,7 @@ class _Calls:
         lib = load()
         fn = getattr(lib, name)
         res = SIGNATURES[name][0]
-        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision', 'npm_dropout_layernorm_fused', 'npm_mha_core_path', 'npm_linear_fwd_planes'):
+        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision', 'npm_dropout_layernorm_fused', 'npm_mha_core_path', 'npm_linear_fwd_planes', 'npm_linear_bwd_dx_planes_rowdot'):
             def call(*args, _fn=fn, _name=name):
                 rc = _fn(*args)
                 if rc != NPM_OK:

@@ -44,15 +44,15 @@ def test_ctypes_table_matches_header():
 def test_struct_layouts_match_the_header():
     from npm_b200 import _lib
     assert ctypes.sizeof(_lib.TensorEntry) == 48          # 4 pointers + 2 int64
-    assert ctypes.sizeof(_lib.MhaStrides) == 12 * 8       # q k v dq dk dv causal path planes q_plane k_plane v_plane
+    assert ctypes.sizeof(_lib.MhaStrides) == 13 * 8       # q k v dq dk dv causal path planes q_plane k_plane v_plane do_ready
     assert _lib.MhaStrides.path.offset == 56
     assert _lib.MhaStrides.causal.offset == 48
     # incl. padding before `residual`; then a_colsum, b_split, b_split_plane
     # incl. a_split, a_split_plane, c_split, c_split_plane
-    assert ctypes.sizeof(_lib.GemmDesc) == 4 * 8 + 3 * 8 + 5 * 8 + 2 * 4 + 6 * 8 + 3 * 4 + 4 + 2 * 8 + 7 * 8
-    assert _lib.GemmDesc.residual.offset == ctypes.sizeof(_lib.GemmDesc) - 16 - 56
-    assert _lib.GemmDesc.a_colsum.offset == ctypes.sizeof(_lib.GemmDesc) - 56
-    assert _lib.GemmDesc.c_split.offset == ctypes.sizeof(_lib.GemmDesc) - 16
+    assert ctypes.sizeof(_lib.GemmDesc) == 4 * 8 + 3 * 8 + 5 * 8 + 2 * 4 + 6 * 8 + 3 * 4 + 4 + 2 * 8 + 7 * 8 + 4 * 8
+    assert _lib.GemmDesc.residual.offset == ctypes.sizeof(_lib.GemmDesc) - 16 - 56 - 32
+    assert _lib.GemmDesc.a_colsum.offset == ctypes.sizeof(_lib.GemmDesc) - 56 - 32
+    assert _lib.GemmDesc.c_split.offset == ctypes.sizeof(_lib.GemmDesc) - 16 - 32
     assert _lib.GemmDesc.alpha.offset == 4 * 8 + 3 * 8 + 5 * 8 + 8 + 6 * 8
 
 

@@ -339,6 +339,52 @@ def test_mha_packed_projection_modes(prec, mode, dims):
     close(layer._bv, params['_bv'] - 0.1 * grads['_bv'], **gtol)
 
 
+@pytest.mark.parametrize('mode', ['qkv', 'kv'])
+@pytest.mark.parametrize('dims', [(2, 200, 136, 2, 64), (1, 384, 384, 3, 64)])
+def test_mha_backward_with_dO_planes_and_row_dots_from_the_gemm(mode, dims, monkeypatch):
+    """Opt-in route (layers/attentions.py `_NO_DO_ROWDOT`): the output projection's dX GEMM writes dO as bf16 planes and
+    D = rowsum(dO o O) per head from its epilogue (npm_gemm_desc.rowdot_*, npm_mha_strides.do_ready) instead of fp32 dO
+    plus the D / split kernel.  Same gradients as the reference algorithm (attentions.py:129-188)."""
+    import npm_b200
+    from layers import MultiHeadAttention, attentions
+    from npm_b200._lib import C
+    from oracle import np_oracle as O
+    npm_b200.set_precision('bf16x3')
+    monkeypatch.setattr(attentions, '_NO_DO_ROWDOT', False)
+    b, sq, skv, h, d = dims
+    if mode == 'qkv':
+        skv = sq
+    rng = np.random.default_rng(sq + 7 * d)
+    dm = h * d
+    query = rng.standard_normal((b, sq, dm), dtype=np.float32)
+    key = rng.standard_normal((b, skv, dm), dtype=np.float32)
+    args = {'qkv': (query,), 'kv': (query, key)}[mode]
+    dy = rng.standard_normal((b, sq, dm), dtype=np.float32)
+    layer = MultiHeadAttention(h)
+    layer(*args)
+    params = {k: (np.asarray(getattr(layer, k)) * (1.0 / np.sqrt(dm) if k.startswith('_w') else 0.1)).astype(np.float32)
+              for k in O.MHA_PARAMS}
+    bind(layer, params)
+    want, cache = O.mha_fwd(params, *args)
+    close(layer(*args), want, **TC)
+    assert layer._path == 2, 'the fused split-bf16 path serves head dim 64'
+    (dq_, dk_, dv_), grads = O.mha_bwd(params, cache, dy)
+    rec = Recorder()
+    launches = C.npm_launch_count()
+    got = layer(dy, backprop=True, optimizer_=rec)
+    used = C.npm_launch_count() - launches
+    close(got[0], dq_, **TC); close(got[1], dk_, **TC); close(got[2], dv_, **TC)
+    gg = grads_of(layer, rec, O.MHA_PARAMS)
+    for k in O.MHA_PARAMS:
+        close(gg[k], grads[k], rtol=1e-3, atol=1e-4 * np.sqrt(b * sq))
+    # the same backward through the default route launches one kernel more (the D / dO-split pass)
+    monkeypatch.setattr(attentions, '_NO_DO_ROWDOT', True)
+    layer(*args)
+    launches = C.npm_launch_count()
+    layer(dy, backprop=True, optimizer_=Recorder())
+    assert C.npm_launch_count() - launches == used + 1
+
+
 @pytest.mark.parametrize('prec', ['bf16x3', '3xtf32', 'tf32'])
 @pytest.mark.parametrize('dims', [(2, 40, 4, 64), (1, 130, 2, 64), (2, 384, 3, 64), (2, 9, 3, 8)])
 def test_mha_causal_extension(prec, dims):
