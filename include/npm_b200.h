@@ -178,6 +178,17 @@ int npm_linear_bwd_dx_planes_rowdot(const float* dy, const float* w, const void*
                                     void* dx_planes, int64_t dx_plane, int64_t m, int64_t k, int64_t n,
                                     int w_out_major, const float* o, int64_t ldo, float* rowdot_out,
                                     int64_t seq, npm_stream_t stream);
+/* An activation that exists ONLY as split-bf16 planes (NPM_PREC_BF16X3): the FFN hidden activation written by the
+ * first FFN GEMM's epilogue (npm_gemm_desc.c_split, ReLU applied: mlp.py:70-72) is the A operand of the second FFN
+ * GEMM and of its dW GEMM as is.
+ * npm_relu_bwd_colsum_planes: ReLU.backward (activations.py:17-19) + the bias gradient (mlp.py:34) for such a y — the
+ *   gate is the sign bit of y's bf16 hi plane `y_hi` ([rows, cols] bf16; bf16 rounding keeps the sign, -0.0 included);
+ *   dz = where(gate, dy, 0) is written as bf16 hi / mid planes (mid `plane` elements after hi), db[cols] = column sums
+ *   of dz.  workspace: npm_colsum_workspace(rows, cols).  NPM_ERR_UNSUPPORTED unless cols %% 4 == 0 and cols <= 16384.
+ * npm_planes_join: out[n] fp32 = hi + mid (exact), for consumers outside the split-bf16 kernels. */
+int npm_relu_bwd_colsum_planes(const void* y_hi, const float* dy, void* dz_planes, int64_t plane, float* db,
+                               int64_t rows, int64_t cols, void* workspace, npm_stream_t stream);
+int npm_planes_join(const void* planes, int64_t plane, float* out, int64_t n, npm_stream_t stream);
 int npm_linear_bwd_dw_db(const float* x, const float* dy, float* dw, float* db,
                          int64_t m, int64_t k, int64_t n, int w_out_major,
                          void* workspace, npm_stream_t stream);

@@ -99,7 +99,7 @@ static int require_sm100() {
 }
 
 int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
-    NPM_REQUIRE((d.a || d.a_split) && d.b && (d.c || d.c_split), "gemm: NULL operand");
+    NPM_REQUIRE((d.a || d.a_split) && (d.b || d.b_split) && (d.c || d.c_split), "gemm: NULL operand");
     NPM_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem m=%lld n=%lld k=%lld", (long long)d.m,
                 (long long)d.n, (long long)d.k);
     NPM_REQUIRE((d.a_rs == 1 || d.a_cs == 1) && (d.b_rs == 1 || d.b_cs == 1),
@@ -113,7 +113,7 @@ int gemm_dispatch(const npm_gemm_desc& d, cudaStream_t stream) {
     static const bool bx_off = getenv("NPM_GEMM_NO_BX") != nullptr;      // A/B switch for tools/
     NPM_REQUIRE(d.a_colsum == nullptr || (bx_mode && !bx_off && gemm_bx_supported(d) && d.a_rs == 1 && d.nb1 <= 1 && d.nb2 <= 1),
                 "gemm: a_colsum is served by the split-bf16 kernel only (precision bf16x3 / bf16, m-contiguous A, unbatched, m > 128)");
-    if ((d.c_split != nullptr || d.a == nullptr || d.rowdot_x != nullptr) && !(bx_mode && !bx_off && gemm_bx_supported(d))) {
+    if ((d.c_split != nullptr || d.a == nullptr || d.b == nullptr || d.rowdot_x != nullptr) && !(bx_mode && !bx_off && gemm_bx_supported(d))) {
         set_error("gemm: split-bf16 input / output planes are served by the split-bf16 kernel only (precision bf16x3 / bf16, m > 128)");
         return NPM_ERR_UNSUPPORTED;
     }

@@ -104,6 +104,17 @@ struct ReluBY { __device__ float operator()(float y, float dy) const { return (_
 struct AddF  { __device__ float operator()(float a, float b) const { return a + b; } };
 struct ScaleF { float s; __device__ float operator()(float x) const { return x * s; } };
 
+// fp32 view of a tensor that exists as split-bf16 planes: out = hi + mid (exact in fp32: 16 significant bits)
+__global__ void __launch_bounds__(kThreads) planes_join_kernel(const uint2* __restrict__ planes, int64_t plane4, float4* __restrict__ out,
+                                                               int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 h = planes[i], m = planes[plane4 + i];
+        out[i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(m.x << 16),
+                             __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(m.x & 0xffff0000u),
+                             __uint_as_float(h.y << 16) + __uint_as_float(m.y << 16),
+                             __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(m.y & 0xffff0000u));
+    }
+}
 __global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ x, float v, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
@@ -263,6 +274,16 @@ int npm_fill(float* x, float v, int64_t n, npm_stream_t stream) {
     fill_kernel<<<bw_grid(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(x, v, n);
     count_launch();
     return check_launch("fill_kernel");
+}
+
+int npm_planes_join(const void* planes, int64_t plane, float* out, int64_t n, npm_stream_t stream) {
+    if (n <= 0) return NPM_OK;
+    NPM_REQUIRE(planes && out && (n & 3) == 0 && (plane & 3) == 0 && (reinterpret_cast<uintptr_t>(planes) & 7u) == 0 &&
+                (reinterpret_cast<uintptr_t>(out) & 15u) == 0, "planes_join: needs n %% 4 == 0, plane %% 4 == 0 and aligned pointers");
+    planes_join_kernel<<<bw_grid(n / 4, kThreads), kThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(planes), plane / 4,
+                                                                                       reinterpret_cast<float4*>(out), n / 4);
+    count_launch();
+    return check_launch("planes_join_kernel");
 }
 
 int npm_dropout_fwd(const float* x, float* y, int64_t n, float keep_prob, uint64_t seed, uint64_t offset,

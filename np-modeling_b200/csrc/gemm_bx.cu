@@ -667,7 +667,10 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     // pre-split A (an activation its producer wrote as bf16 planes): unbatched, three terms; MN-major needs whole 64-row slabs
     const bool a_pre = d.a_split != nullptr && nterms == 3 && nb1 == 1 && nb2 == 1 && (!a_mn || d.m % 64 == 0) && aligned16(d.a_split) &&
                        d.a_split_plane % 8 == 0 && (a_mn ? d.a_cs : d.a_rs) % 8 == 0 && d.a_colsum == nullptr;
-    NPM_REQUIRE(d.a != nullptr || a_pre, "gemm: a_split cannot be used for this problem (alignment / shape) and no fp32 A was given");
+    if (d.a == nullptr && !a_pre) {
+        set_error("gemm: a_split cannot be used for this problem (alignment / shape / mode) and no fp32 A was given");
+        return NPM_ERR_UNSUPPORTED;
+    }
     if (a_pre && !a_mn) {
         const uint64_t dims[4] = {K, M, 2, 1}, st[3] = {(uint64_t)d.a_rs, (uint64_t)d.a_split_plane, (uint64_t)d.a_split_plane * 2};
         const uint32_t box[4] = {kKS, kBM, 2, 1};
@@ -693,6 +696,10 @@ int gemm_bx_launch(const npm_gemm_desc& d, int nterms, cudaStream_t stream) {
     // pre-split B (weights): unbatched, A K-major, three terms; MN-major needs whole 64-column slabs
     const bool b_pre = d.b_split != nullptr && nterms == 3 && nb1 == 1 && nb2 == 1 && (!b_mn || d.n % 64 == 0) &&
                        aligned16(d.b_split) && d.b_split_plane % 8 == 0 && (b_mn ? d.b_rs : d.b_cs) % 8 == 0;   // TMA: 16-byte strides in bf16
+    if (d.b == nullptr && !b_pre) {
+        set_error("gemm: b_split cannot be used for this problem (alignment / shape / mode) and no fp32 B was given");
+        return NPM_ERR_UNSUPPORTED;
+    }
     if (b_pre && !b_mn) {
         const uint64_t dims[4] = {K, N, 2, 1}, st[3] = {(uint64_t)d.b_cs, (uint64_t)d.b_split_plane, (uint64_t)d.b_split_plane * 2};
         const uint32_t box[4] = {kKS, (uint32_t)bn / 2, 2, 1};

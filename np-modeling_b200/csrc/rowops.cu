@@ -502,6 +502,94 @@ __global__ void __launch_bounds__(kRowThreads) colsum_kernel(const float* __rest
     }
     if (threadIdx.x == 0) g_colsum_tickets[ticket_base + blockIdx.x] = 0;     // ready for the next launch on this slot
 }
+// ReLU.backward + bias gradient for an activation that exists only as split-bf16 planes (the FFN hidden activation out of
+// the first FFN GEMM's epilogue, npm_gemm_desc.c_split): the gate is the sign bit of y's bf16 hi plane (bf16_rn keeps the
+// sign, -0.0 included), the masked gradient goes out as bf16 hi / mid planes too — the A operand of the dX GEMM and the
+// B operand of the dW GEMM that follow, which then land it by TMA without converting.  Same slab / ticket scheme as
+// colsum_kernel.  Bytes per element: 4 (dy) + 2 (y hi) + 4 (dz planes) = 10 against 12 of the fp32 form.
+__device__ __forceinline__ void split_pack2(float p0, float p1, uint32_t& hi, uint32_t& mid) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
+    const float r0 = p0 - __uint_as_float(hi << 16), r1 = p1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
+}
+__global__ void __launch_bounds__(kRowThreads) relu_bwd_colsum_planes_kernel(const float* __restrict__ dy, const uint2* __restrict__ y_hi,
+                                                                            uint2* __restrict__ dz, int64_t plane4,
+                                                                            float* __restrict__ partial, float* __restrict__ out,
+                                                                            int64_t rows, int64_t cols, int64_t rows_per_slab,
+                                                                            unsigned ticket_base) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float4 sm[kWarpsPerCta][32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = ((int64_t)blockIdx.x * 32 + lane) * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
+    const int64_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+    float4 acc = make_float4(0, 0, 0, 0);
+    if (c < cols) {
+        constexpr int U = 4;       // rows in flight per thread
+        auto one = [&](float4 v, uint2 y, int64_t r) {
+            v.x = (y.x & 0x8000u) ? 0.0f : v.x; v.y = (y.x & 0x80000000u) ? 0.0f : v.y;
+            v.z = (y.y & 0x8000u) ? 0.0f : v.z; v.w = (y.y & 0x80000000u) ? 0.0f : v.w;
+            uint2 h, m;
+            split_pack2(v.x, v.y, h.x, m.x);
+            split_pack2(v.z, v.w, h.y, m.y);
+            const int64_t i = (r * cols + c) >> 2;
+            dz[i] = h;
+            dz[plane4 + i] = m;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        };
+        int64_t r = r0 + warp;
+        for (; r + (U - 1) * kWarpsPerCta < r1; r += U * kWarpsPerCta) {
+            float4 v[U];
+            uint2 y[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ld_stream(reinterpret_cast<const float4*>(dy + (r + u * kWarpsPerCta) * cols + c));
+#pragma unroll
+            for (int u = 0; u < U; ++u) y[u] = __ldg(y_hi + (((r + u * kWarpsPerCta) * cols + c) >> 2));
+#pragma unroll
+            for (int u = 0; u < U; ++u) one(v[u], y[u], r + u * kWarpsPerCta);
+        }
+        for (; r < r1; r += kWarpsPerCta)
+            one(ld_stream(reinterpret_cast<const float4*>(dy + r * cols + c)), __ldg(y_hi + ((r * cols + c) >> 2)), r);
+    }
+    sm[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c < cols) {
+#pragma unroll
+        for (int w = 1; w < kWarpsPerCta; ++w) {
+            const float4 v = sm[w][lane];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * cols + c) = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&g_colsum_tickets[ticket_base + blockIdx.x], 1u);
+        is_last = (t == gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    acc = make_float4(0, 0, 0, 0);
+    if (c < cols)
+        for (int sl = warp; sl < (int)gridDim.y; sl += kWarpsPerCta) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (size_t)sl * cols + c));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    sm[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c < cols) {
+#pragma unroll
+        for (int w = 1; w < kWarpsPerCta; ++w) {
+            const float4 v = sm[w][lane];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + c) = acc;
+    }
+    if (threadIdx.x == 0) g_colsum_tickets[ticket_base + blockIdx.x] = 0;
+}
 __global__ void __launch_bounds__(256) colsum_generic(const float* x, float* partial, int64_t rows, int64_t cols,
                                                       int64_t rows_per_slab) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -561,6 +649,23 @@ int colsum_relu_launch(const float* x, float* out, int64_t rows, int64_t cols, v
     count_launch();
     return check_launch("reduce_partials_kernel");
 }
+int relu_bwd_colsum_planes_launch(const void* y_hi, const float* dy, void* dz_planes, int64_t plane, float* db, int64_t rows,
+                                  int64_t cols, void* workspace, cudaStream_t s) {
+    NPM_REQUIRE(rows > 0 && cols > 0 && workspace != nullptr, "relu_bwd_colsum_planes: empty input or NULL workspace");
+    const int64_t col_ctas = (cols + 127) / 128;
+    if (!((cols & 3) == 0 && (plane & 3) == 0 && col_ctas <= kTicketCols && aligned16(dy) && aligned16(db) && aligned16(workspace) &&
+          (reinterpret_cast<uintptr_t>(y_hi) & 7u) == 0 && (reinterpret_cast<uintptr_t>(dz_planes) & 7u) == 0)) {
+        set_error("relu_bwd_colsum_planes: needs cols %% 4 == 0, plane %% 4 == 0, cols <= %d and aligned pointers", kTicketCols * 128);
+        return NPM_ERR_UNSUPPORTED;
+    }
+    const int slabs = colsum_slabs(rows, cols);
+    const int64_t rps = (rows + slabs - 1) / slabs;
+    launch_pdl(relu_bwd_colsum_planes_kernel, dim3((unsigned)col_ctas, slabs), dim3(kRowThreads), 0, s, 1, dy,
+               reinterpret_cast<const uint2*>(y_hi), reinterpret_cast<uint2*>(dz_planes), plane / 4, reinterpret_cast<float*>(workspace), db,
+               rows, cols, rps, next_ticket_base(col_ctas));
+    count_launch();
+    return check_launch("relu_bwd_colsum_planes_kernel");
+}
 int colsum_launch(const float* x, float* out, int64_t rows, int64_t cols, void* workspace, cudaStream_t s) {
     return colsum_relu_launch(x, out, rows, cols, workspace, nullptr, nullptr, s);
 }
@@ -599,6 +704,12 @@ int npm_relu_bwd_colsum(const float* y, const float* dy, float* dx, float* db, i
     int rc = npm_relu_bwd_y(y, dy, dx, rows * cols, stream);
     if (rc) return rc;
     return colsum_launch(dx, db, rows, cols, workspace, s);
+}
+
+int npm_relu_bwd_colsum_planes(const void* y_hi, const float* dy, void* dz_planes, int64_t plane, float* db, int64_t rows,
+                               int64_t cols, void* workspace, npm_stream_t stream) {
+    NPM_REQUIRE(y_hi && dy && dz_planes && db, "relu_bwd_colsum_planes: NULL pointer");
+    return relu_bwd_colsum_planes_launch(y_hi, dy, dz_planes, plane, db, rows, cols, workspace, (cudaStream_t)stream);
 }
 
 int npm_softmax_fwd(const float* x, float* y, int64_t rows, int64_t cols, npm_stream_t stream) {

@@ -58,7 +58,7 @@ class TransformerEncoder(layer.Layer):
 
         if self._norm_first:
             out = normalizations.dropout_layernorm_forward(self._dropout2, self._norm2, out)
-        out = self._dense1(out, _alias_ok=True)
+        out = self._dense1(out, _alias_ok=True, _planes_ok=True)
         out = self._dense2(out, _residual=skip)               # `out += skip` (transformer.py:53,155)
         if not self._norm_first:
             out = self._dropout2(out)
@@ -150,7 +150,7 @@ class TransformerDecoder(layer.Layer):
 
         if self._norm_first:
             out = normalizations.dropout_layernorm_forward(self._dropout3, self._norm3, out)
-        out = self._dense1(out, _alias_ok=True)
+        out = self._dense1(out, _alias_ok=True, _planes_ok=True)
         out = self._dense2(out, _residual=skip)               # `out += skip` (transformer.py:53,155)
         if not self._norm_first:
             out = self._dropout3(out)

@@ -173,14 +173,72 @@ class DeviceArray:
         return self
 
 
+class PlanesArray:
+    """An activation that exists ONLY as split-bf16 planes — bf16 hi = bf16_rn(x) and mid = bf16_rn(x - hi), two
+    contiguous [rows, cols] bf16 matrices in one buffer — because the kernel that produced it wrote it that way (the first
+    FFN GEMM's epilogue, the ReLU backward) and the GEMMs that consume it land it by TMA as their operand image without
+    converting (gemm_bx.cu A_PRE / B_PRE).  Only the split-bf16 ('bf16x3') mode makes one, and only between layers of this
+    package that asked for it (`_planes_ok`); everything else goes through `to_fp32()` (exact: 16 significant bits).
+    There is deliberately no `.ptr`: a consumer that is not planes-aware fails loudly instead of reading garbage."""
+    __slots__ = ('buf', '_shape')
+    __array_priority__ = 1000
+
+    def __init__(self, buf: torch.Tensor, shape):
+        self.buf = buf
+        self._shape = tuple(int(v) for v in shape)
+        assert buf.dtype == torch.uint8 and buf.numel() >= 4 * self.size
+
+    shape = property(lambda self: self._shape)
+    ndim = property(lambda self: len(self._shape))
+    size = property(lambda self: int(np.prod(self._shape)) if self._shape else 1)
+    dtype = property(lambda self: np.dtype(np.float32))
+    hi_ptr = property(lambda self: self.buf.data_ptr())      # the bf16 hi plane; the mid plane starts `size` elements later
+    colsum = None
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        shape = tuple(int(v) for v in shape)
+        if -1 in shape:
+            known = int(np.prod([v for v in shape if v != -1]))
+            shape = tuple(self.size // known if v == -1 else v for v in shape)
+        assert int(np.prod(shape)) == self.size, f'cannot reshape {self._shape} to {shape}'
+        return PlanesArray(self.buf, shape)
+
+    def to_fp32(self) -> 'DeviceArray':
+        out = empty(self._shape)
+        C.npm_planes_join(self.hi_ptr, self.size, out.ptr, self.size, stream())
+        return out
+
+    def numpy(self):
+        return self.to_fp32().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __len__(self):
+        return self._shape[0]
+
+    def __repr__(self):
+        return f'PlanesArray(shape={self.shape}, split-bf16)'
+
+
 def asdevice(x) -> DeviceArray:
-    """np.ndarray / scalar sequence / torch tensor / DeviceArray → DeviceArray (fp32, on the current GPU)."""
-    if isinstance(x, DeviceArray):
+    """np.ndarray / scalar sequence / torch tensor / DeviceArray → DeviceArray (fp32, on the current GPU).  A PlanesArray
+    passes through (layers that take one check for it; the others call `.to_fp32()` via `asfp32`)."""
+    if isinstance(x, (DeviceArray, PlanesArray)):
         return x
     if isinstance(x, torch.Tensor):
         return DeviceArray(x.detach().to(device=_device(), dtype=torch.float32).contiguous())
     host = np.ascontiguousarray(np.asarray(x), dtype=np.float32)
     return DeviceArray(torch.from_numpy(host).to(_device(), non_blocking=False))
+
+
+def asfp32(x) -> DeviceArray:
+    """asdevice for consumers that need the fp32 bytes: a PlanesArray is joined (one elementwise kernel)."""
+    x = asdevice(x)
+    return x.to_fp32() if isinstance(x, PlanesArray) else x
 
 
 def from_pinned(host_pinned: torch.Tensor) -> DeviceArray:

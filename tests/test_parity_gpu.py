@@ -548,6 +548,50 @@ def test_decoder_vs_oracle_medium():
         close(got[k], v, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(v).max()))
 
 
+@pytest.mark.parametrize('norm_first', [True, False])
+def test_ffn_hidden_activation_as_split_bf16_planes(norm_first, monkeypatch):
+    """Opt-in route of layers/mlp.py (`_NO_FFN_PLANES`): the FFN hidden activation and its gradient exist only as bf16
+    hi / mid planes (device.PlanesArray) — written by the first GEMM's epilogue / the ReLU backward, landed by the
+    consuming GEMMs without conversion.  The planes hold exactly the pairs the converters would make, so outputs,
+    input gradients and every parameter gradient must equal the fp32 route's to fp32 round-off (mlp.py:21-38, 70-77)."""
+    import npm_b200
+    from layers import TransformerEncoder, mlp
+    from npm_b200 import device
+    from train import iter_parameters
+    npm_b200.set_precision('bf16x3')
+    rng = np.random.default_rng(3)
+    b, s_, d, h, f = 2, 136, 128, 2, 512                   # 272 tokens: the split-bf16 GEMM takes every FFN problem
+    x = rng.standard_normal((b, s_, d)).astype(np.float32)
+    dy = rng.standard_normal((b, s_, d)).astype(np.float32)
+    np.random.seed(3)
+    layer = TransformerEncoder(h, f, norm_first, 0.0)
+    layer(x)
+    for owner, name in iter_parameters(layer):
+        v = np.asarray(getattr(owner, name))
+        if name.startswith('_w'):
+            setattr(owner, name, (v / np.sqrt(max(v.shape[-1], v.shape[0]))).astype(np.float32))
+    results = []
+    for planes_on in (False, True):
+        monkeypatch.setattr(mlp, '_NO_FFN_PLANES', not planes_on)
+        clone = copy.deepcopy(layer)
+        out = clone(x)
+        assert isinstance(clone._dense1._y, device.PlanesArray) == planes_on
+        rec = Recorder()
+        dx = clone(dy, backprop=True, optimizer_=rec)
+        names = [f'{i}.{name}' for i, (owner, name) in enumerate(iter_parameters(clone))]
+        grads = [np.asarray(rec.grads[f'{id(owner)}.{name}']) for owner, name in iter_parameters(clone)]
+        results.append((np.asarray(out), np.asarray(dx), dict(zip(names, grads))))
+    (o0, d0, g0), (o1, d1, g1) = results
+    # same operand values, but the GEMM may pick another tile shape / K split for pre-split operands: fp32 round-off
+    close(o1, o0, rtol=1e-5, atol=2e-5)
+    close(d1, d0, rtol=1e-5, atol=2e-5)
+    for k in g0:
+        close(g1[k], g0[k], rtol=1e-5, atol=2e-5 * max(1.0, np.abs(g0[k]).max()))
+    # the planes join back to fp32 exactly (hi + mid of a value that was split from fp32 has 16 significant bits)
+    hidden = clone._dense1._y
+    assert hidden.shape == (b * s_, f) and np.asarray(hidden).shape == (b * s_, f)
+
+
 # ------------------------------------------------------------------ conv
 @pytest.mark.parametrize('tag', ['c3', 'c8', 'k5', 'k1'])
 def test_conv_golden(tag):
