@@ -104,15 +104,19 @@ struct ReluBY { __device__ float operator()(float y, float dy) const { return (_
 struct AddF  { __device__ float operator()(float a, float b) const { return a + b; } };
 struct ScaleF { float s; __device__ float operator()(float x) const { return x * s; } };
 
-// fp32 view of a tensor that exists as split-bf16 planes: out = hi + mid (exact in fp32: 16 significant bits)
+// fp32 view of a tensor that exists as split-bf16 planes: out = hi + mid (exact in fp32: 16 significant bits; signed zeros kept)
 __global__ void __launch_bounds__(kThreads) planes_join_kernel(const uint2* __restrict__ planes, int64_t plane4, float4* __restrict__ out,
                                                                int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const uint2 h = planes[i], m = planes[plane4 + i];
-        out[i] = make_float4(__uint_as_float(h.x << 16) + __uint_as_float(m.x << 16),
-                             __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(m.x & 0xffff0000u),
-                             __uint_as_float(h.y << 16) + __uint_as_float(m.y << 16),
-                             __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(m.y & 0xffff0000u));
+        // a zero keeps the sign of its hi part: the fused Dense epilogue stores -0.0 for a negative pre-activation
+        // (activations.py:19 gate), and (-0.0) + (+0.0) would be +0.0
+        auto join = [](uint32_t hw, uint32_t mw) {
+            const float s = __uint_as_float(hw) + __uint_as_float(mw);
+            return s == 0.0f ? __uint_as_float(hw & 0x80000000u) : s;
+        };
+        out[i] = make_float4(join(h.x << 16, m.x << 16), join(h.x & 0xffff0000u, m.x & 0xffff0000u),
+                             join(h.y << 16, m.y << 16), join(h.y & 0xffff0000u, m.y & 0xffff0000u));
     }
 }
 __global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ x, float v, int64_t n) {

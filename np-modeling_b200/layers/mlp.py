@@ -11,12 +11,11 @@ from npm_b200._lib import C, GemmDesc
 # Split-bf16 ('bf16x3') mode, transformer FFN only (`_planes_ok`): the hidden activation is written by the first GEMM's
 # epilogue ONLY as bf16 hi / mid planes (device.PlanesArray) and its gradient by the ReLU backward the same way, so the
 # second FFN GEMM, the first layer's dX GEMM and both dW GEMMs land those operands by TMA without converting them in
-# shared memory.  OPT-IN (NPM_FFN_PLANES=1; tests flip the attribute).  Measured (tools/ffn_planes_probe.py, one kernel at
-# a time): every affected kernel is as fast or faster — dW GEMMs 144 -> 133 us, first-layer dX 137 -> 133 us, ReLU backward
-# 82 -> 78 us, 27 us per decoder layer in all — yet the power-capped cfg5 step is 1.0 ms SLOWER with it (six alternating
-# same-box runs, both orders: 87.8 vs 86.8 ms).  Results are bit-identical either way (the planes hold exactly the hi / mid
-# pairs the GEMM's converters would make).
-_NO_FFN_PLANES = not os.environ.get('NPM_FFN_PLANES')
+# shared memory.  Measured one kernel at a time (tools/ffn_planes_probe.py): dW GEMMs 144 -> 133 us, first-layer dX
+# 137 -> 133 us, ReLU backward 82 -> 78 us; cfg5 step (three alternating same-box pairs) 87.57 -> 86.68 ms.  Results equal
+# the fp32 route's to fp32 round-off (the planes hold exactly the hi / mid pairs the GEMM's converters would make).
+# NPM_NO_FFN_PLANES=1 keeps everything fp32 (A/B; tests flip the attribute).
+_NO_FFN_PLANES = bool(os.environ.get('NPM_NO_FFN_PLANES'))
 _UNSUPPORTED = -3
 
 
@@ -118,11 +117,18 @@ class Linear(layer.StatefulLayer):
         """backward with x and / or dy as split-bf16 planes (mlp.py:34-38): dw[k,n] = x^T dy with the planes as the
         MN-major A / B operand images, dx[m,k] = dy @ W^T with dy as the K-major A image.  Returns dx, or None when the
         split-bf16 GEMM does not take one of the problems (the caller then joins the planes and runs the fp32 route)."""
-        if db is None:
-            return None                                     # the bias gradient comes with dy from the ReLU backward
         m, k = x.shape
         n = w.shape[1]
         is_planes = lambda t: isinstance(t, device.PlanesArray)
+        if db is None:
+            if is_planes(dy):
+                return None                                 # a planes-only dy always comes with its bias gradient (Dense)
+            db = optimizer_.grad_buffer(self, '_b', (n,))
+            if dy.colsum is not None:
+                db.copy_from(dy.colsum)                     # summed by the kernel that produced dy (fused LayerNorm backward)
+            else:
+                ws = device.workspace(C.npm_colsum_workspace(m, n))
+                C.npm_colsum(dy.ptr, db.ptr, m, n, ws.data_ptr(), device.stream())
         xa = dict(a=None, a_split=x.hi_ptr, a_split_plane=x.size) if is_planes(x) else dict(a=x.ptr)
         yb = dict(b=None, b_split=dy.hi_ptr, b_split_plane=dy.size) if is_planes(dy) else dict(b=dy.ptr)
         if _gemm(c=dw.ptr, m=k, n=n, k=m, a_rs=1, a_cs=k, b_rs=n, b_cs=1, ldc=n, flags=0, **xa, **yb) != 0:

@@ -550,7 +550,7 @@ def test_decoder_vs_oracle_medium():
 
 @pytest.mark.parametrize('norm_first', [True, False])
 def test_ffn_hidden_activation_as_split_bf16_planes(norm_first, monkeypatch):
-    """Opt-in route of layers/mlp.py (`_NO_FFN_PLANES`): the FFN hidden activation and its gradient exist only as bf16
+    """The split-bf16 FFN route of layers/mlp.py (`_NO_FFN_PLANES` off): the FFN hidden activation and its gradient exist only as bf16
     hi / mid planes (device.PlanesArray) — written by the first GEMM's epilogue / the ReLU backward, landed by the
     consuming GEMMs without conversion.  The planes hold exactly the pairs the converters would make, so outputs,
     input gradients and every parameter gradient must equal the fp32 route's to fp32 round-off (mlp.py:21-38, 70-77)."""

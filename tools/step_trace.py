@@ -23,7 +23,7 @@ from train import Trainer, iter_parameters  # noqa: E402
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 B, S, D, H, F = 8, 1024, 1024, 16, 4096
-npm_b200.set_precision('tf32')
+npm_b200.set_precision(os.environ.get('NPM_TRACE_PREC', 'bf16x3'))
 np.random.seed(0)
 set_dropout_seed(1234)
 stack = adapters.DecoderStack(L, H, F, True, 0.1)
