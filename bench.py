@@ -331,6 +331,7 @@ def run_b200(args):
                 p.zero_()
             else:
                 p.copy_(torch.randn(p.shape, generator=gw, device='cuda') * 0.02)
+            owner._p(name).touched()          # written through the raw tensor: drop what was derived from the old values
         torch.cuda.synchronize()
 
     def timed(trainer, adam, inputs, targets, steps, read_loss):

@@ -426,6 +426,10 @@ typedef struct npm_tensor_entry {
     float*       v;           /* Adam second moment (NULL for SGD)              */
     int64_t      numel;
     int64_t      chunk_begin;
+    void*        planes;      /* NULL, or the bf16 hi plane of this parameter's split-bf16 image (npm_weight_split layout,
+                               * the mid plane `plane_stride` elements further): the update rewrites it from the new value,
+                               * so the next forward pass needs no split pass over the weights (NPM_PREC_BF16X3)      */
+    int64_t      plane_stride;
 } npm_tensor_entry;
 /* param -= lr * grad_scale * grad                              optimizer.py:30-33 */
 int npm_sgd_multi(const npm_tensor_entry* table_dev, int32_t n_tensors,

@@ -70,6 +70,12 @@ __device__ __forceinline__ int find_tensor(const npm_tensor_entry* tab, int n, i
     return lo;
 }
 
+__device__ __forceinline__ void split2(float p0, float p1, uint32_t& hi, uint32_t& mid) {     // bf16 hi / mid pairs of two values
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
+    const float r0 = p0 - __uint_as_float(hi << 16), r1 = p1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
+}
+
 template <bool kAdam>
 __global__ void __launch_bounds__(kThreads) opt_multi_kernel(const npm_tensor_entry* __restrict__ tab, int n_tensors,
                                                              int64_t n_chunks, float lr, float b1, float b2, float eps,
@@ -84,6 +90,8 @@ __global__ void __launch_bounds__(kThreads) opt_multi_kernel(const npm_tensor_en
         float* p = e.param;
         const float* g = e.grad;
         const bool vec = aligned16(p) && aligned16(g) && (!kAdam || (aligned16(e.m) && aligned16(e.v)));
+        // planes ride on the vector path only (the host attaches them to 16-byte aligned tensors of 4k elements)
+        uint2* planes = vec ? reinterpret_cast<uint2*>(e.planes) : nullptr;
         if (vec) {
             const int64_t nv = (end - begin) >> 2;
             for (int64_t i = threadIdx.x; i < nv; i += kThreads) {
@@ -105,6 +113,13 @@ __global__ void __launch_bounds__(kThreads) opt_multi_kernel(const npm_tensor_en
                     pv.x -= lr * gv.x; pv.y -= lr * gv.y; pv.z -= lr * gv.z; pv.w -= lr * gv.w;
                 }
                 *reinterpret_cast<float4*>(p + o) = pv;
+                if (planes != nullptr) {        // the updated weight's split-bf16 image (npm_weight_split layout)
+                    uint2 hi, mid;
+                    split2(pv.x, pv.y, hi.x, mid.x);
+                    split2(pv.z, pv.w, hi.y, mid.y);
+                    planes[o >> 2] = hi;
+                    planes[(e.plane_stride + o) >> 2] = mid;
+                }
             }
         }
         const int64_t tail0 = vec ? begin + (((end - begin) >> 2) << 2) : begin;

@@ -46,7 +46,7 @@ class MhaStrides(Structure):
 
 class TensorEntry(Structure):
     _fields_ = [('param', c_void_p), ('grad', c_void_p), ('m', c_void_p), ('v', c_void_p),
-                ('numel', c_int64), ('chunk_begin', c_int64)]
+                ('numel', c_int64), ('chunk_begin', c_int64), ('planes', c_void_p), ('plane_stride', c_int64)]
 
 
 P, I64, F, I, U64, SZ = c_void_p, c_int64, c_float, c_int, c_uint64, c_size_t

@@ -10,10 +10,14 @@ ndarray surface the reference's glue code uses (`shape`, `size`, `reshape`,
 Every arithmetic operation on it is one of this repo's CUDA kernels, reached
 through the C-ABI; nothing here computes on the host.
 """
+import os
+
 import numpy as np
 import torch
 
 from ._lib import C
+
+_NO_OPT_PLANES = bool(os.environ.get('NPM_NO_OPT_PLANES'))     # A/B: the optimizer does not maintain weight planes
 
 
 def stream():
@@ -39,13 +43,14 @@ class DeviceArray:
     def __init__(self, t: torch.Tensor, colsum=None, _cell=None):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'DeviceArray wraps contiguous fp32 CUDA'
         self.t = t
-        self._cs = _cell if _cell is not None else [None, 0]     # [colsum DeviceArray, numel of the array it sums]
+        # [colsum DeviceArray, numel of the array it sums, weight planes [buffer, base pointer, base numel, fresh, in sync] or None]
+        self._cs = _cell if _cell is not None else [None, 0, None]
         if colsum is not None:
             self.colsum = colsum
 
     @property
     def colsum(self):
-        cs, numel = self._cs
+        cs, numel = self._cs[0], self._cs[1]
         if cs is None or numel != self.t.numel() or self.t.dim() < 1 or cs.size != self.t.shape[-1]:
             return None
         return cs
@@ -54,6 +59,13 @@ class DeviceArray:
     def colsum(self, value):
         self._cs[0] = value
         self._cs[1] = self.t.numel() if value is not None else 0
+
+    def touched(self):
+        """Call after writing the storage behind this array other than through its own methods (a raw write through
+        `.t`): drops everything derived from the old contents (column sums, the split-bf16 image of a weight)."""
+        self._cs[0], self._cs[1] = None, 0
+        if self._cs[2] is not None:
+            self._cs[2][3] = self._cs[2][4] = False
 
     # ---- ndarray-like surface -------------------------------------------------
     @property
@@ -110,7 +122,7 @@ class DeviceArray:
         other = asdevice(other)
         assert other.shape == self.shape, f'{other.shape} vs {self.shape}'
         C.npm_add_inplace(self.ptr, other.ptr, self.size, stream())
-        self.colsum = None
+        self.touched()
         return self
 
     def __add__(self, other):
@@ -153,7 +165,7 @@ class DeviceArray:
         if not isinstance(other, (int, float, np.floating, np.integer)):
             return NotImplemented
         C.npm_scale(self.ptr, float(other), self.size, stream())
-        self.colsum = None
+        self.touched()
         return self
 
     def item(self):
@@ -169,7 +181,7 @@ class DeviceArray:
         else:
             host = np.ascontiguousarray(np.asarray(src), dtype=np.float32).reshape(self.shape)
             self.t.copy_(torch.from_numpy(host), non_blocking=False)
-        self.colsum = None
+        self.touched()
         return self
 
 
@@ -262,15 +274,50 @@ def zeros(shape) -> DeviceArray:
 
 def split_weight(w: 'DeviceArray'):
     """bf16 hi / mid planes of a weight for the split-bf16 ('bf16x3') contraction mode (npm_weight_split), or None in
-    the other modes.  A layer computes them once per forward call; its forward GEMM and its dX GEMM both take them as
-    their B operand without converting it again (gemm_bx.cu, B_PRE)."""
+    the other modes.  A layer asks once per forward call; its forward GEMM and its dX GEMM both take them as their B
+    operand without converting it again (gemm_bx.cu, B_PRE).
+
+    The buffer is kept on the array (shared by its views).  The fused optimizers rewrite it inside their update kernel
+    (npm_tensor_entry.planes) and mark it fresh; a fresh image is handed out ONCE — the first forward after an update
+    needs no split pass over the weights — and every other call splits again, so nothing that writes the weight in any
+    other way in between (a raw write through `.t`, a user optimizer) can leave a stale image behind."""
     from ._lib import PREC_BF16X3, load
     if load().npm_get_precision() != PREC_BF16X3 or w.size % 4 or w.ndim < 2:
         return None
     rows, cols = w.shape[0], w.size // w.shape[0]
-    planes = torch.empty(int(C.npm_weight_split_bytes(rows, cols)), dtype=torch.uint8, device=_device())
+    wp = w._cs[2]
+    if wp is not None and wp[1] == w.ptr and wp[2] == w.size:
+        if wp[3] and not _NO_OPT_PLANES:
+            wp[3] = False
+            return wp[0]
+        planes = wp[0]
+    else:
+        planes = torch.empty(int(C.npm_weight_split_bytes(rows, cols)), dtype=torch.uint8, device=_device())
+        wp = w._cs[2] = [planes, w.ptr, w.size, False, False]
     C.npm_weight_split(w.ptr, planes.data_ptr(), rows, cols, stream())
+    wp[4] = True          # the image matches the weight as of now
     return planes
+
+
+def weight_planes_of(v: 'DeviceArray'):
+    """(hi-plane pointer, plane stride in elements) of the split-bf16 image kept for parameter `v` (a whole array or a
+    view into a packed block), or None: what the fused optimizers put into npm_tensor_entry.planes."""
+    wp = v._cs[2]
+    if wp is None or _NO_OPT_PLANES:
+        return None
+    buf, base, numel, _, synced = wp
+    if not synced:
+        return None           # the weight was written behind the image's back since the last split: the next forward splits again
+    off = v.ptr - base
+    if off < 0 or off + 4 * v.size > 4 * numel or off % 16 or v.size % 4 or v.ptr % 16:
+        return None
+    return buf.data_ptr() + off // 2, numel
+
+
+def mark_weight_planes_fresh(v: 'DeviceArray'):
+    """The update kernel has rewritten `v`'s part of the image (it was given weight_planes_of(v))."""
+    if v._cs[2] is not None and v._cs[2][4]:
+        v._cs[2][3] = True
 
 
 def workspace(nbytes: int) -> torch.Tensor:

@@ -168,15 +168,19 @@ class _FusedOptimizer(Optimizer):
             self.bucket_ready(self, done)
 
     def _table(self, entries, moments):
-        key = tuple((v.ptr, g.ptr, v.size) for (_, v, g) in entries)
+        planes = [device.weight_planes_of(v) for (_, v, _) in entries]
+        key = tuple((v.ptr, g.ptr, v.size, pl) for (_, v, g), pl in zip(entries, planes))
         hit = self._tables.get(key)
         if hit is not None:
+            self._mark_planes(entries, planes)
             return hit
         arr = (TensorEntry * len(entries))()
         chunks = 0
         for i, (ident, v, g) in enumerate(entries):
             arr[i].param = v.ptr
             arr[i].grad = g.ptr
+            if planes[i] is not None:
+                arr[i].planes, arr[i].plane_stride = planes[i]
             if moments is not None:
                 m, s = moments(ident, v)
                 arr[i].m, arr[i].v = m.ptr, s.ptr
@@ -189,7 +193,16 @@ class _FusedOptimizer(Optimizer):
         if len(self._tables) > 64:
             self._tables.clear()
         self._tables[key] = hit
+        self._mark_planes(entries, planes)
         return hit
+
+    @staticmethod
+    def _mark_planes(entries, planes):
+        """The update kernel about to be launched with this table rewrites the split-bf16 image of every weight whose
+        planes are in it (the launch is stream-ordered before anything that can read them)."""
+        for (_, v, _), pl in zip(entries, planes):
+            if pl is not None:
+                device.mark_weight_planes_fresh(v)
 
     def flush(self):
         if not self._pending:
@@ -219,6 +232,7 @@ class SGDOptimizer(_FusedOptimizer):
         table, chunks = self._table(pending, None)
         C.npm_sgd_multi(table.data_ptr(), len(pending), chunks, float(self._learning_rate),
                         float(self.grad_scale), device.stream())
+
 
 
 @dataclasses.dataclass

@@ -158,7 +158,10 @@ class Trainer:
         rank, world = _world()
         if world == 1 or self._synced:
             return
-        npm_dist.broadcast_from_rank0([owner._p(name).t for owner, name in iter_parameters(list(self._layers))])
+        params = [owner._p(name) for owner, name in iter_parameters(list(self._layers))]
+        npm_dist.broadcast_from_rank0([p.t for p in params])
+        for p in params:
+            p.touched()                 # written behind the arrays' back
         self._synced = True
 
     def _install_grad_sync(self, optimizer_):

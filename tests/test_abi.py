@@ -43,7 +43,7 @@ def test_ctypes_table_matches_header():
 
 def test_struct_layouts_match_the_header():
     from npm_b200 import _lib
-    assert ctypes.sizeof(_lib.TensorEntry) == 48          # 4 pointers + 2 int64
+    assert ctypes.sizeof(_lib.TensorEntry) == 64          # 4 pointers + 2 int64 + planes pointer + plane stride
     assert ctypes.sizeof(_lib.MhaStrides) == 13 * 8       # q k v dq dk dv causal path planes q_plane k_plane v_plane do_ready
     assert _lib.MhaStrides.path.offset == 56
     assert _lib.MhaStrides.causal.offset == 48

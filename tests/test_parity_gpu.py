@@ -548,6 +548,58 @@ def test_decoder_vs_oracle_medium():
         close(got[k], v, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(v).max()))
 
 
+@pytest.mark.parametrize('opt_name', ['adam', 'sgd'])
+def test_optimizer_maintains_the_weight_planes(opt_name, monkeypatch):
+    """Split-bf16 mode: the fused optimizers rewrite each weight's bf16 hi / mid image inside their update kernel
+    (npm_tensor_entry.planes), so the forward after an update launches no split pass over the weights.  Same training
+    trajectory, bit for bit, as with a fresh npm_weight_split every forward (optimizer.py:30-33, 50-69)."""
+    import npm_b200
+    import optimizer
+    from layers import TransformerEncoder
+    from npm_b200 import device
+    from npm_b200._lib import C
+    from train import iter_parameters
+    npm_b200.set_precision('bf16x3')
+    rng = np.random.default_rng(9)
+    b, s_, d, h, f = 2, 136, 128, 2, 256
+    x = rng.standard_normal((b, s_, d)).astype(np.float32)
+    dy = (rng.standard_normal((b, s_, d)) * 0.1).astype(np.float32)
+    np.random.seed(9)
+    layer = TransformerEncoder(h, f, True, 0.0)
+    layer(x)
+    for owner, name in iter_parameters(layer):
+        v = np.asarray(getattr(owner, name))
+        if name.startswith('_w'):
+            setattr(owner, name, (v / np.sqrt(max(v.shape[-1], v.shape[0]))).astype(np.float32))
+    runs = []
+    for maintained in (False, True):
+        monkeypatch.setattr(device, '_NO_OPT_PLANES', not maintained)
+        clone = copy.deepcopy(layer)
+        opt = optimizer.AdamOptimizer(learning_rate=1e-2) if opt_name == 'adam' else optimizer.SGDOptimizer(1e-2)
+        counts = []
+        for _ in range(3):
+            before = C.npm_launch_count()
+            clone(x)
+            counts.append(C.npm_launch_count() - before)
+            clone(dy, backprop=True, optimizer_=opt)
+        # a raw write between an update and the next forward must be announced; then the forward splits again
+        p = clone._dense2._p('_w')
+        p.t.mul_(1.0)
+        p.touched()
+        before = C.npm_launch_count()
+        out = clone(x)
+        counts.append(C.npm_launch_count() - before)
+        runs.append((counts, np.asarray(out), {f'{i}.{n}': np.asarray(getattr(o, n)) for i, (o, n) in enumerate(iter_parameters(clone))}))
+    (c0, o0, p0), (c1, o1, p1) = runs
+    n_weights = 4                                           # packed q|k|v, wo, dense1, dense2
+    assert c0[0] == c0[1] == c0[2], 'without the feature every forward splits every weight'
+    assert c1[0] == c0[0] and c1[1] == c1[2] == c0[0] - n_weights, (c0, c1)
+    assert c1[3] == c0[0] - n_weights + 1, 'the touched weight, and only it, is split again'
+    np.testing.assert_array_equal(o1, o0)
+    for k in p0:
+        np.testing.assert_array_equal(p1[k], p0[k])
+
+
 @pytest.mark.parametrize('norm_first', [True, False])
 def test_ffn_hidden_activation_as_split_bf16_planes(norm_first, monkeypatch):
     """The split-bf16 FFN route of layers/mlp.py (`_NO_FFN_PLANES` off): the FFN hidden activation and its gradient exist only as bf16

@@ -43,6 +43,7 @@ for owner, name in iter_parameters(stack):
         p.zero_()
     else:
         p.copy_(torch.randn(p.shape, generator=gw, device='cuda') * 0.02)
+    owner._p(name).touched()
 adam = opt_mod.AdamOptimizer(learning_rate=1e-4)
 for _ in range(3):
     trainer.train((q, kv), t, 1, adam)
