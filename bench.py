@@ -475,7 +475,7 @@ def run_b200(args):
     if not args.no_alt:
         alt = []
         for other in [m for m in ('tf32', 'bf16', '3xtf32') if m != args.precision]:
-            a = measure(other, max(2, args.steps // 4), 3, with_e2e=False)
+            a = measure(other, max(5, args.steps // 2), 4, with_e2e=False)      # a fresh model per mode: its first steps still grow the allocator's pools
             atf, _ = gemm_roofline(other)
             alt.append(dict(precision=other, value=a['value'], ms_per_step=a['ms_per_step'], gemm_tflops=atf,
                             tolerance={'tf32': 'single tensor-core pass, 10-bit operand mantissas: stated 2e-3 relative Frobenius, NOT north_star\'s',
