@@ -644,6 +644,43 @@ def test_ffn_hidden_activation_as_split_bf16_planes(norm_first, monkeypatch):
     assert hidden.shape == (b * s_, f) and np.asarray(hidden).shape == (b * s_, f)
 
 
+def test_ffn_planes_survive_a_precision_change_between_forward_and_backward():
+    """The hidden activation written as split-bf16 planes in bf16x3 mode must still back-propagate when the mode is
+    changed before backward (nothing may misread what forward saved): the GEMMs of the other modes decline the
+    planes (NPM_ERR_UNSUPPORTED), the layer joins them to fp32 and takes the plain route."""
+    import npm_b200
+    from layers import TransformerEncoder
+    from npm_b200 import device
+    from train import iter_parameters
+    rng = np.random.default_rng(5)
+    b, s_, d, h, f = 2, 136, 128, 2, 256
+    x = rng.standard_normal((b, s_, d)).astype(np.float32)
+    dy = rng.standard_normal((b, s_, d)).astype(np.float32)
+    npm_b200.set_precision('bf16x3')
+    np.random.seed(5)
+    layer = TransformerEncoder(h, f, True, 0.0)
+    layer(x)
+    for owner, name in iter_parameters(layer):
+        v = np.asarray(getattr(owner, name))
+        if name.startswith('_w'):
+            setattr(owner, name, (v / np.sqrt(max(v.shape[-1], v.shape[0]))).astype(np.float32))
+    got = []
+    for bwd_mode in ('bf16x3', '3xtf32'):
+        npm_b200.set_precision('bf16x3')
+        clone = copy.deepcopy(layer)
+        clone(x)
+        assert isinstance(clone._dense1._y, device.PlanesArray)
+        npm_b200.set_precision(bwd_mode)
+        rec = Recorder()
+        dx = clone(dy, backprop=True, optimizer_=rec)
+        got.append((np.asarray(dx), [np.asarray(rec.grads[f'{id(o)}.{n}']) for o, n in iter_parameters(clone)]))
+    npm_b200.set_precision('bf16x3')
+    (dx0, g0), (dx1, g1) = got
+    close(dx1, dx0)
+    for a, e in zip(g1, g0):
+        close(a, e, rtol=1e-3, atol=1e-4 * np.sqrt(b * s_) * max(1.0, np.abs(e).max()))
+
+
 # ------------------------------------------------------------------ conv
 @pytest.mark.parametrize('tag', ['c3', 'c8', 'k5', 'k1'])
 def test_conv_golden(tag):
