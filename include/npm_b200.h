@@ -186,6 +186,13 @@ int npm_linear_bwd_dx_planes_rowdot(const float* dy, const float* w, const void*
  *   dz = where(gate, dy, 0) is written as bf16 hi / mid planes (mid `plane` elements after hi), db[cols] = column sums
  *   of dz.  workspace: npm_colsum_workspace(rows, cols).  NPM_ERR_UNSUPPORTED unless cols %% 4 == 0 and cols <= 16384.
  * npm_planes_join: out[n] fp32 = hi + mid (exact), for consumers outside the split-bf16 kernels. */
+/* LayerNormalization.forward (normalizations.py:43-58), optionally with DropOut.forward (:14-23) in front of it (maskbits
+ * != NULL and keep_prob < 1: the same Philox mask and keep bits as npm_dropout_layernorm_fwd), whose result exists only
+ * as split-bf16 planes: the normalised activation of a pre-norm transformer block feeds nothing but the first FFN GEMM
+ * and its dW GEMM, which take the planes as their operand image.  mean / rstd as npm_layernorm_fwd. */
+int npm_layernorm_fwd_planes(const float* x, const float* gamma, const float* beta, void* out_planes, int64_t plane,
+                             float* mean, float* rstd, uint32_t* maskbits, int64_t rows, int64_t cols, float epsilon,
+                             float keep_prob, uint64_t seed, uint64_t offset, npm_stream_t stream);
 int npm_relu_bwd_colsum_planes(const void* y_hi, const float* dy, void* dz_planes, int64_t plane, float* db,
                                int64_t rows, int64_t cols, void* workspace, npm_stream_t stream);
 int npm_planes_join(const void* planes, int64_t plane, float* out, int64_t n, npm_stream_t stream);

@@ -143,13 +143,20 @@ __device__ __forceinline__ uint32_t drop4(float4& v, const DropArgs& d, uint64_t
     v.z = (k & 4u) ? v.z * d.inv_keep : 0.0f; v.w = (k & 8u) ? v.w * d.inv_keep : 0.0f;
     return k;
 }
-template <int NV, bool DROP = false>
+// PLANES: the result goes out ONLY as split-bf16 planes (`out` is the bf16 hi plane, the mid plane plane4 uint2 units
+// further) — the A operand image of the GEMM that follows (the first FFN layer in a pre-norm block), same bytes as fp32.
+__device__ __forceinline__ void ln_split2(float p0, float p1, uint32_t& hi, uint32_t& mid) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p1), "f"(p0));
+    const float r0 = p0 - __uint_as_float(hi << 16), r1 = p1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
+}
+template <int NV, bool DROP = false, bool PLANES = false>
 __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, float* __restrict__ out,
                                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                     int64_t rows, int cols, float eps, DropArgs drop = DropArgs{},
-                                                                    uint32_t* __restrict__ maskbits = nullptr) {
+                                                                    uint32_t* __restrict__ maskbits = nullptr, int64_t plane4 = 0) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -193,7 +200,23 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float*
             r.v[i].w = g.w * ((r.v[i].w - mean) * rstd) + b.w;
         }
     }
-    r.store(out + row * cols, cols, lane);
+    if (PLANES) {
+        uint2* pl = reinterpret_cast<uint2*>(out);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < cols) {
+                uint2 h, m;
+                ln_split2(r.v[i].x, r.v[i].y, h.x, m.x);
+                ln_split2(r.v[i].z, r.v[i].w, h.y, m.y);
+                const int64_t q = (row * cols + c) >> 2;
+                pl[q] = h;
+                pl[plane4 + q] = m;
+            }
+        }
+    } else {
+        r.store(out + row * cols, cols, lane);
+    }
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
@@ -863,6 +886,47 @@ size_t npm_dropout_layernorm_mask_bytes(int64_t rows, int64_t cols) {
     return rows > 0 ? (size_t)rows * 32 * sizeof(uint32_t) : 0;     // 4 keep bits per float4, one word per lane and row
 }
 
+// LayerNormalization forward (and the fused DropOut -> LayerNormalization) whose result exists only as split-bf16 planes.
+// keep_prob >= 1 (or maskbits == NULL) = no dropout.  NPM_ERR_UNSUPPORTED unless cols % 4 == 0, cols <= 1024, plane % 4 == 0.
+int npm_layernorm_fwd_planes(const float* x, const float* gamma, const float* beta, void* out_planes, int64_t plane, float* mean,
+                             float* rstd, uint32_t* maskbits, int64_t rows, int64_t cols, float epsilon, float keep_prob,
+                             uint64_t seed, uint64_t offset, npm_stream_t stream) {
+    if (rows <= 0 || cols <= 0) return NPM_OK;
+    NPM_REQUIRE(x && gamma && beta && out_planes && mean && rstd, "layernorm_fwd_planes: NULL pointer");
+    const bool drop = maskbits != nullptr && keep_prob < 1.0f;
+    NPM_REQUIRE(!drop || keep_prob > 0.0f, "layernorm_fwd_planes: keep_prob %g out of (0,1]", keep_prob);
+    const int nv = nv_for(cols);
+    if (!(nv && nv <= 8 && (cols & 3) == 0 && (plane & 3) == 0 && (rows * cols) % 4 == 0 && aligned16(x) && aligned16(gamma) &&
+          aligned16(beta) && (reinterpret_cast<uintptr_t>(out_planes) & 7u) == 0 && (!drop || (offset & 3) == 0))) {
+        set_error("layernorm_fwd_planes: needs cols %% 4 == 0, cols <= 1024, plane %% 4 == 0, offset %% 4 == 0 and aligned pointers");
+        return NPM_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+    float* out = reinterpret_cast<float*>(out_planes);
+    const int64_t plane4 = plane / 4;
+    if (drop) {
+        const DropArgs d = make_drop(keep_prob, seed, offset);
+        switch (nv) {
+            case 1: launch_pdl(layernorm_fwd_kernel<1, true, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits, plane4); break;
+            case 2: launch_pdl(layernorm_fwd_kernel<2, true, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits, plane4); break;
+            case 4: launch_pdl(layernorm_fwd_kernel<4, true, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits, plane4); break;
+            default: launch_pdl(layernorm_fwd_kernel<8, true, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits, plane4); break;
+        }
+    } else {
+        const DropArgs d = DropArgs{};
+        uint32_t* nomask = nullptr;
+        switch (nv) {
+            case 1: launch_pdl(layernorm_fwd_kernel<1, false, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, nomask, plane4); break;
+            case 2: launch_pdl(layernorm_fwd_kernel<2, false, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, nomask, plane4); break;
+            case 4: launch_pdl(layernorm_fwd_kernel<4, false, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, nomask, plane4); break;
+            default: launch_pdl(layernorm_fwd_kernel<8, false, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, nomask, plane4); break;
+        }
+    }
+    count_launch();
+    return check_launch("layernorm_fwd_planes");
+}
+
 int npm_dropout_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
                               uint32_t* maskbits, int64_t rows, int64_t cols, float epsilon, float keep_prob, uint64_t seed,
                               uint64_t offset, npm_stream_t stream) {
@@ -881,7 +945,7 @@ int npm_dropout_layernorm_fwd(const float* x, const float* gamma, const float* b
         case 1: layernorm_fwd_kernel<1, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
         case 2: layernorm_fwd_kernel<2, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
         case 4: layernorm_fwd_kernel<4, true><<<grid, kRowThreads, 0, s>>>(x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
-        default: launch_pdl(layernorm_fwd_kernel<8, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits); break;
+        default: launch_pdl(layernorm_fwd_kernel<8, true>, dim3(grid), dim3(kRowThreads), 0, s, 1, x, gamma, beta, out, mean, rstd, rows, (int)cols, epsilon, d, maskbits, (int64_t)0); break;
     }
     count_launch();
     return check_launch("dropout_layernorm_fwd");

@@ -6,7 +6,7 @@ import torch
 
 import optimizer
 from layers import layer
-from npm_b200 import device
+from npm_b200 import _lib, device
 from npm_b200 import dist as npm_dist
 from npm_b200._lib import C
 
@@ -137,13 +137,21 @@ class LayerNormalization(layer.StatefulLayer):
 # result-identical to those call sequences (same Philox mask, same arithmetic) but never write the dropped
 # tensor: 1 launch instead of 2 forward, 1 instead of 3 backward.  They fall back to the plain sequence
 # whenever the fused kernel does not apply (no dropout, injected mask, wide or unaligned rows).
-def dropout_layernorm_forward(drop: DropOut, norm: LayerNormalization, x):
+def dropout_layernorm_forward(drop: DropOut, norm: LayerNormalization, x, _planes_out: bool = False):
+    """`_planes_out` (the transformer blocks, for the normalisation in front of the FFN): in split-bf16 mode the result
+    may be a device.PlanesArray — it then exists only as the bf16 hi / mid planes the first FFN GEMM and its dW GEMM take
+    as their operand image (npm_layernorm_fwd_planes)."""
     x = device.asdevice(x)
     if not norm._initialized:
         norm.initialize(x)
         norm._initialized = True
     cols = x.shape[-1]
     rows = x.size // cols
+    if _planes_out and not _NO_LN_PLANES and drop._ext_mask is None and rows > 128 and cols % 8 == 0 and \
+            _lib.load().npm_get_precision() == _lib.PREC_BF16X3 and C.npm_dropout_layernorm_fused(rows, cols):
+        out = _layernorm_planes(drop, norm, x, rows, cols)
+        if out is not None:
+            return out
     if drop._drop_prob == 0.0 or drop._ext_mask is not None or not C.npm_dropout_layernorm_fused(rows, cols):
         return norm(drop(x))
     keep_prob = np.float32(1 - drop._drop_prob)
@@ -160,6 +168,40 @@ def dropout_layernorm_forward(drop: DropOut, norm: LayerNormalization, x):
                                 norm._maskbits.data_ptr(), rows, cols, float(norm._epsilon), keep_prob, seed, offset,
                                 device.stream())
     return out
+
+
+_NO_LN_PLANES = bool(os.environ.get('NPM_NO_LN_PLANES'))          # A/B switch for tools
+
+
+def _layernorm_planes(drop: DropOut, norm: LayerNormalization, x, rows, cols):
+    """(DropOut ->) LayerNormalization with the result written only as split-bf16 planes; None = not taken.  Backward is
+    the fp32 one in both cases: it reads the layer's INPUT (`norm._x`), never its output."""
+    with_drop = drop._drop_prob != 0.0
+    gamma, beta = norm._p('_gamma'), norm._p('_beta')
+    buf = device.workspace(4 * rows * cols)
+    mean, rstd = device.empty((rows,)), device.empty((rows,))
+    keep_prob, seed, offset, maskbits = np.float32(1.0), 0, 0, None
+    if with_drop:
+        keep_prob = np.float32(1 - drop._drop_prob)
+        seed = _philox['seed']
+        offset, new_offset = npm_dist.dropout_range(x.size, _philox['offset'], *npm_dist.world())
+        maskbits = device.workspace(C.npm_dropout_layernorm_mask_bytes(rows, cols))
+    rc = _lib.load().npm_layernorm_fwd_planes(x.ptr, gamma.ptr, beta.ptr, buf.data_ptr(), rows * cols, mean.ptr, rstd.ptr,
+                                             maskbits.data_ptr() if maskbits is not None else None, rows, cols,
+                                             float(norm._epsilon), keep_prob, seed, offset, device.stream())
+    if rc == -3:                                   # NPM_ERR_UNSUPPORTED
+        return None
+    if rc != 0:
+        raise _lib.NpmError(f'npm_layernorm_fwd_planes failed (rc={rc}): {_lib.last_error()}')
+    norm._x, norm._mean, norm._rstd = x, mean, rstd
+    if with_drop:
+        _philox['offset'] = new_offset
+        drop._rng, drop._shape = (seed, offset), x.shape
+        norm._maskbits = maskbits
+        norm._fused = (keep_prob, seed, offset)
+    else:
+        norm._fused = None
+    return device.PlanesArray(buf, x.shape)
 
 
 _NO_COLSUM_RIDE = bool(os.environ.get('NPM_NO_COLSUM_RIDE'))      # A/B switch for tools

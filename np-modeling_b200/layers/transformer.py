@@ -57,7 +57,7 @@ class TransformerEncoder(layer.Layer):
         skip = out
 
         if self._norm_first:
-            out = normalizations.dropout_layernorm_forward(self._dropout2, self._norm2, out)
+            out = normalizations.dropout_layernorm_forward(self._dropout2, self._norm2, out, _planes_out=not mlp._NO_FFN_PLANES)
         out = self._dense1(out, _alias_ok=True, _planes_ok=True)
         out = self._dense2(out, _residual=skip)               # `out += skip` (transformer.py:53,155)
         if not self._norm_first:
@@ -149,7 +149,7 @@ class TransformerDecoder(layer.Layer):
         skip = out
 
         if self._norm_first:
-            out = normalizations.dropout_layernorm_forward(self._dropout3, self._norm3, out)
+            out = normalizations.dropout_layernorm_forward(self._dropout3, self._norm3, out, _planes_out=not mlp._NO_FFN_PLANES)
         out = self._dense1(out, _alias_ok=True, _planes_ok=True)
         out = self._dense2(out, _residual=skip)               # `out += skip` (transformer.py:53,155)
         if not self._norm_first:

@@ -73,6 +73,7 @@ SIGNATURES = {
     'npm_linear_bwd_dw_db': (c_int, [P, P, P, P, I64, I64, I64, I, P, P]),
     'npm_linear_bwd_dx_planes_rowdot': (c_int, [P, P, P, I64, P, I64, I64, I64, I64, I, P, I64, P, I64, P]),
     'npm_relu_bwd_colsum_planes': (c_int, [P, P, P, I64, P, I64, I64, P, P]),
+    'npm_layernorm_fwd_planes': (c_int, [P, P, P, P, I64, P, P, P, I64, I64, F, F, U64, U64, P]),
     'npm_planes_join': (c_int, [P, I64, P, I64, P]),
     'npm_colsum_workspace': (c_size_t, [I64, I64]),
     'npm_colsum': (c_int, [P, P, I64, I64, P, P]),
@@ -158,7 +159,7 @@ class _Calls:
         lib = load()
         fn = getattr(lib, name)
         res = SIGNATURES[name][0]
-        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision', 'npm_dropout_layernorm_fused', 'npm_mha_core_path', 'npm_linear_fwd_planes', 'npm_linear_bwd_dx_planes_rowdot', 'npm_relu_bwd_colsum_planes'):
+        if res is c_int and name not in ('npm_version', 'npm_set_precision', 'npm_get_precision', 'npm_dropout_layernorm_fused', 'npm_mha_core_path', 'npm_linear_fwd_planes', 'npm_linear_bwd_dx_planes_rowdot', 'npm_relu_bwd_colsum_planes', 'npm_layernorm_fwd_planes'):
             def call(*args, _fn=fn, _name=name):
                 rc = _fn(*args)
                 if rc != NPM_OK:
