@@ -70,6 +70,25 @@ def main():
         chunks += (s_ + OPT_CHUNK - 1) // OPT_CHUNK
     table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
     report('adam_multi (16.8 M params, 28 B/param)', 28 * sum(sizes), lambda: C.npm_adam_multi(p(table), len(sizes), chunks, 1e-4, 0.9, 0.999, 1e-7, 1, 1.0, st))
+    # the same update also rewriting the weights' split-bf16 image (npm_tensor_entry.planes): 32 B/param for the weights
+    wsizes = [s_ for s_ in sizes if s_ >= 1024 * 1024]
+    planes = [torch.empty(4 * s_, dtype=torch.uint8, device='cuda') for s_ in sizes]
+    for i, s_ in enumerate(sizes):
+        if s_ >= 1024 * 1024:
+            arr[i].planes, arr[i].plane_stride = planes[i].data_ptr(), s_
+    table2 = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
+    report('adam_multi + weight planes (32 B/param)', 28 * sum(sizes) + 4 * sum(wsizes),
+           lambda: C.npm_adam_multi(p(table2), len(sizes), chunks, 1e-4, 0.9, 0.999, 1e-7, 1, 1.0, st))
+    # split-bf16 activation planes (bf16x3 mode): ReLU backward gated by the hi plane, LayerNorm forward writing planes
+    from npm_b200._lib import load
+    yp = torch.empty(4 * R * F, dtype=torch.uint8, device='cuda')
+    C.npm_weight_split(p(Y), p(yp), R, F, st)
+    dzp = torch.empty(4 * R * F, dtype=torch.uint8, device='cuda')
+    report('relu_bwd+colsum planes [8192,4096] (10 B/elem)', 10 * R * F,
+           lambda: load().npm_relu_bwd_colsum_planes(p(yp), p(X), p(dzp), R * F, p(dbf), R, F, p(ws), st))
+    op = torch.empty(4 * n, dtype=torch.uint8, device='cuda')
+    report('dropout+layernorm fwd -> planes (8 B/elem)', 8 * n,
+           lambda: load().npm_layernorm_fwd_planes(p(x), p(g), p(b), p(op), n, p(mean), p(rstd), p(mb), R, Cn, 1e-3, 0.9, 1, 0, st))
 
 
 if __name__ == '__main__':

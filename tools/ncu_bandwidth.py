@@ -14,6 +14,8 @@ ALGO = [   # launch order of tools/ew_bench.py: (label, algorithmic bytes)
     ('add_inplace', 12 * 8192 * 1024), ('add3', 16 * 8192 * 1024), ('colsum [8192,1024]', 4 * 8192 * 1024),
     ('colsum [8192,4096]', 4 * 8192 * 4096), ('relu_bwd+colsum [8192,4096]', 12 * 8192 * 4096), ('softmax_fwd [8192,1024]', 8 * 8192 * 1024),
     ('adam_multi 16.8M params', 28 * 16798720),
+    ('adam_multi + weight planes', 28 * 16798720 + 4 * 16777216), ('weight_split of y (set-up, not a result)', 8 * 8192 * 4096),
+    ('relu_bwd+colsum planes [8192,4096]', 10 * 8192 * 4096), ('dropout+layernorm fwd -> planes', 8 * 8192 * 1024),
 ]
 
 
