@@ -60,16 +60,24 @@ class Trainer:
                  layers: Sequence[layer.Layer],
                  loss_: Optional[loss.Loss] = None,
                  verbose: bool = True,
-                 shard_inputs: bool = True):
+                 shard_inputs: bool = True,
+                 cuda_graph: bool = False):
         """`verbose=False` silences the reference's Step/Loss prints; `shard_inputs=False` says the
         arrays passed to train()/eval() already are this rank's shard.  Extension over the reference:
         `inputs` may be a tuple — it is splatted into the first layer (e.g. `(q, kv)` for a
-        DecoderStack), and a tuple gradient is reduced to its first element between layers."""
+        DecoderStack), and a tuple gradient is reduced to its first element between layers.
+        `cuda_graph=True` (single process, SGDOptimizer, no stochastic layer, `verbose=False`): after two eager steps of
+        a `train()` call the whole step — forward chain, loss, reverse chain, fused update — is captured once into a
+        CUDA graph and replayed for the remaining steps, one launch per step instead of one per kernel (a launch-bound
+        model such as cfg1's MLP is otherwise bound by ~15 us of host work per kernel); anything that does not
+        qualify, or whose capture fails, runs the eager loop."""
         self._layers = layers
         self._loss = loss_ or loss.MSELoss()
         self._verbose = verbose
         self._shard_inputs = shard_inputs
         self._synced = False
+        self._cuda_graph = cuda_graph
+        self._graphs = {}          # (input shapes, optimizer) -> captured step
         self._pinned = {}
         self._prefetched = {}      # key -> (host object, device arrays, event) uploaded ahead of time on the copy stream
         self._copy_stream = None
@@ -212,9 +220,16 @@ class Trainer:
             self._forward(self._to_device('inputs', inputs))
             self._broadcast_parameters()
 
-        for i in range(steps):
+        i = 0
+        while i < steps:
+            if self._graph_ready(optimizer_, i, steps):
+                done = self._train_graphed(inputs, targets, steps - i, optimizer_, orig_inputs, orig_targets)
+                if done:
+                    return
+                self._cuda_graph = False       # capture failed: eager from here on
             if self._verbose:
                 print('Step: ', i)
+            i += 1
 
             logging.info('Running forward pass')
             y = self._to_device('inputs', inputs, orig=orig_inputs)
@@ -241,6 +256,74 @@ class Trainer:
                 # printed after the backward pass is enqueued so the host never stalls the GPU
                 # mid-step; the text is the reference's (train.py:32)
                 print('Loss: ', self.last_loss)
+
+    # ---- CUDA-graph replay of a whole step (opt-in, see __init__) --------------------------------
+    def _graph_ready(self, optimizer_, i, steps) -> bool:
+        if not self._cuda_graph or self._verbose or _world()[1] > 1 or not isinstance(optimizer_, optimizer.SGDOptimizer):
+            return False
+        if optimizer_.grad_sync is not None or optimizer_.bucket_ready is not None:
+            return False
+        return i >= 2 and steps - i >= 2          # two eager steps first: lazy init, allocator pools, kernel attributes
+
+    def _one_step(self, y, t, optimizer_):
+        y = self._forward(y)
+        l = self._loss(y, t)
+        dy = self._loss(backprop=True)
+        optimizer_._enter()
+        try:
+            for layer_ in reversed(self._layers):
+                dy = layer_(dy, backprop=True, optimizer_=optimizer_)
+                if isinstance(dy, tuple):
+                    dy = dy[0]
+        finally:
+            optimizer_._exit()
+        return l
+
+    def _train_graphed(self, inputs, targets, steps, optimizer_, orig_inputs, orig_targets) -> bool:
+        from layers import normalizations
+        as_tuple = lambda v: v if isinstance(v, tuple) else (v,)
+        first_in = self._to_device('inputs', inputs, orig=orig_inputs)
+        first_t = self._to_device('targets', targets, orig=orig_targets)
+        # a captured step is tied to the buffers it was captured with: input shapes, the optimizer (its gradient arena)
+        # and every parameter's storage (an attribute rebound by the user gets a new buffer, and with it a new capture)
+        key = (tuple(a.shape for a in as_tuple(first_in)), first_t.shape, id(optimizer_),
+               tuple(owner._p(name).ptr for owner, name in iter_parameters(list(self._layers))))
+        entry = self._graphs.get(key)
+        if entry is None:
+            # static input buffers: the graph reads these addresses on every replay
+            stat_in = tuple(device.empty(a.shape) for a in as_tuple(first_in))
+            stat_t = device.empty(first_t.shape)
+            for dst, src in zip(stat_in + (stat_t,), as_tuple(first_in) + (first_t,)):
+                dst.t.copy_(src.t)
+            before = normalizations._philox['offset']
+            graph = torch.cuda.CUDAGraph()
+            try:
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph):
+                    l = self._one_step(stat_in if isinstance(first_in, tuple) else stat_in[0], stat_t, optimizer_)
+            except Exception as exc:                      # noqa: BLE001 — any capture problem means: stay eager
+                logging.warning('Trainer: CUDA-graph capture failed (%s); running eagerly', exc)
+                torch.cuda.synchronize()
+                return False
+            if normalizations._philox['offset'] != before or not isinstance(l, device.DeviceScalar):
+                # a stochastic layer baked one dropout mask into the graph, or the loss is not a device value: not replayable
+                logging.warning('Trainer: the step is not replayable as a CUDA graph; running eagerly')
+                return False
+            entry = self._graphs[key] = (graph, stat_in, stat_t, l._t)
+            # capture does not execute: the captured step still has to run for this iteration
+        graph, stat_in, stat_t, loss_t = entry
+        for k in range(steps):
+            if k > 0:
+                ins = as_tuple(self._to_device('inputs', inputs, orig=orig_inputs))
+                tgt = self._to_device('targets', targets, orig=orig_targets)
+            else:
+                ins, tgt = as_tuple(first_in), first_t
+            for dst, src in zip(stat_in + (stat_t,), ins + (tgt,)):
+                if dst.ptr != src.ptr:
+                    dst.t.copy_(src.t, non_blocking=True)
+            graph.replay()
+            self.last_loss = device.DeviceScalar(device.DeviceArray(loss_t.clone()))
+        return True
 
     # ---- checkpoint / resume (the reference has none) -------------------------
     def save_checkpoint(self, path: str, optimizer_: Optional[optimizer.Optimizer] = None) -> None:

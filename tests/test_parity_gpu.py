@@ -548,6 +548,47 @@ def test_decoder_vs_oracle_medium():
         close(got[k], v, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(v).max()))
 
 
+def test_trainer_cuda_graph_replay_equals_the_eager_loop():
+    """Trainer(cuda_graph=True): after two eager steps the whole step (forward chain, loss, reverse chain, fused SGD update)
+    is captured once and replayed; parameters and losses must equal the eager loop's (to the last bits: atomic sums), with
+    different data in every step (train.py:20-39).  Adam (host-side bias correction) and stochastic layers stay eager."""
+    import loss
+    import optimizer
+    from layers import Dense, Softmax
+    from npm_b200._lib import C
+    from train import Trainer, iter_parameters
+    rng = np.random.default_rng(21)
+    xs = [rng.standard_normal((64, 96)).astype(np.float32) for _ in range(7)]
+    ts = [np.eye(10, dtype=np.float32)[rng.integers(0, 10, 64)] for _ in range(7)]
+    runs = []
+    for graphed in (False, True):
+        np.random.seed(21)
+        layers_ = [Dense(48), Dense(10, activation=Softmax())]
+        tr = Trainer(layers_, loss.CrossEntropyLoss(), verbose=False, cuda_graph=graphed)
+        opt = optimizer.SGDOptimizer(1e-3)
+        tr._forward(tr._to_device('inputs', xs[0]))
+        for owner, name in iter_parameters(layers_):
+            v = np.asarray(getattr(owner, name))
+            setattr(owner, name, (v / np.sqrt(v.shape[0])).astype(np.float32) if name == '_w' else v)
+        losses = []
+        # one call with the same batch six times (graph from the third step on), then per-batch calls of four steps each
+        tr.train(xs[0], ts[0], 6, opt)
+        losses.append(float(tr.last_loss))
+        for x, t in zip(xs[1:], ts[1:]):
+            before = C.npm_launch_count()
+            tr.train(x, t, 4, opt)
+            launched = C.npm_launch_count() - before
+            losses.append(float(tr.last_loss))
+        runs.append((losses, [np.asarray(getattr(o, n)) for o, n in iter_parameters(layers_)], launched, len(tr._graphs)))
+    (l0, p0, n0, g0), (l1, p1, n1, g1) = runs
+    assert g0 == 0 and g1 == 1, 'one capture, reused by the later train() calls'
+    assert n1 < n0, 'replayed steps launch nothing through the C-ABI'
+    # same kernels on the same data; the loss sum and the split-K reductions add in an order that is not fixed run to run
+    np.testing.assert_allclose(np.array(l1), np.array(l0), rtol=1e-6)
+    for a, e in zip(p1, p0):
+        np.testing.assert_allclose(a, e, rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize('opt_name', ['adam', 'sgd'])
 def test_optimizer_maintains_the_weight_planes(opt_name, monkeypatch):
     """Split-bf16 mode: the fused optimizers rewrite each weight's bf16 hi / mid image inside their update kernel

@@ -34,14 +34,16 @@ def scale_weights(layers_):
             setattr(owner, name, np.zeros_like(v))
 
 
-def timeit(name, layers_, loss_, opt, x, t, steps, flop=None, tokens=None):
-    tr = Trainer(layers_, loss_, verbose=False)
+def timeit(name, layers_, loss_, opt, x, t, steps, flop=None, tokens=None, cuda_graph=False):
+    tr = Trainer(layers_, loss_, verbose=False, cuda_graph=cuda_graph)
     xd = device.asdevice(x) if not isinstance(x, tuple) else tuple(device.asdevice(a) for a in x)
     td = device.asdevice(t)
     tr._forward(xd)                     # lazy init only (an update with the unscaled reference init would overflow)
     scale_weights(layers_)
     for _ in range(3):
         tr.train(xd, td, 1, opt)
+    if cuda_graph:
+        tr.train(xd, td, 6, opt)        # captures (and instantiates) the step once; the timed call below replays it
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -62,6 +64,8 @@ x = rng.standard_normal((64, 784)).astype(np.float32)
 t = np.eye(10, dtype=np.float32)[rng.integers(0, 10, 64)]
 timeit('cfg1 MLP 784-256-10 b64 CE SGD', [Dense(256), Dense(10, activation=Softmax())], loss.CrossEntropyLoss(),
        optimizer.SGDOptimizer(1e-4), x, t, 50, flop=78.1e6)
+timeit('cfg1 (same, step replayed as a CUDA graph)', [Dense(256), Dense(10, activation=Softmax())], loss.CrossEntropyLoss(),
+       optimizer.SGDOptimizer(1e-4), x, t, 50, flop=78.1e6, cuda_graph=True)
 # cfg2: conv stack
 x = rng.standard_normal((256, 32, 32, 3)).astype(np.float32)
 t = rng.standard_normal((256, 32, 32, 128)).astype(np.float32)
