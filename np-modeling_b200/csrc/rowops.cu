@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kRowThreads) relu_bwd_colsum_planes_kernel(con
     const int64_t r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
     float4 acc = make_float4(0, 0, 0, 0);
     if (c < cols) {
-        constexpr int U = 4;       // rows in flight per thread
+        constexpr int U = 4;       // rows in flight per thread (measured at [8192, 4096]: 2 -> 80.7 us, 4 -> 78.9 us, 8 -> 86.9 us)
         auto one = [&](float4 v, uint2 y, int64_t r) {
             v.x = (y.x & 0x8000u) ? 0.0f : v.x; v.y = (y.x & 0x80000000u) ? 0.0f : v.y;
             v.z = (y.y & 0x8000u) ? 0.0f : v.z; v.w = (y.y & 0x80000000u) ? 0.0f : v.w;
