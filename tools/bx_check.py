@@ -3,7 +3,6 @@ combination, ragged edges, batches, split-K, bias / residual / ReLU epilogues.  
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

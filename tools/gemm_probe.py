@@ -8,7 +8,6 @@ one-hot inputs land (to debug descriptor / swizzle layouts).
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
